@@ -1,0 +1,136 @@
+"""torch.autograd.Function wrappers: the only place where kernels meet autograd.
+
+Every Function's forward/backward launches libidrk kernels.  Where the reference needs SECOND-order
+derivatives (ImplicitNetwork.gradient uses create_graph=True, implicit_differentiable_renderer.py:116-128)
+the backward pass is expressed through other differentiable Functions / device tensor ops whenever
+grad mode is on, so double backward works without hand-written second-order kernels.
+"""
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import kernels as K
+from ._lib import IdrkError
+
+TWO_PI = 2.0 * math.pi
+
+
+# ---------------------------------------------------------------------------------------------
+# hash grid (+ Fourier prefix)
+# ---------------------------------------------------------------------------------------------
+class _HashEncode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, B, spec, *tables):
+        out = K.hash_encode_fwd(spec, x, tables, B)
+        ctx.spec = spec
+        ctx.has_B = B is not None
+        ctx.save_for_backward(x, *( [B] if B is not None else [] ), *tables)
+        return out[:, :spec.width]
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec = ctx.spec
+        saved = ctx.saved_tensors
+        x = saved[0]
+        B = saved[1] if ctx.has_B else None
+        tables = saved[2:] if ctx.has_B else saved[1:]
+        need_dx = ctx.needs_input_grad[0]
+        need_tab = any(ctx.needs_input_grad[3:])
+        C = spec.n_fourier
+        second_order = need_dx and torch.is_grad_enabled() and (dy.requires_grad or x.requires_grad)
+        grads: List[Optional[torch.Tensor]] = [None] * len(tables)
+        gt = None
+        if need_tab:
+            flat = torch.zeros(sum(r * spec.n_feat for r in spec.rows), device=dy.device, dtype=torch.float32)
+            gt, off = [], 0
+            for r in spec.rows:
+                gt.append(flat[off:off + r * spec.n_feat].view(r, spec.n_feat))
+                off += r * spec.n_feat
+            grads = list(gt)
+        dx = None
+        if second_order:
+            # differentiable form of d/dx: only the Fourier prefix depends on x in reference mode
+            if C > 0:
+                xp = torch.matmul(TWO_PI * x[:, :3], B)
+                dxp = dy[:, 3:3 + C] * torch.cos(xp) - dy[:, 3 + C:3 + 2 * C] * torch.sin(xp)
+                dx = dy[:, :3] + TWO_PI * torch.matmul(dxp, B.t())
+            if spec.frac_mode == K._lib.HASH_TRILINEAR:
+                with torch.no_grad():
+                    zero_pre = dy.detach().clone()
+                    if C > 0:
+                        zero_pre[:, :3 + 2 * C] = 0
+                    hx = K.hash_encode_bwd(spec, x.detach(), tables, B, zero_pre, None, True)
+                dx = hx if dx is None else dx + hx
+            if need_tab:
+                with torch.no_grad():
+                    K.hash_encode_bwd(spec, x.detach(), tables, B, dy.detach(), gt, False) if spec.n_levels else None
+        elif need_dx or need_tab:
+            kernel_dx = need_dx and (C > 0 or spec.frac_mode == K._lib.HASH_TRILINEAR)
+            if kernel_dx or (need_tab and spec.n_levels > 0):
+                with torch.no_grad():
+                    dx = K.hash_encode_bwd(spec, x.detach(), tables, B, dy.detach(), gt, kernel_dx)
+            if need_dx and dx is None:
+                dx = torch.zeros_like(x[:, :3])
+        if dx is not None and x.shape[1] != 3:
+            pad = torch.zeros_like(x)
+            pad[:, :3] = dx
+            dx = pad
+        return (dx, None, None, *grads)
+
+
+def hash_encode(x: torch.Tensor, spec: K.HashGridSpec, tables: Sequence[torch.Tensor], B: Optional[torch.Tensor]):
+    """[..., 3] -> [..., width]; last-dim layout [x | sin | cos | levels]."""
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    y = _HashEncode.apply(x2, B, spec, *tables)
+    return y if len(lead) == 1 else y.reshape(*lead, spec.width)
+
+
+_EMPTY_SPEC_CACHE = {}
+
+
+def fourier_feature(x: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """[x | sin(2 pi x B) | cos(2 pi x B)]  (FourierFeature.forward, frequency_enc.py:63-67)."""
+    C = B.shape[1]
+    spec = _EMPTY_SPEC_CACHE.get(C)
+    if spec is None:
+        spec = _EMPTY_SPEC_CACHE[C] = K.HashGridSpec([], [], 2, 0, C)
+    return hash_encode(x, spec, (), B.contiguous())
+
+
+# ---------------------------------------------------------------------------------------------
+# positional encoding
+# ---------------------------------------------------------------------------------------------
+class _PosEnc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bands, include_input):
+        out = K.posenc_fwd(x, bands, include_input)
+        ctx.bands, ctx.include_input = bands, include_input
+        ctx.save_for_backward(x)
+        return out[:, :K.posenc_width(x.shape[1], len(bands), include_input)]
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        bands, inc = ctx.bands, ctx.include_input
+        if torch.is_grad_enabled() and (dy.requires_grad or x.requires_grad):
+            d = x.shape[1]
+            base = 2 * d if inc else 0
+            dx = dy[:, :d] + dy[:, d:2 * d] if inc else torch.zeros_like(x)
+            for q, f in enumerate(bands):
+                a = x * f
+                dx = dx + f * (dy[:, base + 2 * q * d: base + (2 * q + 1) * d] * torch.cos(a)
+                               - dy[:, base + (2 * q + 1) * d: base + (2 * q + 2) * d] * torch.sin(a))
+            return dx, None, None
+        with torch.no_grad():
+            return K.posenc_bwd(x.detach(), bands, inc, dy.detach()), None, None
+
+
+def positional_encoding(x: torch.Tensor, bands: Sequence[float], include_input: bool) -> torch.Tensor:
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    y = _PosEnc.apply(x2, tuple(bands), bool(include_input))
+    return y if len(lead) == 1 else y.reshape(*lead, y.shape[-1])

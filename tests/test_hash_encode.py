@@ -1,0 +1,165 @@
+"""GPU parity of K1/K2 (hash-grid encode fwd/bwd, posenc) against the oracle and the golden vectors.
+Tolerances: hash indices and hash features bit-exact; Fourier/posenc columns abs <= 4e-6 (accurate
+sinf/cosf vs the host libm); table gradients rel <= 1e-5 of max-abs (fp32 atomics reorder sums)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import sd_from
+from oracle import idr_oracle as O
+from tests_support import load_sd_into
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def T(a):
+    return torch.from_numpy(np.array(a))
+
+
+def make_grid(L, F, log2T, base, desired, mode="reference", seed=0, std=0.5):
+    from idrk.model.embeddings.hashGridEmbedding import MultiResHashGridMLP
+    gen = torch.Generator().manual_seed(seed)
+    sd = O.make_hashgrid_sd("", L, F, log2T, base, desired, gen, table_std=std)
+    m = MultiResHashGridMLP(True, 3, L, F, log2T, base, desired, frac_mode=mode)
+    load_sd_into(m, sd)
+    return m.to(DEV), sd
+
+
+@pytest.mark.parametrize("tag", ["e1", "e2"])
+def test_golden_embedding_and_grads(golden, tag):
+    from idrk.model.embeddings.hashGridEmbedding import MultiResHashGridMLP
+    g = golden("hashgrid")
+    L, F, log2T, base, desired = [int(v) for v in g["emb_args_" + tag]]
+    m = MultiResHashGridMLP(True, 3, L, F, log2T, base, desired)
+    load_sd_into(m, sd_from(g, "sd_%s/" % tag))
+    m = m.to(DEV)
+    x = T(g["x"]).to(DEV)
+    y = m(x)
+    ref = T(g["emb_" + tag])
+    assert y.shape == ref.shape
+    assert torch.equal(y[:, 3 + 2 * L:].cpu(), ref[:, 3 + 2 * L:])
+    assert torch.allclose(y[:, :3 + 2 * L].cpu(), ref[:, :3 + 2 * L], atol=4e-6, rtol=0)
+    (y * T(g["w_" + tag]).to(DEV)).sum().backward()
+    for l, lvl in enumerate(m.levels):
+        r = T(g["grad_%s/%d" % (tag, l)])
+        assert torch.allclose(lvl.embedding.weight.grad.cpu(), r, atol=1e-5 * max(r.abs().max().item(), 1e-9), rtol=1e-5)
+
+
+def test_golden_corner_indices_bit_exact(golden):
+    from idrk import kernels as K
+    g = golden("hashgrid")
+    x = T(g["x"]).to(DEV)
+    for tag in ("a", "b", "c"):
+        res, rows = [int(v) for v in g["meta_" + tag]]
+        spec = K.HashGridSpec([res], [rows], 2, 0, 0)
+        table = torch.zeros(rows, 2, device=DEV)
+        _, idx = K.hash_encode_fwd(spec, x, (table,), None, want_idx=True)
+        got = idx[:, 0, :].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        assert np.array_equal(got, g["idx_" + tag])
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 257, 8192, 100003])
+def test_reference_mode_vs_oracle_sizes(n):
+    m, sd = make_grid(16, 2, 19, 16, 2048)
+    x = torch.rand(n, 3, generator=torch.Generator().manual_seed(n)) * 2 - 1
+    y = m(x.to(DEV)).cpu()
+    assert y.shape == (n, 67)
+    if n == 0:
+        return
+    ref = O.hashgrid_embed(x, sd, "", 16, 16, 2048)
+    assert torch.equal(y[:, 35:], ref[:, 35:])
+    assert torch.allclose(y[:, :35], ref[:, :35], atol=4e-6, rtol=0)
+
+
+@pytest.mark.parametrize("F", [1, 2, 4, 8])
+@pytest.mark.parametrize("mode", ["reference", "trilinear"])
+def test_feature_widths_and_modes(F, mode):
+    m, sd = make_grid(5, F, 9, 8, 96, mode=mode, seed=3)
+    x = torch.rand(3001, 3, generator=torch.Generator().manual_seed(1)) * 1.6 - 0.3
+    y = m(x.to(DEV)).cpu()
+    ref = O.hashgrid_embed(x, sd, "", 5, 8, 96, mode)
+    pre = 3 + 2 * 5
+    if mode == "reference":
+        assert torch.equal(y[:, pre:], ref[:, pre:])
+    else:
+        assert torch.allclose(y[:, pre:], ref[:, pre:], atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["reference", "trilinear"])
+def test_backward_tables_and_dx(mode):
+    L, F = 8, 2
+    m, sd = make_grid(L, F, 10, 8, 256, mode=mode, seed=5)
+    gen = torch.Generator().manual_seed(2)
+    x = torch.rand(5000, 3, generator=gen) * 2 - 1
+    w = torch.randn(5000, 3 + 2 * L + L * F, generator=gen)
+    xd = x.to(DEV).requires_grad_(True)
+    (m(xd) * w.to(DEV)).sum().backward()
+    for v in sd.values():
+        v.requires_grad_(v.dim() == 2 and v.shape[0] != 3)
+    xo = x.clone().requires_grad_(True)
+    (O.hashgrid_embed(xo, sd, "", L, 8, 256, mode) * w).sum().backward()
+    for l, lvl in enumerate(m.levels):
+        r = sd["levels.%d.embedding.weight" % l].grad
+        got = lvl.embedding.weight.grad.cpu()
+        assert torch.allclose(got, r, atol=1e-5 * r.abs().max().item(), rtol=1e-4), l
+    if mode == "reference":
+        assert torch.allclose(xd.grad.cpu(), xo.grad, atol=2e-5 * xo.grad.abs().max().item(), rtol=1e-4)
+
+
+def test_tiny_tables_shared_accumulation():
+    """Reference configs use T = 32 rows per level: every point collides (CTA-local accumulators)."""
+    L, F = 6, 2
+    m, sd = make_grid(L, F, 5, 64, 512, seed=7)
+    gen = torch.Generator().manual_seed(4)
+    x = torch.rand(20000, 3, generator=gen) * 2 - 1
+    w = torch.randn(20000, 3 + 2 * L + L * F, generator=gen)
+    (m(x.to(DEV)) * w.to(DEV)).sum().backward()
+    for v in sd.values():
+        v.requires_grad_(v.dim() == 2 and v.shape[0] != 3)
+    (O.hashgrid_embed(x, sd, "", L, 64, 512) * w).sum().backward()
+    for l, lvl in enumerate(m.levels):
+        r = sd["levels.%d.embedding.weight" % l].grad
+        assert torch.allclose(lvl.embedding.weight.grad.cpu(), r, atol=2e-5 * r.abs().max().item(), rtol=1e-4)
+
+
+def test_linearity_and_checksum_at_full_size():
+    """Size-independent properties at a BASELINE-sized microbench case (4M points, 2^19 table):
+    gradient scatter conserves mass (sum of table grads == sum of upstream grads) and the encode is
+    a pure gather (every output value is one of the table's values)."""
+    L, F = 16, 2
+    m, _ = make_grid(L, F, 19, 16, 2048, seed=9)
+    n = 1 << 22
+    x = torch.rand(n, 3, device=DEV)
+    y = m(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    for l, lvl in enumerate(m.levels):
+        got = lvl.embedding.weight.grad.double().sum().item()
+        want = dy[:, 35 + 2 * l: 37 + 2 * l].double().sum().item()
+        assert abs(got - want) <= 1e-3 * max(1.0, abs(want)) + 0.5, (l, got, want)
+    lvl0 = m.levels[0].embedding.weight
+    vals = torch.unique(lvl0.detach()[:, 0])
+    assert torch.isin(y[:4096, 35], vals).all()
+
+
+def test_posenc_and_fourier(golden):
+    from idrk.model.embeddings.frequency_enc import PositionalEncoding, get_embedder, FourierFeature
+    g = golden("encoders")
+    x = T(g["x"]).to(DEV)
+    pe = PositionalEncoding(include_input=True, input_dims=3, max_freq_log2=5, num_freqs=6, log_sampling=True,
+                            periodic_fns=[torch.sin, torch.cos])
+    assert torch.allclose(pe(x).cpu(), T(g["posenc_6_5"]), atol=4e-6)
+    fn, od = get_embedder(4)
+    assert od == int(g["view_nerfpos4_outdim"][0])
+    assert torch.allclose(fn(x).cpu(), T(g["view_nerfpos4"]), atol=4e-6)
+    xr = x.clone().requires_grad_(True)
+    w = torch.randn(x.shape[0], 42, device=DEV)
+    (pe(xr) * w).sum().backward()
+    xo = T(g["x"]).clone().requires_grad_(True)
+    (O.positional_encoding(xo, 6, 5, True) * w.cpu()).sum().backward()
+    assert torch.allclose(xr.grad.cpu(), xo.grad, atol=1e-4 * xo.grad.abs().max().item())
+    ff = FourierFeature(3, 1.0, 3).to(DEV)
+    y = ff(x)
+    ref = O.fourier_feature(T(g["x"]), ff.B.cpu())
+    assert torch.allclose(y.cpu(), ref, atol=4e-6)
