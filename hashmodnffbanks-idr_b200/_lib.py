@@ -34,7 +34,23 @@ _lib = None
 
 # every symbol include/idrk.h declares (tests check the library exports all of them)
 EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk_hash_encode_bwd",
-           "idrk_posenc_fwd", "idrk_posenc_bwd"]
+           "idrk_posenc_fwd", "idrk_posenc_bwd", "idrk_gemm", "idrk_split_tf32", "idrk_weight_norm_fwd",
+           "idrk_weight_norm_bwd", "idrk_colsum", "idrk_sdf_head", "idrk_sdf_squash"]
+
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_3XTF32 = 0, 1, 3
+EPI_NONE, EPI_SOFTPLUS, EPI_RELU, EPI_MUL_AUX, EPI_SINE, EPI_TANH = 0, 1, 2, 3, 4, 5
+
+
+class Epilogue(ctypes.Structure):
+    """Mirror of idrk_epilogue_t."""
+    _fields_ = [
+        ("C", ctypes.c_void_p), ("C_hi", ctypes.c_void_p), ("C_lo", ctypes.c_void_p), ("S", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p), ("aux", ctypes.c_void_p),
+        ("ldc", ctypes.c_int32), ("lds", ctypes.c_int32), ("ldaux", ctypes.c_int32),
+        ("mode", ctypes.c_int32), ("act_param", ctypes.c_float), ("scale", ctypes.c_float),
+        ("accumulate", ctypes.c_int32),
+    ]
 
 _ARG_ERRORS = {-1: "bad argument", -2: "pointer or leading dimension not 16-byte aligned",
                -3: "unsupported configuration", -4: "CUDA driver entry point unavailable"}
@@ -62,6 +78,13 @@ def _declare(L):
     fp = c.POINTER(c.c_float)
     L.idrk_posenc_fwd.argtypes = [vp, i64, i32, i32, fp, i32, i32, vp, i32, vp]
     L.idrk_posenc_bwd.argtypes = [vp, i64, i32, i32, fp, i32, i32, vp, i32, vp, i32, vp]
+    L.idrk_gemm.argtypes = [i32, i32, i64, i32, i32, vp, vp, i32, vp, vp, i32, c.POINTER(Epilogue), vp, i32, vp]
+    L.idrk_split_tf32.argtypes = [vp, i64, i32, i32, vp, vp, i32, vp, vp]
+    L.idrk_weight_norm_fwd.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp]
+    L.idrk_weight_norm_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]
+    L.idrk_colsum.argtypes = [vp, i64, i32, i32, vp, vp]
+    L.idrk_sdf_head.argtypes = [vp, i64, i32, i32, vp, vp, f32, vp, vp, vp]
+    L.idrk_sdf_squash.argtypes = [vp, i64, f32, vp, vp, vp]
     for fn in EXPORTS:
         getattr(L, fn).restype = c.c_int
 

@@ -1,0 +1,202 @@
+// Small memory-bound helpers around the MLP tiles: TF32 hi/lo operand split, weight-norm forward /
+// backward (legacy nn.utils.weight_norm, dim=0: W = g * v / ||v||_row), bias gradients (column sums)
+// and the SDF head (last Linear row 0 + the Laplace-density squash of
+// implicit_differentiable_renderer.py:112 / density_net.py:20-30).
+#include "common.cuh"
+
+namespace idrk {
+
+__device__ __forceinline__ float tf32_round(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ x, long long rows, int cols, int ldx,
+                                  float* __restrict__ hi, float* __restrict__ lo, int ldo, const int* __restrict__ m_count) {
+    long long r_eff = rows;
+    if (m_count) { const long long c = *m_count; r_eff = c < rows ? c : rows; }
+    const long long total = r_eff * (long long)ldo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / ldo;
+        const int c = (int)(i - r * ldo);
+        float h = 0.f, l = 0.f;
+        if (c < cols) { const float v = x[r * ldx + c]; h = tf32_round(v); l = tf32_round(v - h); }
+        hi[i] = h; lo[i] = l;
+    }
+}
+
+// one warp per output row n
+__global__ void weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v, int N, int K, int ldv,
+                                       float* __restrict__ W, float* __restrict__ W_hi, float* __restrict__ W_lo, int ldw,
+                                       float* __restrict__ Wt, float* __restrict__ Wt_hi, float* __restrict__ Wt_lo, int ldwt) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const float* row = v + (long long)n * ldv;
+    float ss = 0.f;
+    for (int k = lane; k < K; k += 32) ss = fmaf(row[k], row[k], ss);
+    ss = warp_sum(ss);
+    const float scale = g ? g[n] / sqrtf(ss) : 1.f;
+    for (int k = lane; k < ldw; k += 32) {
+        const float w = k < K ? row[k] * scale : 0.f;
+        const float h = tf32_round(w), l = tf32_round(w - h);
+        if (W) W[(long long)n * ldw + k] = w;
+        if (W_hi) { W_hi[(long long)n * ldw + k] = h; W_lo[(long long)n * ldw + k] = l; }
+        if (k < K) {
+            if (Wt) Wt[(long long)k * ldwt + n] = w;
+            if (Wt_hi) { Wt_hi[(long long)k * ldwt + n] = h; Wt_lo[(long long)k * ldwt + n] = l; }
+        }
+    }
+}
+
+__global__ void weight_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v, const float* __restrict__ dW,
+                                       int N, int K, int ldv, int lddw, float* __restrict__ dg, float* __restrict__ dv, int lddv) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const float* vr = v + (long long)n * ldv;
+    const float* dr = dW + (long long)n * lddw;
+    float ss = 0.f, dot = 0.f;
+    for (int k = lane; k < K; k += 32) { ss = fmaf(vr[k], vr[k], ss); dot = fmaf(vr[k], dr[k], dot); }
+    ss = warp_sum(ss); dot = warp_sum(dot);
+    const float nrm = sqrtf(ss);
+    const float gn = g[n];
+    if (lane == 0) dg[n] = dot / nrm;
+    const float a = gn / nrm, b = gn * dot / (nrm * ss);
+    for (int k = lane; k < K; k += 32) dv[(long long)n * lddv + k] = a * dr[k] - b * vr[k];
+}
+
+// out[c] += sum_r x[r, c]
+__global__ void colsum_kernel(const float* __restrict__ x, long long rows, int cols, int ldx, float* __restrict__ out) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;                    // 8 row lanes
+    __shared__ float part[8][33];
+    float acc = 0.f;
+    if (c < cols) {
+        const long long chunk = (rows + gridDim.y - 1) / gridDim.y;
+        const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+        for (long long r = r0 + ry; r < r1; r += 8) acc += x[r * ldx + c];
+    }
+    part[ry][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (ry == 0 && c < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
+        atomicAdd(out + c, s);
+    }
+}
+
+__device__ __forceinline__ float sdf_squash(float s, float beta) {
+    // rho = (1/beta) * (0.5 + 0.5 * sign(s) * expm1(-|s| / beta))   (density_net.py:27)
+    const float sg = s > 0.f ? 1.f : (s < 0.f ? -1.f : 0.f);
+    const float rho = (1.f / beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(s) / beta));
+    return tanhf(s / (2.f + rho));
+}
+
+// one warp per point: sdf = squash(dot(h[p, :K], w) + b)
+__global__ void sdf_head_kernel(const float* __restrict__ h, long long rows, int K, int ldh, const float* __restrict__ w,
+                                const float* __restrict__ bias, float beta, float* __restrict__ out,
+                                const int* __restrict__ m_count) {
+    long long r_eff = rows;
+    if (m_count) { const long long c = *m_count; r_eff = c < rows ? c : rows; }
+    const int lane = threadIdx.x & 31;
+    const long long wpg = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long p = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); p < r_eff; p += wpg) {
+        const float* row = h + p * ldh;
+        float acc = 0.f;
+        for (int k = lane; k < K; k += 32) acc = fmaf(row[k], __ldg(w + k), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) out[p] = sdf_squash(acc + bias[0], beta);
+    }
+}
+
+__global__ void sdf_squash_kernel(const float* __restrict__ s, long long n, float beta, float* __restrict__ out, float* __restrict__ dout) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = s[i];
+        const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+        const float rho = (1.f / beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(v) / beta));
+        const float t = tanhf(v / (2.f + rho));
+        out[i] = t;
+        if (dout) dout[i] = (1.f - t * t) / (2.f + rho);
+    }
+}
+
+static inline int ew_blocks(long long total, int threads) {
+    long long b = (total + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace idrk
+
+using namespace idrk;
+
+extern "C" int idrk_split_tf32(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* hi, float* lo, int32_t ld_out,
+                               const int32_t* m_count, void* stream) {
+    if (!x || !hi || !lo || rows < 0 || cols < 1 || ldx < cols || ld_out < cols) return IDRK_E_ARG;
+    if (rows == 0) return 0;
+    split_tf32_kernel<<<ew_blocks(rows * (long long)ld_out, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, hi, lo, ld_out, m_count);
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_weight_norm_fwd(const float* g, const float* v, int32_t N, int32_t K, int32_t ldv,
+                                    float* W, float* W_hi, float* W_lo, int32_t ldw,
+                                    float* Wt, float* Wt_hi, float* Wt_lo, int32_t ldwt, void* stream) {
+    if (!v || N < 1 || K < 1 || ldv < K || ldw < K) return IDRK_E_ARG;
+    if ((W_hi == nullptr) != (W_lo == nullptr) || (Wt_hi == nullptr) != (Wt_lo == nullptr)) return IDRK_E_ARG;
+    if ((Wt || Wt_hi) && ldwt < N) return IDRK_E_ARG;
+    weight_norm_fwd_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, v, N, K, ldv, W, W_hi, W_lo, ldw, Wt, Wt_hi, Wt_lo, ldwt);
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_weight_norm_bwd(const float* g, const float* v, const float* dW, int32_t N, int32_t K, int32_t ldv,
+                                    int32_t lddw, float* dg, float* dv, int32_t lddv, void* stream) {
+    if (!g || !v || !dW || !dg || !dv || N < 1 || K < 1 || ldv < K || lddw < K || lddv < K) return IDRK_E_ARG;
+    weight_norm_bwd_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, v, dW, N, K, ldv, lddw, dg, dv, lddv);
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_colsum(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* out, void* stream) {
+    if (!x || !out || rows < 0 || cols < 1 || ldx < cols) return IDRK_E_ARG;
+    if (rows == 0) return 0;
+    long long ysplit = rows / 512;
+    if (ysplit < 1) ysplit = 1;
+    if (ysplit > 64) ysplit = 64;
+    dim3 grid((cols + 31) / 32, (unsigned)ysplit);
+    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, out);
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_sdf_head(const float* h, int64_t rows, int32_t K, int32_t ldh, const float* w, const float* bias,
+                             float beta, float* out, const int32_t* m_count, void* stream) {
+    if (!h || !w || !bias || !out || rows < 0 || K < 1 || ldh < K || !(beta > 0.f)) return IDRK_E_ARG;
+    if (rows == 0) return 0;
+    long long blocks = (rows + 7) / 8;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    sdf_head_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(h, rows, K, ldh, w, bias, beta, out, m_count);
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_sdf_squash(const float* s, int64_t n, float beta, float* out, float* dout, void* stream) {
+    if (!s || !out || n < 0 || !(beta > 0.f)) return IDRK_E_ARG;
+    if (n == 0) return 0;
+    sdf_squash_kernel<<<ew_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(s, n, beta, out, dout);
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}

@@ -144,3 +144,131 @@ def posenc_bwd(x: torch.Tensor, bands: Sequence[float], include_input: bool, dy:
     check(lib().idrk_posenc_bwd(ptr(x), n, d, ld_of(x), hb, len(bands), int(include_input), ptr(dy), ld_of(dy),
                                 ptr(dx), ld_of(dx), stream_ptr()), "idrk_posenc_bwd")
     return dx
+
+
+# ---------------------------------------------------------------------------------------------
+# MLP contraction tiles
+# ---------------------------------------------------------------------------------------------
+from ._lib import (Epilogue, GEMM_NT, GEMM_NN, GEMM_TN, PREC_FP32, PREC_TF32, PREC_3XTF32,  # noqa: E402
+                   EPI_NONE, EPI_SOFTPLUS, EPI_RELU, EPI_MUL_AUX, EPI_SINE, EPI_TANH)
+
+_PRECISION = {"fp32": PREC_FP32, "tf32": PREC_TF32, "3xtf32": PREC_3XTF32}
+_default_precision = PREC_3XTF32
+
+
+def set_precision(name: str):
+    """'3xtf32' (default, fp32-accurate tensor-core split), 'tf32' (one pass) or 'fp32' (FFMA tiles)."""
+    global _default_precision
+    _default_precision = _PRECISION[name]
+
+
+def get_precision() -> int:
+    return _default_precision
+
+
+def empty_padded(rows: int, cols: int, device) -> torch.Tensor:
+    """[rows, cols] view of a [rows, pad4(cols)] buffer (16-byte aligned rows for TMA / float4)."""
+    return torch.empty((rows, pad4(cols)), device=device, dtype=torch.float32)[:, :cols]
+
+
+def operand(t: torch.Tensor, name: str = "operand") -> torch.Tensor:
+    """2-D fp32 CUDA tensor usable by the tensor-core path: unit column stride, ld % 4 == 0, 16B base."""
+    _f32c(t, name)
+    if t.dim() != 2:
+        raise _lib.IdrkError("%s must be 2-D" % name)
+    ok = t.stride(1) == 1 and (t.shape[0] <= 1 or (t.stride(0) % 4 == 0 and t.stride(0) >= t.shape[1])) \
+        and t.data_ptr() % 16 == 0
+    if ok:
+        return t
+    buf = empty_padded(t.shape[0], t.shape[1], t.device)
+    buf.copy_(t)
+    return buf
+
+
+def op_ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else pad4(t.shape[1])
+
+
+def split_tf32(x: torch.Tensor, m_count: Optional[torch.Tensor] = None):
+    """(hi, lo) with hi = tf32(x), lo = tf32(x - hi); both padded like `operand`."""
+    x = rows2d(x, "x")
+    r, c = x.shape
+    hi = empty_padded(r, c, x.device)
+    lo = empty_padded(r, c, x.device)
+    if r:
+        check(lib().idrk_split_tf32(ptr(x), r, c, ld_of(x), ptr(hi), ptr(lo), pad4(c), ptr(m_count), stream_ptr()),
+              "idrk_split_tf32")
+    return hi, lo
+
+
+def gemm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int, *, precision: Optional[int] = None,
+         A_lo=None, B_lo=None, C=None, C_hi=None, C_lo=None, S=None, bias=None, aux=None, mode=EPI_NONE,
+         act=0.0, scale=1.0, accumulate=False, m_count=None, split_k=1):
+    """Raw launcher.  All operands must already satisfy `operand()`; output buffers are caller-owned."""
+    prec = _default_precision if precision is None else precision
+    e = Epilogue()
+    outs = [t for t in (C, C_hi, C_lo) if t is not None]
+    if not outs:
+        raise _lib.IdrkError("gemm needs an output")
+    e.C, e.C_hi, e.C_lo, e.S = (t.data_ptr() if t is not None else None for t in (C, C_hi, C_lo, S))
+    e.bias = bias.data_ptr() if bias is not None else None
+    e.aux = aux.data_ptr() if aux is not None else None
+    e.ldc = op_ld(outs[0])
+    e.lds = op_ld(S) if S is not None else 0
+    e.ldaux = op_ld(aux) if aux is not None else 0
+    e.mode, e.act_param, e.scale, e.accumulate = mode, float(act), float(scale), int(bool(accumulate))
+    check(lib().idrk_gemm(layout, prec, M, N, Kc, ptr(A), ptr(A_lo), op_ld(A), ptr(B), ptr(B_lo), op_ld(B),
+                          ctypes.byref(e), ptr(m_count), split_k, stream_ptr()), "idrk_gemm")
+
+
+def weight_norm_fwd(g: Optional[torch.Tensor], v: torch.Tensor, want_split: bool, want_t: bool):
+    """Returns dict with W (+ W_hi/W_lo, Wt (+ Wt_hi/Wt_lo)), all padded operands."""
+    v = rows2d(v, "weight_v")
+    N, Kd = v.shape
+    dev = v.device
+    out = {"W": empty_padded(N, Kd, dev)}
+    if want_split:
+        out["W_hi"], out["W_lo"] = empty_padded(N, Kd, dev), empty_padded(N, Kd, dev)
+    if want_t:
+        out["Wt"] = empty_padded(Kd, N, dev)
+        if want_split:
+            out["Wt_hi"], out["Wt_lo"] = empty_padded(Kd, N, dev), empty_padded(Kd, N, dev)
+    gg = g.reshape(-1).contiguous() if g is not None else None
+    check(lib().idrk_weight_norm_fwd(ptr(gg), ptr(v), N, Kd, ld_of(v), ptr(out["W"]), ptr(out.get("W_hi")), ptr(out.get("W_lo")),
+                                     pad4(Kd), ptr(out.get("Wt")), ptr(out.get("Wt_hi")), ptr(out.get("Wt_lo")), pad4(N),
+                                     stream_ptr()), "idrk_weight_norm_fwd")
+    return out
+
+
+def weight_norm_bwd(g: torch.Tensor, v: torch.Tensor, dW: torch.Tensor):
+    v = rows2d(v, "weight_v")
+    dW = rows2d(dW, "dW")
+    N, Kd = v.shape
+    dg = torch.empty((N, 1), device=v.device, dtype=torch.float32)
+    dv = torch.empty((N, Kd), device=v.device, dtype=torch.float32)
+    check(lib().idrk_weight_norm_bwd(ptr(g.reshape(-1).contiguous()), ptr(v), ptr(dW), N, Kd, ld_of(v), ld_of(dW),
+                                     ptr(dg), ptr(dv), Kd, stream_ptr()), "idrk_weight_norm_bwd")
+    return dg, dv
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    x = rows2d(x, "x")
+    out = torch.zeros(x.shape[1], device=x.device, dtype=torch.float32)
+    if x.shape[0]:
+        check(lib().idrk_colsum(ptr(x), x.shape[0], x.shape[1], ld_of(x), ptr(out), stream_ptr()), "idrk_colsum")
+    return out
+
+
+def sdf_head(h: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, beta: float, out: torch.Tensor, rows: int,
+             m_count=None):
+    check(lib().idrk_sdf_head(ptr(h), rows, w.numel(), op_ld(h), ptr(w), ptr(bias), float(beta), ptr(out), ptr(m_count),
+                              stream_ptr()), "idrk_sdf_head")
+
+
+def sdf_squash(s: torch.Tensor, beta: float, want_grad: bool):
+    s = s.contiguous()
+    out = torch.empty_like(s)
+    d = torch.empty_like(s) if want_grad else None
+    if s.numel():
+        check(lib().idrk_sdf_squash(ptr(s), s.numel(), float(beta), ptr(out), ptr(d), stream_ptr()), "idrk_sdf_squash")
+    return out, d

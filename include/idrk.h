@@ -80,6 +80,71 @@ int idrk_posenc_fwd(const float* x, int64_t n, int32_t d, int32_t ldx, const flo
 int idrk_posenc_bwd(const float* x, int64_t n, int32_t d, int32_t ldx, const float* h_bands, int32_t n_bands,
                     int32_t include_input, const float* dy, int32_t ld_dy, float* dx, int32_t ld_dx, void* stream);
 
+/* -- K4: MLP contraction tiles (tcgen05 / TMEM / TMA) --------------------------------------
+ * Replaces the nn.Linear + activation pairs of ImplicitNetwork.forward
+ * (implicit_differentiable_renderer.py:96-112), RenderingNetwork.forward (:215-223), the SIREN layers
+ * of FourierFilterBanks.forward (nffb3d.py:163-184) and their autograd (data / weight gradients).
+ *   layout NT: A[M,K] B[N,K]  C = A B^T   (forward: activations x weights)
+ *   layout NN: A[M,K] B[K,N]  C = A B     (gradient w.r.t. the layer input)
+ *   layout TN: A[K,M] B[K,N]  C = A^T B   (gradient w.r.t. the weights; contraction over points)
+ * precision: FP32 = plain FFMA tiles; TF32 = one tensor-core pass; 3XTF32 = hi/lo split operands
+ * (A_lo / B_lo hold  tf32(x - tf32(x)),  A / B hold tf32(x)), fp32-accurate.
+ * Tensor-core modes need 16-byte aligned operands with lda, ldb % 4 == 0.
+ * m_count (nullable, device): only rows < min(M, *m_count) are computed (device-side compaction).
+ * split_k > 1 accumulates partial tiles with atomics into C (caller zero-fills, epilogue must be NONE). */
+#define IDRK_GEMM_NT 0
+#define IDRK_GEMM_NN 1
+#define IDRK_GEMM_TN 2
+#define IDRK_PREC_FP32   0
+#define IDRK_PREC_TF32   1
+#define IDRK_PREC_3XTF32 3
+#define IDRK_EPI_NONE     0   /* v = acc + bias                                              */
+#define IDRK_EPI_SOFTPLUS 1   /* v = softplus(acc + bias; beta = act_param, threshold 20), S = sigmoid */
+#define IDRK_EPI_RELU     2   /* v = max(acc + bias, 0), S = step                             */
+#define IDRK_EPI_MUL_AUX  3   /* v = (acc + bias) * aux[row, col]                             */
+#define IDRK_EPI_SINE     4   /* v = sin(act_param * (acc + bias)), S = act_param * cos(...)  */
+#define IDRK_EPI_TANH     5   /* v = tanh(acc + bias), S = 1 - v^2                            */
+
+typedef struct idrk_epilogue {
+    float* C;            /* [M, ldc] fp32 result (nullable when C_hi/C_lo are given)            */
+    float* C_hi;         /* [M, ldc] tf32(v)          } pre-split operands for a following      */
+    float* C_lo;         /* [M, ldc] tf32(v - tf32(v))} 3xTF32 contraction (both or neither)    */
+    float* S;            /* [M, lds] activation derivative (nullable)                           */
+    const float* bias;   /* [N] (nullable)                                                      */
+    const float* aux;    /* [M, ldaux] multiplier for IDRK_EPI_MUL_AUX                          */
+    int32_t ldc, lds, ldaux;
+    int32_t mode;        /* IDRK_EPI_*                                                          */
+    float act_param;     /* softplus beta / sine w0                                             */
+    float scale;         /* v *= scale after the activation (1/sqrt(2) of the skip connection)  */
+    int32_t accumulate;  /* 1: C += v with atomics                                              */
+} idrk_epilogue_t;
+
+int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N, int32_t K,
+              const float* A, const float* A_lo, int32_t lda, const float* B, const float* B_lo, int32_t ldb,
+              const idrk_epilogue_t* h_epi, const int32_t* m_count, int32_t split_k, void* stream);
+
+/* -- helpers around the MLP tiles ----------------------------------------------------------
+ * idrk_split_tf32: hi = tf32(x), lo = tf32(x - hi) for 3xTF32 operands; pads [cols, ld_out) with 0.
+ * idrk_weight_norm_fwd/bwd: legacy nn.utils.weight_norm(dim=0) used by every lin{l}
+ *   (implicit_differentiable_renderer.py:80-81,195-196): W = g * v / ||v||_row.  g == NULL copies v.
+ *   Optional outputs: W, its hi/lo split, and the transposed copies Wt[K, ldwt] (K-major operand of
+ *   the input-gradient contraction).
+ * idrk_colsum: out[c] += sum_r x[r, c]  (bias gradients).
+ * idrk_sdf_head: sdf = tanh(s / (2 + rho(s))), s = <h[p, :K], w> + bias[0]  - the only output column the
+ *   ray tracer consumes (implicit_differentiable_renderer.py:112, :257; density_net.py:20-30).
+ * idrk_sdf_squash: the same squash on precomputed s (+ optional derivative d out / d s). */
+int idrk_split_tf32(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* hi, float* lo, int32_t ld_out,
+                    const int32_t* m_count, void* stream);
+int idrk_weight_norm_fwd(const float* g, const float* v, int32_t N, int32_t K, int32_t ldv,
+                         float* W, float* W_hi, float* W_lo, int32_t ldw,
+                         float* Wt, float* Wt_hi, float* Wt_lo, int32_t ldwt, void* stream);
+int idrk_weight_norm_bwd(const float* g, const float* v, const float* dW, int32_t N, int32_t K, int32_t ldv,
+                         int32_t lddw, float* dg, float* dv, int32_t lddv, void* stream);
+int idrk_colsum(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* out, void* stream);
+int idrk_sdf_head(const float* h, int64_t rows, int32_t K, int32_t ldh, const float* w, const float* bias,
+                  float beta, float* out, const int32_t* m_count, void* stream);
+int idrk_sdf_squash(const float* s, int64_t n, float beta, float* out, float* dout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,112 @@
+"""GPU checks of the MLP contraction tiles (tcgen05/TMEM/TMA kernel and the FFMA kernel) against
+fp64 matmul.  Tolerances relative to sum|a||b| per output: fp32 1e-6, 3xTF32 1e-5, TF32 2e-3."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+TOL = {"fp32": 2e-6, "3xtf32": 1e-5, "tf32": 3e-3}
+
+
+def _mk(shape, seed):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)).to(DEV)
+
+
+def _run(layout, prec, M, N, Kc, **kw):
+    from idrk import kernels as K
+    A = _mk((M, Kc), 1) if layout != K.GEMM_TN else _mk((Kc, M), 1)
+    B = _mk((N, Kc), 2) if layout == K.GEMM_NT else _mk((Kc, N), 2)
+    Ao, Bo = K.operand(A), K.operand(B)
+    p = K._PRECISION[prec]
+    A_lo = B_lo = None
+    Au, Bu = Ao, Bo
+    if p == K.PREC_3XTF32:
+        Au, A_lo = K.split_tf32(Ao)
+        Bu, B_lo = K.split_tf32(Bo)
+    C = K.empty_padded(M, N, DEV)
+    C.fill_(float("nan"))
+    K.gemm(layout, Au, Bu, M, N, Kc, precision=p, A_lo=A_lo, B_lo=B_lo, C=C, **kw)
+    A64 = A.double() if layout != K.GEMM_TN else A.double().t()
+    B64 = B.double() if layout == K.GEMM_NT else B.double().t()
+    ref = A64 @ B64.t()
+    mag = A64.abs() @ B64.abs().t()
+    return C, ref, mag
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "3xtf32"])
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(128, 128, 32), (300, 445, 67), (2048, 512, 512), (77, 3, 512), (1000, 257, 40)])
+def test_gemm_plain(layout, prec, shape):
+    M, N, Kc = shape
+    C, ref, mag = _run(layout, prec, M, N, Kc)
+    err = ((C.double() - ref).abs() / (mag + 1e-30)).max().item()
+    assert err < TOL[prec], err
+
+
+@pytest.mark.parametrize("prec", ["tf32", "3xtf32"])
+def test_gemm_split_k(prec):
+    from idrk import kernels as K
+    M, N, Kc = 512, 512, 5000
+    A = _mk((Kc, M), 3)
+    B = _mk((Kc, N), 4)
+    p = K._PRECISION[prec]
+    Au, A_lo = K.split_tf32(A)
+    Bu, B_lo = K.split_tf32(B)
+    C = torch.zeros(M, N, device=DEV)
+    K.gemm(K.GEMM_TN, Au, Bu, M, N, Kc, precision=p, A_lo=A_lo, B_lo=B_lo, C=C, split_k=8)
+    ref = A.double().t() @ B.double()
+    mag = A.double().abs().t() @ B.double().abs()
+    assert ((C.double() - ref).abs() / mag).max().item() < TOL[prec]
+
+
+def test_gemm_softplus_epilogue_and_split_outputs():
+    from idrk import kernels as K
+    M, N, Kc = 700, 445, 67
+    A, W, b = _mk((M, Kc), 5) * 0.1, _mk((N, Kc), 6) * 0.1, _mk((N,), 7) * 0.01
+    Au, A_lo = K.split_tf32(A)
+    Wu, W_lo = K.split_tf32(W)
+    H, Hh, Hl, S = (K.empty_padded(M, N, DEV) for _ in range(4))
+    K.gemm(K.GEMM_NT, Au, Wu, M, N, Kc, precision=K.PREC_3XTF32, A_lo=A_lo, B_lo=W_lo, C=H, C_hi=Hh, C_lo=Hl, S=S,
+           bias=b, mode=K.EPI_SOFTPLUS, act=100.0, scale=0.5)
+    z = (A.double() @ W.double().t() + b.double())
+    ref = torch.nn.functional.softplus(z, beta=100) * 0.5
+    assert torch.allclose(H.double(), ref, atol=1e-6, rtol=1e-5)
+    assert torch.allclose(S.double(), torch.sigmoid(100 * z), atol=2e-5)
+    assert torch.allclose((Hh + Hl).double(), ref, atol=1e-6, rtol=1e-5)
+
+
+def test_gemm_m_count_masks_rows():
+    from idrk import kernels as K
+    M, N, Kc = 1000, 128, 64
+    A, W = _mk((M, Kc), 8), _mk((N, Kc), 9)
+    C = K.empty_padded(M, N, DEV)
+    C.fill_(-7.0)
+    cnt = torch.tensor([300], device=DEV, dtype=torch.int32)
+    K.gemm(K.GEMM_NT, A, W, M, N, Kc, precision=K.PREC_TF32, C=C, m_count=cnt)
+    assert (C[300:] == -7.0).all()
+    assert torch.allclose(C[:300], A[:300] @ W.t(), atol=0.2, rtol=1e-2)
+
+
+def test_weight_norm_and_helpers():
+    from idrk import kernels as K
+    v, g = _mk((445, 512), 10), _mk((445, 1), 11).abs() + 0.1
+    out = K.weight_norm_fwd(g, v, True, True)
+    ref = torch._weight_norm(v, g, 0)
+    assert torch.allclose(out["W"], ref, atol=1e-6, rtol=1e-5)
+    assert torch.allclose(out["Wt"], ref.t(), atol=1e-6, rtol=1e-5)
+    assert torch.allclose(out["W_hi"] + out["W_lo"], ref, atol=1e-6, rtol=1e-5)
+    dW = _mk((445, 512), 12)
+    vr, gr = v.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    (torch._weight_norm(vr, gr, 0) * dW).sum().backward()
+    dg, dv = K.weight_norm_bwd(g, v, dW)
+    assert torch.allclose(dg, gr.grad, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(dv, vr.grad, atol=1e-5, rtol=1e-4)
+    x = _mk((3000, 257), 13)
+    assert torch.allclose(K.colsum(x), x.sum(0), atol=1e-3, rtol=1e-4)
+    s = _mk((5000,), 14) * 3
+    sq, d = K.sdf_squash(s, 0.9001, True)
+    beta = 0.9001
+    rho = (1 / beta) * (0.5 + 0.5 * s.sign() * torch.expm1(-s.abs() / beta))
+    assert torch.allclose(sq, torch.tanh(s / (2 + rho)), atol=1e-6)
+    assert torch.allclose(d, (1 - sq * sq) / (2 + rho), atol=1e-6)
