@@ -35,7 +35,18 @@ _lib = None
 # every symbol include/idrk.h declares (tests check the library exports all of them)
 EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk_hash_encode_bwd",
            "idrk_posenc_fwd", "idrk_posenc_bwd", "idrk_gemm", "idrk_split_tf32", "idrk_weight_norm_fwd",
-           "idrk_weight_norm_bwd", "idrk_colsum", "idrk_sdf_head", "idrk_sdf_squash"]
+           "idrk_weight_norm_bwd", "idrk_colsum", "idrk_sdf_head", "idrk_sdf_squash",
+           "idrk_rt_init", "idrk_rt_top", "idrk_rt_step", "idrk_rt_linesearch", "idrk_rt_end",
+           "idrk_rt_select_sampler", "idrk_rt_sampler_points", "idrk_rt_sampler_resolve", "idrk_rt_secant",
+           "idrk_rt_select_minsdf", "idrk_rt_minsdf_points", "idrk_rt_minsdf_resolve"]
+
+
+class RayStateDesc(ctypes.Structure):
+    """Mirror of idrk_ray_state_t."""
+    _fields_ = [("cam_loc", ctypes.c_void_p), ("ray_dirs", ctypes.c_void_p),
+                ("n_rays", ctypes.c_int32), ("num_pixels", ctypes.c_int32)] + \
+               [(n, ctypes.c_void_p) for n in ("t0", "t1", "cur_s", "cur_e", "nxt_s", "nxt_e", "ps", "pe", "min_dis",
+                                               "max_dis", "unf_s", "unf_e", "slot_s", "slot_e")]
 
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_3XTF32 = 0, 1, 3
@@ -73,18 +84,31 @@ def _declare(L):
     vp, i32, i64, f32 = c.c_void_p, c.c_int32, c.c_int64, c.c_float
     L.idrk_version.restype = c.c_int
     L.idrk_device_sm_count.argtypes = [c.POINTER(c.c_int)]
-    L.idrk_hash_encode_fwd.argtypes = [c.POINTER(HashGridDesc), vp, i64, i32, vp, i32, vp, vp]
+    L.idrk_hash_encode_fwd.argtypes = [c.POINTER(HashGridDesc), vp, i64, i32, vp, i32, vp, vp, vp]
     L.idrk_hash_encode_bwd.argtypes = [c.POINTER(HashGridDesc), vp, i64, i32, vp, i32, c.POINTER(vp), vp, vp]
     fp = c.POINTER(c.c_float)
     L.idrk_posenc_fwd.argtypes = [vp, i64, i32, i32, fp, i32, i32, vp, i32, vp]
     L.idrk_posenc_bwd.argtypes = [vp, i64, i32, i32, fp, i32, i32, vp, i32, vp, i32, vp]
     L.idrk_gemm.argtypes = [i32, i32, i64, i32, i32, vp, vp, i32, vp, vp, i32, c.POINTER(Epilogue), vp, i32, vp]
-    L.idrk_split_tf32.argtypes = [vp, i64, i32, i32, vp, vp, i32, vp, vp]
+    L.idrk_split_tf32.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp]
     L.idrk_weight_norm_fwd.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp]
     L.idrk_weight_norm_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]
     L.idrk_colsum.argtypes = [vp, i64, i32, i32, vp, vp]
     L.idrk_sdf_head.argtypes = [vp, i64, i32, i32, vp, vp, f32, vp, vp, vp]
     L.idrk_sdf_squash.argtypes = [vp, i64, f32, vp, vp, vp]
+    rs = c.POINTER(RayStateDesc)
+    L.idrk_rt_init.argtypes = [rs, vp, vp, vp, vp, vp]
+    L.idrk_rt_top.argtypes = [rs, vp, i32, f32, vp, vp]
+    L.idrk_rt_step.argtypes = [rs, vp, vp, vp, vp]
+    L.idrk_rt_linesearch.argtypes = [rs, vp, vp, i32, f32, vp, vp, vp]
+    L.idrk_rt_end.argtypes = [rs, vp, vp, i32, vp]
+    L.idrk_rt_select_sampler.argtypes = [rs, vp, vp, vp, vp]
+    L.idrk_rt_sampler_points.argtypes = [rs, vp, i32, i32, i32, vp, vp, vp]
+    L.idrk_rt_sampler_resolve.argtypes = [rs, vp, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.idrk_rt_secant.argtypes = [rs, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.idrk_rt_select_minsdf.argtypes = [rs, vp, vp, vp, vp, vp, vp, vp]
+    L.idrk_rt_minsdf_points.argtypes = [rs, vp, i32, i32, i32, vp, vp, vp]
+    L.idrk_rt_minsdf_resolve.argtypes = [rs, vp, i32, i32, vp, vp, vp]
     for fn in EXPORTS:
         getattr(L, fn).restype = c.c_int
 

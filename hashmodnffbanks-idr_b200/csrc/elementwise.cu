@@ -18,17 +18,23 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__global__ void split_tf32_kernel(const float* __restrict__ x, long long rows, int cols, int ldx,
-                                  float* __restrict__ hi, float* __restrict__ lo, int ldo, const int* __restrict__ m_count) {
+__global__ void split_tf32_kernel(const float* __restrict__ x, long long rows, int cols, int ldx, float scale,
+                                  float* __restrict__ hi, float* __restrict__ lo, int ldo, int pad_cols,
+                                  const int* __restrict__ m_count) {
     long long r_eff = rows;
     if (m_count) { const long long c = *m_count; r_eff = c < rows ? c : rows; }
-    const long long total = r_eff * (long long)ldo;
+    const int w = cols + pad_cols;
+    const long long total = r_eff * (long long)w;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / ldo;
-        const int c = (int)(i - r * ldo);
+        const long long r = i / w;
+        const int c = (int)(i - r * w);
         float h = 0.f, l = 0.f;
-        if (c < cols) { const float v = x[r * ldx + c]; h = tf32_round(v); l = tf32_round(v - h); }
-        hi[i] = h; lo[i] = l;
+        if (c < cols) {
+            const float v = x[r * ldx + c] * scale;
+            if (lo) { h = tf32_round(v); l = tf32_round(v - h); } else { h = v; }
+        }
+        hi[r * ldo + c] = h;
+        if (lo) lo[r * ldo + c] = l;
     }
 }
 
@@ -141,11 +147,12 @@ static inline int ew_blocks(long long total, int threads) {
 
 using namespace idrk;
 
-extern "C" int idrk_split_tf32(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* hi, float* lo, int32_t ld_out,
-                               const int32_t* m_count, void* stream) {
-    if (!x || !hi || !lo || rows < 0 || cols < 1 || ldx < cols || ld_out < cols) return IDRK_E_ARG;
+extern "C" int idrk_split_tf32(const float* x, int64_t rows, int32_t cols, int32_t ldx, float scale, float* hi, float* lo,
+                               int32_t ld_out, int32_t pad_cols, const int32_t* m_count, void* stream) {
+    if (!x || !hi || rows < 0 || cols < 1 || ldx < cols || pad_cols < 0 || ld_out < cols + pad_cols) return IDRK_E_ARG;
     if (rows == 0) return 0;
-    split_tf32_kernel<<<ew_blocks(rows * (long long)ld_out, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, hi, lo, ld_out, m_count);
+    split_tf32_kernel<<<ew_blocks(rows * (long long)(cols + pad_cols), 256), 256, 0, (cudaStream_t)stream>>>(
+        x, rows, cols, ldx, scale, hi, lo, ld_out, pad_cols, m_count);
     IDRK_LAUNCH_CHECK();
     return 0;
 }

@@ -91,8 +91,10 @@ __device__ __forceinline__ void scatter_add(float* table, uint32_t idx, const fl
 template <int F, int MODE, int ROWS>
 __global__ void __launch_bounds__(ROWS)
 hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
-                       float* __restrict__ out, int ld_out, uint32_t* __restrict__ idx_dbg) {
+                       float* __restrict__ out, int ld_out, uint32_t* __restrict__ idx_dbg,
+                       const int* __restrict__ m_count) {
     extern __shared__ float smem[];
+    if (m_count != nullptr) { const long long c = *m_count; n = c < n ? c : n; }
     const int lds = ld_out | 1;                 // odd stride: per-thread row writes hit distinct banks
     float* s_rows = smem;                       // [ROWS][lds]
     float* s_B = smem + ROWS * lds;             // [3][C]
@@ -369,12 +371,12 @@ static int persistent_grid(K kernel, int threads, size_t smem, long long n_tiles
 
 template <int F, int MODE, int ROWS>
 static int launch_fwd(const GridDev& g, const float* x, long long n, int ldx, float* out, int ld_out,
-                      uint32_t* idx_dbg, cudaStream_t st) {
+                      uint32_t* idx_dbg, const int* m_count, cudaStream_t st) {
     const size_t smem = ((size_t)ROWS * (ld_out | 1) + 3 * g.n_fourier) * sizeof(float);
     auto kern = hash_encode_fwd_kernel<F, MODE, ROWS>;
     IDRK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = persistent_grid(kern, ROWS, smem, (n + ROWS - 1) / ROWS);
-    kern<<<grid, ROWS, smem, st>>>(g, x, n, ldx, out, ld_out, idx_dbg);
+    kern<<<grid, ROWS, smem, st>>>(g, x, n, ldx, out, ld_out, idx_dbg, m_count);
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -419,7 +421,8 @@ extern "C" int idrk_device_sm_count(int* out_sms) {
 }
 
 extern "C" int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
-                                    float* out, int32_t ld_out, uint32_t* idx_debug, void* stream) {
+                                    float* out, int32_t ld_out, uint32_t* idx_debug, const int32_t* m_count,
+                                    void* stream) {
     GridDev g;
     int rc = fill_grid(h_grid, g);
     if (rc) return rc;
@@ -430,11 +433,11 @@ extern "C" int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* 
     const int mode = h_grid->frac_mode;
     const size_t row_bytes = (size_t)(ld_out | 1) * sizeof(float);
     if (row_bytes * 256 <= 72 * 1024) {
-#define CALL(F, M) launch_fwd<F, M, 256>(g, x, n, ldx, out, ld_out, idx_debug, st)
+#define CALL(F, M) launch_fwd<F, M, 256>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
         IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
     } else if (row_bytes * 64 <= 200 * 1024) {
-#define CALL(F, M) launch_fwd<F, M, 64>(g, x, n, ldx, out, ld_out, idx_debug, st)
+#define CALL(F, M) launch_fwd<F, M, 64>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
         IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
     }

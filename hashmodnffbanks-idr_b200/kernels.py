@@ -77,10 +77,10 @@ class HashGridSpec:
 
 
 def hash_encode_fwd(spec: HashGridSpec, x: torch.Tensor, tables, B, out: Optional[torch.Tensor] = None,
-                    want_idx: bool = False):
+                    want_idx: bool = False, m_count: Optional[torch.Tensor] = None, rows: Optional[int] = None):
     """K1.  x [n, >=3] -> out [n, pad4(width)] (returned tensor is the padded storage)."""
     x = rows2d(x, "x")
-    n = x.shape[0]
+    n = x.shape[0] if rows is None else rows
     ld = pad4(spec.width)
     if out is None:
         out = torch.empty((n, ld), device=x.device, dtype=torch.float32)
@@ -89,7 +89,7 @@ def hash_encode_fwd(spec: HashGridSpec, x: torch.Tensor, tables, B, out: Optiona
         return (out, idx) if want_idx else out
     d = spec.desc(tables, B)
     check(lib().idrk_hash_encode_fwd(ctypes.byref(d), ptr(x), n, ld_of(x), ptr(out), ld_of(out),
-                                     ptr(idx), stream_ptr()), "idrk_hash_encode_fwd")
+                                     ptr(idx), ptr(m_count), stream_ptr()), "idrk_hash_encode_fwd")
     return (out, idx) if want_idx else out
 
 
@@ -196,9 +196,16 @@ def split_tf32(x: torch.Tensor, m_count: Optional[torch.Tensor] = None):
     hi = empty_padded(r, c, x.device)
     lo = empty_padded(r, c, x.device)
     if r:
-        check(lib().idrk_split_tf32(ptr(x), r, c, ld_of(x), ptr(hi), ptr(lo), pad4(c), ptr(m_count), stream_ptr()),
-              "idrk_split_tf32")
+        check(lib().idrk_split_tf32(ptr(x), r, c, ld_of(x), 1.0, ptr(hi), ptr(lo), pad4(c), pad4(c) - c, ptr(m_count),
+                                    stream_ptr()), "idrk_split_tf32")
     return hi, lo
+
+
+def split_into(x: torch.Tensor, rows: int, cols: int, scale: float, hi: torch.Tensor, lo: Optional[torch.Tensor],
+               ld_out: int, pad_cols: int = 0, m_count: Optional[torch.Tensor] = None):
+    """Raw form: writes scale*x (split when `lo` is given) into caller-owned buffers (column offsets via views)."""
+    check(lib().idrk_split_tf32(ptr(x), rows, cols, ld_of(x), float(scale), ptr(hi), ptr(lo), ld_out, pad_cols,
+                                ptr(m_count), stream_ptr()), "idrk_split_tf32")
 
 
 def gemm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int, *, precision: Optional[int] = None,

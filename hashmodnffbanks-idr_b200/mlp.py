@@ -1,0 +1,353 @@
+"""MLP building blocks on top of the contraction kernel (csrc/gemm.cu).
+
+Two execution paths share the same kernel:
+
+* differentiable path - torch.autograd.Functions (`linear`, `linear_act`, `mm_nt/nn/tn`) whose
+  backward is itself expressed with these Functions, so the reference's second-order use
+  (ImplicitNetwork.gradient with create_graph=True, implicit_differentiable_renderer.py:116-128, then a
+  loss on that gradient) works to any order without hand-derived double-backward kernels;
+* inference path (`SdfPipeline`) - no autograd, weights folded (weight-norm) and hi/lo-split once per
+  parameter version, activations handed from epilogue to next layer already split, device-side row
+  count (`m_count`) so the ray tracer never syncs with the host.
+"""
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import kernels as K
+from ._lib import IdrkError
+
+SQRT2_INV = 1.0 / math.sqrt(2.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# operand preparation
+# ---------------------------------------------------------------------------------------------
+def _prep(t: torch.Tensor):
+    """(main, lo) operand pair for the current precision."""
+    t = K.operand(t.detach())
+    if K.get_precision() == K.PREC_3XTF32:
+        return K.split_tf32(t)
+    return t, None
+
+
+def _raw_mm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int, bias=None,
+            mode=K.EPI_NONE, act=0.0, scale=1.0, want_s=False):
+    dev = A.device
+    C = K.empty_padded(M, N, dev)
+    S = K.empty_padded(M, N, dev) if want_s else None
+    if M == 0:
+        return C, S
+    a, a_lo = _prep(A)
+    b, b_lo = _prep(B)
+    split_k = 1
+    if layout == K.GEMM_TN and Kc >= 4096:
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        split_k = max(1, min(Kc // 1024, (2 * 148) // max(tiles, 1)))
+        if split_k > 1:
+            C.zero_()
+    K.gemm(layout, a, b, M, N, Kc, A_lo=a_lo, B_lo=b_lo, C=C, S=S, bias=bias, mode=mode, act=act, scale=scale,
+           split_k=split_k)
+    return C, S
+
+
+# ---------------------------------------------------------------------------------------------
+# differentiable contractions (closed under differentiation)
+# ---------------------------------------------------------------------------------------------
+class _MMNT(torch.autograd.Function):
+    """C[M,N] = A[M,K] @ B[N,K]^T"""
+
+    @staticmethod
+    def forward(ctx, A, B):
+        ctx.save_for_backward(A, B)
+        return _raw_mm(K.GEMM_NT, A, B, A.shape[0], B.shape[0], A.shape[1])[0]
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, B = ctx.saved_tensors
+        dA = mm_nn(dC, B) if ctx.needs_input_grad[0] else None
+        dB = mm_tn(dC, A) if ctx.needs_input_grad[1] else None
+        return dA, dB
+
+
+class _MMNN(torch.autograd.Function):
+    """C[M,N] = A[M,K] @ B[K,N]"""
+
+    @staticmethod
+    def forward(ctx, A, B):
+        ctx.save_for_backward(A, B)
+        return _raw_mm(K.GEMM_NN, A, B, A.shape[0], B.shape[1], A.shape[1])[0]
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, B = ctx.saved_tensors
+        dA = mm_nt(dC, B) if ctx.needs_input_grad[0] else None
+        dB = mm_tn(A, dC) if ctx.needs_input_grad[1] else None
+        return dA, dB
+
+
+class _MMTN(torch.autograd.Function):
+    """C[M,N] = A[K,M]^T @ B[K,N]   (contraction over rows: weight gradients)"""
+
+    @staticmethod
+    def forward(ctx, A, B):
+        ctx.save_for_backward(A, B)
+        return _raw_mm(K.GEMM_TN, A, B, A.shape[1], B.shape[1], A.shape[0])[0]
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, B = ctx.saved_tensors
+        dA = mm_nt(B, dC) if ctx.needs_input_grad[0] else None
+        dB = mm_nn(A, dC) if ctx.needs_input_grad[1] else None
+        return dA, dB
+
+
+def mm_nt(A, B):
+    return _MMNT.apply(A, B)
+
+
+def mm_nn(A, B):
+    return _MMNN.apply(A, B)
+
+
+def mm_tn(A, B):
+    return _MMTN.apply(A, B)
+
+
+class _ColSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.rows = x.shape[0]
+        return K.colsum(x.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.unsqueeze(0).expand(ctx.rows, -1)
+
+
+def colsum(x):
+    return _ColSum.apply(x)
+
+
+class _Linear(torch.autograd.Function):
+    """Z = X W^T + b  (bias fused in the epilogue)."""
+
+    @staticmethod
+    def forward(ctx, X, W, b):
+        ctx.save_for_backward(X, W)
+        ctx.has_bias = b is not None
+        return _raw_mm(K.GEMM_NT, X, W, X.shape[0], W.shape[0], X.shape[1], bias=b.detach() if b is not None else None)[0]
+
+    @staticmethod
+    def backward(ctx, dZ):
+        X, W = ctx.saved_tensors
+        dX = mm_nn(dZ, W) if ctx.needs_input_grad[0] else None
+        dW = mm_tn(dZ, X) if ctx.needs_input_grad[1] else None
+        db = colsum(dZ) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dX, dW, db
+
+
+def linear(X, W, b=None):
+    return _Linear.apply(X, W, b)
+
+
+_ACT_MODES = {"softplus": K.EPI_SOFTPLUS, "relu": K.EPI_RELU, "sine": K.EPI_SINE, "tanh": K.EPI_TANH}
+
+
+class _LinearAct(torch.autograd.Function):
+    """(H, S) = act(X W^T + b) and its derivative, both from one kernel epilogue.
+
+    H = scale * act(Z),  S = act'(Z).  S is returned as a differentiable output so that when the
+    backward pass is itself recorded (create_graph) the dependence of act' on Z is tracked:
+    d S / d Z = act''(Z), written below per activation in terms of the saved outputs."""
+
+    @staticmethod
+    def forward(ctx, X, W, b, mode, act, scale):
+        H, S = _raw_mm(K.GEMM_NT, X, W, X.shape[0], W.shape[0], X.shape[1],
+                       bias=b.detach() if b is not None else None, mode=_ACT_MODES[mode], act=act, scale=scale,
+                       want_s=True)
+        ctx.mode, ctx.act, ctx.scale, ctx.has_bias = mode, act, scale, b is not None
+        ctx.save_for_backward(X, W, H, S)
+        ctx.set_materialize_grads(False)
+        return H, S
+
+    @staticmethod
+    def backward(ctx, dH, dS):
+        X, W, H, S = ctx.saved_tensors
+        dZ = None
+        if dH is not None:
+            dZ = dH * S if ctx.scale == 1.0 else dH * (S * ctx.scale)
+        if dS is not None:
+            if ctx.mode == "softplus":
+                s2 = (ctx.act * S) * (1.0 - S)
+            elif ctx.mode == "sine":
+                s2 = H * (-(ctx.act ** 2) / ctx.scale)
+            elif ctx.mode == "tanh":
+                s2 = (H * S) * (-2.0 / ctx.scale)
+            else:
+                s2 = None
+            if s2 is not None:
+                dZ = dS * s2 if dZ is None else dZ + dS * s2
+        if dZ is None:
+            return None, None, None, None, None, None
+        dX = mm_nn(dZ, W) if ctx.needs_input_grad[0] else None
+        dW = mm_tn(dZ, X) if ctx.needs_input_grad[1] else None
+        db = colsum(dZ) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dX, dW, db, None, None, None
+
+
+def linear_act(X, W, b, mode: str, act: float = 0.0, scale: float = 1.0):
+    """scale * act(X W^T + b); activations: softplus(beta=act), relu, sine(w0=act), tanh."""
+    return _LinearAct.apply(X, W, b, mode, float(act), float(scale))[0]
+
+
+class _WeightNorm(torch.autograd.Function):
+    """W = g * v / ||v||_row  (legacy nn.utils.weight_norm, dim=0)."""
+
+    @staticmethod
+    def forward(ctx, g, v):
+        ctx.save_for_backward(g, v)
+        return K.weight_norm_fwd(g.detach(), v.detach(), False, False)["W"]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dW):
+        g, v = ctx.saved_tensors
+        dg, dv = K.weight_norm_bwd(g, v, dW)
+        return dg, dv
+
+
+def weight_norm(g, v):
+    return _WeightNorm.apply(g, v)
+
+
+def layer_weight(lin: torch.nn.Module) -> torch.Tensor:
+    """Effective weight of a (possibly weight-normalised) nn.Linear, differentiable."""
+    if hasattr(lin, "weight_g"):
+        return weight_norm(lin.weight_g, lin.weight_v)
+    return lin.weight
+
+
+# ---------------------------------------------------------------------------------------------
+# inference pipeline (no autograd)
+# ---------------------------------------------------------------------------------------------
+class FoldedLayer:
+    __slots__ = ("W", "W_lo", "Wfull", "bias", "n_out", "n_in")
+
+    def __init__(self, lin: torch.nn.Module, split: bool):
+        with torch.no_grad():
+            if hasattr(lin, "weight_g"):
+                out = K.weight_norm_fwd(lin.weight_g, lin.weight_v, split, False)
+            else:
+                out = K.weight_norm_fwd(None, lin.weight, split, False)
+        self.W = out["W_hi"] if split else out["W"]
+        self.W_lo = out.get("W_lo")
+        self.Wfull = out["W"]
+        self.bias = lin.bias.detach()
+        self.n_out, self.n_in = (lin.weight_v if hasattr(lin, "weight_v") else lin.weight).shape
+
+
+def params_version(params: Sequence[torch.Tensor]) -> Tuple:
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+class SdfPipeline:
+    """ImplicitNetwork forward without autograd, as the ray tracer and the eval consumers use it
+    (implicit_differentiable_renderer.py:89-113 under no_grad; ray_tracing.py calls it ~50x per step).
+
+    * weights: weight-norm folded and hi/lo-split once per parameter version;
+    * activations: written by each layer's epilogue directly as the next layer's (split) operand;
+      the skip concat is realised by letting layer (skip-1) write scale 1/sqrt(2) into the left
+      columns of a shared buffer and copying the scaled embedding into the right columns;
+    * `m_count` (device int32): number of valid rows, so compacted ray sets need no host sync;
+    * want="sdf": the last Linear is reduced to its row 0 + the Laplace squash (the only column
+      the tracer consumes, 6.7 % fewer MACs);  want="full": all 1 + feature columns.
+    """
+
+    def __init__(self, net):
+        self.net = net
+        self.n_lin = net.num_layers - 1
+        self._folded = None
+        self._version = None
+        self._precision = None
+        self._bufs: Dict = {}
+        self._beta = None
+        self._beta_version = None
+
+    # -- cached state --------------------------------------------------------------------
+    def layers(self):
+        return [getattr(self.net, "lin%d" % l) for l in range(self.n_lin)]
+
+    def folded(self) -> List["FoldedLayer"]:
+        params = [p for l in self.layers() for p in l.parameters()]
+        ver = params_version(params)
+        prec = K.get_precision()
+        if self._folded is None or ver != self._version or prec != self._precision:
+            self._folded = [FoldedLayer(l, prec == K.PREC_3XTF32) for l in self.layers()]
+            self._version, self._precision = ver, prec
+        return self._folded
+
+    def beta(self) -> float:
+        p = self.net.dencity_net.beta
+        ver = (p.data_ptr(), p._version)
+        if self._beta is None or ver != self._beta_version:
+            self._beta = abs(float(p.detach().cpu())) + 1e-4
+            self._beta_version = ver
+        return self._beta
+
+    def _buf(self, name, rows, cols, device):
+        key = (name, cols)
+        b = self._bufs.get(key)
+        if b is None or b.shape[0] < rows or b.device != device:
+            b = torch.empty((max(rows, 1), K.pad4(cols)), device=device, dtype=torch.float32)
+            self._bufs[key] = b
+        return b
+
+    # -- execution -----------------------------------------------------------------------
+    @torch.no_grad()
+    def run(self, emb: torch.Tensor, rows: int, want: str = "sdf", m_count: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """emb: fp32 embedding buffer [>=rows, ld] (padded operand), width = net input width."""
+        net = self.net
+        fl = self.folded()
+        split = K.get_precision() == K.PREC_3XTF32
+        dev = emb.device
+        E = fl[0].n_in
+        if split:
+            cur = self._buf("emb_hi", rows, E, dev)
+            cur_lo = self._buf("emb_lo", rows, E, dev)
+            K.split_into(emb, rows, E, 1.0, cur, cur_lo, K.pad4(E), K.pad4(E) - E, m_count)
+        else:
+            cur, cur_lo = emb, None
+        cur_dim = E
+        n = self.n_lin
+        for l, f in enumerate(fl):
+            last = l == n - 1
+            if last:
+                if want == "sdf":
+                    res = out if out is not None else torch.empty(rows, device=dev, dtype=torch.float32)
+                    K.sdf_head(cur, f.Wfull[0], f.bias, self.beta(), res, rows, m_count)
+                    return res
+                C = self._buf("full_out", rows, f.n_out, dev) if out is None else out
+                K.gemm(K.GEMM_NT, cur, f.W, rows, f.n_out, cur_dim, A_lo=cur_lo, B_lo=f.W_lo, C=C, bias=f.bias,
+                       m_count=m_count)
+                res = C[:rows, :f.n_out]
+                sq, _ = K.sdf_squash(res[:, 0].contiguous(), self.beta(), False)
+                res[:, 0] = sq
+                return res
+            feeds_skip = (l + 1) in net.skip_in
+            width = f.n_out + (E if feeds_skip else 0)
+            head_next = (l == n - 2) and want == "sdf"           # next consumer is the fp32 SDF head
+            use_split = split and not head_next
+            nxt = self._buf(("h", l & 1), rows, width, dev)
+            nxt_lo = self._buf(("l", l & 1), rows, width, dev) if use_split else None
+            K.gemm(K.GEMM_NT, cur, f.W, rows, f.n_out, cur_dim, A_lo=cur_lo, B_lo=f.W_lo,
+                   C=None if use_split else nxt, C_hi=nxt if use_split else None, C_lo=nxt_lo, bias=f.bias,
+                   mode=K.EPI_SOFTPLUS, act=100.0, scale=SQRT2_INV if feeds_skip else 1.0, m_count=m_count)
+            if feeds_skip:
+                ldw = K.pad4(width)
+                K.split_into(emb, rows, E, SQRT2_INV, nxt[:, f.n_out:], nxt_lo[:, f.n_out:] if use_split else None,
+                             ldw, ldw - width, m_count)
+            cur, cur_lo, cur_dim = nxt, nxt_lo, width
+        raise IdrkError("unreachable")

@@ -1,0 +1,286 @@
+"""ImplicitNetwork, RenderingNetwork and IDRNetwork with the reference's constructor signatures,
+attribute names and state-dict keys (model/implicit_differentiable_renderer.py:11-329), so that
+
+    train.model_class = idrk.model.implicit_differentiable_renderer.IDRNetwork
+
+drops into the reference's IDR training loop.  Every Linear / activation pair runs in the tcgen05
+contraction kernel (idrk.mlp), the encoders in the hash-grid / filter-bank kernels and ray tracing in
+the ray-state kernels; torch only carries tensors, the autograd tape and O(rays) glue.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import kernels as K
+from .. import mlp
+from ..utils import rend_util
+from .custom_embedder_decoder import Custom_Embedding_Network
+from .density_net import LaplaceDensity
+from .embeddings.frequency_enc import SHEncoder, get_embedder
+from .ray_tracing import RayTracing
+from .sample_network import SampleNetwork
+
+
+def _geometric_init(lin, l, n_layers, dims, out_dim, bias, multires, skip_in):
+    """Sphere initialisation of the SDF MLP (IGR / reference :64-78)."""
+    if l == n_layers - 2:
+        torch.nn.init.normal_(lin.weight, mean=np.sqrt(np.pi) / np.sqrt(dims[l]), std=0.0001)
+        torch.nn.init.constant_(lin.bias, -bias)
+        return
+    torch.nn.init.constant_(lin.bias, 0.0)
+    std = np.sqrt(2) / np.sqrt(out_dim)
+    if multires > 0 and l == 0:
+        torch.nn.init.constant_(lin.weight[:, 3:], 0.0)
+        torch.nn.init.normal_(lin.weight[:, :3], 0.0, std)
+    elif multires > 0 and l in skip_in:
+        torch.nn.init.normal_(lin.weight, 0.0, std)
+        torch.nn.init.constant_(lin.weight[:, -(dims[0] - 3):], 0.0)
+    else:
+        torch.nn.init.normal_(lin.weight, 0.0, std)
+
+
+class ImplicitNetwork(nn.Module):
+    def __init__(self, feature_vector_size, d_in, d_out, dims, geometric_init=True, bias=1.0, skip_in=(),
+                 weight_norm=True, multires=0, embed_type=None, log2_max_hash_size=10, max_points_per_entry=2,
+                 base_resolution=64, desired_resolution=None, bound: float = 1.0):
+        super().__init__()
+        dims = [d_in] + list(dims) + [d_out + feature_vector_size]
+        self.embed_fn = None
+        self.embed_type = embed_type
+        self.multires = multires
+        self.dencity_net = LaplaceDensity(params_init={'beta': 0.9})
+        if embed_type and multires > 0:
+            self.embed_model = Custom_Embedding_Network(input_dims=d_in, network_dims=dims, embed_type=embed_type,
+                                                        multires=multires, log2_max_hash_size=log2_max_hash_size,
+                                                        max_points_per_entry=max_points_per_entry,
+                                                        base_resolution=base_resolution,
+                                                        desired_resolution=desired_resolution, bound=bound)
+            self.embed_fn = self.embed_model.forward
+            dims[0] = self.embed_model.embeddings_dim
+        self.num_layers = len(dims)
+        self.skip_in = tuple(skip_in)
+        for l in range(self.num_layers - 1):
+            out_dim = dims[l + 1] - dims[0] if (l + 1) in self.skip_in else dims[l + 1]
+            lin = nn.Linear(dims[l], out_dim)
+            if geometric_init:
+                _geometric_init(lin, l, self.num_layers, dims, out_dim, bias, multires, self.skip_in)
+            if weight_norm:
+                lin = nn.utils.weight_norm(lin)
+            setattr(self, "lin" + str(l), lin)
+        self.softplus = nn.Softplus(beta=100)
+        self._pipeline = mlp.SdfPipeline(self)
+
+    # -- embedding -------------------------------------------------------------------------
+    def _embed(self, x):
+        return self.embed_fn(x) if self.embed_fn is not None else x
+
+    # -- inference paths (no autograd) -----------------------------------------------------
+    @torch.no_grad()
+    def sdf(self, x: torch.Tensor) -> torch.Tensor:
+        """SDF column only, [P].  What `lambda x: implicit_network(x)[:, 0]` computes in the reference
+        (implicit_differentiable_renderer.py:257) without the 256 unused feature columns."""
+        x = x.reshape(-1, x.shape[-1])
+        if x.shape[0] == 0:
+            return torch.empty(0, device=x.device)
+        emb = K.operand(self._embed(x))
+        return self._pipeline.run(emb, x.shape[0], want="sdf")
+
+    def supports_device_count(self) -> bool:
+        """True when the encoder can take its row count from device memory (no host sync in the tracer)."""
+        if self.embed_fn is None:
+            return True
+        return getattr(self.embed_model, "embed_type", None) == "HashGrid"
+
+    @torch.no_grad()
+    def sdf_compacted(self, pts: torch.Tensor, rows: int, m_count, out: torch.Tensor) -> None:
+        """SDF of the first min(rows, *m_count) points of a contiguous [>=rows, 3] buffer, written to out[:rows]."""
+        pipe = self._pipeline
+        if self.embed_fn is None:
+            emb = pipe._buf("emb", rows, 3, pts.device)
+            K.split_into(pts, rows, 3, 1.0, emb, None, 4, 1, m_count)
+        elif self.embed_model.embed_type == "HashGrid":
+            grid = self.embed_model.embedder_obj
+            emb = pipe._buf("emb", rows, grid.embeddings_dim, pts.device)
+            K.hash_encode_fwd(grid.spec(), pts, grid.tables(), grid.freq_encoding.B, out=emb, m_count=m_count, rows=rows)
+        else:
+            if m_count is not None:
+                raise K._lib.IdrkError("this encoder needs a host-side row count")
+            emb = K.operand(self._embed(pts[:rows]))
+        pipe.run(emb, rows, want="sdf", m_count=m_count, out=out)
+
+    def _forward_inference(self, x):
+        emb = K.operand(self._embed(x))
+        return self._pipeline.run(emb, x.shape[0], want="full").clone()
+
+    # -- reference API -----------------------------------------------------------------------
+    def forward(self, input, compute_grad=False):
+        if not torch.is_grad_enabled():
+            if input.shape[0] == 0:
+                return torch.empty(0, getattr(self, "lin%d" % (self.num_layers - 2)).bias.shape[0], device=input.device)
+            return self._forward_inference(input)
+        emb = self._embed(input)
+        x = emb
+        n_lin = self.num_layers - 1
+        for l in range(n_lin):
+            lin = getattr(self, "lin" + str(l))
+            if l in self.skip_in:
+                x = torch.cat([x, emb], 1) / np.sqrt(2)
+            W = mlp.layer_weight(lin)
+            if l < n_lin - 1:
+                x = mlp.linear_act(x, W, lin.bias, "softplus", 100.0)
+            else:
+                x = mlp.linear(x, W, lin.bias)
+        s = x[:, 0]
+        rho = self.dencity_net(s.detach())
+        s = torch.tanh(s / (2 + rho))
+        return torch.cat([s.unsqueeze(1), x[:, 1:]], dim=1)
+
+    def gradient(self, x):
+        """d sdf / d x, [P, 1, 3], recorded on the tape (create_graph) like the reference (:116-128)."""
+        x.requires_grad_(True)
+        with torch.enable_grad():
+            y = self.forward(x)[:, :1]
+            g = torch.autograd.grad(outputs=y, inputs=x, grad_outputs=torch.ones_like(y), create_graph=True,
+                                    retain_graph=True, only_inputs=True)[0]
+        return g.unsqueeze(1)
+
+
+class RenderingNetwork(nn.Module):
+    def __init__(self, feature_vector_size, mode, d_in, d_out, dims, weight_norm=True, multires_view=0,
+                 viewdirs_embed_type='NerfPos'):
+        super().__init__()
+        self.feature_vector_size = feature_vector_size
+        self.mode = mode
+        dims = [d_in + feature_vector_size] + list(dims) + [d_out]
+        self.multires_view = multires_view
+        self.d_in = d_in
+        self.embedview_fn = None
+        deep = ('HashGrid', 'FFB', 'StyleModNFFB', 'FourierFeatures', 'HashGridCUDA', 'FFBTcnn', 'HashGridTcnn')
+        if viewdirs_embed_type == 'SHEncoder':
+            if multires_view > 0 and mode == 'idr':
+                enc = SHEncoder(3, degree=multires_view)
+                self.sh_encoder = enc
+                self.embedview_fn = enc.forward
+                dims[0] += enc.embeddings_dim - 3
+        elif viewdirs_embed_type == 'NerfPos':
+            if multires_view > 0 and mode == 'idr':
+                self.embedview_fn, input_ch = get_embedder(multires_view)
+                dims[0] += input_ch
+        elif viewdirs_embed_type in deep:
+            if multires_view > 0 and mode == 'idr':
+                self.embed_model = Custom_Embedding_Network(input_dims=3, network_dims=dims,
+                                                            embed_type=viewdirs_embed_type, multires=multires_view,
+                                                            max_points_per_entry=2,
+                                                            log2_max_hash_size=multires_view - 1, base_resolution=16,
+                                                            desired_resolution=512, bound=1.0)
+                self.embedview_fn = self.embed_model.forward
+                dims[0] += self.embed_model.embeddings_dim - 3
+        else:
+            raise ValueError('No Embedding Network config provided for VIEWDIRS')
+        self.num_layers = len(dims)
+        for l in range(self.num_layers - 1):
+            lin = nn.Linear(dims[l], dims[l + 1])
+            if weight_norm:
+                lin = nn.utils.weight_norm(lin)
+            setattr(self, "lin" + str(l), lin)
+        self.relu = nn.ReLU()
+        self.tanh = nn.Tanh()
+
+    def forward(self, points, normals, view_dirs, feature_vectors):
+        if self.embedview_fn is not None:
+            view_dirs = self.embedview_fn(view_dirs)
+        if self.mode == 'idr':
+            x = torch.cat([points, view_dirs, normals, feature_vectors], dim=-1)
+        elif self.mode == 'no_view_dir':
+            x = torch.cat([points, normals, feature_vectors], dim=-1)
+        elif self.mode == 'no_normal':
+            x = torch.cat([points, view_dirs, feature_vectors], dim=-1)
+        else:
+            raise ValueError("unknown rendering mode %r" % self.mode)
+        n_lin = self.num_layers - 1
+        for l in range(n_lin):
+            lin = getattr(self, "lin" + str(l))
+            W = mlp.layer_weight(lin)
+            x = mlp.linear_act(x, W, lin.bias, "relu" if l < n_lin - 1 else "tanh")
+        return x
+
+
+class IDRNetwork(nn.Module):
+    def __init__(self, conf):
+        super().__init__()
+        self.feature_vector_size = conf.get_int('feature_vector_size')
+        implicit_kwargs = dict(conf.get_config('implicit_network'))
+        embedding_conf = conf.get_config('embedding_network')
+        if embedding_conf is not None:
+            implicit_kwargs.update(dict(embedding_conf))
+        self.implicit_network = ImplicitNetwork(self.feature_vector_size, **implicit_kwargs)
+        self.rendering_network = RenderingNetwork(self.feature_vector_size, **dict(conf.get_config('rendering_network')))
+        self.ray_tracer = RayTracing(**dict(conf.get_config('ray_tracer')))
+        self.sample_network = SampleNetwork()
+        self.object_bounding_sphere = conf.get_float('ray_tracer.object_bounding_sphere')
+        # host-side RNG draws (eikonal points, min-SDF steps) may be injected for exact parity runs
+        self.injected_eikonal_points = None
+
+    def forward(self, input):
+        intrinsics, uv, pose = input["intrinsics"], input["uv"], input["pose"]
+        object_mask = input["object_mask"].reshape(-1)
+        ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics)
+        batch_size, num_pixels, _ = ray_dirs.shape
+        device = ray_dirs.device
+
+        self.implicit_network.eval()
+        with torch.no_grad():
+            self.ray_tracer.train(self.training)
+            points, network_object_mask, dists = self.ray_tracer(sdf=self.implicit_network.sdf, cam_loc=cam_loc,
+                                                                 object_mask=object_mask, ray_directions=ray_dirs)
+        self.implicit_network.train()
+        points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
+        sdf_output = self.implicit_network(points)[:, 0:1]
+        ray_dirs = ray_dirs.reshape(-1, 3)
+
+        if self.training:
+            surface_mask = network_object_mask & object_mask
+            surface_points = points[surface_mask]
+            surface_dists = dists[surface_mask].unsqueeze(-1)
+            surface_ray_dirs = ray_dirs[surface_mask]
+            surface_cam_loc = cam_loc.unsqueeze(1).repeat(1, num_pixels, 1).reshape(-1, 3)[surface_mask]
+            surface_output = sdf_output[surface_mask]
+            N = surface_points.shape[0]
+
+            n_eik = batch_size * num_pixels // 2
+            if self.injected_eikonal_points is not None:
+                eik = self.injected_eikonal_points.to(device)
+            else:   # drawn on the host generator, like the reference (:279)
+                r = self.object_bounding_sphere
+                eik = torch.empty(n_eik, 3).uniform_(-r, r).to(device)
+            eikonal_points = torch.cat([eik, points.clone().detach()], 0)
+            points_all = torch.cat([surface_points, eikonal_points], dim=0)
+
+            with torch.no_grad():
+                surface_sdf_values = self.implicit_network(surface_points)[:N, 0:1] if N > 0 \
+                    else torch.zeros(0, 1, device=device)
+            g = self.implicit_network.gradient(points_all)
+            surface_points_grad = g[:N, 0, :].clone().detach()
+            grad_theta = g[N:, 0, :]
+            differentiable_surface_points = self.sample_network(surface_output, surface_sdf_values,
+                                                                surface_points_grad, surface_dists,
+                                                                surface_cam_loc, surface_ray_dirs)
+        else:
+            surface_mask = network_object_mask
+            differentiable_surface_points = points[surface_mask]
+            grad_theta = None
+
+        view = -ray_dirs[surface_mask]
+        rgb_values = torch.ones_like(points).float()
+        if differentiable_surface_points.shape[0] > 0:
+            rgb_values[surface_mask] = self.get_rbg_value(differentiable_surface_points, view)
+
+        return {'points': points, 'rgb_values': rgb_values, 'sdf_output': sdf_output,
+                'network_object_mask': network_object_mask, 'object_mask': object_mask, 'grad_theta': grad_theta}
+
+    def get_rbg_value(self, points, view_dirs):
+        output = self.implicit_network(points)
+        g = self.implicit_network.gradient(points)
+        normals = g[:, 0, :]
+        feature_vectors = output[:, 1:]
+        return self.rendering_network(points, normals, view_dirs, feature_vectors)

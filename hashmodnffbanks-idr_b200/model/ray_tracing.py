@@ -1,0 +1,216 @@
+"""RayTracing with the reference's constructor and call signature (model/ray_tracing.py:5-95):
+
+    RayTracing(object_bounding_sphere, sdf_threshold, line_search_step, line_step_iters,
+               sphere_tracing_iters, n_steps, n_secant_steps)
+    .forward(sdf, cam_loc, object_mask, ray_directions) -> (points, network_object_mask, dists)
+
+The per-ray state machine runs in csrc/ray_tracing.cu; between its phases the SDF is evaluated on
+compacted point lists.  Two ways to evaluate:
+
+* `sdf` is `ImplicitNetwork.sdf` of this package with a device-count capable encoder: the whole
+  sphere-tracing loop (up to 44 SDF evaluations) is enqueued without a single host sync - kernels take
+  the list length from device memory; two syncs remain (sampler / min-SDF list sizes);
+* any other callable (e.g. an analytic SDF in the parity tests, or the reference's lambda): the list
+  length is read back after each compaction and `sdf(points[:n])` is called like the reference does.
+
+Extensions (keyword-only, default to the reference behaviour): `min_sdf_steps` injects the U(0,1)
+vector of ray_tracing.py:277 and `sphere_intersections=(t, hit)` the result of
+rend_util.get_sphere_intersection, so parity runs can share host-side randomness / inputs.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from .. import kernels as K
+from .._lib import RayStateDesc, check, lib, ptr, stream_ptr
+from ..utils import rend_util
+
+_SDF_CHUNK_POINTS = 32768          # points per SDF call in the sampler / min-SDF sweeps
+
+
+class _Evaluator:
+    """Evaluates the SDF on the first `count` rows of a point buffer."""
+
+    def __init__(self, sdf):
+        owner = getattr(sdf, "__self__", None)
+        self.fast = (owner is not None and hasattr(owner, "sdf_compacted") and owner.supports_device_count()
+                     and getattr(sdf, "__func__", None) is getattr(type(owner), "sdf", None))
+        self.owner = owner
+        self.sdf = sdf
+        self.calls = 0
+        self.points = 0
+
+    def on_device_count(self, pts, cap, counter, out):
+        """Sphere-tracing phases: list length lives in `counter` (device int32[1])."""
+        self.calls += 1
+        if self.fast:
+            self.owner.sdf_compacted(pts, cap, counter, out)
+            return
+        n = int(counter.item())
+        self.points += n
+        if n > 0:
+            out[:n] = self.sdf(pts[:n]).reshape(-1)
+
+    def on_host_count(self, pts, n, out):
+        self.calls += 1
+        self.points += n
+        if n == 0:
+            return
+        if self.fast:
+            self.owner.sdf_compacted(pts, n, None, out)
+        else:
+            out[:n] = self.sdf(pts[:n]).reshape(-1)
+
+
+class RayTracing(nn.Module):
+    def __init__(self, object_bounding_sphere=1.0, sdf_threshold=5.0e-5, line_search_step=0.5, line_step_iters=1,
+                 sphere_tracing_iters=10, n_steps=100, n_secant_steps=8):
+        super().__init__()
+        self.object_bounding_sphere = object_bounding_sphere
+        self.sdf_threshold = sdf_threshold
+        self.sphere_tracing_iters = sphere_tracing_iters
+        self.line_step_iters = line_step_iters
+        self.line_search_step = line_search_step
+        self.n_steps = n_steps
+        self.n_secant_steps = n_secant_steps
+        self.last_stats = {}
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, sdf, cam_loc, object_mask, ray_directions, *, min_sdf_steps=None, sphere_intersections=None):
+        K.require_cuda(ray_directions, "ray_directions")
+        L = lib()
+        dev = ray_directions.device
+        B, P, _ = ray_directions.shape
+        N = B * P
+        ev = _Evaluator(sdf)
+        with torch.no_grad():
+            if sphere_intersections is None:
+                t_sph, hit = rend_util.get_sphere_intersection(cam_loc, ray_directions, r=self.object_bounding_sphere)
+            else:
+                t_sph, hit = sphere_intersections
+            t_sph = t_sph.reshape(N, 2).contiguous().float()
+            hit_u8 = hit.reshape(N).to(torch.uint8).contiguous()
+            obj_u8 = object_mask.reshape(N).to(torch.uint8).contiguous()
+            cam = cam_loc.reshape(B, 3).contiguous().float()
+            dirs = ray_directions.reshape(N, 3).contiguous().float()
+
+            fbuf = torch.empty(16 * N, device=dev, dtype=torch.float32)
+            t0, t1, cur_s, cur_e, nxt_s, nxt_e, min_dis, max_dis = (fbuf[i * N:(i + 1) * N] for i in range(8))
+            ps = fbuf[8 * N:11 * N].view(N, 3)
+            pe = fbuf[11 * N:14 * N].view(N, 3)
+            bbuf = torch.empty(3 * N, device=dev, dtype=torch.uint8)
+            unf_s, unf_e, net_mask = bbuf[:N], bbuf[N:2 * N], bbuf[2 * N:]
+            ibuf = torch.empty(3 * N, device=dev, dtype=torch.int32)
+            slot_s, slot_e, ray_of_slot = ibuf[:N], ibuf[N:2 * N], ibuf[2 * N:]
+            n_ls = int(self.line_step_iters)
+            n_it = int(self.sphere_tracing_iters)
+            counters = torch.zeros(8 + (n_it + 1) * (n_ls + 3), device=dev, dtype=torch.int32)
+            cidx = [0]
+
+            def new_counter():
+                c = counters[cidx[0]:cidx[0] + 1]
+                cidx[0] += 1
+                return c
+
+            st = RayStateDesc()
+            st.cam_loc, st.ray_dirs, st.n_rays, st.num_pixels = cam.data_ptr(), dirs.data_ptr(), N, P
+            for name, t in (("t0", t0), ("t1", t1), ("cur_s", cur_s), ("cur_e", cur_e), ("nxt_s", nxt_s), ("nxt_e", nxt_e),
+                            ("ps", ps), ("pe", pe), ("min_dis", min_dis), ("max_dis", max_dis), ("unf_s", unf_s),
+                            ("unf_e", unf_e), ("slot_s", slot_s), ("slot_e", slot_e)):
+                setattr(st, name, t.data_ptr())
+            S = ctypes.byref(st)
+            sp = stream_ptr()
+
+            cap = 2 * N
+            pts = torch.empty((cap, 3), device=dev, dtype=torch.float32)
+            vals = torch.empty(cap, device=dev, dtype=torch.float32)
+
+            # ---- sphere tracing (reference :98-187) ------------------------------------------------
+            c = new_counter()
+            check(L.idrk_rt_init(S, ptr(t_sph), ptr(hit_u8), ptr(pts), ptr(c), sp), "idrk_rt_init")
+            ev.on_device_count(pts, cap, c, vals)
+            gate = new_counter()
+            check(L.idrk_rt_top(S, ptr(vals), 1, float(self.sdf_threshold), ptr(gate), sp), "idrk_rt_top")
+            for it in range(n_it):
+                c = new_counter()
+                check(L.idrk_rt_step(S, ptr(gate), ptr(pts), ptr(c), sp), "idrk_rt_step")
+                ev.on_device_count(pts, cap, c, vals)
+                for k in range(n_ls):
+                    c = new_counter()
+                    factor = (1 - self.line_search_step) / (2 ** k)
+                    check(L.idrk_rt_linesearch(S, ptr(gate), ptr(vals), 1 if k == 0 else 2, float(factor), ptr(pts),
+                                               ptr(c), sp), "idrk_rt_linesearch")
+                    ev.on_device_count(pts, cap, c, vals)
+                check(L.idrk_rt_end(S, ptr(gate), ptr(vals), 1 if n_ls == 0 else 2, sp), "idrk_rt_end")
+                gate = new_counter()
+                check(L.idrk_rt_top(S, None, 0, float(self.sdf_threshold), ptr(gate), sp), "idrk_rt_top")
+
+            # ---- sampler + secant for the non-convergent rays (:41-59, :189-268) ------------------------
+            c_samp = new_counter()
+            check(L.idrk_rt_select_sampler(S, ptr(net_mask), ptr(ray_of_slot), ptr(c_samp), sp), "idrk_rt_select_sampler")
+            sampler_mask = unf_s.clone()
+            n_samp = int(c_samp.item())
+            n_sec = 0
+            ns = int(self.n_steps)
+            if n_samp > 0:
+                lin = torch.linspace(0, 1, steps=ns).to(dev)
+                big_vals = torch.empty(n_samp * ns, device=dev, dtype=torch.float32)
+                rays_per_chunk = max(1, _SDF_CHUNK_POINTS // ns)
+                cpts = torch.empty((min(n_samp, rays_per_chunk) * ns, 3), device=dev, dtype=torch.float32)
+                for s0 in range(0, n_samp, rays_per_chunk):
+                    m = min(rays_per_chunk, n_samp - s0)
+                    check(L.idrk_rt_sampler_points(S, ptr(ray_of_slot), s0, m, ns, ptr(lin), ptr(cpts), sp),
+                          "idrk_rt_sampler_points")
+                    ev.on_host_count(cpts, m * ns, big_vals[s0 * ns:(s0 + m) * ns])
+                zbuf = torch.empty(4 * n_samp, device=dev, dtype=torch.float32)
+                z_lo, z_hi, s_lo, s_hi = (zbuf[i * n_samp:(i + 1) * n_samp] for i in range(4))
+                sec_slots = torch.empty(n_samp, device=dev, dtype=torch.int32)
+                c_sec = new_counter()
+                check(L.idrk_rt_sampler_resolve(S, ptr(ray_of_slot), n_samp, ns, ptr(lin), ptr(big_vals), ptr(obj_u8),
+                                                int(self.training), ptr(net_mask), ptr(z_lo), ptr(z_hi), ptr(s_lo),
+                                                ptr(s_hi), ptr(sec_slots), ptr(c_sec), sp), "idrk_rt_sampler_resolve")
+                n_sec = int(c_sec.item())
+                if n_sec > 0:
+                    spts = torch.empty((n_sec, 3), device=dev, dtype=torch.float32)
+                    svals = torch.empty(n_sec, device=dev, dtype=torch.float32)
+                    nsec_steps = int(self.n_secant_steps)
+
+                    def secant(mode):
+                        check(L.idrk_rt_secant(S, ptr(ray_of_slot), ptr(sec_slots), n_sec, mode, ptr(svals), ptr(z_lo),
+                                               ptr(z_hi), ptr(s_lo), ptr(s_hi), ptr(spts), sp), "idrk_rt_secant")
+                    if nsec_steps == 0:
+                        secant(3)
+                    else:
+                        secant(0)
+                        for i in range(nsec_steps):
+                            ev.on_host_count(spts, n_sec, svals)
+                            secant(1 if i < nsec_steps - 1 else 2)
+
+            self.last_stats = {"sdf_calls": ev.calls, "n_sampler": n_samp, "n_secant": n_sec, "fast_path": ev.fast}
+            net_mask_b = net_mask.bool()
+            if not self.training:
+                return ps.clone(), net_mask_b.clone(), t0.clone()
+
+            # ---- training only: rays that miss, minimal-SDF points for the mask loss (:71-92, :270-298) --
+            c_min = new_counter()
+            check(L.idrk_rt_select_minsdf(S, ptr(net_mask), ptr(obj_u8), ptr(hit_u8), ptr(sampler_mask), ptr(ray_of_slot),
+                                          ptr(c_min), sp), "idrk_rt_select_minsdf")
+            n_min = int(c_min.item())
+            if n_min > 0:
+                if min_sdf_steps is None:       # drawn on the host generator like the reference (:277)
+                    u = torch.empty(ns).uniform_(0.0, 1.0).to(dev)
+                else:
+                    u = min_sdf_steps.to(dev).float().contiguous()
+                big_vals = torch.empty(n_min * ns, device=dev, dtype=torch.float32)
+                rays_per_chunk = max(1, _SDF_CHUNK_POINTS // ns)
+                cpts = torch.empty((min(n_min, rays_per_chunk) * ns, 3), device=dev, dtype=torch.float32)
+                for s0 in range(0, n_min, rays_per_chunk):
+                    m = min(rays_per_chunk, n_min - s0)
+                    check(L.idrk_rt_minsdf_points(S, ptr(ray_of_slot), s0, m, ns, ptr(u), ptr(cpts), sp),
+                          "idrk_rt_minsdf_points")
+                    ev.on_host_count(cpts, m * ns, big_vals[s0 * ns:(s0 + m) * ns])
+                check(L.idrk_rt_minsdf_resolve(S, ptr(ray_of_slot), n_min, ns, ptr(u), ptr(big_vals), sp),
+                      "idrk_rt_minsdf_resolve")
+            self.last_stats.update({"sdf_calls": ev.calls, "n_minsdf": n_min})
+            return ps.clone(), net_mask_b.clone(), t0.clone()

@@ -57,9 +57,10 @@ int idrk_device_sm_count(int* out_sms);        /* SM count of the current device
  * FourierFeature.forward (frequency_enc.py:63-67) ++ _HashGridMLP.forward x L (:81-102)
  * ++ hash_func (:32-40).   x [n, ldx>=3], out [n, ld_out], ld_out >= width; columns
  * width..ld_out-1 are written as zeros.  idx_debug (nullable) receives the uint32 table row
- * of all 8 corners, [n, L, 8]. */
+ * of all 8 corners, [n, L, 8].  m_count (nullable, device int32): only the first min(n, *m_count)
+ * points are encoded (device-side compaction in the ray tracer). */
 int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
-                         float* out, int32_t ld_out, uint32_t* idx_debug, void* stream);
+                         float* out, int32_t ld_out, uint32_t* idx_debug, const int32_t* m_count, void* stream);
 
 /* -- K2: hash-grid encode backward ------------------------------------------------------
  * Replaces autograd through the same functions: embedding_dense_backward scatter-add into
@@ -124,7 +125,9 @@ int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N, int32_t K
               const idrk_epilogue_t* h_epi, const int32_t* m_count, int32_t split_k, void* stream);
 
 /* -- helpers around the MLP tiles ----------------------------------------------------------
- * idrk_split_tf32: hi = tf32(x), lo = tf32(x - hi) for 3xTF32 operands; pads [cols, ld_out) with 0.
+ * idrk_split_tf32: v = scale * x; hi = tf32(v), lo = tf32(v - hi) for 3xTF32 operands (lo nullable -> plain
+ *   scaled copy rounded to tf32 is NOT applied: hi then receives v itself); columns [cols, cols+pad_cols)
+ *   of the outputs are zero-filled.
  * idrk_weight_norm_fwd/bwd: legacy nn.utils.weight_norm(dim=0) used by every lin{l}
  *   (implicit_differentiable_renderer.py:80-81,195-196): W = g * v / ||v||_row.  g == NULL copies v.
  *   Optional outputs: W, its hi/lo split, and the transposed copies Wt[K, ldwt] (K-major operand of
@@ -133,8 +136,8 @@ int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N, int32_t K
  * idrk_sdf_head: sdf = tanh(s / (2 + rho(s))), s = <h[p, :K], w> + bias[0]  - the only output column the
  *   ray tracer consumes (implicit_differentiable_renderer.py:112, :257; density_net.py:20-30).
  * idrk_sdf_squash: the same squash on precomputed s (+ optional derivative d out / d s). */
-int idrk_split_tf32(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* hi, float* lo, int32_t ld_out,
-                    const int32_t* m_count, void* stream);
+int idrk_split_tf32(const float* x, int64_t rows, int32_t cols, int32_t ldx, float scale, float* hi, float* lo,
+                    int32_t ld_out, int32_t pad_cols, const int32_t* m_count, void* stream);
 int idrk_weight_norm_fwd(const float* g, const float* v, int32_t N, int32_t K, int32_t ldv,
                          float* W, float* W_hi, float* W_lo, int32_t ldw,
                          float* Wt, float* Wt_hi, float* Wt_lo, int32_t ldwt, void* stream);
@@ -144,6 +147,53 @@ int idrk_colsum(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* 
 int idrk_sdf_head(const float* h, int64_t rows, int32_t K, int32_t ldh, const float* w, const float* bias,
                   float beta, float* out, const int32_t* m_count, void* stream);
 int idrk_sdf_squash(const float* s, int64_t n, float beta, float* out, float* dout, void* stream);
+
+/* -- K5: ray-state kernels of RayTracing ----------------------------------------------------
+ * Replace model/ray_tracing.py (forward :26-95, sphere_tracing :98-187, ray_sampler :189-249,
+ * secant :251-268, minimal_sdf_points :270-298).  The caller owns all per-ray arrays (host struct of
+ * device pointers below) and evaluates the SDF on the compacted point lists between calls.
+ * `counter` arguments are device int32 append counters (caller zeroes them), `gate` arguments are
+ * device int32 flags: the kernel is a no-op when *gate == 0 (the reference's `break`). */
+typedef struct idrk_ray_state {
+    const float* cam_loc;    /* [B, 3]                                                    */
+    const float* ray_dirs;   /* [N, 3], N = B * num_pixels                                */
+    int32_t n_rays, num_pixels;
+    float *t0, *t1;          /* acc_start_dis, acc_end_dis                                */
+    float *cur_s, *cur_e, *nxt_s, *nxt_e;   /* curr / next sdf at both ends               */
+    float *ps, *pe;          /* curr_start_points, curr_end_points [N, 3]                 */
+    float *min_dis, *max_dis;
+    uint8_t *unf_s, *unf_e;  /* unfinished masks                                          */
+    int32_t *slot_s, *slot_e;/* list slot of the point submitted for evaluation, -1 none  */
+} idrk_ray_state_t;
+
+int idrk_rt_init(const idrk_ray_state_t* h_state, const float* t_sph, const uint8_t* hit, float* pts, int32_t* counter,
+                 void* stream);
+/* gather_mode: 0 none, 1 nxt = slot >= 0 ? vals[slot] : 0, 2 nxt = vals[slot] where slot >= 0 */
+int idrk_rt_top(const idrk_ray_state_t* h_state, const float* vals, int32_t gather_mode, float sdf_threshold,
+                int32_t* n_unfinished, void* stream);
+int idrk_rt_step(const idrk_ray_state_t* h_state, const int32_t* gate, float* pts, int32_t* counter, void* stream);
+int idrk_rt_linesearch(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, int32_t gather_mode,
+                       float factor, float* pts, int32_t* counter, void* stream);
+int idrk_rt_end(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, int32_t gather_mode, void* stream);
+int idrk_rt_select_sampler(const idrk_ray_state_t* h_state, uint8_t* net_mask, int32_t* ray_of_slot, int32_t* counter,
+                           void* stream);
+int idrk_rt_sampler_points(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t slot0, int32_t n_slots,
+                           int32_t n_steps, const float* lin, float* pts, void* stream);
+int idrk_rt_sampler_resolve(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t n_slots, int32_t n_steps,
+                            const float* lin, const float* vals, const uint8_t* object_mask, int32_t training,
+                            uint8_t* net_mask, float* z_lo, float* z_hi, float* s_lo, float* s_hi,
+                            int32_t* sec_slots, int32_t* sec_counter, void* stream);
+/* mode 0: emit first prediction, 1: consume sdf + emit next, 2: consume + write result, 3: write initial prediction */
+int idrk_rt_secant(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, const int32_t* sec_slots, int32_t n_sec,
+                   int32_t mode, const float* vals, float* z_lo, float* z_hi, float* s_lo, float* s_hi, float* pts,
+                   void* stream);
+int idrk_rt_select_minsdf(const idrk_ray_state_t* h_state, const uint8_t* net_mask, const uint8_t* object_mask,
+                          const uint8_t* hit, const uint8_t* sampler_mask, int32_t* ray_of_slot, int32_t* counter,
+                          void* stream);
+int idrk_rt_minsdf_points(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t slot0, int32_t n_slots,
+                          int32_t n_steps, const float* u, float* pts, void* stream);
+int idrk_rt_minsdf_resolve(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t n_slots, int32_t n_steps,
+                           const float* u, const float* vals, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,115 @@
+"""GPU parity of the ray tracer.  When both sides see the same SDF values (the analytic SDF is evaluated by
+the same host function for the oracle and for the CUDA tracer) masks, distances and points must be BIT-EXACT;
+for the golden fixtures, whose SDFs are evaluated with device torch ops that differ from the host in the last
+ulp, mismatching rays are counted and bounded."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import idr_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+CONF = dict(object_bounding_sphere=1.0, sdf_threshold=5.0e-5, line_search_step=0.5, line_step_iters=3,
+            sphere_tracing_iters=10, n_steps=100, n_secant_steps=8)
+
+
+def T(a):
+    return torch.from_numpy(np.array(a))
+
+
+def r2(p):
+    return torch.sqrt(p[:, 0] * p[:, 0] + p[:, 1] * p[:, 1] + p[:, 2] * p[:, 2])
+
+
+EXACT_SDFS = {
+    "sphere": lambda p: r2(p) - 0.5,
+    "bumpy": lambda p: (r2(p) - 0.55) * 0.7 + (p[:, 0] * p[:, 1]) * 0.3 - (p[:, 2] * p[:, 2]) * 0.2,
+    "torus": lambda p: torch.sqrt((torch.sqrt(p[:, 0] * p[:, 0] + p[:, 2] * p[:, 2]) - 0.45) *
+                                  (torch.sqrt(p[:, 0] * p[:, 0] + p[:, 2] * p[:, 2]) - 0.45) + p[:, 1] * p[:, 1]) - 0.18,
+    "slab": lambda p: p[:, 2] * p[:, 2] * 4.0 - 0.05 + p[:, 0] * 0.0,
+}
+
+
+def rays(n, seed, tz=-3.0, f=500.0):
+    pose = torch.eye(4).unsqueeze(0)
+    pose[0, 2, 3] = tz
+    Kc = torch.eye(4).unsqueeze(0)
+    Kc[0, 0, 0] = Kc[0, 1, 1] = f
+    Kc[0, 0, 2] = Kc[0, 1, 2] = 128.0
+    uv = torch.rand(1, n, 2, generator=torch.Generator().manual_seed(seed)) * 256
+    mask = torch.rand(1, n, generator=torch.Generator().manual_seed(seed + 1)) > 0.5
+    dirs, cam = O.camera_rays(uv, pose, Kc)
+    return dirs, cam, mask.reshape(-1)
+
+
+@pytest.mark.parametrize("kind", list(EXACT_SDFS))
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("n,f", [(777, 500.0), (2048, 150.0)])
+def test_bit_exact_vs_oracle(kind, training, n, f):
+    from idrk.model.ray_tracing import RayTracing
+    dirs, cam, mask = rays(n, 5, f=f)                      # f = 150: many rays miss the unit sphere
+    u = torch.rand(100, generator=torch.Generator().manual_seed(9))
+    sdf = EXACT_SDFS[kind]
+    orc = O.RayTracerOracle(**CONF)
+    orc.training = training
+    p_ref, m_ref, d_ref = orc(sdf, cam, mask, dirs, u)
+    t_sph, hit = O.sphere_intersection(cam, dirs, 1.0)
+    tr = RayTracing(**CONF)
+    tr.train(training)
+    p, m, d = tr(lambda q: sdf(q.cpu()).to(DEV), cam.to(DEV), mask.to(DEV), dirs.to(DEV), min_sdf_steps=u,
+                 sphere_intersections=(t_sph.to(DEV), hit.to(DEV)))
+    assert torch.equal(m.cpu(), m_ref)
+    assert torch.equal(d.cpu(), d_ref)
+    assert torch.equal(p.cpu(), p_ref)
+
+
+@pytest.mark.parametrize("kind", ["sphere", "bumpy", "torus"])
+@pytest.mark.parametrize("training", [True, False])
+def test_golden_fixtures(golden, kind, training):
+    from idrk.model.ray_tracing import RayTracing
+    g = golden("raytracing")
+    sdfs = {"sphere": lambda p: p.norm(2, dim=1) - 0.5,
+            "bumpy": lambda p: (p.norm(2, dim=1) - 0.55) * 0.7 + 0.05 * torch.sin(9.0 * p[:, 0]) * torch.sin(7.0 * p[:, 1]),
+            "torus": lambda p: torch.stack([torch.sqrt(p[:, 0] ** 2 + p[:, 2] ** 2) - 0.45, p[:, 1]], 1).norm(2, dim=1) - 0.18}
+    tr = RayTracing(**CONF)
+    tr.train(training)
+    p, m, d = tr(sdfs[kind], T(g["cam"]).to(DEV), T(g["mask"]).reshape(-1).to(DEV), T(g["dirs"]).to(DEV),
+                 min_sdf_steps=T(g["min_sdf_steps"]))
+    tag = "%s_%s" % (kind, "train" if training else "eval")
+    m_ref, d_ref = T(g["net_" + tag]), T(g["dist_" + tag])
+    n = m_ref.numel()
+    flips = (m.cpu() != m_ref).sum().item()
+    assert flips <= max(1, n // 200), flips                 # <= 0.5 % borderline rays
+    bad = ((d.cpu() - d_ref).abs() > 1e-4).sum().item()
+    assert bad <= max(2, n // 50), bad                      # argmin ties of the 100-sample sweeps
+
+
+def test_device_count_path_equals_callable_path():
+    """The sync-free path (device-side list lengths) and the generic callable path give identical results."""
+    from idrk.model.implicit_differentiable_renderer import ImplicitNetwork
+    from idrk.model.ray_tracing import RayTracing
+    from tests_support import load_sd_into, quiet_build
+    cfg = O.EmbedCfg("HashGrid", 6, 5, 2, 64, 512, 1.0)
+    sd = O.make_implicit_sd(cfg, torch.Generator().manual_seed(1), perturb=0.02)
+    net = quiet_build(ImplicitNetwork, 256, 3, 1, [512] * 8, True, 0.6, (4,), True, 6, "HashGrid", 5, 2, 64, 512, 1.0)
+    load_sd_into(net, sd, "implicit_network.")
+    net = net.to(DEV)
+    dirs, cam, mask = rays(2048, 3)
+    u = torch.rand(100, generator=torch.Generator().manual_seed(2))
+    tr = RayTracing(**CONF)
+    a = tr(net.sdf, cam.to(DEV), mask.to(DEV), dirs.to(DEV), min_sdf_steps=u)
+    assert tr.last_stats["fast_path"]
+    b = tr(lambda x: net.sdf(x), cam.to(DEV), mask.to(DEV), dirs.to(DEV), min_sdf_steps=u)
+    assert not tr.last_stats["fast_path"]
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    # and against the oracle tracer driven by the oracle network (fp32 CPU): report-level agreement
+    orc = O.RayTracerOracle(**CONF)
+    with torch.no_grad():
+        p_ref, m_ref, d_ref = orc(lambda x: O.implicit_forward(x, sd, cfg)[:, 0], cam, mask, dirs, u)
+    flips = (a[1].cpu() != m_ref).sum().item()
+    assert flips <= 2048 // 100, flips
+    agree = a[1].cpu() == m_ref
+    bad = ((a[2].cpu() - d_ref).abs()[agree] > 1e-3).sum().item()
+    assert bad <= 2048 // 20, bad

@@ -35,3 +35,59 @@ def smoke_check(device):
     assert torch.equal(y[:, 3 + 2 * L:], ref[:, 3 + 2 * L:]), "hash block must be bit exact"
     assert torch.allclose(y[:, :3 + 2 * L], ref[:, :3 + 2 * L], atol=4e-6, rtol=0), "fourier prefix"
     return True
+
+
+class DictConf(dict):
+    """Stand-in for a pyhocon ConfigTree (the getters IDRNetwork uses)."""
+
+    def _walk(self, key):
+        node = self
+        for part in key.split("."):
+            node = node[part]
+        return node
+
+    def get_int(self, key):
+        return int(self._walk(key))
+
+    def get_float(self, key):
+        return float(self._walk(key))
+
+    def get_string(self, key):
+        return str(self._walk(key))
+
+    def get_list(self, key):
+        return list(self._walk(key))
+
+    def get_config(self, key):
+        try:
+            node = self._walk(key)
+        except KeyError:
+            return None
+        return DictConf(node) if isinstance(node, dict) else node
+
+
+RAY_TRACER_CONF = {"object_bounding_sphere": 1.0, "sdf_threshold": 5.0e-5, "line_search_step": 0.5,
+                   "line_step_iters": 3, "sphere_tracing_iters": 10, "n_steps": 100, "n_secant_steps": 8}
+
+
+def make_conf(embed_type, multires, log2T, base, desired, bound=1.0, view_type="NerfPos", width=512, feature=256):
+    """model{} section of the reference's confs as a dict-conf (values per confs/embedder_conf_var/*)."""
+    return DictConf({
+        "feature_vector_size": feature,
+        "implicit_network": {"d_in": 3, "d_out": 1, "dims": [width] * 8, "geometric_init": True, "bias": 0.6,
+                             "skip_in": [4], "weight_norm": True, "multires": multires},
+        "rendering_network": {"mode": "idr", "d_in": 9, "d_out": 3, "viewdirs_embed_type": view_type,
+                              "dims": [width] * 4, "weight_norm": True, "multires_view": 4},
+        "ray_tracer": dict(RAY_TRACER_CONF),
+        "embedding_network": {"embed_type": embed_type, "log2_max_hash_size": log2T, "max_points_per_entry": 2,
+                              "base_resolution": base, "desired_resolution": desired, "bound": bound},
+    })
+
+
+def quiet_build(fn, *a, **k):
+    import contextlib
+    import io
+    import warnings
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return fn(*a, **k)
