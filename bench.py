@@ -1,0 +1,333 @@
+"""bench.py - headline benchmark of the IDR hash-grid rendering hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision 3xtf32|tf32|fp32]
+
+A "step" is one full IDR training step on one batch of synthetic rays: ray trace (sphere tracing +
+sampler + secant + min-SDF) + hash encode + SDF / rendering MLP forward + backward (incl. the eikonal
+double backward) + loss + global-norm clip + Adam - what idr_train.py:294-308 of the reference runs per
+image.  Workload = BASELINE.json configs[1]: dtu_fixed_cameras MultiResHash config (6 levels, T = 2^5,
+F = 2, base 64 -> 512, 8x512 SDF MLP, 4x512 rendering MLP, NerfPos views), 2048 rays/step/GPU,
+synthetic camera of SURVEY.md §8(d).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS = 2048
+WORKLOAD = ("IDR train step, dtu_fixed_cameras MultiResHashPointsPosencViews model "
+            "(HashGrid L=6 T=2^5 F=2 res 64->512, SDF MLP 8x512 skip@4, render MLP 4x512, NerfPos views), "
+            "%d synthetic rays/step/GPU, full RayTracing (10 sphere iters, 3 line-search, 100 samples, 8 secant)" % N_RAYS)
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p["hbm_gbs"], p["bf16_tflops"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def model_conf():
+    from tests_support import make_conf
+    return make_conf("HashGrid", 6, 5, 64, 512, 1.0)
+
+
+def oracle_cfg():
+    from oracle import idr_oracle as O
+    from tests_support import RAY_TRACER_CONF
+    return O.IDRCfg(O.EmbedCfg("HashGrid", 6, 5, 2, 64, 512, 1.0), ray_tracer=dict(RAY_TRACER_CONF))
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's own PyTorch path on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(n_rays, seed=0):
+    import torch
+    from oracle import idr_oracle as O
+    cfg = oracle_cfg()
+    sd = O.make_idr_sd(cfg, seed=seed)
+    params = []
+    for k, v in sd.items():
+        if v.dtype == torch.float32 and not k.endswith(".B") and not k.endswith("dencity_net.beta"):
+            v.requires_grad_(True)
+            params.append(v)
+    opt = torch.optim.Adam(params, lr=1e-4)
+    inp, rgb = O.synthetic_batch(n_rays, seed=1)
+
+    def step():
+        out = O.idr_forward(inp, sd, cfg, True)
+        lo = O.idr_loss(out, rgb)
+        opt.zero_grad()
+        lo["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
+        opt.step()
+        return float(lo["loss"].detach())
+    return step
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    probe = cpu_step_fn(256)
+    t = time.perf_counter()
+    probe()
+    t_probe = time.perf_counter() - t
+    budget = 150.0
+    n = N_RAYS
+    total = args.steps + args.warmup
+    while n > 128 and t_probe * (n / 256.0) * total > budget:
+        n //= 2
+    step = cpu_step_fn(n)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = n / dt
+    sample = "%d of %d rays per step (same model/config), %d threads" % (n, N_RAYS, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "idr_train_rays_per_s", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step": n},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def hash_encode_section(torch, hbm, src):
+    """Hash-encode microbench (BASELINE cfg5 slice): 2^24 points, L=16, F=2, T=2^19, both frac modes."""
+    from scripts.hash_microbench import run
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    out = {}
+    for mode in ("trilinear", "reference"):
+        r = run(1 << 24, 19, mode, flush=flush)
+        out[mode] = {"fwd_mpts_per_s": round(r["fwd_mpts"], 1), "bwd_mpts_per_s": round(r["bwd_mpts"], 1),
+                     "fwd_frac_of_hbm_peak": round(r["fwd_frac"], 4), "bwd_frac_of_hbm_peak": round(r["bwd_frac"], 4),
+                     "algorithmic_bytes_per_point": r["bytes_per_pt"]}
+    out["points"] = 1 << 24
+    out["table"] = "L=16, F=2, T=2^19 (48.5 MB)"
+    out["peak_gbs"] = hbm
+    out["peak_source"] = src
+    del flush
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0 and not os.path.exists(os.path.join(ROOT, "hashmodnffbanks-idr_b200", "csrc", "libidrk.so")):
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from idrk import _lib, kernels as K
+    from idrk.model.implicit_differentiable_renderer import IDRNetwork
+    from idrk.model.loss import IDRLoss
+    from idrk.dist import DataParallelTrainer
+    from oracle import idr_oracle as O          # synthetic-input recipe + cpu_baseline leg only
+    from tests_support import quiet_build
+
+    K.set_precision(args.precision)
+    torch.manual_seed(0)
+    model = quiet_build(IDRNetwork, model_conf()).to(dev).train()
+    loss_fn = IDRLoss(eikonal_weight=0.1, mask_weight=100.0, alpha=50.0)
+    trainer = DataParallelTrainer(model, loss_fn, lr=1e-4, max_norm=1.0, world_size=world)
+
+    # per-rank synthetic batch (weak scaling: every GPU traces its own 2048 rays)
+    inp_cpu, rgb_cpu = O.synthetic_batch(N_RAYS, seed=1 + 10 * rank)
+    pinned = {k: v.pin_memory() for k, v in inp_cpu.items()}
+    rgb_pin = rgb_cpu.pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values()) + rgb_pin.numel() * 4
+    inp_dev = {k: v.to(dev) for k, v in inp_cpu.items()}
+    gt_dev = {"rgb": rgb_cpu.to(dev)}
+
+    def step_resident():
+        return trainer.step(inp_dev, gt_dev)
+
+    def step_e2e():
+        inp = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        gt = {"rgb": rgb_pin.to(dev, non_blocking=True)}
+        loss = trainer.step(inp, gt)
+        return float(loss.detach().cpu())          # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.LAUNCHES[0]
+    ms = timed(step_resident, args.steps)
+    launches = _lib.LAUNCHES[0] - l0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # instrumented pass: device time and algorithmic FLOPs of the dominant kernel (the MLP contraction)
+    K.PROFILE.reset(enabled=True)
+    barrier()
+    for _ in range(2):
+        step_resident()
+    barrier()
+    prof = K.PROFILE.summary()
+    K.PROFILE.reset(enabled=False)
+    stats = dict(model.ray_tracer.last_stats)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, bf16, bf16_sus, src = peaks()
+    tf32_peak = 0.5 * bf16_sus
+    g = prof.get("idrk_gemm", {"ms": 0.0, "flops": 0.0, "calls": 0})
+    achieved = (g["flops"] / (g["ms"] * 1e-3) / 1e12) if g["ms"] > 0 else 0.0
+    share = g["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9)
+    value = world * N_RAYS * args.steps / (ms * 1e-3)
+    e2e_value = world * N_RAYS * args.steps / (ms_e2e * 1e-3)
+
+    cpu_fn = cpu_step_fn(512)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_fn()
+    t0 = time.perf_counter()
+    cpu_fn()
+    cpu_dt = time.perf_counter() - t0
+
+    line = {
+        "metric": "idr_train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"3xtf32": "tf32x3 (fp32-accurate split, fp32 accumulate)", "tf32": "tf32",
+                                       "fp32": "f32"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N_RAYS, "parallelism": "dp%d" % world,
+                   "l2": "L2 flushed by the step itself: activations of the 100-sample sweeps (>= 2 x 64 MB per layer) "
+                         "exceed L2 between reuses; no cached outputs",
+                   "tracer": stats},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"kernel": "gemm_tf32_kernel (tcgen05 MLP contraction tiles)", "bound": "tensor",
+                     "achieved": round(achieved, 2), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                     "frac": round(achieved / tf32_peak, 4), "traffic": None,
+                     "peak_source": "%s: 0.5 x sustained bf16 (TF32 rate)" % src,
+                     "note": "algorithmic 2*M*N*K FLOPs of the launches (rows actually traced) / summed CUDA-event "
+                             "time of those launches; 3xTF32 issues 3 MMAs per algorithmic MAC",
+                     "launches_per_step": g["calls"] // 2, "share_of_kernel_time": round(share, 3)},
+        "kernel_time_ms_per_step": {k: round(v["ms"] / 2, 3) for k, v in sorted(prof.items())},
+        "cpu_baseline": {"value": 512 / cpu_dt, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": "1 full train step on 512 of the 2048 rays, oracle port of the reference's "
+                                   "PyTorch path, %d threads" % cores},
+    }
+    try:
+        line["hash_encode"] = hash_encode_section(torch, hbm, src)
+    except Exception as exc:      # the microbench must never take the headline down
+        line["hash_encode"] = {"error": repr(exc)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "fp32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

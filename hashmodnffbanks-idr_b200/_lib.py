@@ -31,6 +31,64 @@ class HashGridDesc(ctypes.Structure):
 
 
 _lib = None
+LAUNCHES = [0]          # number of kernel launches issued through the C ABI (bench.py reports it)
+
+
+class _Profile:
+    """Optional per-entry-point device timing with CUDA events (bench.py's roofline leg)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+        self.pending_flops = None
+
+    def reset(self, enabled):
+        self.enabled = enabled
+        self.records = []
+        self.pending_flops = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e, flops in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "calls": 0})
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+            if flops is not None:
+                d["flops"] += float(flops()) if callable(flops) else float(flops)
+        return out
+
+
+PROFILE = _Profile()
+
+
+class _Proxy:
+    """Counts launches and (when profiling) brackets every call with CUDA events on the current stream."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._cdll, name)
+
+            def fn(*args, _raw=raw, _name=name):
+                if PROFILE.enabled:
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    flops, PROFILE.pending_flops = PROFILE.pending_flops, None
+                    s.record()
+                    rc = _raw(*args)
+                    e.record()
+                    PROFILE.records.append((_name, s, e, flops))
+                else:
+                    rc = _raw(*args)
+                if rc == 0:
+                    LAUNCHES[0] += 1
+                return rc
+            self._cache[name] = fn
+        return fn
 
 # every symbol include/idrk.h declares (tests check the library exports all of them)
 EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk_hash_encode_bwd",
@@ -38,7 +96,8 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_weight_norm_bwd", "idrk_colsum", "idrk_sdf_head", "idrk_sdf_squash",
            "idrk_rt_init", "idrk_rt_top", "idrk_rt_step", "idrk_rt_linesearch", "idrk_rt_end",
            "idrk_rt_select_sampler", "idrk_rt_sampler_points", "idrk_rt_sampler_resolve", "idrk_rt_secant",
-           "idrk_rt_select_minsdf", "idrk_rt_minsdf_points", "idrk_rt_minsdf_resolve"]
+           "idrk_rt_select_minsdf", "idrk_rt_minsdf_points", "idrk_rt_minsdf_resolve",
+           "idrk_sumsq", "idrk_clip_adam"]
 
 
 class RayStateDesc(ctypes.Structure):
@@ -74,8 +133,9 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise IdrkError("libidrk.so is missing (%s). Build it with `python hashmodnffbanks-idr_b200/csrc/build.py`; "
                             "there is no CPU or PyTorch fallback." % LIB_PATH)
-        _lib = ctypes.CDLL(LIB_PATH)
-        _declare(_lib)
+        cdll = ctypes.CDLL(LIB_PATH)
+        _declare(cdll)
+        _lib = _Proxy(cdll)
     return _lib
 
 
@@ -109,6 +169,8 @@ def _declare(L):
     L.idrk_rt_select_minsdf.argtypes = [rs, vp, vp, vp, vp, vp, vp, vp]
     L.idrk_rt_minsdf_points.argtypes = [rs, vp, i32, i32, i32, vp, vp, vp]
     L.idrk_rt_minsdf_resolve.argtypes = [rs, vp, i32, i32, vp, vp, vp]
+    L.idrk_sumsq.argtypes = [vp, i64, vp, vp]
+    L.idrk_clip_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp, f32, vp]
     for fn in EXPORTS:
         getattr(L, fn).restype = c.c_int
 

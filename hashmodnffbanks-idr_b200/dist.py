@@ -1,0 +1,103 @@
+"""Data-parallel training of the IDR step (north-star subsystem 4; the reference has no multi-GPU code).
+
+One process per GPU.  Parameters are replicated, the ray batch is sharded (each rank traces its own
+rays), and after the local backward ONE all-reduce (NCCL over NVLink / NVSwitch) sums a single flat fp32
+gradient bucket [hash tables | MLP weights]; the fused clip + Adam kernel (csrc/optim.cu) then applies
+the identical update on every rank (1/world folded into the kernel), so replicas stay bit-identical
+without broadcasting parameters.  Equal shard sizes are required because IDRLoss normalises by the local
+ray count (reference loss.py:19,48): mean over ranks of the local gradients == gradient of the global loss.
+"""
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+
+
+class FlatBucket:
+    """Re-homes a module's parameters (and their .grad) as views of two flat fp32 tensors."""
+
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]        # keep every view 16-byte aligned
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        total = self.offsets[-1]
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, self.offsets):
+            view = self.flat[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):     # autograd may have replaced .grad; re-attach the views
+            g = p.grad
+            if g is None or g.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+    def gather_stray_grads(self):
+        """If autograd installed a fresh .grad tensor (first accumulation) copy it into the bucket."""
+        for p, o in zip(self.params, self.offsets):
+            g = p.grad
+            if g is not None and g.data_ptr() != self.grad.data_ptr() + 4 * o:
+                self.grad[o:o + p.numel()].view_as(p).copy_(g)
+                p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+
+def shard_rays(model_input: Dict[str, torch.Tensor], ground_truth: Dict[str, torch.Tensor], rank: int, world: int):
+    """Contiguous, equal-sized ray shards of a [B, N, ...] batch (uv / object_mask / rgb)."""
+    n = model_input["uv"].shape[1]
+    if n % world:
+        raise ValueError("ray count %d must be divisible by world size %d (IDRLoss normalises per shard)" % (n, world))
+    s = n // world
+    sl = slice(rank * s, (rank + 1) * s)
+    inp = dict(model_input)
+    inp["uv"] = model_input["uv"][:, sl]
+    inp["object_mask"] = model_input["object_mask"][:, sl]
+    gt = {"rgb": ground_truth["rgb"][:, sl]}
+    return inp, gt
+
+
+def allreduce_mean_(flat_grad: torch.Tensor, world: int, group=None) -> float:
+    """Sums the bucket over ranks in place; returns the scale the optimiser must still apply."""
+    if world > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+class DataParallelTrainer:
+    """model + loss + clip + Adam, replicated per rank, gradients all-reduced once per step."""
+
+    def __init__(self, model: torch.nn.Module, loss_fn, lr: float = 1e-4, max_norm: float = 1.0, world_size: int = 1,
+                 betas=(0.9, 0.999), eps: float = 1e-8):
+        self.model, self.loss_fn = model, loss_fn
+        self.lr, self.max_norm, self.world, self.betas, self.eps = lr, max_norm, world_size, betas, eps
+        self.bucket = FlatBucket(list(model.parameters()))
+        self.m = torch.zeros_like(self.bucket.flat)
+        self.v = torch.zeros_like(self.bucket.flat)
+        self.sumsq = torch.zeros(1, device=self.bucket.flat.device, dtype=torch.float32)
+        self.t = 0
+
+    def step(self, model_input, ground_truth) -> torch.Tensor:
+        b = self.bucket
+        out = self.model(model_input)
+        losses = self.loss_fn(out, ground_truth)
+        b.zero_grad()
+        losses["loss"].backward()
+        b.gather_stray_grads()
+        scale = allreduce_mean_(b.grad, self.world)
+        self.t += 1
+        self.sumsq.zero_()
+        K.sumsq(b.grad, self.sumsq)
+        K.clip_adam(b.flat, b.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t,
+                    self.max_norm, self.sumsq, scale)
+        self.last_losses = losses
+        return losses["loss"]

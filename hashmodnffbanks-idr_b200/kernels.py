@@ -7,7 +7,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import HashGridDesc, check, lib, ptr, require_cuda, stream_ptr
+from ._lib import HashGridDesc, PROFILE, check, lib, ptr, require_cuda, stream_ptr
 
 
 def pad4(n: int) -> int:
@@ -224,6 +224,12 @@ def gemm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int,
     e.lds = op_ld(S) if S is not None else 0
     e.ldaux = op_ld(aux) if aux is not None else 0
     e.mode, e.act_param, e.scale, e.accumulate = mode, float(act), float(scale), int(bool(accumulate))
+    if PROFILE.enabled:
+        if m_count is not None:
+            cnt = m_count.clone()
+            PROFILE.pending_flops = lambda cnt=cnt, M=M, N=N, Kc=Kc: 2.0 * min(M, int(cnt.item())) * N * Kc
+        else:
+            PROFILE.pending_flops = 2.0 * M * N * Kc
     check(lib().idrk_gemm(layout, prec, M, N, Kc, ptr(A), ptr(A_lo), op_ld(A), ptr(B), ptr(B_lo), op_ld(B),
                           ctypes.byref(e), ptr(m_count), split_k, stream_ptr()), "idrk_gemm")
 
@@ -279,3 +285,15 @@ def sdf_squash(s: torch.Tensor, beta: float, want_grad: bool):
     if s.numel():
         check(lib().idrk_sdf_squash(ptr(s), s.numel(), float(beta), ptr(out), ptr(d), stream_ptr()), "idrk_sdf_squash")
     return out, d
+
+
+# ---------------------------------------------------------------------------------------------
+# optimiser on the flat bucket
+# ---------------------------------------------------------------------------------------------
+def sumsq(g: torch.Tensor, out: torch.Tensor):
+    check(lib().idrk_sumsq(ptr(g), g.numel(), ptr(out), stream_ptr()), "idrk_sumsq")
+
+
+def clip_adam(p, g, m, v, lr, beta1, beta2, eps, step, max_norm, sumsq_buf, grad_scale):
+    check(lib().idrk_clip_adam(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+                               int(step), float(max_norm), ptr(sumsq_buf), float(grad_scale), stream_ptr()), "idrk_clip_adam")

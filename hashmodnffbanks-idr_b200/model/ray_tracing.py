@@ -75,6 +75,7 @@ class RayTracing(nn.Module):
         self.n_steps = n_steps
         self.n_secant_steps = n_secant_steps
         self.last_stats = {}
+        self.injected_min_sdf_steps = None      # parity runs: the U(0,1) vector of reference :277
 
     # ------------------------------------------------------------------------------------------
     def forward(self, sdf, cam_loc, object_mask, ray_directions, *, min_sdf_steps=None, sphere_intersections=None):
@@ -198,6 +199,8 @@ class RayTracing(nn.Module):
                                           ptr(c_min), sp), "idrk_rt_select_minsdf")
             n_min = int(c_min.item())
             if n_min > 0:
+                if min_sdf_steps is None:
+                    min_sdf_steps = self.injected_min_sdf_steps
                 if min_sdf_steps is None:       # drawn on the host generator like the reference (:277)
                     u = torch.empty(ns).uniform_(0.0, 1.0).to(dev)
                 else:

@@ -195,6 +195,16 @@ int idrk_rt_minsdf_points(const idrk_ray_state_t* h_state, const int32_t* ray_of
 int idrk_rt_minsdf_resolve(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t n_slots, int32_t n_steps,
                            const float* u, const float* vals, void* stream);
 
+/* -- K6: optimiser step on the flat bucket ------------------------------------------------
+ * Replaces clip_grad_norm_(params, max_norm) + torch.optim.Adam.step() of idr_train.py:306-308 for
+ * the data-parallel trainer.  idrk_sumsq: *out += sum(g^2) (caller zeroes out).  idrk_clip_adam: g is
+ * first scaled by grad_scale (1/world_size after the all-reduce), clipped by
+ * min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6)) when max_norm > 0, then Adam (no weight decay,
+ * bias correction with `step` >= 1) updates p, m, v in place. */
+int idrk_sumsq(const float* g, int64_t n, float* out, void* stream);
+int idrk_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, int32_t step, float max_norm, const float* sumsq, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,81 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: ray sharding, flat gradient bucket,
+all-reduce averaging.  DP(2 ranks) gradients on half batches == single-process gradients on the full batch."""
+import os
+import tempfile
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from idrk.dist import FlatBucket, allreduce_mean_, shard_rays
+
+
+def toy_model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+
+
+def toy_loss(model, uv, rgb):
+    # normalised by the LOCAL number of rays, like IDRLoss (reference loss.py:19,48)
+    pred = model(torch.cat([uv, uv ** 2, uv[..., :1]], -1))
+    return (pred - rgb).abs().sum() / float(uv.shape[1])
+
+
+def batch(n=64):
+    g = torch.Generator().manual_seed(3)
+    return ({"uv": torch.rand(1, n, 2, generator=g), "object_mask": torch.rand(1, n, generator=g) > 0.5,
+             "pose": torch.eye(4)[None], "intrinsics": torch.eye(4)[None]},
+            {"rgb": torch.rand(1, n, 3, generator=g)})
+
+
+def _worker(rank, world, init_file, ret):
+    dist.init_process_group("gloo", init_method="file://" + init_file, rank=rank, world_size=world)
+    model = toy_model()
+    bucket = FlatBucket(list(model.parameters()))
+    inp, gt = batch()
+    sinp, sgt = shard_rays(inp, gt, rank, world)
+    assert sinp["uv"].shape[1] == 32 and sinp["object_mask"].shape[1] == 32
+    bucket.zero_grad()
+    toy_loss(model, sinp["uv"], sgt["rgb"]).backward()
+    bucket.gather_stray_grads()
+    scale = allreduce_mean_(bucket.grad, world)
+    ret[rank] = (bucket.grad * scale).clone()
+    dist.destroy_process_group()
+
+
+def test_dp_gradients_equal_single_process():
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mgr = mp.Manager()
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, os.path.join(d, "init"), ret), nprocs=world, join=True)
+        g0, g1 = ret[0], ret[1]
+    assert torch.equal(g0, g1)                        # replicas see the same reduced bucket
+    model = toy_model()
+    bucket = FlatBucket(list(model.parameters()))
+    inp, gt = batch()
+    bucket.zero_grad()
+    toy_loss(model, inp["uv"], gt["rgb"]).backward()
+    bucket.gather_stray_grads()
+    assert torch.allclose(g0, bucket.grad, atol=1e-6, rtol=1e-5)
+
+
+def test_flat_bucket_views_and_alignment():
+    model = toy_model()
+    ref = [p.detach().clone() for p in model.parameters()]
+    b = FlatBucket(list(model.parameters()))
+    for p, r, o in zip(model.parameters(), ref, b.offsets):
+        assert torch.equal(p.detach(), r)
+        assert p.data_ptr() == b.flat.data_ptr() + 4 * o and o % 4 == 0
+    b.flat.mul_(2.0)
+    for p, r in zip(model.parameters(), ref):
+        assert torch.equal(p.detach(), 2 * r)
+
+
+def test_shard_rays_rejects_uneven():
+    inp, gt = batch(63)
+    try:
+        shard_rays(inp, gt, 0, 2)
+    except ValueError:
+        return
+    raise AssertionError("uneven shards must be rejected")

@@ -1,0 +1,62 @@
+"""GPU checks of the flat-bucket optimiser (clip + Adam kernel == clip_grad_norm_ + torch.optim.Adam) and of the
+DataParallelTrainer step at world size 1."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_clip_adam_matches_torch():
+    from idrk import kernels as K
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(100003, generator=g).to(DEV)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    ss = torch.zeros(1, device=DEV)
+    for t in range(1, 6):
+        grad = (torch.randn(100003, generator=g) * (3.0 if t % 2 else 0.001)).to(DEV)
+        pr.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([pr], max_norm=1.0)
+        opt.step()
+        ss.zero_()
+        K.sumsq(grad, ss)
+        K.clip_adam(p, grad, m, v, 1e-3, 0.9, 0.999, 1e-8, t, 1.0, ss, 1.0)
+        assert torch.allclose(p, pr.detach(), atol=2e-6, rtol=1e-5), t
+
+
+def test_trainer_step_reduces_loss_and_matches_manual_step():
+    from idrk.dist import DataParallelTrainer
+    from idrk.model.implicit_differentiable_renderer import IDRNetwork
+    from idrk.model.loss import IDRLoss
+    from oracle import idr_oracle as O
+    from tests_support import make_conf, quiet_build
+    torch.manual_seed(0)
+    conf = make_conf("HashGrid", 6, 5, 64, 512, 1.0, width=128, feature=32)
+    model = quiet_build(IDRNetwork, conf).to(DEV).train()
+    ref = quiet_build(IDRNetwork, conf).to(DEV).train()
+    ref.load_state_dict(model.state_dict())
+    inp, rgb = O.synthetic_batch(512, seed=1)
+    inp = {k: v.to(DEV) for k, v in inp.items()}
+    gt = {"rgb": rgb.to(DEV)}
+    eik = torch.rand(256, 3, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    u = torch.rand(100, generator=torch.Generator().manual_seed(2))
+    for mdl in (model, ref):
+        mdl.injected_eikonal_points, mdl.ray_tracer.injected_min_sdf_steps = eik, u
+    loss_fn = IDRLoss(0.1, 100.0, 50.0)
+    tr = DataParallelTrainer(model, loss_fn, lr=1e-3, max_norm=1.0, world_size=1)
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    l_a = tr.step(inp, gt)
+    lo = loss_fn(ref(inp), gt)
+    opt.zero_grad()
+    lo["loss"].backward()
+    torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+    opt.step()
+    assert abs(float(l_a) - float(lo["loss"])) < 1e-5 * max(1.0, abs(float(l_a)))
+    for (n1, a), (n2, b) in zip(model.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(a, b, atol=5e-6, rtol=1e-4), n1
+    first = float(l_a)
+    for _ in range(5):
+        last = float(tr.step(inp, gt))
+    assert last < first

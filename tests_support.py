@@ -20,9 +20,13 @@ def load_sd_into(module: torch.nn.Module, sd: dict, prefix: str = "", strict: bo
 
 
 def smoke_check(device):
-    """One small invocation of the hot path on `device`, checked against the oracle."""
+    """One small invocation of the hot path on `device`, checked against the oracle: hash encode (bit exact)
+    and one IDR training step (ray trace + encode + MLP fwd/bwd + eikonal) on 256 rays."""
+    import numpy as np
     from oracle import idr_oracle as O
     from idrk.model.embeddings.hashGridEmbedding import MultiResHashGridMLP
+    from idrk.model.implicit_differentiable_renderer import IDRNetwork
+    from idrk.model.loss import IDRLoss
     gen = torch.Generator().manual_seed(0)
     L, F, log2T, base, desired = 16, 2, 12, 16, 2048
     sd = O.make_hashgrid_sd("", L, F, log2T, base, desired, gen, table_std=0.5)
@@ -34,6 +38,28 @@ def smoke_check(device):
     ref = O.hashgrid_embed(x, sd, "", L, base, desired)
     assert torch.equal(y[:, 3 + 2 * L:], ref[:, 3 + 2 * L:]), "hash block must be bit exact"
     assert torch.allclose(y[:, :3 + 2 * L], ref[:, :3 + 2 * L], atol=4e-6, rtol=0), "fourier prefix"
+
+    cfg = O.IDRCfg(O.EmbedCfg("HashGrid", 6, 5, 2, 64, 512, 1.0), ray_tracer=dict(RAY_TRACER_CONF))
+    conf = make_conf("HashGrid", 6, 5, 64, 512, 1.0, width=128, feature=32)
+    model = quiet_build(IDRNetwork, conf)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(device).train()
+    inp, rgb = O.synthetic_batch(256, seed=1)
+    eik = torch.rand(128, 3, generator=gen) * 2 - 1
+    u = torch.rand(100, generator=gen)
+    model.injected_eikonal_points, model.ray_tracer.injected_min_sdf_steps = eik, u
+    out = model({k: v.to(device) for k, v in inp.items()})
+    lo = IDRLoss(0.1, 100.0, 50.0)(out, {"rgb": rgb.to(device)})
+    lo["loss"].backward()
+    for v in sd.values():
+        if v.dtype == torch.float32 and v.dim() > 0:
+            v.requires_grad_(True)
+    oout = O.idr_forward(inp, sd, cfg, True, eik, u)
+    olo = O.idr_loss(oout, rgb)
+    flips = (out["network_object_mask"].cpu() != oout["network_object_mask"]).sum().item()
+    assert flips <= 3, "hit/miss masks: %d flips" % flips
+    assert abs(float(lo["loss"].detach()) - float(olo["loss"].detach())) <= 2e-2 * max(1.0, abs(float(olo["loss"].detach())))
+    assert model.implicit_network.lin0.weight_v.grad is not None
     return True
 
 
