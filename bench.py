@@ -200,7 +200,8 @@ def run_ours(args):
     torch.manual_seed(0)
     model = quiet_build(IDRNetwork, model_conf()).to(dev).train()
     loss_fn = IDRLoss(eikonal_weight=0.1, mask_weight=100.0, alpha=50.0)
-    trainer = DataParallelTrainer(model, loss_fn, lr=1e-4, max_norm=1.0, world_size=world)
+    trainer = DataParallelTrainer(model, loss_fn, lr=1e-4, max_norm=1.0, world_size=world,
+                                  use_cuda_graph=not args.no_graph)
 
     # per-rank synthetic batch (weak scaling: every GPU traces its own 2048 rays)
     inp_cpu, rgb_cpu = O.synthetic_batch(N_RAYS, seed=1 + 10 * rank)
@@ -252,6 +253,7 @@ def run_ours(args):
 
     # instrumented pass: device time and algorithmic FLOPs of the dominant kernel (the MLP contraction)
     K.PROFILE.reset(enabled=True)
+    trainer.use_cuda_graph = False          # CUDA events cannot bracket kernels inside a replayed graph
     barrier()
     for _ in range(2):
         step_resident()
@@ -322,6 +324,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="run the differentiable part eagerly (no CUDA graph)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

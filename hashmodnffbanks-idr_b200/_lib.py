@@ -41,11 +41,15 @@ class _Profile:
         self.enabled = False
         self.records = []
         self.pending_flops = None
+        self.pending_tag = None
+        self.detail = False
 
-    def reset(self, enabled):
+    def reset(self, enabled, detail=False):
         self.enabled = enabled
         self.records = []
         self.pending_flops = None
+        self.pending_tag = None
+        self.detail = detail
 
     def summary(self):
         torch.cuda.synchronize()
@@ -78,10 +82,11 @@ class _Proxy:
                 if PROFILE.enabled:
                     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     flops, PROFILE.pending_flops = PROFILE.pending_flops, None
+                    tag, PROFILE.pending_tag = PROFILE.pending_tag, None
                     s.record()
                     rc = _raw(*args)
                     e.record()
-                    PROFILE.records.append((_name, s, e, flops))
+                    PROFILE.records.append((_name + (tag or "") if PROFILE.detail else _name, s, e, flops))
                 else:
                     rc = _raw(*args)
                 if rc == 0:

@@ -8,9 +8,10 @@
 //   RenderingNetwork.forward  implicit_differentiable_renderer.py:215-223 (Linear + ReLU / tanh)
 //   and their autograd (grad wrt input = NN form, grad wrt weight = TN form).
 //
-// One CTA = one 128 x BN output tile (optionally one K split).  Warp roles (192 threads):
+// Persistent grid (one CTA per SM) walking 128 x BN output tiles (x K splits).  Warp roles (320 threads):
 //   warp 0  : TMA producer (one elected lane)        warp 1 : TMEM alloc + tcgen05.mma issuer (one lane)
-//   warps 2-5: epilogue - tcgen05.ld the accumulator, bias / activation / hi-lo split, global stores.
+//   warps 2-9: epilogue - tcgen05.ld the accumulator, bias / activation / hi-lo split, global stores.
+// Two TMEM accumulator stages: the epilogue of tile i overlaps the mainloop of tile i+1.
 // Layouts (row-major storage):   NT: A[M,K] B[N,K]    NN: A[M,K] B[K,N]    TN: A[K,M] B[K,N]
 // K-major operands use the canonical K-major SW128 smem layout, MN-major operands SW128 with a 32-byte base
 // (cute/atom/mma_traits_sm100.hpp make_umma_desc documents both), so no transposes are ever materialised.
@@ -163,42 +164,68 @@ struct SmemPlan {
     static constexpr int STAGE_BYTES = (TERMS == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
     static constexpr int BUDGET = 200 * 1024;
     static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SCRATCH_BYTES = 8 * 32 * 33 * 4;   // per-epilogue-warp transpose tile [32][33] floats
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + SCRATCH_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+constexpr int ACC_STAGES = 2;                  // TMEM accumulator double buffer: epilogue(i) overlaps mainloop(i+1)
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS_V2 = 64 + 32 * EPI_WARPS;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+// fast epilogue math of the tensor-core path: 2-3 MUFU ops per element (ex2 / lg2 / rcp approximations,
+// abs error of softplus(beta=100) <= 3e-9, of its derivative <= 2e-7)
+__device__ __forceinline__ float epi_value_fast(const EpiParams& e, float z, long long row, int col, float& s) {
+    if (e.mode == IDRK_EPI_SOFTPLUS) {
+        const float bz = z * e.act;
+        if (bz > 20.f) { s = 1.f; return z * e.scale; }
+        const float ez = __expf(bz);
+        s = __fdividef(ez, ez + 1.f);
+        return __fdividef(__logf(1.f + ez), e.act) * e.scale;
+    }
+    return epi_value(e, z, row, col, s);
+}
+
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+ TMEM alloc),
+// warps 2..9 = epilogue (two warps per TMEM lane quarter, each owning half of the BN columns).
 template <bool A_MN, bool B_MN, int BN, int TERMS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS_V2, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-                 long long M, int N, int K, EpiParams e, const int* __restrict__ m_count, int kb_per_split) {
+                 long long M, int N, int K, EpiParams e, const int* __restrict__ m_count, int kb_per_split, int splits) {
     using P = SmemPlan<BN, TERMS>;
     long long m_eff = M;
     if (m_count != nullptr) { const long long c = *m_count; m_eff = c < M ? c : M; }
-    const long long m0 = (long long)blockIdx.x * BM;
-    if (m0 >= m_eff) return;
-    const int n0 = blockIdx.y * BN;
+    const int m_tiles = (int)((m_eff + BM - 1) / BM);
+    const int n_tiles = (N + BN - 1) / BN;
+    const int items = m_tiles * n_tiles * splits;
+    if ((int)blockIdx.x >= items) return;
     const int kb_total = (K + BK - 1) / BK;
-    const int kb0 = blockIdx.z * kb_per_split;
-    const int kb1 = min(kb_total, kb0 + kb_per_split);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::STAGES * P::STAGE_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P::STAGES + 1);
+    float* epi_scratch = reinterpret_cast<float*>(smem + P::STAGES * P::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::STAGES * P::STAGE_BYTES + P::SCRATCH_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P::STAGES + 2 * ACC_STAGES);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (P::STAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * P::STAGES);
+    auto acc_full_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + a); };
+    auto acc_empty_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + ACC_STAGES + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < P::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(acc_full_bar(a), 1); mbar_init(acc_empty_bar(a), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)(ACC_STAGES * BN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -206,31 +233,45 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // work item -> (m tile, n tile, k range); n fastest so concurrently running CTAs share A rows in L2
+    auto decode = [&](int item, long long& m0, int& n0, int& kb0, int& kb1) {
+        const int z = item % splits;
+        const int t = item / splits;
+        n0 = (t % n_tiles) * BN;
+        m0 = (long long)(t / n_tiles) * BM;
+        kb0 = z * kb_per_split;
+        kb1 = min(kb_total, kb0 + kb_per_split);
+    };
+
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                const int s = it % P::STAGES;
-                const uint32_t ph = (it / P::STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_expect_tx(full_bar(s), P::STAGE_BYTES);
-                const uint32_t st = smem_base + s * P::STAGE_BYTES;
-                const int k0 = kb * BK;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                long long m0; int n0, kb0, kb1;
+                decode(item, m0, n0, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % P::STAGES;
+                    const uint32_t ph = (it / P::STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), P::STAGE_BYTES);
+                    const uint32_t st = smem_base + s * P::STAGE_BYTES;
+                    const int k0 = kb * BK;
 #pragma unroll
-                for (int t = 0; t < (TERMS == 3 ? 2 : 1); ++t) {
-                    const uint32_t sA = st + t * (P::A_BYTES + P::B_BYTES);
-                    const uint32_t sB = sA + P::A_BYTES;
-                    const CUtensorMap* ta = t ? &tmAlo : &tmA;
-                    const CUtensorMap* tb = t ? &tmBlo : &tmB;
-                    if constexpr (!A_MN) tma_load_2d(sA, ta, full_bar(s), k0, (int)m0);
-                    else {
+                    for (int t = 0; t < (TERMS == 3 ? 2 : 1); ++t) {
+                        const uint32_t sA = st + t * (P::A_BYTES + P::B_BYTES);
+                        const uint32_t sB = sA + P::A_BYTES;
+                        const CUtensorMap* ta = t ? &tmAlo : &tmA;
+                        const CUtensorMap* tb = t ? &tmBlo : &tmB;
+                        if constexpr (!A_MN) tma_load_2d(sA, ta, full_bar(s), k0, (int)m0);
+                        else {
 #pragma unroll
-                        for (int c = 0; c < BM / 32; ++c) tma_load_2d(sA + c * (BK * 128), ta, full_bar(s), (int)m0 + 32 * c, k0);
-                    }
-                    if constexpr (!B_MN) tma_load_2d(sB, tb, full_bar(s), k0, n0);
-                    else {
+                            for (int c = 0; c < BM / 32; ++c) tma_load_2d(sA + c * (BK * 128), ta, full_bar(s), (int)m0 + 32 * c, k0);
+                        }
+                        if constexpr (!B_MN) tma_load_2d(sB, tb, full_bar(s), k0, n0);
+                        else {
 #pragma unroll
-                        for (int c = 0; c < BN / 32; ++c) tma_load_2d(sB + c * (BK * 128), tb, full_bar(s), n0 + 32 * c, k0);
+                            for (int c = 0; c < BN / 32; ++c) tma_load_2d(sB + c * (BK * 128), tb, full_bar(s), n0 + 32 * c, k0);
+                        }
                     }
                 }
             }
@@ -240,63 +281,106 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t idesc = make_idesc<A_MN, B_MN, BN>();
             constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
             constexpr uint32_t a_step = A_MN ? (1024 >> 4) : (32 >> 4), b_step = B_MN ? (1024 >> 4) : (32 >> 4);
-            int it = 0;
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                const int s = it % P::STAGES;
-                const uint32_t ph = (it / P::STAGES) & 1;
-                mbar_wait(full_bar(s), ph);
+            constexpr uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
+            constexpr uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
+            int it = 0, ti = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
+                long long m0; int n0, kb0, kb1;
+                decode(item, m0, n0, kb0, kb1);
+                const int a = ti & 1;
+                mbar_wait(acc_empty_bar(a), ((ti >> 1) & 1) ^ 1u);
                 tc_fence_after();
-                const uint32_t st = smem_base + s * P::STAGE_BYTES;
-                constexpr uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
-                constexpr uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
-                const uint64_t a_hi = umma_desc(st, a_lbo, a_sbo, a_lt);
-                const uint64_t b_hi = umma_desc(st + P::A_BYTES, b_lbo, b_sbo, b_lt);
-                const uint64_t a_lo = umma_desc(st + P::A_BYTES + P::B_BYTES, a_lbo, a_sbo, a_lt);
-                const uint64_t b_lo = umma_desc(st + 2 * P::A_BYTES + P::B_BYTES, b_lbo, b_sbo, b_lt);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % P::STAGES;
+                    const uint32_t ph = (it / P::STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + s * P::STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc(st, a_lbo, a_sbo, a_lt);
+                    const uint64_t b_hi = umma_desc(st + P::A_BYTES, b_lbo, b_sbo, b_lt);
+                    const uint64_t a_lo = umma_desc(st + P::A_BYTES + P::B_BYTES, a_lbo, a_sbo, a_lt);
+                    const uint64_t b_lo = umma_desc(st + 2 * P::A_BYTES + P::B_BYTES, b_lbo, b_sbo, b_lt);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-                    if constexpr (TERMS == 3) {
-                        tc_mma_tf32(tmem_base, a_lo + k * a_step, b_hi + k * b_step, idesc, first);
-                        tc_mma_tf32(tmem_base, a_hi + k * a_step, b_lo + k * b_step, idesc, 1u);
-                        tc_mma_tf32(tmem_base, a_hi + k * a_step, b_hi + k * b_step, idesc, 1u);
-                    } else {
-                        tc_mma_tf32(tmem_base, a_hi + k * a_step, b_hi + k * b_step, idesc, first);
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+                        if constexpr (TERMS == 3) {
+                            tc_mma_tf32(d_tmem, a_lo + k * a_step, b_hi + k * b_step, idesc, acc);
+                            tc_mma_tf32(d_tmem, a_hi + k * a_step, b_lo + k * b_step, idesc, 1u);
+                            tc_mma_tf32(d_tmem, a_hi + k * a_step, b_hi + k * b_step, idesc, 1u);
+                        } else {
+                            tc_mma_tf32(d_tmem, a_hi + k * a_step, b_hi + k * b_step, idesc, acc);
+                        }
                     }
+                    tc_commit(empty_bar(s));
                 }
-                tc_commit(empty_bar(s));
+                tc_commit(acc_full_bar(a));
             }
-            tc_commit(tmem_full_bar);
         }
     } else {
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const long long row = m0 + q * 32 + lane;
-        const bool vec_ok = ((e.ldc & 3) == 0) && !e.accumulate && (e.S == nullptr || (e.lds & 3) == 0);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            if (n0 + c0 >= N) break;                    // warp-uniform
-            uint32_t r[32];
-            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (row < m_eff) {
+        const int half = (warp - 2) >> 2;               // which half of the BN columns
+        constexpr int COLS = BN / 2;
+        int ti = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
+            long long m0; int n0, kb0, kb1;
+            decode(item, m0, n0, kb0, kb1);
+            const int a = ti & 1;
+            mbar_wait(acc_full_bar(a), (ti >> 1) & 1);
+            tc_fence_after();
+            uint32_t r[COLS];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + half * COLS);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int col = n0 + c0 + j;
-                    if (col >= N) break;
-                    float v[4], sd[4];
+            for (int c = 0; c < COLS; c += 32) tc_ld32(taddr + c, *reinterpret_cast<uint32_t(*)[32]>(&r[c]));
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty_bar(a));       // accumulator drained: MMA may reuse it
+            // Each lane owns one accumulator row; the 32 x 32 chunk is transposed through a private shared-memory
+            // tile so that every store instruction writes one full 128-byte line of one output row.
+            float* tile = epi_scratch + (warp - 2) * (32 * 33);
+            const long long row_base = m0 + q * 32;
+            const long long my_row = row_base + lane;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int cc = col + i;
-                        const float z = __uint_as_float(r[j + i]) + ((e.bias != nullptr && cc < N) ? __ldg(e.bias + cc) : 0.f);
-                        v[i] = (cc < N) ? epi_value(e, z, row, cc, sd[i]) : 0.f;
-                        if (cc >= N) sd[i] = 0.f;
+            for (int c = 0; c < COLS; c += 32) {
+                const int col0 = n0 + half * COLS + c;
+                if (col0 >= N) break;
+                // one coalesced bias load per chunk, broadcast by shuffle (a per-element __ldg serialises the
+                // epilogue on the long scoreboard: 64 dependent global loads per thread per tile)
+                const float bias_lane = (e.bias != nullptr && col0 + lane < N) ? __ldg(e.bias + col0 + lane) : 0.f;
+                float h[32], sd[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int cc = col0 + j;
+                    const float z = __uint_as_float(r[c + j]) + __shfl_sync(0xffffffffu, bias_lane, j);
+                    h[j] = (cc < N && my_row < m_eff) ? epi_value_fast(e, z, my_row, cc, sd[j]) : 0.f;
+                }
+                const int my_col = col0 + lane;
+                auto emit = [&](float* dst, int ld, const float (&vals)[32], int xform, bool atomic) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float v = vals[j];
+                        if (xform == 1) v = tf32_rn(v);
+                        else if (xform == 2) v = tf32_rn(v - tf32_rn(v));
+                        tile[lane * 33 + j] = v;
                     }
-                    if (vec_ok && col + 3 < N) epi_store4(e, row, col, v, sd);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) if (col + i < N) epi_store(e, row, col + i, v[i], sd[i]);
+                    __syncwarp();
+                    if (my_col < N) {
+#pragma unroll 4
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const long long grow = row_base + rr;
+                            if (grow >= m_eff) break;
+                            const float v = tile[rr * 33 + lane];
+                            if (atomic) atomicAdd(dst + grow * ld + my_col, v);
+                            else dst[grow * ld + my_col] = v;
+                        }
                     }
+                    __syncwarp();
+                };
+                if (e.accumulate) emit(e.C, e.ldc, h, 0, true);
+                else {
+                    if (e.C) emit(e.C, e.ldc, h, 0, false);
+                    if (e.C_hi) { emit(e.C_hi, e.ldc, h, 1, false); emit(e.C_lo, e.ldc, h, 2, false); }
+                    if (e.S) emit(e.S, e.lds, sd, 0, false);
                 }
             }
         }
@@ -304,7 +388,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(ACC_STAGES * BN)) : "memory");
     }
 }
 
@@ -425,8 +509,9 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtens
     const int kb_total = (K + BK - 1) / BK;
     int kbps = (kb_total + splits - 1) / splits;
     splits = (kb_total + kbps - 1) / kbps;
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)splits);
-    kern<<<grid, GEMM_THREADS, P::TOTAL, st>>>(tA, tAl, tB, tBl, M, N, K, e, m_count, kbps);
+    const long long items = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
+    const long long grid = items < sm_count() ? items : sm_count();      // persistent: one CTA per SM
+    kern<<<(unsigned)grid, GEMM_THREADS_V2, P::TOTAL, st>>>(tA, tAl, tB, tBl, M, N, K, e, m_count, kbps, splits);
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -470,7 +555,7 @@ extern "C" int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N
 
     const int terms = precision == IDRK_PREC_3XTF32 ? 3 : 1;
     if (terms == 3 && (!A_lo || !B_lo)) return IDRK_E_ARG;
-    const int bn = (N <= 64) ? 64 : 128;
+    const int bn = (N <= 64 || M <= 4096) ? 64 : 128;      // small row counts: more, shorter tiles
     CUtensorMap tA, tAl, tB, tBl;
     int rc;
     // K-major: dims (K, rows) box (32, rows_per_tile).  MN-major: dims (rows_mn, K) box (32, BK)

@@ -74,10 +74,14 @@ def allreduce_mean_(flat_grad: torch.Tensor, world: int, group=None) -> float:
 
 
 class DataParallelTrainer:
-    """model + loss + clip + Adam, replicated per rank, gradients all-reduced once per step."""
+    """model + loss + clip + Adam, replicated per rank, gradients all-reduced once per step.
+
+    step() = trace (eager, device-driven) -> shade + loss + backward -> all-reduce -> fused clip/Adam.
+    With `use_cuda_graph` the shade + loss + backward part - fixed shapes, no host syncs - is captured once
+    into a CUDA graph and replayed every step (the launch-bound part of the step: ~600 small kernels)."""
 
     def __init__(self, model: torch.nn.Module, loss_fn, lr: float = 1e-4, max_norm: float = 1.0, world_size: int = 1,
-                 betas=(0.9, 0.999), eps: float = 1e-8):
+                 betas=(0.9, 0.999), eps: float = 1e-8, use_cuda_graph: bool = False):
         self.model, self.loss_fn = model, loss_fn
         self.lr, self.max_norm, self.world, self.betas, self.eps = lr, max_norm, world_size, betas, eps
         self.bucket = FlatBucket(list(model.parameters()))
@@ -85,19 +89,63 @@ class DataParallelTrainer:
         self.v = torch.zeros_like(self.bucket.flat)
         self.sumsq = torch.zeros(1, device=self.bucket.flat.device, dtype=torch.float32)
         self.t = 0
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._static = None
+        self._static_out = None
+        self._graph_key = None
+
+    # -- differentiable part ---------------------------------------------------------------------
+    def _shade_and_backward(self, traced, eik, rgb):
+        out = self.model.shade(traced, eik)
+        losses = self.loss_fn(out, {"rgb": rgb})
+        self.bucket.zero_grad()
+        losses["loss"].backward()
+        self.bucket.gather_stray_grads()
+        return losses
+
+    def _graphed(self, traced, eik, rgb):
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(traced.items())) + (tuple(eik.shape), tuple(rgb.shape))
+        if self._graph is None or key != self._graph_key:
+            self._static = ({k: v.detach().clone() for k, v in traced.items()}, eik.clone(), rgb.clone())
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                       # warm-up outside capture (allocator, lazy inits)
+                    self._shade_and_backward(*self._static)
+            torch.cuda.current_stream().wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                losses = self._shade_and_backward(*self._static)
+                self._static_out = {k: v.detach() for k, v in losses.items()}
+            self._graph_key = key
+        st_traced, st_eik, st_rgb = self._static
+        for k, v in traced.items():
+            st_traced[k].copy_(v)
+        st_eik.copy_(eik)
+        st_rgb.copy_(rgb)
+        self._graph.replay()
+        return self._static_out
 
     def step(self, model_input, ground_truth) -> torch.Tensor:
+        from . import mlp
         b = self.bucket
-        out = self.model(model_input)
-        losses = self.loss_fn(out, ground_truth)
-        b.zero_grad()
-        losses["loss"].backward()
-        b.gather_stray_grads()
+        model = self.model
+        traced = model.trace(model_input)
+        dev = traced["dists"].device
+        n = traced["dists"].shape[0]
+        eik = model._draw_eikonal(n, dev)
+        rgb = ground_truth["rgb"].to(dev)
+        if self.use_cuda_graph and model.training:
+            losses = self._graphed(traced, eik, rgb)
+        else:
+            losses = self._shade_and_backward(traced, eik, rgb)
         scale = allreduce_mean_(b.grad, self.world)
         self.t += 1
         self.sumsq.zero_()
         K.sumsq(b.grad, self.sumsq)
         K.clip_adam(b.flat, b.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t,
                     self.max_norm, self.sumsq, scale)
+        mlp.weights_changed()
         self.last_losses = losses
         return losses["loss"]

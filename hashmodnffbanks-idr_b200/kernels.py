@@ -225,6 +225,9 @@ def gemm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int,
     e.ldaux = op_ld(aux) if aux is not None else 0
     e.mode, e.act_param, e.scale, e.accumulate = mode, float(act), float(scale), int(bool(accumulate))
     if PROFILE.enabled:
+        PROFILE.pending_tag = "[%s M=%d N=%d K=%d mode=%d%s%s]" % ("NT NN TN".split()[layout], M, N, Kc, mode,
+                                                                  " cnt" if m_count is not None else "",
+                                                                  " split%d" % split_k if split_k > 1 else "")
         if m_count is not None:
             cnt = m_count.clone()
             PROFILE.pending_flops = lambda cnt=cnt, M=M, N=N, Kc=Kc: 2.0 * min(M, int(cnt.item())) * N * Kc

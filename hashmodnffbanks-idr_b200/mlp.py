@@ -20,35 +20,77 @@ from ._lib import IdrkError
 
 SQRT2_INV = 1.0 / math.sqrt(2.0)
 
+# Bumped by whoever updates parameters behind torch's back (the fused optimiser kernel writes the flat
+# bucket through a raw pointer, so tensor._version does not move): invalidates folded-weight caches.
+WEIGHTS_EPOCH = [0]
+
+
+def weights_changed():
+    WEIGHTS_EPOCH[0] += 1
+
 
 # ---------------------------------------------------------------------------------------------
 # operand preparation
 # ---------------------------------------------------------------------------------------------
-def _prep(t: torch.Tensor):
+def _three_pass() -> bool:
+    return K.get_precision() == K.PREC_3XTF32
+
+
+def tag_split(t: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
+    """Remembers the (hi, lo) 3xTF32 operand pair of `t` on the tensor object (valid for its current version)."""
+    t._idrk_split = (hi, lo, t._version)
+    return t
+
+
+def split_of(t: torch.Tensor):
+    """(hi, lo) pair produced by an upstream kernel epilogue for exactly this tensor, or None."""
+    sp = getattr(t, "_idrk_split", None)
+    if sp is None or sp[2] != t._version or not _three_pass():
+        return None
+    return sp[0], sp[1]
+
+
+def make_split(t: torch.Tensor):
+    """(hi, lo) operand pair of `t` for the current precision (None when a single pass is used)."""
+    if not _three_pass():
+        return None
+    sp = split_of(t)
+    return sp if sp is not None else K.split_tf32(K.operand(t.detach()))
+
+
+def _prep(t: torch.Tensor, split=None):
     """(main, lo) operand pair for the current precision."""
-    t = K.operand(t.detach())
-    if K.get_precision() == K.PREC_3XTF32:
-        return K.split_tf32(t)
-    return t, None
+    if _three_pass():
+        if split is None:
+            split = split_of(t)
+        if split is not None:
+            return split
+        return K.split_tf32(K.operand(t.detach()))
+    return K.operand(t.detach()), None
 
 
 def _raw_mm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int, bias=None,
-            mode=K.EPI_NONE, act=0.0, scale=1.0, want_s=False):
+            mode=K.EPI_NONE, act=0.0, scale=1.0, want_s=False, a_split=None, b_split=None, split_out=False):
     dev = A.device
     C = K.empty_padded(M, N, dev)
     S = K.empty_padded(M, N, dev) if want_s else None
     if M == 0:
         return C, S
-    a, a_lo = _prep(A)
-    b, b_lo = _prep(B)
+    a, a_lo = _prep(A, a_split)
+    b, b_lo = _prep(B, b_split)
     split_k = 1
-    if layout == K.GEMM_TN and Kc >= 4096:
-        tiles = ((M + 127) // 128) * ((N + 127) // 128)
-        split_k = max(1, min(Kc // 1024, (2 * 148) // max(tiles, 1)))
+    if layout == K.GEMM_TN and Kc >= 1024:
+        tiles = ((M + 127) // 128) * ((N + 63) // 64)
+        split_k = max(1, min(Kc // 256, 148 // max(tiles, 1)))
         if split_k > 1:
             C.zero_()
-    K.gemm(layout, a, b, M, N, Kc, A_lo=a_lo, B_lo=b_lo, C=C, S=S, bias=bias, mode=mode, act=act, scale=scale,
-           split_k=split_k)
+    C_hi = C_lo = None
+    if split_out and _three_pass() and split_k == 1:
+        C_hi, C_lo = K.empty_padded(M, N, dev), K.empty_padded(M, N, dev)
+    K.gemm(layout, a, b, M, N, Kc, A_lo=a_lo, B_lo=b_lo, C=C, C_hi=C_hi, C_lo=C_lo, S=S, bias=bias, mode=mode, act=act,
+           scale=scale, split_k=split_k)
+    if C_hi is not None:
+        tag_split(C, C_hi, C_lo)
     return C, S
 
 
@@ -59,60 +101,66 @@ class _MMNT(torch.autograd.Function):
     """C[M,N] = A[M,K] @ B[N,K]^T"""
 
     @staticmethod
-    def forward(ctx, A, B):
+    def forward(ctx, A, B, a_split, b_split):
+        ctx.a_split, ctx.b_split = (a_split or split_of(A)), (b_split or split_of(B))
         ctx.save_for_backward(A, B)
-        return _raw_mm(K.GEMM_NT, A, B, A.shape[0], B.shape[0], A.shape[1])[0]
+        return _raw_mm(K.GEMM_NT, A, B, A.shape[0], B.shape[0], A.shape[1], a_split=ctx.a_split, b_split=ctx.b_split)[0]
 
     @staticmethod
     def backward(ctx, dC):
         A, B = ctx.saved_tensors
-        dA = mm_nn(dC, B) if ctx.needs_input_grad[0] else None
-        dB = mm_tn(dC, A) if ctx.needs_input_grad[1] else None
-        return dA, dB
+        dsp = make_split(dC) if (ctx.needs_input_grad[0] and ctx.needs_input_grad[1]) else None
+        dA = mm_nn(dC, B, dsp, ctx.b_split) if ctx.needs_input_grad[0] else None
+        dB = mm_tn(dC, A, dsp, ctx.a_split) if ctx.needs_input_grad[1] else None
+        return dA, dB, None, None
 
 
 class _MMNN(torch.autograd.Function):
     """C[M,N] = A[M,K] @ B[K,N]"""
 
     @staticmethod
-    def forward(ctx, A, B):
+    def forward(ctx, A, B, a_split, b_split):
+        ctx.a_split, ctx.b_split = (a_split or split_of(A)), (b_split or split_of(B))
         ctx.save_for_backward(A, B)
-        return _raw_mm(K.GEMM_NN, A, B, A.shape[0], B.shape[1], A.shape[1])[0]
+        return _raw_mm(K.GEMM_NN, A, B, A.shape[0], B.shape[1], A.shape[1], a_split=ctx.a_split, b_split=ctx.b_split)[0]
 
     @staticmethod
     def backward(ctx, dC):
         A, B = ctx.saved_tensors
-        dA = mm_nt(dC, B) if ctx.needs_input_grad[0] else None
-        dB = mm_tn(A, dC) if ctx.needs_input_grad[1] else None
-        return dA, dB
+        dsp = make_split(dC) if (ctx.needs_input_grad[0] and ctx.needs_input_grad[1]) else None
+        dA = mm_nt(dC, B, dsp, ctx.b_split) if ctx.needs_input_grad[0] else None
+        dB = mm_tn(A, dC, ctx.a_split, dsp) if ctx.needs_input_grad[1] else None
+        return dA, dB, None, None
 
 
 class _MMTN(torch.autograd.Function):
     """C[M,N] = A[K,M]^T @ B[K,N]   (contraction over rows: weight gradients)"""
 
     @staticmethod
-    def forward(ctx, A, B):
+    def forward(ctx, A, B, a_split, b_split):
+        ctx.a_split, ctx.b_split = (a_split or split_of(A)), (b_split or split_of(B))
         ctx.save_for_backward(A, B)
-        return _raw_mm(K.GEMM_TN, A, B, A.shape[1], B.shape[1], A.shape[0])[0]
+        return _raw_mm(K.GEMM_TN, A, B, A.shape[1], B.shape[1], A.shape[0], a_split=ctx.a_split, b_split=ctx.b_split)[0]
 
     @staticmethod
     def backward(ctx, dC):
         A, B = ctx.saved_tensors
-        dA = mm_nt(B, dC) if ctx.needs_input_grad[0] else None
-        dB = mm_nn(A, dC) if ctx.needs_input_grad[1] else None
-        return dA, dB
+        dsp = make_split(dC) if (ctx.needs_input_grad[0] and ctx.needs_input_grad[1]) else None
+        dA = mm_nt(B, dC, ctx.b_split, dsp) if ctx.needs_input_grad[0] else None
+        dB = mm_nn(A, dC, ctx.a_split, dsp) if ctx.needs_input_grad[1] else None
+        return dA, dB, None, None
 
 
-def mm_nt(A, B):
-    return _MMNT.apply(A, B)
+def mm_nt(A, B, a_split=None, b_split=None):
+    return _MMNT.apply(A, B, a_split, b_split)
 
 
-def mm_nn(A, B):
-    return _MMNN.apply(A, B)
+def mm_nn(A, B, a_split=None, b_split=None):
+    return _MMNN.apply(A, B, a_split, b_split)
 
 
-def mm_tn(A, B):
-    return _MMTN.apply(A, B)
+def mm_tn(A, B, a_split=None, b_split=None):
+    return _MMTN.apply(A, B, a_split, b_split)
 
 
 class _ColSum(torch.autograd.Function):
@@ -130,22 +178,34 @@ def colsum(x):
     return _ColSum.apply(x)
 
 
+def _layer_backward(ctx, dZ, X, W):
+    """Shared backward of Z = X W^T + b: one hi/lo split of dZ feeds both contractions."""
+    need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    dsp = make_split(dZ) if (need_x and need_w) else None
+    dX = mm_nn(dZ, W, dsp, ctx.w_split) if need_x else None
+    dW = mm_tn(dZ, X, dsp, ctx.x_split) if need_w else None
+    db = colsum(dZ) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+    return dX, dW, db
+
+
 class _Linear(torch.autograd.Function):
     """Z = X W^T + b  (bias fused in the epilogue)."""
 
     @staticmethod
     def forward(ctx, X, W, b):
+        ctx.x_split, ctx.w_split = split_of(X), split_of(W)
+        if _three_pass():
+            ctx.x_split = ctx.x_split or make_split(X)
+            ctx.w_split = ctx.w_split or make_split(W)
         ctx.save_for_backward(X, W)
         ctx.has_bias = b is not None
-        return _raw_mm(K.GEMM_NT, X, W, X.shape[0], W.shape[0], X.shape[1], bias=b.detach() if b is not None else None)[0]
+        return _raw_mm(K.GEMM_NT, X, W, X.shape[0], W.shape[0], X.shape[1], bias=b.detach() if b is not None else None,
+                       a_split=ctx.x_split, b_split=ctx.w_split)[0]
 
     @staticmethod
     def backward(ctx, dZ):
         X, W = ctx.saved_tensors
-        dX = mm_nn(dZ, W) if ctx.needs_input_grad[0] else None
-        dW = mm_tn(dZ, X) if ctx.needs_input_grad[1] else None
-        db = colsum(dZ) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return dX, dW, db
+        return _layer_backward(ctx, dZ, X, W)
 
 
 def linear(X, W, b=None):
@@ -160,13 +220,18 @@ class _LinearAct(torch.autograd.Function):
 
     H = scale * act(Z),  S = act'(Z).  S is returned as a differentiable output so that when the
     backward pass is itself recorded (create_graph) the dependence of act' on Z is tracked:
-    d S / d Z = act''(Z), written below per activation in terms of the saved outputs."""
+    d S / d Z = act''(Z), written below per activation in terms of the saved outputs.
+    In 3xTF32 mode the epilogue also writes H pre-split (hi/lo) for the next layer's contraction."""
 
     @staticmethod
     def forward(ctx, X, W, b, mode, act, scale):
+        ctx.x_split, ctx.w_split = split_of(X), split_of(W)
+        if _three_pass():
+            ctx.x_split = ctx.x_split or make_split(X)
+            ctx.w_split = ctx.w_split or make_split(W)
         H, S = _raw_mm(K.GEMM_NT, X, W, X.shape[0], W.shape[0], X.shape[1],
                        bias=b.detach() if b is not None else None, mode=_ACT_MODES[mode], act=act, scale=scale,
-                       want_s=True)
+                       want_s=True, a_split=ctx.x_split, b_split=ctx.w_split, split_out=True)
         ctx.mode, ctx.act, ctx.scale, ctx.has_bias = mode, act, scale, b is not None
         ctx.save_for_backward(X, W, H, S)
         ctx.set_materialize_grads(False)
@@ -191,10 +256,7 @@ class _LinearAct(torch.autograd.Function):
                 dZ = dS * s2 if dZ is None else dZ + dS * s2
         if dZ is None:
             return None, None, None, None, None, None
-        dX = mm_nn(dZ, W) if ctx.needs_input_grad[0] else None
-        dW = mm_tn(dZ, X) if ctx.needs_input_grad[1] else None
-        db = colsum(dZ) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return dX, dW, db, None, None, None
+        return (*_layer_backward(ctx, dZ, X, W), None, None, None)
 
 
 def linear_act(X, W, b, mode: str, act: float = 0.0, scale: float = 1.0):
@@ -208,7 +270,12 @@ class _WeightNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, g, v):
         ctx.save_for_backward(g, v)
-        return K.weight_norm_fwd(g.detach(), v.detach(), False, False)["W"]
+        split = _three_pass()
+        out = K.weight_norm_fwd(g.detach(), v.detach(), split, False)
+        W = out["W"]
+        if split:
+            tag_split(W, out["W_hi"], out["W_lo"])
+        return W
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -249,7 +316,7 @@ class FoldedLayer:
 
 
 def params_version(params: Sequence[torch.Tensor]) -> Tuple:
-    return tuple((p.data_ptr(), p._version) for p in params)
+    return (WEIGHTS_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
 
 
 class SdfPipeline:
@@ -290,7 +357,7 @@ class SdfPipeline:
 
     def beta(self) -> float:
         p = self.net.dencity_net.beta
-        ver = (p.data_ptr(), p._version)
+        ver = (p.data_ptr(), p._version, WEIGHTS_EPOCH[0] if p.requires_grad and p.grad is not None else 0)
         if self._beta is None or ver != self._beta_version:
             self._beta = abs(float(p.detach().cpu())) + 1e-4
             self._beta_version = ver

@@ -23,7 +23,7 @@ class LaplaceDensity(Density):
         self.beta_min = torch.tensor(beta_min)
 
     def get_beta(self):
-        return self.beta.abs() + self.beta_min.to(self.beta.device)
+        return self.beta.abs() + float(self.beta_min)
 
     @torch.no_grad()
     def density_func(self, sdf, beta=None):

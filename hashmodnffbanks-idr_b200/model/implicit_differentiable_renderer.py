@@ -222,61 +222,80 @@ class IDRNetwork(nn.Module):
         self.injected_eikonal_points = None
 
     def forward(self, input):
+        return self.shade(self.trace(input))
+
+    def trace(self, input):
+        """Ray generation + RayTracing under no_grad (reference :243-261).  Returns what the differentiable
+        part needs: ray_dirs [B,N,3], cam_loc [B,3], dists [B*N], network_object_mask, object_mask."""
         intrinsics, uv, pose = input["intrinsics"], input["uv"], input["pose"]
         object_mask = input["object_mask"].reshape(-1)
         ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics)
-        batch_size, num_pixels, _ = ray_dirs.shape
-        device = ray_dirs.device
-
         self.implicit_network.eval()
         with torch.no_grad():
             self.ray_tracer.train(self.training)
-            points, network_object_mask, dists = self.ray_tracer(sdf=self.implicit_network.sdf, cam_loc=cam_loc,
-                                                                 object_mask=object_mask, ray_directions=ray_dirs)
+            _, network_object_mask, dists = self.ray_tracer(sdf=self.implicit_network.sdf, cam_loc=cam_loc,
+                                                            object_mask=object_mask, ray_directions=ray_dirs)
         self.implicit_network.train()
+        return {"ray_dirs": ray_dirs, "cam_loc": cam_loc, "dists": dists, "network_object_mask": network_object_mask,
+                "object_mask": object_mask}
+
+    def shade(self, traced, eikonal_points=None):
+        """Differentiable part of the forward (reference :262-319) given the traced distances."""
+        ray_dirs, cam_loc, dists = traced["ray_dirs"], traced["cam_loc"], traced["dists"]
+        network_object_mask, object_mask = traced["network_object_mask"], traced["object_mask"]
+        batch_size, num_pixels, _ = ray_dirs.shape
+        device = ray_dirs.device
         points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
         sdf_output = self.implicit_network(points)[:, 0:1]
         ray_dirs = ray_dirs.reshape(-1, 3)
 
         if self.training:
-            surface_mask = network_object_mask & object_mask
-            surface_points = points[surface_mask]
-            surface_dists = dists[surface_mask].unsqueeze(-1)
-            surface_ray_dirs = ray_dirs[surface_mask]
-            surface_cam_loc = cam_loc.unsqueeze(1).repeat(1, num_pixels, 1).reshape(-1, 3)[surface_mask]
-            surface_output = sdf_output[surface_mask]
-            N = surface_points.shape[0]
-
-            n_eik = batch_size * num_pixels // 2
-            if self.injected_eikonal_points is not None:
-                eik = self.injected_eikonal_points.to(device)
-            else:   # drawn on the host generator, like the reference (:279)
-                r = self.object_bounding_sphere
-                eik = torch.empty(n_eik, 3).uniform_(-r, r).to(device)
-            eikonal_points = torch.cat([eik, points.clone().detach()], 0)
-            points_all = torch.cat([surface_points, eikonal_points], dim=0)
-
-            with torch.no_grad():
-                surface_sdf_values = self.implicit_network(surface_points)[:N, 0:1] if N > 0 \
-                    else torch.zeros(0, 1, device=device)
-            g = self.implicit_network.gradient(points_all)
-            surface_points_grad = g[:N, 0, :].clone().detach()
-            grad_theta = g[N:, 0, :]
-            differentiable_surface_points = self.sample_network(surface_output, surface_sdf_values,
-                                                                surface_points_grad, surface_dists,
-                                                                surface_cam_loc, surface_ray_dirs)
+            if eikonal_points is None:
+                eikonal_points = self._draw_eikonal(batch_size * num_pixels, device)
+            cam_rep = cam_loc.unsqueeze(1).repeat(1, num_pixels, 1).reshape(-1, 3)
+            rgb_values, grad_theta = self.render_training(points, dists, ray_dirs, cam_rep, sdf_output,
+                                                          network_object_mask & object_mask, eikonal_points)
         else:
             surface_mask = network_object_mask
             differentiable_surface_points = points[surface_mask]
             grad_theta = None
-
-        view = -ray_dirs[surface_mask]
-        rgb_values = torch.ones_like(points).float()
-        if differentiable_surface_points.shape[0] > 0:
-            rgb_values[surface_mask] = self.get_rbg_value(differentiable_surface_points, view)
+            view = -ray_dirs[surface_mask]
+            rgb_values = torch.ones_like(points).float()
+            if differentiable_surface_points.shape[0] > 0:
+                rgb_values[surface_mask] = self.get_rbg_value(differentiable_surface_points, view)
 
         return {'points': points, 'rgb_values': rgb_values, 'sdf_output': sdf_output,
                 'network_object_mask': network_object_mask, 'object_mask': object_mask, 'grad_theta': grad_theta}
+
+    def _draw_eikonal(self, n_rays, device):
+        if self.injected_eikonal_points is not None:
+            return self.injected_eikonal_points.to(device)
+        r = self.object_bounding_sphere      # drawn on the host generator, like the reference (:279)
+        return torch.empty(n_rays // 2, 3).uniform_(-r, r).to(device)
+
+    def render_training(self, points, dists, ray_dirs, cam_rep, sdf_output, surface_mask, eik):
+        """Training branch of the reference forward (:268-308) on FIXED shapes.
+
+        The reference gathers the N_s surface rays with boolean masks and evaluates the network on
+        [surface | eikonal | all] points.  Surface points are a subset of `points`, so the same numbers are
+        obtained by evaluating ONE gradient() on [eikonal | all points] and reading the surface rows out of
+        it, and by running sample network + rendering on all N rays with the non-surface rows masked out
+        afterwards (their rgb is the constant 1 and they receive zero gradient, exactly as in the reference).
+        Fixed shapes keep the step free of host syncs and capturable in a CUDA graph."""
+        n = points.shape[0]
+        n_eik = eik.shape[0]
+        g = self.implicit_network.gradient(torch.cat([eik, points.clone().detach()], 0))
+        grad_theta = g[:, 0, :]
+        normals0 = g[n_eik:, 0, :].clone().detach()
+        sdf0 = sdf_output.detach()
+        mask = surface_mask.unsqueeze(-1)
+        denom = (normals0 * ray_dirs.detach()).sum(dim=-1, keepdim=True)
+        denom = torch.where(mask, denom, torch.ones_like(denom))
+        t_theta = dists.unsqueeze(-1) - (sdf_output - sdf0) / denom           # sample_network.py:10-20
+        diff_points = cam_rep + t_theta * ray_dirs
+        rgb = self.get_rbg_value(diff_points, -ray_dirs)
+        rgb_values = torch.where(mask, rgb, torch.ones_like(rgb))
+        return rgb_values, grad_theta
 
     def get_rbg_value(self, points, view_dirs):
         output = self.implicit_network(points)

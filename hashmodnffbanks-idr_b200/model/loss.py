@@ -13,13 +13,13 @@ class IDRLoss(nn.Module):
         self.mask_weight = mask_weight
         self.alpha = alpha
 
+    # All three terms are written as masked reductions over fixed-shape tensors (no boolean indexing,
+    # no data-dependent branches): same values as the reference's indexed sums - an empty selection simply
+    # contributes 0 - and the whole loss can be captured in a CUDA graph.
     def get_rgb_loss(self, rgb_values, rgb_gt, network_object_mask, object_mask):
-        both = network_object_mask & object_mask
-        sel = rgb_values[both]
-        if sel.shape[0] == 0:
-            return torch.zeros((), device=rgb_values.device)
-        gt = rgb_gt.reshape(-1, 3)[both]
-        return (sel - gt).abs().sum() / float(object_mask.shape[0])
+        both = (network_object_mask & object_mask).unsqueeze(-1)
+        diff = torch.where(both, rgb_values - rgb_gt.reshape(-1, 3), torch.zeros_like(rgb_values))
+        return diff.abs().sum() / float(object_mask.shape[0])
 
     def get_eikonal_loss(self, grad_theta):
         if grad_theta.shape[0] == 0:
@@ -28,12 +28,10 @@ class IDRLoss(nn.Module):
 
     def get_mask_loss(self, sdf_output, network_object_mask, object_mask):
         neg = ~(network_object_mask & object_mask)
-        logits = -self.alpha * sdf_output[neg]
-        if logits.shape[0] == 0:
-            return torch.zeros((), device=sdf_output.device)
-        gt = object_mask[neg].float()
-        bce = F.binary_cross_entropy_with_logits(logits.squeeze(-1), gt, reduction='sum')
-        return (1 / self.alpha) * bce / float(object_mask.shape[0])
+        logits = -self.alpha * sdf_output.reshape(-1)
+        bce = F.binary_cross_entropy_with_logits(logits, object_mask.float(), reduction='none')
+        total = torch.where(neg, bce, torch.zeros_like(bce)).sum()
+        return (1 / self.alpha) * total / float(object_mask.shape[0])
 
     def forward(self, model_outputs, ground_truth):
         rgb_gt = ground_truth['rgb'].to(model_outputs['rgb_values'].device)

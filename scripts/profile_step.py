@@ -1,0 +1,51 @@
+"""Per-entry-point / per-shape device time of one IDR training step (CUDA events), for optimisation work."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    from idrk import kernels as K
+    from idrk.dist import DataParallelTrainer
+    from idrk.model.implicit_differentiable_renderer import IDRNetwork
+    from idrk.model.loss import IDRLoss
+    from oracle import idr_oracle as O
+    from tests_support import quiet_build
+    prec = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
+    K.set_precision(prec)
+    torch.manual_seed(0)
+    model = quiet_build(IDRNetwork, bench.model_conf()).cuda().train()
+    use_graph = len(sys.argv) > 2 and sys.argv[2] == "graph"
+    tr = DataParallelTrainer(model, IDRLoss(0.1, 100.0, 50.0), lr=1e-4, use_cuda_graph=use_graph)
+    inp, rgb = O.synthetic_batch(bench.N_RAYS, seed=1)
+    inp = {k: v.cuda() for k, v in inp.items()}
+    gt = {"rgb": rgb.cuda()}
+    for _ in range(3):
+        tr.step(inp, gt)
+    torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    for _ in range(5):
+        tr.step(inp, gt)
+    torch.cuda.synchronize()
+    print("wall ms/step (plain): %.2f" % ((time.perf_counter() - t0) / 5 * 1e3))
+    tr.use_cuda_graph = False
+    K.PROFILE.reset(enabled=True, detail=True)
+    tr.step(inp, gt)
+    prof = K.PROFILE.summary()
+    K.PROFILE.reset(enabled=False)
+    rows = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
+    tot = sum(v["ms"] for v in prof.values())
+    print("total kernel ms: %.2f" % tot)
+    for k, v in rows[:45]:
+        tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["flops"] else 0
+        print("%8.3f ms %5d calls %7.1f us/call %7.1f TF/s  %s" % (v["ms"], v["calls"], v["ms"] / v["calls"] * 1e3, tf, k))
+
+
+if __name__ == "__main__":
+    main()

