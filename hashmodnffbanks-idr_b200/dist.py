@@ -90,6 +90,8 @@ class DataParallelTrainer:
         self.sumsq = torch.zeros(1, device=self.bucket.flat.device, dtype=torch.float32)
         self.t = 0
         self.use_cuda_graph = use_cuda_graph
+        if hasattr(model, "ray_tracer"):
+            model.ray_tracer.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._static = None
         self._static_out = None

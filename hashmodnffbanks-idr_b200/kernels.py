@@ -237,18 +237,20 @@ def gemm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int,
                           ctypes.byref(e), ptr(m_count), split_k, stream_ptr()), "idrk_gemm")
 
 
-def weight_norm_fwd(g: Optional[torch.Tensor], v: torch.Tensor, want_split: bool, want_t: bool):
-    """Returns dict with W (+ W_hi/W_lo, Wt (+ Wt_hi/Wt_lo)), all padded operands."""
+def weight_norm_fwd(g: Optional[torch.Tensor], v: torch.Tensor, want_split: bool, want_t: bool, out=None):
+    """Returns dict with W (+ W_hi/W_lo, Wt (+ Wt_hi/Wt_lo)), all padded operands.  `out` reuses the buffers of a
+    previous call (in-place refresh: pointers stay valid for CUDA graphs)."""
     v = rows2d(v, "weight_v")
     N, Kd = v.shape
     dev = v.device
-    out = {"W": empty_padded(N, Kd, dev)}
-    if want_split:
-        out["W_hi"], out["W_lo"] = empty_padded(N, Kd, dev), empty_padded(N, Kd, dev)
-    if want_t:
-        out["Wt"] = empty_padded(Kd, N, dev)
+    if out is None:
+        out = {"W": empty_padded(N, Kd, dev)}
         if want_split:
-            out["Wt_hi"], out["Wt_lo"] = empty_padded(Kd, N, dev), empty_padded(Kd, N, dev)
+            out["W_hi"], out["W_lo"] = empty_padded(N, Kd, dev), empty_padded(N, Kd, dev)
+        if want_t:
+            out["Wt"] = empty_padded(Kd, N, dev)
+            if want_split:
+                out["Wt_hi"], out["Wt_lo"] = empty_padded(Kd, N, dev), empty_padded(Kd, N, dev)
     gg = g.reshape(-1).contiguous() if g is not None else None
     check(lib().idrk_weight_norm_fwd(ptr(gg), ptr(v), N, Kd, ld_of(v), ptr(out["W"]), ptr(out.get("W_hi")), ptr(out.get("W_lo")),
                                      pad4(Kd), ptr(out.get("Wt")), ptr(out.get("Wt_hi")), ptr(out.get("Wt_lo")), pad4(N),

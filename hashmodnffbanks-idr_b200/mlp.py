@@ -300,19 +300,25 @@ def layer_weight(lin: torch.nn.Module) -> torch.Tensor:
 # inference pipeline (no autograd)
 # ---------------------------------------------------------------------------------------------
 class FoldedLayer:
-    __slots__ = ("W", "W_lo", "Wfull", "bias", "n_out", "n_in")
+    """Effective (weight-norm folded) weight of one Linear, optionally hi/lo split, in persistent buffers."""
+    __slots__ = ("lin", "split", "bufs", "W", "W_lo", "Wfull", "bias", "n_out", "n_in")
 
     def __init__(self, lin: torch.nn.Module, split: bool):
-        with torch.no_grad():
-            if hasattr(lin, "weight_g"):
-                out = K.weight_norm_fwd(lin.weight_g, lin.weight_v, split, False)
-            else:
-                out = K.weight_norm_fwd(None, lin.weight, split, False)
-        self.W = out["W_hi"] if split else out["W"]
-        self.W_lo = out.get("W_lo")
-        self.Wfull = out["W"]
-        self.bias = lin.bias.detach()
+        self.lin, self.split, self.bufs = lin, split, None
+        self.refresh()
         self.n_out, self.n_in = (lin.weight_v if hasattr(lin, "weight_v") else lin.weight).shape
+
+    @torch.no_grad()
+    def refresh(self):
+        lin = self.lin
+        if hasattr(lin, "weight_g"):
+            self.bufs = K.weight_norm_fwd(lin.weight_g, lin.weight_v, self.split, False, out=self.bufs)
+        else:
+            self.bufs = K.weight_norm_fwd(None, lin.weight, self.split, False, out=self.bufs)
+        self.W = self.bufs["W_hi"] if self.split else self.bufs["W"]
+        self.W_lo = self.bufs.get("W_lo")
+        self.Wfull = self.bufs["W"]
+        self.bias = lin.bias.detach()
 
 
 def params_version(params: Sequence[torch.Tensor]) -> Tuple:
@@ -346,13 +352,16 @@ class SdfPipeline:
     def layers(self):
         return [getattr(self.net, "lin%d" % l) for l in range(self.n_lin)]
 
-    def folded(self) -> List["FoldedLayer"]:
+    def folded(self, force: bool = False) -> List["FoldedLayer"]:
         params = [p for l in self.layers() for p in l.parameters()]
         ver = params_version(params)
         prec = K.get_precision()
-        if self._folded is None or ver != self._version or prec != self._precision:
+        if self._folded is None or prec != self._precision:
             self._folded = [FoldedLayer(l, prec == K.PREC_3XTF32) for l in self.layers()]
-            self._version, self._precision = ver, prec
+        elif force or ver != self._version:
+            for f in self._folded:
+                f.refresh()                    # in place: buffer addresses captured in CUDA graphs stay valid
+        self._version, self._precision = ver, prec
         return self._folded
 
     def beta(self) -> float:

@@ -85,6 +85,11 @@ class ImplicitNetwork(nn.Module):
         emb = K.operand(self._embed(x))
         return self._pipeline.run(emb, x.shape[0], want="sdf")
 
+    def refresh_inference_weights(self, force: bool = False):
+        """(Re)folds the weight-normalised layers into the inference buffers (and caches beta)."""
+        self._pipeline.folded(force=force)
+        self._pipeline.beta()
+
     def supports_device_count(self) -> bool:
         """True when the encoder can take its row count from device memory (no host sync in the tracer)."""
         if self.embed_fn is None:

@@ -63,6 +63,46 @@ class _Evaluator:
             out[:n] = self.sdf(pts[:n]).reshape(-1)
 
 
+class _TraceState:
+    """Per-(B, P, device) persistent ray-state buffers (so the launch sequence can live in a CUDA graph)."""
+
+    def __init__(self, B, P, n_it, n_ls, dev):
+        N = B * P
+        self.B, self.P, self.N, self.dev = B, P, N, dev
+        self.t_sph = torch.empty((N, 2), device=dev, dtype=torch.float32)
+        self.hit_u8 = torch.empty(N, device=dev, dtype=torch.uint8)
+        self.cam = torch.empty((B, 3), device=dev, dtype=torch.float32)
+        self.dirs = torch.empty((N, 3), device=dev, dtype=torch.float32)
+        fbuf = torch.empty(16 * N, device=dev, dtype=torch.float32)
+        (self.t0, self.t1, self.cur_s, self.cur_e, self.nxt_s, self.nxt_e, self.min_dis,
+         self.max_dis) = (fbuf[i * N:(i + 1) * N] for i in range(8))
+        self.ps = fbuf[8 * N:11 * N].view(N, 3)
+        self.pe = fbuf[11 * N:14 * N].view(N, 3)
+        self._fbuf = fbuf
+        bbuf = torch.empty(3 * N, device=dev, dtype=torch.uint8)
+        self.unf_s, self.unf_e, self.net_mask = bbuf[:N], bbuf[N:2 * N], bbuf[2 * N:]
+        ibuf = torch.empty(3 * N, device=dev, dtype=torch.int32)
+        self.slot_s, self.slot_e, self.ray_of_slot = ibuf[:N], ibuf[N:2 * N], ibuf[2 * N:]
+        self.counters = torch.zeros(8 + (n_it + 1) * (n_ls + 3), device=dev, dtype=torch.int32)
+        self.cidx = 0
+        self.cap = 2 * N
+        self.pts = torch.empty((self.cap, 3), device=dev, dtype=torch.float32)
+        self.vals = torch.empty(self.cap, device=dev, dtype=torch.float32)
+        st = RayStateDesc()
+        st.cam_loc, st.ray_dirs, st.n_rays, st.num_pixels = self.cam.data_ptr(), self.dirs.data_ptr(), N, P
+        for name in ("t0", "t1", "cur_s", "cur_e", "nxt_s", "nxt_e", "ps", "pe", "min_dis", "max_dis", "unf_s", "unf_e",
+                     "slot_s", "slot_e"):
+            setattr(st, name, getattr(self, name).data_ptr())
+        self.desc = st
+        self.graph = None
+        self.warm = False
+
+    def new_counter(self):
+        c = self.counters[self.cidx:self.cidx + 1]
+        self.cidx += 1
+        return c
+
+
 class RayTracing(nn.Module):
     def __init__(self, object_bounding_sphere=1.0, sdf_threshold=5.0e-5, line_search_step=0.5, line_step_iters=1,
                  sphere_tracing_iters=10, n_steps=100, n_secant_steps=8):
@@ -76,8 +116,45 @@ class RayTracing(nn.Module):
         self.n_secant_steps = n_secant_steps
         self.last_stats = {}
         self.injected_min_sdf_steps = None      # parity runs: the U(0,1) vector of reference :277
+        self.use_cuda_graph = False             # replay the sphere-tracing launch sequence from a CUDA graph
+        self._states = {}
 
     # ------------------------------------------------------------------------------------------
+    def _sphere_trace(self, T, ev):
+        """Enqueues the whole bidirectional sphere-tracing loop (reference :98-187): a fixed launch sequence whose
+        data-dependent exits are device-side gates, so it can be captured in a CUDA graph."""
+        L = lib()
+        S = ctypes.byref(T.desc)
+        sp = stream_ptr()
+        n_ls, n_it = int(self.line_step_iters), int(self.sphere_tracing_iters)
+        T.counters.zero_()
+        T.cidx = 0
+        c = T.new_counter()
+        check(L.idrk_rt_init(S, ptr(T.t_sph), ptr(T.hit_u8), ptr(T.pts), ptr(c), sp), "idrk_rt_init")
+        ev.on_device_count(T.pts, T.cap, c, T.vals)
+        gate = T.new_counter()
+        check(L.idrk_rt_top(S, ptr(T.vals), 1, float(self.sdf_threshold), ptr(gate), sp), "idrk_rt_top")
+        for it in range(n_it):
+            c = T.new_counter()
+            check(L.idrk_rt_step(S, ptr(gate), ptr(T.pts), ptr(c), sp), "idrk_rt_step")
+            ev.on_device_count(T.pts, T.cap, c, T.vals)
+            for k in range(n_ls):
+                c = T.new_counter()
+                factor = (1 - self.line_search_step) / (2 ** k)
+                check(L.idrk_rt_linesearch(S, ptr(gate), ptr(T.vals), 1 if k == 0 else 2, float(factor), ptr(T.pts),
+                                           ptr(c), sp), "idrk_rt_linesearch")
+                ev.on_device_count(T.pts, T.cap, c, T.vals)
+            check(L.idrk_rt_end(S, ptr(gate), ptr(T.vals), 1 if n_ls == 0 else 2, sp), "idrk_rt_end")
+            gate = T.new_counter()
+            check(L.idrk_rt_top(S, None, 0, float(self.sdf_threshold), ptr(gate), sp), "idrk_rt_top")
+
+    def _state(self, B, P, dev):
+        key = (B, P, str(dev), int(self.sphere_tracing_iters), int(self.line_step_iters))
+        T = self._states.get(key)
+        if T is None:
+            T = self._states[key] = _TraceState(B, P, int(self.sphere_tracing_iters), int(self.line_step_iters), dev)
+        return T
+
     def forward(self, sdf, cam_loc, object_mask, ray_directions, *, min_sdf_steps=None, sphere_intersections=None):
         K.require_cuda(ray_directions, "ray_directions")
         L = lib()
@@ -90,62 +167,35 @@ class RayTracing(nn.Module):
                 t_sph, hit = rend_util.get_sphere_intersection(cam_loc, ray_directions, r=self.object_bounding_sphere)
             else:
                 t_sph, hit = sphere_intersections
-            t_sph = t_sph.reshape(N, 2).contiguous().float()
-            hit_u8 = hit.reshape(N).to(torch.uint8).contiguous()
+            T = self._state(B, P, dev)
+            T.t_sph.copy_(t_sph.reshape(N, 2))
+            T.hit_u8.copy_(hit.reshape(N))
+            T.cam.copy_(cam_loc.reshape(B, 3))
+            T.dirs.copy_(ray_directions.reshape(N, 3))
+            hit_u8 = T.hit_u8
             obj_u8 = object_mask.reshape(N).to(torch.uint8).contiguous()
-            cam = cam_loc.reshape(B, 3).contiguous().float()
-            dirs = ray_directions.reshape(N, 3).contiguous().float()
-
-            fbuf = torch.empty(16 * N, device=dev, dtype=torch.float32)
-            t0, t1, cur_s, cur_e, nxt_s, nxt_e, min_dis, max_dis = (fbuf[i * N:(i + 1) * N] for i in range(8))
-            ps = fbuf[8 * N:11 * N].view(N, 3)
-            pe = fbuf[11 * N:14 * N].view(N, 3)
-            bbuf = torch.empty(3 * N, device=dev, dtype=torch.uint8)
-            unf_s, unf_e, net_mask = bbuf[:N], bbuf[N:2 * N], bbuf[2 * N:]
-            ibuf = torch.empty(3 * N, device=dev, dtype=torch.int32)
-            slot_s, slot_e, ray_of_slot = ibuf[:N], ibuf[N:2 * N], ibuf[2 * N:]
-            n_ls = int(self.line_step_iters)
-            n_it = int(self.sphere_tracing_iters)
-            counters = torch.zeros(8 + (n_it + 1) * (n_ls + 3), device=dev, dtype=torch.int32)
-            cidx = [0]
-
-            def new_counter():
-                c = counters[cidx[0]:cidx[0] + 1]
-                cidx[0] += 1
-                return c
-
-            st = RayStateDesc()
-            st.cam_loc, st.ray_dirs, st.n_rays, st.num_pixels = cam.data_ptr(), dirs.data_ptr(), N, P
-            for name, t in (("t0", t0), ("t1", t1), ("cur_s", cur_s), ("cur_e", cur_e), ("nxt_s", nxt_s), ("nxt_e", nxt_e),
-                            ("ps", ps), ("pe", pe), ("min_dis", min_dis), ("max_dis", max_dis), ("unf_s", unf_s),
-                            ("unf_e", unf_e), ("slot_s", slot_s), ("slot_e", slot_e)):
-                setattr(st, name, t.data_ptr())
-            S = ctypes.byref(st)
+            t0, ps, unf_s, net_mask, ray_of_slot = T.t0, T.ps, T.unf_s, T.net_mask, T.ray_of_slot
+            S = ctypes.byref(T.desc)
             sp = stream_ptr()
-
-            cap = 2 * N
-            pts = torch.empty((cap, 3), device=dev, dtype=torch.float32)
-            vals = torch.empty(cap, device=dev, dtype=torch.float32)
+            new_counter = T.new_counter
 
             # ---- sphere tracing (reference :98-187) ------------------------------------------------
-            c = new_counter()
-            check(L.idrk_rt_init(S, ptr(t_sph), ptr(hit_u8), ptr(pts), ptr(c), sp), "idrk_rt_init")
-            ev.on_device_count(pts, cap, c, vals)
-            gate = new_counter()
-            check(L.idrk_rt_top(S, ptr(vals), 1, float(self.sdf_threshold), ptr(gate), sp), "idrk_rt_top")
-            for it in range(n_it):
-                c = new_counter()
-                check(L.idrk_rt_step(S, ptr(gate), ptr(pts), ptr(c), sp), "idrk_rt_step")
-                ev.on_device_count(pts, cap, c, vals)
-                for k in range(n_ls):
-                    c = new_counter()
-                    factor = (1 - self.line_search_step) / (2 ** k)
-                    check(L.idrk_rt_linesearch(S, ptr(gate), ptr(vals), 1 if k == 0 else 2, float(factor), ptr(pts),
-                                               ptr(c), sp), "idrk_rt_linesearch")
-                    ev.on_device_count(pts, cap, c, vals)
-                check(L.idrk_rt_end(S, ptr(gate), ptr(vals), 1 if n_ls == 0 else 2, sp), "idrk_rt_end")
-                gate = new_counter()
-                check(L.idrk_rt_top(S, None, 0, float(self.sdf_threshold), ptr(gate), sp), "idrk_rt_top")
+            if self.use_cuda_graph and ev.fast:
+                if not T.warm:                       # first call: eager (allocations, lazy attribute setup)
+                    self._sphere_trace(T, ev)
+                    T.warm = True
+                else:
+                    if T.graph is None:
+                        torch.cuda.synchronize()
+                        T.graph = torch.cuda.CUDAGraph()
+                        ev.owner.refresh_inference_weights()
+                        with torch.cuda.graph(T.graph):
+                            ev.owner.refresh_inference_weights(force=True)   # weight folding is part of the graph
+                            self._sphere_trace(T, ev)
+                    T.graph.replay()
+                    T.cidx = T.counters.numel() - 8
+            else:
+                self._sphere_trace(T, ev)
 
             # ---- sampler + secant for the non-convergent rays (:41-59, :189-268) ------------------------
             c_samp = new_counter()
