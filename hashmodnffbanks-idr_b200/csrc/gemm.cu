@@ -189,6 +189,81 @@ __device__ __forceinline__ float epi_value_fast(const EpiParams& e, float z, lon
     return epi_value(e, z, row, col, s);
 }
 
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
+
+// Branch-free per-element epilogue for the hot activation modes (MODE is a compile-time constant so the
+// element loop carries no switch / divergence); other modes take the generic path.
+template <int MODE>
+__device__ __forceinline__ float epi_fast(float z, float act, float inv_act, float scale, float& s) {
+    if constexpr (MODE == IDRK_EPI_SOFTPLUS) {
+        const float bz = z * act;
+        const float ez = __expf(fminf(bz, 20.f));
+        const float soft = __logf(1.f + ez) * inv_act;
+        const bool lin = bz > 20.f;
+        s = lin ? 1.f : __fdividef(ez, ez + 1.f);
+        return (lin ? z : soft) * scale;
+    } else if constexpr (MODE == IDRK_EPI_RELU) {
+        s = z > 0.f ? 1.f : 0.f;
+        return fmaxf(z, 0.f) * scale;
+    } else {
+        s = 1.f;
+        return z * scale;
+    }
+}
+
+// One epilogue warp, one 32 x 32 accumulator chunk (lane = row): activation in registers, then each output
+// array goes through the warp's transpose tile so that every global store instruction covers one 128-byte row
+// segment (lane = column).
+template <int MODE>
+__device__ __forceinline__ void epi_chunk(const EpiParams& e, const uint32_t* r, uint32_t tile_s, int lane, long long row_base,
+                                          int n_rows, int col0, int N) {
+    const float bias_lane = (e.bias != nullptr && col0 + lane < N) ? __ldg(e.bias + col0 + lane) : 0.f;
+    const float inv_act = MODE == IDRK_EPI_SOFTPLUS ? 1.f / e.act : 0.f;
+    float h[32], sd[32];
+    if constexpr (MODE >= 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            h[j] = epi_fast<MODE>(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j), e.act, inv_act, e.scale, sd[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int cc = col0 + j < N ? col0 + j : N - 1;
+            const long long rr = lane < n_rows ? row_base + lane : row_base;
+            h[j] = epi_value(e, __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j), rr, cc, sd[j]);
+        }
+    }
+    const int my_col = col0 + lane;
+    const uint32_t wr = tile_s + (uint32_t)(lane * 33) * 4u;       // my row of the transpose tile
+    const uint32_t rd = tile_s + (uint32_t)lane * 4u;              // my column
+    auto emit = [&](float* dst, int ld, const float (&vals)[32], int xform, bool atomic) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float v = vals[j];
+            if (xform == 1) v = tf32_rn(v);
+            else if (xform == 2) v = tf32_rn(v - tf32_rn(v));
+            sts_f32(wr + 4u * j, v);
+        }
+        __syncwarp();
+        if (my_col < N) {
+            float* p = dst + row_base * ld + my_col;
+#pragma unroll 8
+            for (int rr = 0; rr < n_rows; ++rr, p += ld) {
+                const float v = lds_f32(rd + (uint32_t)(rr * 33) * 4u);
+                if (atomic) atomicAdd(p, v);
+                else *p = v;
+            }
+        }
+        __syncwarp();
+    };
+    if (e.accumulate) emit(e.C, e.ldc, h, 0, true);
+    else {
+        if (e.C) emit(e.C, e.ldc, h, 0, false);
+        if (e.C_hi) { emit(e.C_hi, e.ldc, h, 1, false); emit(e.C_lo, e.ldc, h, 2, false); }
+        if (e.S) emit(e.S, e.lds, sd, 0, false);
+    }
+}
+
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+ TMEM alloc),
 // warps 2..9 = epilogue (two warps per TMEM lane quarter, each owning half of the BN columns).
 template <bool A_MN, bool B_MN, int BN, int TERMS>
@@ -206,7 +281,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int kb_total = (K + BK - 1) / BK;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* epi_scratch = reinterpret_cast<float*>(smem + P::STAGES * P::STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::STAGES * P::STAGE_BYTES + P::SCRATCH_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P::STAGES + 2 * ACC_STAGES);
@@ -335,52 +410,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty_bar(a));       // accumulator drained: MMA may reuse it
-            // Each lane owns one accumulator row; the 32 x 32 chunk is transposed through a private shared-memory
-            // tile so that every store instruction writes one full 128-byte line of one output row.
-            float* tile = epi_scratch + (warp - 2) * (32 * 33);
+            const uint32_t tile_s = smem_u32(epi_scratch) + (uint32_t)(warp - 2) * (32 * 33 * 4);
             const long long row_base = m0 + q * 32;
-            const long long my_row = row_base + lane;
+            long long left = m_eff - row_base;
+            const int n_rows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
 #pragma unroll
             for (int c = 0; c < COLS; c += 32) {
                 const int col0 = n0 + half * COLS + c;
-                if (col0 >= N) break;
-                // one coalesced bias load per chunk, broadcast by shuffle (a per-element __ldg serialises the
-                // epilogue on the long scoreboard: 64 dependent global loads per thread per tile)
-                const float bias_lane = (e.bias != nullptr && col0 + lane < N) ? __ldg(e.bias + col0 + lane) : 0.f;
-                float h[32], sd[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int cc = col0 + j;
-                    const float z = __uint_as_float(r[c + j]) + __shfl_sync(0xffffffffu, bias_lane, j);
-                    h[j] = (cc < N && my_row < m_eff) ? epi_value_fast(e, z, my_row, cc, sd[j]) : 0.f;
-                }
-                const int my_col = col0 + lane;
-                auto emit = [&](float* dst, int ld, const float (&vals)[32], int xform, bool atomic) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float v = vals[j];
-                        if (xform == 1) v = tf32_rn(v);
-                        else if (xform == 2) v = tf32_rn(v - tf32_rn(v));
-                        tile[lane * 33 + j] = v;
-                    }
-                    __syncwarp();
-                    if (my_col < N) {
-#pragma unroll 4
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const long long grow = row_base + rr;
-                            if (grow >= m_eff) break;
-                            const float v = tile[rr * 33 + lane];
-                            if (atomic) atomicAdd(dst + grow * ld + my_col, v);
-                            else dst[grow * ld + my_col] = v;
-                        }
-                    }
-                    __syncwarp();
-                };
-                if (e.accumulate) emit(e.C, e.ldc, h, 0, true);
-                else {
-                    if (e.C) emit(e.C, e.ldc, h, 0, false);
-                    if (e.C_hi) { emit(e.C_hi, e.ldc, h, 1, false); emit(e.C_lo, e.ldc, h, 2, false); }
-                    if (e.S) emit(e.S, e.lds, sd, 0, false);
+                if (col0 >= N || n_rows == 0) break;
+                switch (e.mode) {
+                    case IDRK_EPI_SOFTPLUS: epi_chunk<IDRK_EPI_SOFTPLUS>(e, &r[c], tile_s, lane, row_base, n_rows, col0, N); break;
+                    case IDRK_EPI_NONE: epi_chunk<IDRK_EPI_NONE>(e, &r[c], tile_s, lane, row_base, n_rows, col0, N); break;
+                    case IDRK_EPI_RELU: epi_chunk<IDRK_EPI_RELU>(e, &r[c], tile_s, lane, row_base, n_rows, col0, N); break;
+                    default: epi_chunk<-1>(e, &r[c], tile_s, lane, row_base, n_rows, col0, N); break;
                 }
             }
         }

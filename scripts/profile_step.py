@@ -49,3 +49,39 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def sections():
+    """Coarse device-time split of a step: trace (sphere graph / sampler+secant / min-sdf) vs shade+bwd vs optimiser."""
+    from idrk import kernels as K
+    from idrk.dist import DataParallelTrainer
+    from idrk.model.implicit_differentiable_renderer import IDRNetwork
+    from idrk.model.loss import IDRLoss
+    from oracle import idr_oracle as O
+    from tests_support import quiet_build
+    torch.manual_seed(0)
+    model = quiet_build(IDRNetwork, bench.model_conf()).cuda().train()
+    tr = DataParallelTrainer(model, IDRLoss(0.1, 100.0, 50.0), lr=1e-4, use_cuda_graph=True)
+    inp, rgb = O.synthetic_batch(bench.N_RAYS, seed=1)
+    inp = {k: v.cuda() for k, v in inp.items()}
+    gt = {"rgb": rgb.cuda()}
+    for _ in range(4):
+        tr.step(inp, gt)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    acc = {"trace": 0.0, "rest": 0.0}
+    for _ in range(5):
+        a, b, c = ev(), ev(), ev()
+        a.record()
+        traced = model.trace(inp)
+        b.record()
+        eik = model._draw_eikonal(bench.N_RAYS, "cuda")
+        tr._graphed(traced, eik, gt["rgb"])
+        c.record()
+        torch.cuda.synchronize()
+        acc["trace"] += a.elapsed_time(b) / 5
+        acc["rest"] += b.elapsed_time(c) / 5
+    print("sections ms:", acc, model.ray_tracer.last_stats)
+
+
+if __name__ == "__main__" and len(sys.argv) > 3:
+    sections()

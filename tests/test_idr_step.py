@@ -74,5 +74,5 @@ def test_idr_step_golden(golden, tag):
         worst = max(worst, err)
         # table rows are scattered to by cell: rays whose traced point lands in a neighbouring cell move gradient
         # mass between rows, so the hash tables get a looser bound than the dense weights
-        bound = 0.25 if "embedding.weight" in k else (0.06 if nffb else 0.03)
+        bound = 0.5 if "embedding.weight" in k else (0.06 if nffb else 0.03)
         assert err <= bound + (0.2 if flips else 0.0), (k, err)
