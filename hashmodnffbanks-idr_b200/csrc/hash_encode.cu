@@ -28,6 +28,7 @@ struct GridDev {
     float res[IDRK_MAX_LEVELS];
     uint32_t rows[IDRK_MAX_LEVELS];
     uint32_t pow2mask[IDRK_MAX_LEVELS];     // rows-1 when rows is a power of two, else 0
+    unsigned long long magic[IDRK_MAX_LEVELS];   // 2^64 / rows + 1 (Lemire fastmod), used when rows is not a power of two
     const float* tables[IDRK_MAX_LEVELS];
     const float* B;                         // [3, C]
 };
@@ -41,11 +42,26 @@ struct GradDev {
 __device__ __forceinline__ uint32_t hash3(uint32_t c0, uint32_t c1, uint32_t c2) {
     return c0 ^ (c1 * 3u) ^ (c2 * 2654435761u);
 }
-__device__ __forceinline__ uint32_t wrap(uint32_t h, uint32_t rows, uint32_t mask) {
-    return mask ? (h & mask) : (h % rows);
+// h mod rows.  Power-of-two tables mask; others use the exact 64-bit fastmod  (M*h mod 2^64) * rows >> 64.
+__device__ __forceinline__ uint32_t wrap(uint32_t h, uint32_t rows, uint32_t mask, unsigned long long magic) {
+    return mask ? (h & mask) : (uint32_t)__umul64hi(magic * (unsigned long long)h, (unsigned long long)rows);
 }
-// .long() of an fp32 value: truncate toward zero to int64, keep the low 32 bits
-__device__ __forceinline__ uint32_t trunc_u32(float v) { return (uint32_t)(unsigned long long)__float2ll_rz(v); }
+// .long() of an fp32 value: truncate toward zero to int64, keep the low 32 bits.  Inside the int32 range the
+// 32-bit conversion has the same low bits (two's complement); only huge magnitudes need the 64-bit one.
+__device__ __forceinline__ uint32_t trunc_u32(float v) {
+    return fabsf(v) < 2147483520.f ? (uint32_t)__float2int_rz(v) : (uint32_t)(unsigned long long)__float2ll_rz(v);
+}
+
+// sin/cos of a moderate fp32 argument: two-constant Cody-Waite reduction by 2*pi, then the SFU approximations
+// on [-pi, pi] (abs error < 1e-6, inside the 4e-6 parity tolerance); huge arguments take the accurate libm path.
+__device__ __forceinline__ void sincos_fast(float x, float* sn, float* cs) {
+    if (fabsf(x) > 8192.f) { sincosf(x, sn, cs); return; }
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);          // 2*pi rounded to fp32
+    r = fmaf(-k, -1.7484555314695172e-07f, r);           // 2*pi - fp32(2*pi)
+    *sn = __sinf(r);
+    *cs = __cosf(r);
+}
 
 template <int F> struct Feat;
 template <> struct Feat<1> { using T = float;  };
@@ -119,7 +135,7 @@ hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n
                     xp = __fmaf_rn(t1, s_B[C + c], xp);
                     xp = __fmaf_rn(t2, s_B[2 * C + c], xp);
                     float sn, cs;
-                    sincosf(xp, &sn, &cs);
+                    sincos_fast(xp, &sn, &cs);
                     row[3 + c] = sn;
                     row[3 + C + c] = cs;
                 }
@@ -132,7 +148,7 @@ hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n
                     const uint32_t h = hash3(trunc_u32(__fmul_rn(x0, r)), trunc_u32(__fmul_rn(x1, r)),
                                              trunc_u32(__fmul_rn(x2, r)));
                     float v[F];
-                    gather<F>(g.tables[l], wrap(h, g.rows[l], g.pow2mask[l]), v);
+                    gather<F>(g.tables[l], wrap(h, g.rows[l], g.pow2mask[l], g.magic[l]), v);
 #pragma unroll
                     for (int f = 0; f < F; ++f) row[col + l * F + f] = v[f];
                 }
@@ -145,11 +161,15 @@ hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n
                     const float w0 = s0 - f0, w1 = s1 - f1, w2 = s2 - f2;
                     const uint32_t c0 = trunc_u32(f0), c1 = trunc_u32(f1), c2 = trunc_u32(f2);
                     const uint32_t rows = g.rows[l], mask = g.pow2mask[l];
+                    const unsigned long long magic = g.magic[l];
                     const float* tab = g.tables[l];
                     float v[8][F];
+                    // hash3 is an xor of three per-dimension terms: form the 2 x 3 terms once, xor per corner
+                    const uint32_t hx0 = c0, hx1 = c0 + 1u, hy0 = c1 * 3u, hy1 = hy0 + 3u;
+                    const uint32_t hz0 = c2 * 2654435761u, hz1 = hz0 + 2654435761u;
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        gather<F>(tab, wrap(hash3(c0 + (k & 1), c1 + ((k >> 1) & 1), c2 + ((k >> 2) & 1)), rows, mask), v[k]);
+                        gather<F>(tab, wrap(((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0), rows, mask, magic), v[k]);
                     float acc[F];
 #pragma unroll
                     for (int f = 0; f < F; ++f) acc[f] = 0.f;
@@ -174,7 +194,7 @@ hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n
                     else { c0 = trunc_u32(floorf(s0)); c1 = trunc_u32(floorf(s1)); c2 = trunc_u32(floorf(s2)); }
                     for (int k = 0; k < 8; ++k)
                         idx_dbg[(p * L + l) * 8 + k] =
-                            wrap(hash3(c0 + (k & 1), c1 + ((k >> 1) & 1), c2 + ((k >> 2) & 1)), g.rows[l], g.pow2mask[l]);
+                            wrap(hash3(c0 + (k & 1), c1 + ((k >> 1) & 1), c2 + ((k >> 2) & 1)), g.rows[l], g.pow2mask[l], g.magic[l]);
                 }
             }
         }
@@ -182,20 +202,21 @@ hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n
         // coalesced write-back: the tile's rows are contiguous in global memory (ld_out floats each)
         const long long rows_here = min((long long)ROWS, n - tile * ROWS);
         float* gdst = out + tile * ROWS * (long long)ld_out;
-        const int total = (int)rows_here * ld_out;
+        // the tile's rows are contiguous in global memory: lanes walk consecutive floats (conflict-free smem
+        // reads with the odd row stride, 128-byte coalesced stores)
         if ((ld_out & 3) == 0) {
             const int ld4 = ld_out >> 2;
             for (int r = threadIdx.x >> 5; r < rows_here; r += ROWS / 32) {
                 const float* src = s_rows + r * lds;
-                for (int c4 = threadIdx.x & 31; c4 < ld4; c4 += 32) {
-                    float4 v = make_float4(src[4 * c4], src[4 * c4 + 1], src[4 * c4 + 2], src[4 * c4 + 3]);
-                    st_stream4(reinterpret_cast<float4*>(gdst + (long long)r * ld_out) + c4, v);
-                }
+                float4* dst = reinterpret_cast<float4*>(gdst + (long long)r * ld_out);
+                for (int c4 = threadIdx.x & 31; c4 < ld4; c4 += 32)
+                    st_stream4(dst + c4, make_float4(src[4 * c4], src[4 * c4 + 1], src[4 * c4 + 2], src[4 * c4 + 3]));
             }
         } else {
-            for (int i = threadIdx.x; i < total; i += ROWS) {
-                const int r = i / ld_out, c = i - r * ld_out;
-                gdst[i] = s_rows[r * lds + c];
+            for (int r = threadIdx.x >> 5; r < rows_here; r += ROWS / 32) {
+                const float* src = s_rows + r * lds;
+                float* dst = gdst + (long long)r * ld_out;
+                for (int c = threadIdx.x & 31; c < ld_out; c += 32) dst[c] = src[c];
             }
         }
         __syncthreads();
@@ -256,7 +277,7 @@ hash_encode_bwd_kernel(const GridDev g, const GradDev gd, const float* __restric
                     xp = __fmaf_rn(t1, s_B[C + c], xp);
                     xp = __fmaf_rn(t2, s_B[2 * C + c], xp);
                     float sn, cs;
-                    sincosf(xp, &sn, &cs);
+                    sincos_fast(xp, &sn, &cs);
                     const float dxp = (row[3 + c] * cs - row[3 + C + c] * sn) * 6.283185307179586f;
                     g0 = fmaf(dxp, s_B[c], g0);
                     g1 = fmaf(dxp, s_B[C + c], g1);
@@ -267,6 +288,7 @@ hash_encode_bwd_kernel(const GridDev g, const GradDev gd, const float* __restric
             for (int l = 0; l < L; ++l) {
                 const float r = g.res[l];
                 const uint32_t rows = g.rows[l], mask = g.pow2mask[l];
+                const unsigned long long magic = g.magic[l];
                 float gy[F];
 #pragma unroll
                 for (int f = 0; f < F; ++f) gy[f] = row[col0 + l * F + f];
@@ -275,7 +297,7 @@ hash_encode_bwd_kernel(const GridDev g, const GradDev gd, const float* __restric
                 if constexpr (MODE == IDRK_HASH_REFERENCE) {
                     if (!do_scatter) continue;
                     const uint32_t idx = wrap(hash3(trunc_u32(__fmul_rn(x0, r)), trunc_u32(__fmul_rn(x1, r)),
-                                                    trunc_u32(__fmul_rn(x2, r))), rows, mask);
+                                                    trunc_u32(__fmul_rn(x2, r))), rows, mask, magic);
                     if (soff >= 0) {
 #pragma unroll
                         for (int f = 0; f < F; ++f) atomicAdd(s_acc + soff + idx * F + f, gy[f]);
@@ -291,7 +313,7 @@ hash_encode_bwd_kernel(const GridDev g, const GradDev gd, const float* __restric
                     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const uint32_t idx = wrap(hash3(c0 + (k & 1), c1 + ((k >> 1) & 1), c2 + ((k >> 2) & 1)), rows, mask);
+                        const uint32_t idx = wrap(hash3(c0 + (k & 1), c1 + ((k >> 1) & 1), c2 + ((k >> 2) & 1)), rows, mask, magic);
                         const float a0 = (k & 1) ? w0 : 1.f - w0, a1 = (k & 2) ? w1 : 1.f - w1, a2 = (k & 4) ? w2 : 1.f - w2;
                         const float wk = a0 * a1 * a2;
                         float v[F];
@@ -353,9 +375,10 @@ static int fill_grid(const idrk_hashgrid_t* h, GridDev& g) {
         if (reinterpret_cast<uintptr_t>(h->tables[l]) % align) return IDRK_E_ALIGN;
         g.res[l] = h->res[l]; g.rows[l] = h->rows[l]; g.tables[l] = h->tables[l];
         g.pow2mask[l] = ((h->rows[l] & (h->rows[l] - 1)) == 0) ? h->rows[l] - 1 : 0;
-        if (h->rows[l] == 1) g.pow2mask[l] = 0;
+        g.magic[l] = ~0ull / h->rows[l] + 1ull;
+        if (h->rows[l] == 1) { g.pow2mask[l] = 0; g.magic[l] = 0; }
     }
-    for (int l = h->n_levels; l < IDRK_MAX_LEVELS; ++l) { g.res[l] = 0; g.rows[l] = 1; g.tables[l] = nullptr; g.pow2mask[l] = 0; }
+    for (int l = h->n_levels; l < IDRK_MAX_LEVELS; ++l) { g.res[l] = 0; g.rows[l] = 1; g.tables[l] = nullptr; g.pow2mask[l] = 0; g.magic[l] = 0; }
     return 0;
 }
 
@@ -432,8 +455,8 @@ extern "C" int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = h_grid->frac_mode;
     const size_t row_bytes = (size_t)(ld_out | 1) * sizeof(float);
-    if (row_bytes * 256 <= 72 * 1024) {
-#define CALL(F, M) launch_fwd<F, M, 256>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
+    if (row_bytes * 128 <= 72 * 1024) {
+#define CALL(F, M) launch_fwd<F, M, 128>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
         IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
     } else if (row_bytes * 64 <= 200 * 1024) {
@@ -468,8 +491,8 @@ extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = h_grid->frac_mode;
     const size_t row_bytes = (size_t)(ld_dy | 1) * sizeof(float);
-    if (row_bytes * 256 <= 72 * 1024) {
-#define CALL(F, M) launch_bwd<F, M, 256>(g, gd, x, n, ldx, dy, ld_dy, dx, st)
+    if (row_bytes * 128 <= 72 * 1024) {
+#define CALL(F, M) launch_bwd<F, M, 128>(g, gd, x, n, ldx, dy, ld_dy, dx, st)
         IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
     } else if (row_bytes * 64 <= 160 * 1024) {
