@@ -254,6 +254,7 @@ def run_ours(args):
     # instrumented pass: device time and algorithmic FLOPs of the dominant kernel (the MLP contraction)
     K.PROFILE.reset(enabled=True)
     trainer.use_cuda_graph = False          # CUDA events cannot bracket kernels inside a replayed graph
+    model.ray_tracer.use_cuda_graph = False
     barrier()
     for _ in range(2):
         step_resident()
@@ -302,7 +303,9 @@ def run_ours(args):
                      "peak_source": "%s: 0.5 x sustained bf16 (TF32 rate)" % src,
                      "note": "algorithmic 2*M*N*K FLOPs of the launches (rows actually traced) / summed CUDA-event "
                              "time of those launches; 3xTF32 issues 3 MMAs per algorithmic MAC",
-                     "launches_per_step": g["calls"] // 2, "share_of_kernel_time": round(share, 3)},
+                     "launches_per_step": g["calls"] // 2, "share_of_idrk_kernel_time": round(share, 3),
+                     "measured_in": "an instrumented eager pass (2 steps) after the timed region: CUDA graphs off so that "
+                                    "events can bracket each launch"},
         "kernel_time_ms_per_step": {k: round(v["ms"] / 2, 3) for k, v in sorted(prof.items())},
         "cpu_baseline": {"value": 512 / cpu_dt, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": "1 full train step on 512 of the 2048 rays, oracle port of the reference's "

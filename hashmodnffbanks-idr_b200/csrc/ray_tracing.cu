@@ -163,8 +163,21 @@ __global__ void rt_select_sampler_kernel(RayState S, unsigned char* __restrict__
 }
 
 // sample points of slots [slot0, slot0 + n_slots): z = tmin + lin[j] * (tmax - tmin)   (:197-200)
+// n_dev (nullable): device-side number of valid slots; the chunk then covers slots [slot0, min(slot0 + n_slots, *n_dev))
+__device__ __forceinline__ int chunk_slots(int slot0, int n_slots, const int* n_dev) {
+    if (n_dev == nullptr) return n_slots;
+    const int left = *n_dev - slot0;
+    return left < 0 ? 0 : (left < n_slots ? left : n_slots);
+}
+
+__global__ void rt_chunk_counts_kernel(const int* __restrict__ n_dev, int per_chunk, int mult, int n_chunks, int* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_chunks) out[c] = chunk_slots(c * per_chunk, per_chunk, n_dev) * mult;
+}
+
 __global__ void rt_sampler_points_kernel(RayState S, const int* __restrict__ ray_of_slot, int slot0, int n_slots, int n_steps,
-                                         const float* __restrict__ lin, float* __restrict__ pts) {
+                                         const float* __restrict__ lin, float* __restrict__ pts, const int* __restrict__ n_dev) {
+    n_slots = chunk_slots(slot0, n_slots, n_dev);
     const long long total = (long long)n_slots * n_steps;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
         const int s = (int)(k / n_steps), j = (int)(k - (long long)s * n_steps);
@@ -183,9 +196,10 @@ __global__ void rt_sampler_resolve_kernel(RayState S, const int* __restrict__ ra
                                           const unsigned char* __restrict__ object_mask, int training,
                                           unsigned char* __restrict__ net_mask, float* __restrict__ z_lo, float* __restrict__ z_hi,
                                           float* __restrict__ s_lo, float* __restrict__ s_hi, int* __restrict__ sec_slots,
-                                          int* __restrict__ sec_counter) {
+                                          int* __restrict__ sec_counter, const int* __restrict__ n_dev) {
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    n_slots = chunk_slots(0, n_slots, n_dev);
     if (s >= n_slots) return;
     const int i = ray_of_slot[s];
     const float* v = vals + (long long)s * n_steps;
@@ -237,8 +251,10 @@ __device__ __forceinline__ float secant_pred(float s_lo, float s_hi, float z_lo,
 // 3 = write the initial prediction (n_secant_steps == 0)
 __global__ void rt_secant_kernel(RayState S, const int* __restrict__ ray_of_slot, const int* __restrict__ sec_slots, int n_sec,
                                  int mode, const float* __restrict__ vals, float* __restrict__ z_lo, float* __restrict__ z_hi,
-                                 float* __restrict__ s_lo, float* __restrict__ s_hi, float* __restrict__ pts) {
+                                 float* __restrict__ s_lo, float* __restrict__ s_hi, float* __restrict__ pts,
+                                 const int* __restrict__ n_dev) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    n_sec = chunk_slots(0, n_sec, n_dev);
     if (k >= n_sec) return;
     const int s = sec_slots[k];
     const int i = ray_of_slot[s];
@@ -286,7 +302,8 @@ __global__ void rt_select_minsdf_kernel(RayState S, const unsigned char* __restr
 
 // steps = u[j] * (max_dis - min_dis) + min_dis  (:277-286)
 __global__ void rt_minsdf_points_kernel(RayState S, const int* __restrict__ ray_of_slot, int slot0, int n_slots, int n_steps,
-                                        const float* __restrict__ u, float* __restrict__ pts) {
+                                        const float* __restrict__ u, float* __restrict__ pts, const int* __restrict__ n_dev) {
+    n_slots = chunk_slots(slot0, n_slots, n_dev);
     const long long total = (long long)n_slots * n_steps;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
         const int s = (int)(k / n_steps), j = (int)(k - (long long)s * n_steps);
@@ -298,9 +315,10 @@ __global__ void rt_minsdf_points_kernel(RayState S, const int* __restrict__ ray_
 }
 
 __global__ void rt_minsdf_resolve_kernel(RayState S, const int* __restrict__ ray_of_slot, int n_slots, int n_steps,
-                                         const float* __restrict__ u, const float* __restrict__ vals) {
+                                         const float* __restrict__ u, const float* __restrict__ vals, const int* __restrict__ n_dev) {
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    n_slots = chunk_slots(0, n_slots, n_dev);
     if (s >= n_slots) return;
     const int i = ray_of_slot[s];
     const float* v = vals + (long long)s * n_steps;
@@ -396,7 +414,7 @@ extern "C" int idrk_rt_select_sampler(const idrk_ray_state_t* h_state, uint8_t* 
 }
 
 extern "C" int idrk_rt_sampler_points(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t slot0, int32_t n_slots,
-                                      int32_t n_steps, const float* lin, float* pts, void* stream) {
+                                      int32_t n_steps, const float* lin, float* pts, const int32_t* n_dev, void* stream) {
     RT_PRELUDE();
     (void)blocks;
     if (!ray_of_slot || !lin || !pts || n_slots < 0 || n_steps < 1) return IDRK_E_ARG;
@@ -404,7 +422,7 @@ extern "C" int idrk_rt_sampler_points(const idrk_ray_state_t* h_state, const int
     long long b = ((long long)n_slots * n_steps + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
     if (b > cap) b = cap;
-    rt_sampler_points_kernel<<<(int)b, threads, 0, st>>>(S, ray_of_slot, slot0, n_slots, n_steps, lin, pts);
+    rt_sampler_points_kernel<<<(int)b, threads, 0, st>>>(S, ray_of_slot, slot0, n_slots, n_steps, lin, pts, n_dev);
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -412,27 +430,27 @@ extern "C" int idrk_rt_sampler_points(const idrk_ray_state_t* h_state, const int
 extern "C" int idrk_rt_sampler_resolve(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t n_slots, int32_t n_steps,
                                        const float* lin, const float* vals, const uint8_t* object_mask, int32_t training,
                                        uint8_t* net_mask, float* z_lo, float* z_hi, float* s_lo, float* s_hi,
-                                       int32_t* sec_slots, int32_t* sec_counter, void* stream) {
+                                       int32_t* sec_slots, int32_t* sec_counter, const int32_t* n_dev, void* stream) {
     RT_PRELUDE();
     (void)blocks;
     if (!ray_of_slot || !lin || !vals || !object_mask || !net_mask || !z_lo || !z_hi || !s_lo || !s_hi || !sec_slots || !sec_counter)
         return IDRK_E_ARG;
     if (n_slots <= 0) return 0;
     rt_sampler_resolve_kernel<<<(n_slots + 7) / 8, 256, 0, st>>>(S, ray_of_slot, n_slots, n_steps, lin, vals, object_mask, training,
-                                                                net_mask, z_lo, z_hi, s_lo, s_hi, sec_slots, sec_counter);
+                                                                net_mask, z_lo, z_hi, s_lo, s_hi, sec_slots, sec_counter, n_dev);
     IDRK_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int idrk_rt_secant(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, const int32_t* sec_slots, int32_t n_sec,
                               int32_t mode, const float* vals, float* z_lo, float* z_hi, float* s_lo, float* s_hi, float* pts,
-                              void* stream) {
+                              const int32_t* n_dev, void* stream) {
     RT_PRELUDE();
     (void)blocks;
     if (!ray_of_slot || !sec_slots || !z_lo || !z_hi || !s_lo || !s_hi || ((mode == 1 || mode == 2) && !vals) || (mode < 2 && !pts)) return IDRK_E_ARG;
     if (n_sec <= 0) return 0;
     rt_secant_kernel<<<(n_sec + threads - 1) / threads, threads, 0, st>>>(S, ray_of_slot, sec_slots, n_sec, mode, vals, z_lo, z_hi,
-                                                                       s_lo, s_hi, pts);
+                                                                       s_lo, s_hi, pts, n_dev);
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -448,7 +466,7 @@ extern "C" int idrk_rt_select_minsdf(const idrk_ray_state_t* h_state, const uint
 }
 
 extern "C" int idrk_rt_minsdf_points(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t slot0, int32_t n_slots,
-                                     int32_t n_steps, const float* u, float* pts, void* stream) {
+                                     int32_t n_steps, const float* u, float* pts, const int32_t* n_dev, void* stream) {
     RT_PRELUDE();
     (void)blocks;
     if (!ray_of_slot || !u || !pts || n_slots < 0 || n_steps < 1) return IDRK_E_ARG;
@@ -456,18 +474,26 @@ extern "C" int idrk_rt_minsdf_points(const idrk_ray_state_t* h_state, const int3
     long long b = ((long long)n_slots * n_steps + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
     if (b > cap) b = cap;
-    rt_minsdf_points_kernel<<<(int)b, threads, 0, st>>>(S, ray_of_slot, slot0, n_slots, n_steps, u, pts);
+    rt_minsdf_points_kernel<<<(int)b, threads, 0, st>>>(S, ray_of_slot, slot0, n_slots, n_steps, u, pts, n_dev);
     IDRK_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int idrk_rt_minsdf_resolve(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t n_slots, int32_t n_steps,
-                                      const float* u, const float* vals, void* stream) {
+                                      const float* u, const float* vals, const int32_t* n_dev, void* stream) {
     RT_PRELUDE();
     (void)blocks;
     if (!ray_of_slot || !u || !vals) return IDRK_E_ARG;
     if (n_slots <= 0) return 0;
-    rt_minsdf_resolve_kernel<<<(n_slots + 7) / 8, 256, 0, st>>>(S, ray_of_slot, n_slots, n_steps, u, vals);
+    rt_minsdf_resolve_kernel<<<(n_slots + 7) / 8, 256, 0, st>>>(S, ray_of_slot, n_slots, n_steps, u, vals, n_dev);
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_rt_chunk_counts(const int32_t* n_dev, int32_t per_chunk, int32_t mult, int32_t n_chunks, int32_t* out, void* stream) {
+    if (!n_dev || !out || per_chunk < 1 || mult < 1 || n_chunks < 0) return IDRK_E_ARG;
+    if (n_chunks == 0) return 0;
+    rt_chunk_counts_kernel<<<(n_chunks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_dev, per_chunk, mult, n_chunks, out);
     IDRK_LAUNCH_CHECK();
     return 0;
 }

@@ -117,9 +117,11 @@ class DataParallelTrainer:
                     self._shade_and_backward(*self._static)
             torch.cuda.current_stream().wait_stream(side)
             self._graph = torch.cuda.CUDAGraph()
+            l0 = K._lib.LAUNCHES[0]
             with torch.cuda.graph(self._graph):
                 losses = self._shade_and_backward(*self._static)
                 self._static_out = {k: v.detach() for k, v in losses.items()}
+            self._graph_launches = K._lib.LAUNCHES[0] - l0
             self._graph_key = key
         st_traced, st_eik, st_rgb = self._static
         for k, v in traced.items():
@@ -127,6 +129,7 @@ class DataParallelTrainer:
         st_eik.copy_(eik)
         st_rgb.copy_(rgb)
         self._graph.replay()
+        K._lib.LAUNCHES[0] += self._graph_launches          # idrk kernels inside the replayed graph
         return self._static_out
 
     def step(self, model_input, ground_truth) -> torch.Tensor:

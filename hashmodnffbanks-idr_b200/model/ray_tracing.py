@@ -94,8 +94,33 @@ class _TraceState:
                      "slot_s", "slot_e"):
             setattr(st, name, getattr(self, name).data_ptr())
         self.desc = st
-        self.graph = None
-        self.warm = False
+        self.graphs = {}
+        self.warm = set()
+        self._tail = None
+
+    def tail(self, ns):
+        """Static buffers of the device-driven sampler / secant / min-SDF phases (allocated on first use)."""
+        if self._tail is None or self._tail["ns"] != ns:
+            N, dev = self.N, self.dev
+            rpc = max(1, _SDF_CHUNK_POINTS // ns)
+            n_chunks = (N + rpc - 1) // rpc
+            zbuf = torch.empty(4 * N, device=dev, dtype=torch.float32)
+            self._tail = {
+                "ns": ns, "rpc": rpc, "n_chunks": n_chunks,
+                "obj_u8": torch.empty(N, device=dev, dtype=torch.uint8),
+                "sampler_mask": torch.empty(N, device=dev, dtype=torch.uint8),
+                "u": torch.empty(ns, device=dev, dtype=torch.float32),
+                "lin": torch.linspace(0, 1, steps=ns).to(dev),
+                "chunk_cnt": torch.zeros(n_chunks, device=dev, dtype=torch.int32),
+                "big_vals": torch.empty(N * ns, device=dev, dtype=torch.float32),
+                "cpts": torch.empty((rpc * ns, 3), device=dev, dtype=torch.float32),
+                "z": [zbuf[i * N:(i + 1) * N] for i in range(4)],
+                "sec_slots": torch.empty(N, device=dev, dtype=torch.int32),
+                "spts": torch.empty((N, 3), device=dev, dtype=torch.float32),
+                "svals": torch.empty(N, device=dev, dtype=torch.float32),
+                "counts": None,
+            }
+        return self._tail
 
     def new_counter(self):
         c = self.counters[self.cidx:self.cidx + 1]
@@ -114,7 +139,8 @@ class RayTracing(nn.Module):
         self.line_search_step = line_search_step
         self.n_steps = n_steps
         self.n_secant_steps = n_secant_steps
-        self.last_stats = {}
+        self._stats = {}
+        self._pending_counts = None
         self.injected_min_sdf_steps = None      # parity runs: the U(0,1) vector of reference :277
         self.use_cuda_graph = False             # replay the sphere-tracing launch sequence from a CUDA graph
         self._states = {}
@@ -148,6 +174,70 @@ class RayTracing(nn.Module):
             gate = T.new_counter()
             check(L.idrk_rt_top(S, None, 0, float(self.sdf_threshold), ptr(gate), sp), "idrk_rt_top")
 
+    def _tail_device(self, T, ev):
+        """Sampler + secant (+ min-SDF when training) with every list length kept on the device
+        (reference :41-59, :71-92, :189-298): a fixed launch sequence, no host reads."""
+        L = lib()
+        S = ctypes.byref(T.desc)
+        sp = stream_ptr()
+        ns = int(self.n_steps)
+        t = T.tail(ns)
+        N, rpc, n_chunks = T.N, t["rpc"], t["n_chunks"]
+        z_lo, z_hi, s_lo, s_hi = t["z"]
+        c_samp = T.new_counter()
+        check(L.idrk_rt_select_sampler(S, ptr(T.net_mask), ptr(T.ray_of_slot), ptr(c_samp), sp), "idrk_rt_select_sampler")
+        t["sampler_mask"].copy_(T.unf_s)
+        check(L.idrk_rt_chunk_counts(ptr(c_samp), rpc, ns, n_chunks, ptr(t["chunk_cnt"]), sp), "idrk_rt_chunk_counts")
+        for c in range(n_chunks):
+            check(L.idrk_rt_sampler_points(S, ptr(T.ray_of_slot), c * rpc, rpc, ns, ptr(t["lin"]), ptr(t["cpts"]),
+                                           ptr(c_samp), sp), "idrk_rt_sampler_points")
+            ev.on_device_count(t["cpts"], rpc * ns, t["chunk_cnt"][c:c + 1], t["big_vals"][c * rpc * ns:])
+        c_sec = T.new_counter()
+        check(L.idrk_rt_sampler_resolve(S, ptr(T.ray_of_slot), N, ns, ptr(t["lin"]), ptr(t["big_vals"]), ptr(t["obj_u8"]),
+                                        int(self.training), ptr(T.net_mask), ptr(z_lo), ptr(z_hi), ptr(s_lo), ptr(s_hi),
+                                        ptr(t["sec_slots"]), ptr(c_sec), ptr(c_samp), sp), "idrk_rt_sampler_resolve")
+
+        def secant(mode):
+            check(L.idrk_rt_secant(S, ptr(T.ray_of_slot), ptr(t["sec_slots"]), N, mode, ptr(t["svals"]), ptr(z_lo),
+                                   ptr(z_hi), ptr(s_lo), ptr(s_hi), ptr(t["spts"]), ptr(c_sec), sp), "idrk_rt_secant")
+        n_secant = int(self.n_secant_steps)
+        if n_secant == 0:
+            secant(3)
+        else:
+            secant(0)
+            for i in range(n_secant):
+                ev.on_device_count(t["spts"], N, c_sec, t["svals"])
+                secant(1 if i < n_secant - 1 else 2)
+        c_min = None
+        if self.training:
+            c_min = T.new_counter()
+            check(L.idrk_rt_select_minsdf(S, ptr(T.net_mask), ptr(t["obj_u8"]), ptr(T.hit_u8), ptr(t["sampler_mask"]),
+                                          ptr(T.ray_of_slot), ptr(c_min), sp), "idrk_rt_select_minsdf")
+            check(L.idrk_rt_chunk_counts(ptr(c_min), rpc, ns, n_chunks, ptr(t["chunk_cnt"]), sp), "idrk_rt_chunk_counts")
+            for c in range(n_chunks):
+                check(L.idrk_rt_minsdf_points(S, ptr(T.ray_of_slot), c * rpc, rpc, ns, ptr(t["u"]), ptr(t["cpts"]),
+                                              ptr(c_min), sp), "idrk_rt_minsdf_points")
+                ev.on_device_count(t["cpts"], rpc * ns, t["chunk_cnt"][c:c + 1], t["big_vals"][c * rpc * ns:])
+            check(L.idrk_rt_minsdf_resolve(S, ptr(T.ray_of_slot), N, ns, ptr(t["u"]), ptr(t["big_vals"]), ptr(c_min), sp),
+                  "idrk_rt_minsdf_resolve")
+        t["counts"] = (c_samp, c_sec, c_min)
+
+    def _trace_device(self, T, ev):
+        self._sphere_trace(T, ev)
+        self._tail_device(T, ev)
+
+    @property
+    def last_stats(self):
+        """Tracer statistics of the last call (reads the device counters lazily: one host sync when accessed)."""
+        st = dict(self._stats)
+        pend = self._pending_counts
+        if pend is not None:
+            c_samp, c_sec, c_min = pend
+            st.update({"n_sampler": int(c_samp.item()), "n_secant": int(c_sec.item())})
+            if c_min is not None:
+                st["n_minsdf"] = int(c_min.item())
+        return st
+
     def _state(self, B, P, dev):
         key = (B, P, str(dev), int(self.sphere_tracing_iters), int(self.line_step_iters))
         T = self._states.get(key)
@@ -179,23 +269,42 @@ class RayTracing(nn.Module):
             sp = stream_ptr()
             new_counter = T.new_counter
 
-            # ---- sphere tracing (reference :98-187) ------------------------------------------------
-            if self.use_cuda_graph and ev.fast:
-                if not T.warm:                       # first call: eager (allocations, lazy attribute setup)
-                    self._sphere_trace(T, ev)
-                    T.warm = True
+            if ev.fast:
+                # ---- fully device-driven trace: fixed launch sequence, optionally replayed from a CUDA graph ----
+                t = T.tail(int(self.n_steps))
+                t["obj_u8"].copy_(obj_u8)
+                if self.training:
+                    if min_sdf_steps is None:
+                        min_sdf_steps = self.injected_min_sdf_steps
+                    if min_sdf_steps is None:       # drawn on the host generator like the reference (:277)
+                        min_sdf_steps = torch.empty(int(self.n_steps)).uniform_(0.0, 1.0)
+                    t["u"].copy_(min_sdf_steps.to(dev, non_blocking=True).float())
+                key = bool(self.training)
+                if not self.use_cuda_graph:
+                    self._trace_device(T, ev)
+                elif key not in T.warm:              # first call: eager (allocations, lazy attribute setup)
+                    self._trace_device(T, ev)
+                    T.warm.add(key)
                 else:
-                    if T.graph is None:
+                    if key not in T.graphs:
                         torch.cuda.synchronize()
-                        T.graph = torch.cuda.CUDAGraph()
+                        graph = torch.cuda.CUDAGraph()
                         ev.owner.refresh_inference_weights()
-                        with torch.cuda.graph(T.graph):
+                        l0 = K._lib.LAUNCHES[0]
+                        with torch.cuda.graph(graph):
                             ev.owner.refresh_inference_weights(force=True)   # weight folding is part of the graph
-                            self._sphere_trace(T, ev)
-                    T.graph.replay()
-                    T.cidx = T.counters.numel() - 8
-            else:
-                self._sphere_trace(T, ev)
+                            self._trace_device(T, ev)
+                        T.graphs[key] = (graph, K._lib.LAUNCHES[0] - l0, ev.calls)
+                    graph, n_launches, n_calls = T.graphs[key]
+                    graph.replay()
+                    K._lib.LAUNCHES[0] += n_launches            # kernels launched by the replayed graph
+                    ev.calls = n_calls
+                self._stats = {"sdf_calls": ev.calls, "fast_path": True, "cuda_graph": bool(self.use_cuda_graph)}
+                self._pending_counts = t["counts"]
+                return ps.clone(), net_mask.bool().clone(), t0.clone()
+
+            # ---- generic callable: host reads the list lengths and calls sdf(points[:n]) -------------------------
+            self._sphere_trace(T, ev)
 
             # ---- sampler + secant for the non-convergent rays (:41-59, :189-268) ------------------------
             c_samp = new_counter()
@@ -211,7 +320,7 @@ class RayTracing(nn.Module):
                 cpts = torch.empty((min(n_samp, rays_per_chunk) * ns, 3), device=dev, dtype=torch.float32)
                 for s0 in range(0, n_samp, rays_per_chunk):
                     m = min(rays_per_chunk, n_samp - s0)
-                    check(L.idrk_rt_sampler_points(S, ptr(ray_of_slot), s0, m, ns, ptr(lin), ptr(cpts), sp),
+                    check(L.idrk_rt_sampler_points(S, ptr(ray_of_slot), s0, m, ns, ptr(lin), ptr(cpts), None, sp),
                           "idrk_rt_sampler_points")
                     ev.on_host_count(cpts, m * ns, big_vals[s0 * ns:(s0 + m) * ns])
                 zbuf = torch.empty(4 * n_samp, device=dev, dtype=torch.float32)
@@ -220,7 +329,7 @@ class RayTracing(nn.Module):
                 c_sec = new_counter()
                 check(L.idrk_rt_sampler_resolve(S, ptr(ray_of_slot), n_samp, ns, ptr(lin), ptr(big_vals), ptr(obj_u8),
                                                 int(self.training), ptr(net_mask), ptr(z_lo), ptr(z_hi), ptr(s_lo),
-                                                ptr(s_hi), ptr(sec_slots), ptr(c_sec), sp), "idrk_rt_sampler_resolve")
+                                                ptr(s_hi), ptr(sec_slots), ptr(c_sec), None, sp), "idrk_rt_sampler_resolve")
                 n_sec = int(c_sec.item())
                 if n_sec > 0:
                     spts = torch.empty((n_sec, 3), device=dev, dtype=torch.float32)
@@ -229,7 +338,7 @@ class RayTracing(nn.Module):
 
                     def secant(mode):
                         check(L.idrk_rt_secant(S, ptr(ray_of_slot), ptr(sec_slots), n_sec, mode, ptr(svals), ptr(z_lo),
-                                               ptr(z_hi), ptr(s_lo), ptr(s_hi), ptr(spts), sp), "idrk_rt_secant")
+                                               ptr(z_hi), ptr(s_lo), ptr(s_hi), ptr(spts), None, sp), "idrk_rt_secant")
                     if nsec_steps == 0:
                         secant(3)
                     else:
@@ -238,7 +347,8 @@ class RayTracing(nn.Module):
                             ev.on_host_count(spts, n_sec, svals)
                             secant(1 if i < nsec_steps - 1 else 2)
 
-            self.last_stats = {"sdf_calls": ev.calls, "n_sampler": n_samp, "n_secant": n_sec, "fast_path": ev.fast}
+            self._stats = {"sdf_calls": ev.calls, "n_sampler": n_samp, "n_secant": n_sec, "fast_path": ev.fast}
+            self._pending_counts = None
             net_mask_b = net_mask.bool()
             if not self.training:
                 return ps.clone(), net_mask_b.clone(), t0.clone()
@@ -260,10 +370,10 @@ class RayTracing(nn.Module):
                 cpts = torch.empty((min(n_min, rays_per_chunk) * ns, 3), device=dev, dtype=torch.float32)
                 for s0 in range(0, n_min, rays_per_chunk):
                     m = min(rays_per_chunk, n_min - s0)
-                    check(L.idrk_rt_minsdf_points(S, ptr(ray_of_slot), s0, m, ns, ptr(u), ptr(cpts), sp),
+                    check(L.idrk_rt_minsdf_points(S, ptr(ray_of_slot), s0, m, ns, ptr(u), ptr(cpts), None, sp),
                           "idrk_rt_minsdf_points")
                     ev.on_host_count(cpts, m * ns, big_vals[s0 * ns:(s0 + m) * ns])
-                check(L.idrk_rt_minsdf_resolve(S, ptr(ray_of_slot), n_min, ns, ptr(u), ptr(big_vals), sp),
+                check(L.idrk_rt_minsdf_resolve(S, ptr(ray_of_slot), n_min, ns, ptr(u), ptr(big_vals), None, sp),
                       "idrk_rt_minsdf_resolve")
-            self.last_stats.update({"sdf_calls": ev.calls, "n_minsdf": n_min})
+            self._stats.update({"sdf_calls": ev.calls, "n_minsdf": n_min})
             return ps.clone(), net_mask_b.clone(), t0.clone()

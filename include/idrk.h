@@ -177,23 +177,27 @@ int idrk_rt_linesearch(const idrk_ray_state_t* h_state, const int32_t* gate, con
 int idrk_rt_end(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, int32_t gather_mode, void* stream);
 int idrk_rt_select_sampler(const idrk_ray_state_t* h_state, uint8_t* net_mask, int32_t* ray_of_slot, int32_t* counter,
                            void* stream);
+/* n_dev (nullable, device int32): when given, the number of valid slots is min(host bound, *n_dev) so the caller
+ * needs no host read of the list length; idrk_rt_chunk_counts writes, per chunk c of `per_chunk` slots,
+ * out[c] = mult * clamp(*n_dev - c * per_chunk, 0, per_chunk)  (row limits for the SDF kernels). */
+int idrk_rt_chunk_counts(const int32_t* n_dev, int32_t per_chunk, int32_t mult, int32_t n_chunks, int32_t* out, void* stream);
 int idrk_rt_sampler_points(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t slot0, int32_t n_slots,
-                           int32_t n_steps, const float* lin, float* pts, void* stream);
+                           int32_t n_steps, const float* lin, float* pts, const int32_t* n_dev, void* stream);
 int idrk_rt_sampler_resolve(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t n_slots, int32_t n_steps,
                             const float* lin, const float* vals, const uint8_t* object_mask, int32_t training,
                             uint8_t* net_mask, float* z_lo, float* z_hi, float* s_lo, float* s_hi,
-                            int32_t* sec_slots, int32_t* sec_counter, void* stream);
+                            int32_t* sec_slots, int32_t* sec_counter, const int32_t* n_dev, void* stream);
 /* mode 0: emit first prediction, 1: consume sdf + emit next, 2: consume + write result, 3: write initial prediction */
 int idrk_rt_secant(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, const int32_t* sec_slots, int32_t n_sec,
                    int32_t mode, const float* vals, float* z_lo, float* z_hi, float* s_lo, float* s_hi, float* pts,
-                   void* stream);
+                   const int32_t* n_dev, void* stream);
 int idrk_rt_select_minsdf(const idrk_ray_state_t* h_state, const uint8_t* net_mask, const uint8_t* object_mask,
                           const uint8_t* hit, const uint8_t* sampler_mask, int32_t* ray_of_slot, int32_t* counter,
                           void* stream);
 int idrk_rt_minsdf_points(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t slot0, int32_t n_slots,
-                          int32_t n_steps, const float* u, float* pts, void* stream);
+                          int32_t n_steps, const float* u, float* pts, const int32_t* n_dev, void* stream);
 int idrk_rt_minsdf_resolve(const idrk_ray_state_t* h_state, const int32_t* ray_of_slot, int32_t n_slots, int32_t n_steps,
-                           const float* u, const float* vals, void* stream);
+                           const float* u, const float* vals, const int32_t* n_dev, void* stream);
 
 /* -- K6: optimiser step on the flat bucket ------------------------------------------------
  * Replaces clip_grad_norm_(params, max_norm) + torch.optim.Adam.step() of idr_train.py:306-308 for
