@@ -86,7 +86,11 @@ class _Proxy:
                     s.record()
                     rc = _raw(*args)
                     e.record()
-                    PROFILE.records.append((_name + (tag or "") if PROFILE.detail else _name, s, e, flops))
+                    if PROFILE.detail:
+                        key = _name + (tag or "")
+                    else:
+                        key = _name + "_2cta" if (tag or "").startswith("_2cta") else _name
+                    PROFILE.records.append((key, s, e, flops))
                 else:
                     rc = _raw(*args)
                 if rc == 0:

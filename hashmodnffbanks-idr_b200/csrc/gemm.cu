@@ -16,6 +16,7 @@
 // K-major operands use the canonical K-major SW128 smem layout, MN-major operands SW128 with a 32-byte base
 // (cute/atom/mma_traits_sm100.hpp make_umma_desc documents both), so no transposes are ever materialised.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace idrk {
@@ -164,12 +165,12 @@ struct SmemPlan {
     static constexpr int STAGE_BYTES = (TERMS == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
     static constexpr int BUDGET = 200 * 1024;
     static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
-    static constexpr int SCRATCH_BYTES = 8 * 32 * 33 * 4;   // per-epilogue-warp transpose tile [32][33] floats
+    static constexpr int SCRATCH_BYTES = 0;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + SCRATCH_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 constexpr int ACC_STAGES = 2;                  // TMEM accumulator double buffer: epilogue(i) overlaps mainloop(i+1)
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;                 // 4 TMEM lane quarters x 4 column groups
 constexpr int GEMM_THREADS_V2 = 64 + 32 * EPI_WARPS;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -189,8 +190,38 @@ __device__ __forceinline__ float epi_value_fast(const EpiParams& e, float z, lon
     return epi_value(e, z, row, col, s);
 }
 
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
+// tcgen05.ld 16x256b: thread t of the warp receives, per 8-column block i, the accumulator values
+//   regs[4i+0..1] = row (t/4),     cols 8i + 2(t%4) + {0,1}
+//   regs[4i+2..3] = row (t/4) + 8, same columns
+// (cute/atom/copy_traits_sm100.hpp SM100_TMEM_LOAD_16dp256b8x).  Four neighbouring threads therefore hold 8
+// consecutive floats of one row: a float2 store per thread writes complete 32-byte sectors without any
+// shared-memory transposition, and every thread needs only its own 2 bias columns per block.
+__device__ __forceinline__ void tc_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Branch-free per-element epilogue for the hot activation modes (MODE is a compile-time constant so the
 // element loop carries no switch / divergence); other modes take the generic path.
@@ -212,55 +243,71 @@ __device__ __forceinline__ float epi_fast(float z, float act, float inv_act, flo
     }
 }
 
-// One epilogue warp, one 32 x 32 accumulator chunk (lane = row): activation in registers, then each output
-// array goes through the warp's transpose tile so that every global store instruction covers one 128-byte row
-// segment (lane = column).
-template <int MODE>
-__device__ __forceinline__ void epi_chunk(const EpiParams& e, const uint32_t* r, uint32_t tile_s, int lane, long long row_base,
-                                          int n_rows, int col0, int N) {
-    const float bias_lane = (e.bias != nullptr && col0 + lane < N) ? __ldg(e.bias + col0 + lane) : 0.f;
-    const float inv_act = MODE == IDRK_EPI_SOFTPLUS ? 1.f / e.act : 0.f;
-    float h[32], sd[32];
-    if constexpr (MODE >= 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            h[j] = epi_fast<MODE>(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j), e.act, inv_act, e.scale, sd[j]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int cc = col0 + j < N ? col0 + j : N - 1;
-            const long long rr = lane < n_rows ? row_base + lane : row_base;
-            h[j] = epi_value(e, __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bias_lane, j), rr, cc, sd[j]);
-        }
+// two consecutive columns of one row -> every enabled output array
+__device__ __forceinline__ void epi_store2(const EpiParams& e, long long row, int col, int N, float v0, float v1, float s0, float s1) {
+    const long long o = row * e.ldc + col;
+    const bool both = col + 1 < N;
+    if (e.accumulate) {
+        atomicAdd(e.C + o, v0);
+        if (both) atomicAdd(e.C + o + 1, v1);
+        return;
     }
-    const int my_col = col0 + lane;
-    const uint32_t wr = tile_s + (uint32_t)(lane * 33) * 4u;       // my row of the transpose tile
-    const uint32_t rd = tile_s + (uint32_t)lane * 4u;              // my column
-    auto emit = [&](float* dst, int ld, const float (&vals)[32], int xform, bool atomic) {
+    if (both) {
+        if (e.C) *reinterpret_cast<float2*>(e.C + o) = make_float2(v0, v1);
+        if (e.C_hi) {
+            const float h0 = tf32_rn(v0), h1 = tf32_rn(v1);
+            *reinterpret_cast<float2*>(e.C_hi + o) = make_float2(h0, h1);
+            *reinterpret_cast<float2*>(e.C_lo + o) = make_float2(tf32_rn(v0 - h0), tf32_rn(v1 - h1));
+        }
+        if (e.S) *reinterpret_cast<float2*>(e.S + row * e.lds + col) = make_float2(s0, s1);
+    } else {
+        if (e.C) e.C[o] = v0;
+        if (e.C_hi) { const float h0 = tf32_rn(v0); e.C_hi[o] = h0; e.C_lo[o] = tf32_rn(v0 - h0); }
+        if (e.S) e.S[row * e.lds + col] = s0;
+    }
+}
+
+// NB 8-column blocks of a 16-row half (rows row0 + g and row0 + g + 8, g = lane / 4)
+template <int MODE, int NB>
+__device__ __forceinline__ void epi_frag(const EpiParams& e, const uint32_t* r, int lane, long long row0, long long m_eff,
+                                         int col0, int N) {
+    const int t = lane & 3, g = lane >> 2;
+    const long long ra = row0 + g, rb = ra + 8;
+    const bool va = ra < m_eff, vb = rb < m_eff;
+    const float inv_act = MODE == IDRK_EPI_SOFTPLUS ? 1.f / e.act : 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float v = vals[j];
-            if (xform == 1) v = tf32_rn(v);
-            else if (xform == 2) v = tf32_rn(v - tf32_rn(v));
-            sts_f32(wr + 4u * j, v);
+    for (int i = 0; i < NB; ++i) {
+        const int col = col0 + 8 * i + 2 * t;
+        if (col >= N) continue;
+        float b0 = 0.f, b1 = 0.f;
+        if (e.bias != nullptr) { b0 = __ldg(e.bias + col); b1 = (col + 1 < N) ? __ldg(e.bias + col + 1) : 0.f; }
+        float v[4], sd[4];
+        if constexpr (MODE >= 0) {
+            v[0] = epi_fast<MODE>(__uint_as_float(r[4 * i + 0]) + b0, e.act, inv_act, e.scale, sd[0]);
+            v[1] = epi_fast<MODE>(__uint_as_float(r[4 * i + 1]) + b1, e.act, inv_act, e.scale, sd[1]);
+            v[2] = epi_fast<MODE>(__uint_as_float(r[4 * i + 2]) + b0, e.act, inv_act, e.scale, sd[2]);
+            v[3] = epi_fast<MODE>(__uint_as_float(r[4 * i + 3]) + b1, e.act, inv_act, e.scale, sd[3]);
+        } else {
+            const int c1 = col + 1 < N ? col + 1 : col;
+            const long long qa = va ? ra : row0, qb = vb ? rb : row0;
+            v[0] = epi_value(e, __uint_as_float(r[4 * i + 0]) + b0, qa, col, sd[0]);
+            v[1] = epi_value(e, __uint_as_float(r[4 * i + 1]) + b1, qa, c1, sd[1]);
+            v[2] = epi_value(e, __uint_as_float(r[4 * i + 2]) + b0, qb, col, sd[2]);
+            v[3] = epi_value(e, __uint_as_float(r[4 * i + 3]) + b1, qb, c1, sd[3]);
         }
-        __syncwarp();
-        if (my_col < N) {
-            float* p = dst + row_base * ld + my_col;
-#pragma unroll 8
-            for (int rr = 0; rr < n_rows; ++rr, p += ld) {
-                const float v = lds_f32(rd + (uint32_t)(rr * 33) * 4u);
-                if (atomic) atomicAdd(p, v);
-                else *p = v;
-            }
-        }
-        __syncwarp();
-    };
-    if (e.accumulate) emit(e.C, e.ldc, h, 0, true);
-    else {
-        if (e.C) emit(e.C, e.ldc, h, 0, false);
-        if (e.C_hi) { emit(e.C_hi, e.ldc, h, 1, false); emit(e.C_lo, e.ldc, h, 2, false); }
-        if (e.S) emit(e.S, e.lds, sd, 0, false);
+        if (va) epi_store2(e, ra, col, N, v[0], v[1], sd[0], sd[1]);
+        if (vb) epi_store2(e, rb, col, N, v[2], v[3], sd[2], sd[3]);
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void epi_frag_dispatch(const EpiParams& e, const uint32_t* r, int lane, long long row0, long long m_eff,
+                                                  int col0, int N) {
+    switch (e.mode) {
+        case IDRK_EPI_SOFTPLUS: epi_frag<IDRK_EPI_SOFTPLUS, NB>(e, r, lane, row0, m_eff, col0, N); break;
+        case IDRK_EPI_NONE: epi_frag<IDRK_EPI_NONE, NB>(e, r, lane, row0, m_eff, col0, N); break;
+        case IDRK_EPI_RELU: epi_frag<IDRK_EPI_RELU, NB>(e, r, lane, row0, m_eff, col0, N); break;
+        default: epi_frag<-1, NB>(e, r, lane, row0, m_eff, col0, N); break;
     }
 }
 
@@ -282,7 +329,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* epi_scratch = reinterpret_cast<float*>(smem + P::STAGES * P::STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::STAGES * P::STAGE_BYTES + P::SCRATCH_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P::STAGES + 2 * ACC_STAGES);
     const uint32_t smem_base = smem_u32(smem);
@@ -394,8 +440,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;               // which half of the BN columns
-        constexpr int COLS = BN / 2;
+        const int half = (warp - 2) >> 2;               // which quarter of the BN columns
+        constexpr int COLS = BN / 4;                    // 32 or 16 columns per epilogue warp
+        constexpr int NB = COLS / 8;
         int ti = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
             long long m0; int n0, kb0, kb1;
@@ -403,27 +450,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int a = ti & 1;
             mbar_wait(acc_full_bar(a), (ti >> 1) & 1);
             tc_fence_after();
-            uint32_t r[COLS];
+            uint32_t ra[4 * NB], rb[4 * NB];            // rows +0..15 and +16..31 of this warp's quarter
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + half * COLS);
-#pragma unroll
-            for (int c = 0; c < COLS; c += 32) tc_ld32(taddr + c, *reinterpret_cast<uint32_t(*)[32]>(&r[c]));
+            if constexpr (NB == 4) { tc_ld_16x256b_x4(taddr, ra); tc_ld_16x256b_x4(taddr + (16u << 16), rb); }
+            else { tc_ld_16x256b_x2(taddr, ra); tc_ld_16x256b_x2(taddr + (16u << 16), rb); }
+            tc_wait_ld();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty_bar(a));       // accumulator drained: MMA may reuse it
-            const uint32_t tile_s = smem_u32(epi_scratch) + (uint32_t)(warp - 2) * (32 * 33 * 4);
             const long long row_base = m0 + q * 32;
-            long long left = m_eff - row_base;
-            const int n_rows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
-#pragma unroll
-            for (int c = 0; c < COLS; c += 32) {
-                const int col0 = n0 + half * COLS + c;
-                if (col0 >= N || n_rows == 0) break;
-                switch (e.mode) {
-                    case IDRK_EPI_SOFTPLUS: epi_chunk<IDRK_EPI_SOFTPLUS>(e, &r[c], tile_s, lane, row_base, n_rows, col0, N); break;
-                    case IDRK_EPI_NONE: epi_chunk<IDRK_EPI_NONE>(e, &r[c], tile_s, lane, row_base, n_rows, col0, N); break;
-                    case IDRK_EPI_RELU: epi_chunk<IDRK_EPI_RELU>(e, &r[c], tile_s, lane, row_base, n_rows, col0, N); break;
-                    default: epi_chunk<-1>(e, &r[c], tile_s, lane, row_base, n_rows, col0, N); break;
-                }
+            const int col0 = n0 + half * COLS;
+            if (col0 < N && row_base < m_eff) {
+                epi_frag_dispatch<NB>(e, ra, lane, row_base, m_eff, col0, N);
+                epi_frag_dispatch<NB>(e, rb, lane, row_base + 16, m_eff, col0, N);
             }
         }
     }
@@ -431,6 +470,201 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(ACC_STAGES * BN)) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256 x 256 output tile per cluster of two CTAs.  Each CTA stages its own
+// 128 rows of A and HALF of the B tile (128 of the 256 columns); the leader CTA issues tcgen05.mma.cta_group::2,
+// which reads both CTAs' shared memory, so every SM ingests half the B bytes per FLOP of the single-CTA kernel
+// (3xTF32 with fp32 hi/lo operands is bound by L2->SM operand traffic, not by the tensor pipe).  Each CTA keeps
+// its 128 x 256 accumulator half in its own TMEM and runs the same epilogue.  NT layout (forward / inference).
+// ------------------------------------------------------------------------------------------
+constexpr int BN2 = 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(dst), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar_cluster) : "memory");
+}
+
+template <int TERMS>
+struct SmemPlan2 {
+    static constexpr int A_BYTES = BM * BK * 4;                 // this CTA's 128 rows
+    static constexpr int B_BYTES = (BN2 / 2) * BK * 4;          // this CTA's half of the B tile
+    static constexpr int STAGE_BYTES = (TERMS == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = TERMS == 3 ? 3 : 6;
+    static constexpr int SCRATCH_BYTES = 0;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + SCRATCH_BYTES + 1024 + 256;
+};
+
+template <int TERMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS_V2, 1)
+gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                      long long M, int N, int K, EpiParams e, const int* __restrict__ m_count) {
+    using P = SmemPlan2<TERMS>;
+    long long m_eff = M;
+    if (m_count != nullptr) { const long long c = *m_count; m_eff = c < M ? c : M; }
+    const int m_tiles = (int)((m_eff + 2 * BM - 1) / (2 * BM));
+    const int n_tiles = (N + BN2 - 1) / BN2;
+    const int items = m_tiles * n_tiles;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    if (pair >= items) return;                                   // uniform for both CTAs of the cluster
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int kb_total = (K + BK - 1) / BK;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::STAGES * P::STAGE_BYTES + P::SCRATCH_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P::STAGES + 2 * ACC_STAGES);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (P::STAGES + s); };
+    auto acc_full_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + a); };
+    auto acc_empty_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + ACC_STAGES + a); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(acc_full_bar(a), 1); mbar_init(acc_empty_bar(a), 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)(ACC_STAGES * BN2)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                          // peer barriers initialised before any remote signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int item, long long& m0, int& n0) {
+        n0 = (item % n_tiles) * BN2;
+        m0 = (long long)(item / n_tiles) * (2 * BM) + (long long)rank * BM;     // this CTA's 128 rows
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int item = pair; item < items; item += n_pairs) {
+                long long m0; int n0;
+                decode(item, m0, n0);
+                const int nb = n0 + (int)rank * (BN2 / 2);       // this CTA's half of the B columns
+                for (int kb = 0; kb < kb_total; ++kb, ++it) {
+                    const int s = it % P::STAGES;
+                    const uint32_t ph = (it / P::STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (leader) mbar_expect_tx(full_bar(s), 2 * P::STAGE_BYTES);    // bytes of both CTAs
+                    const uint32_t fb = mapa_cluster(full_bar(s), 0);               // the leader's barrier
+                    const uint32_t st = smem_base + s * P::STAGE_BYTES;
+                    const int k0 = kb * BK;
+#pragma unroll
+                    for (int t = 0; t < (TERMS == 3 ? 2 : 1); ++t) {
+                        const uint32_t sA = st + t * (P::A_BYTES + P::B_BYTES);
+                        const uint32_t sB = sA + P::A_BYTES;
+                        tma_load_2d_2sm(sA, t ? &tmAlo : &tmA, fb, k0, (int)m0);
+                        tma_load_2d_2sm(sB, t ? &tmBlo : &tmB, fb, k0, nb);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            // instruction shape M = 256 (both CTAs), N = 256, K = 8, K-major tf32 operands, f32 accumulate
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            int it = 0, ti = 0;
+            for (int item = pair; item < items; item += n_pairs, ++ti) {
+                const int a = ti & 1;
+                mbar_wait(acc_empty_bar(a), ((ti >> 1) & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN2);
+                for (int kb = 0; kb < kb_total; ++kb, ++it) {
+                    const int s = it % P::STAGES;
+                    const uint32_t ph = (it / P::STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + s * P::STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc(st, 16, 1024, 2);
+                    const uint64_t b_hi = umma_desc(st + P::A_BYTES, 16, 1024, 2);
+                    const uint64_t a_lo = umma_desc(st + P::A_BYTES + P::B_BYTES, 16, 1024, 2);
+                    const uint64_t b_lo = umma_desc(st + 2 * P::A_BYTES + P::B_BYTES, 16, 1024, 2);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        if constexpr (TERMS == 3) {
+                            tc_mma_tf32_2sm(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, acc);
+                            tc_mma_tf32_2sm(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                            tc_mma_tf32_2sm(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                        } else {
+                            tc_mma_tf32_2sm(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, acc);
+                        }
+                    }
+                    tc_commit_2sm(empty_bar(s));                 // frees the stage in BOTH CTAs
+                }
+                tc_commit_2sm(acc_full_bar(a));                  // accumulator ready in BOTH CTAs
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int COLS = BN2 / 4;                            // 64 columns per epilogue warp
+        int ti = 0;
+        for (int item = pair; item < items; item += n_pairs, ++ti) {
+            long long m0; int n0;
+            decode(item, m0, n0);
+            const int a = ti & 1;
+            mbar_wait(acc_full_bar(a), (ti >> 1) & 1);
+            tc_fence_after();
+            const long long row_base = m0 + q * 32;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN2 + half * COLS);
+            const int col0 = n0 + half * COLS;
+            const bool live = col0 < N && row_base < m_eff;
+#pragma unroll 1
+            for (int hrow = 0; hrow < 2; ++hrow) {               // rows +0..15, then +16..31 (keeps registers < 96)
+                uint32_t r[32];
+                tc_ld_16x256b_x8(taddr + ((uint32_t)(16 * hrow) << 16), r);
+                tc_wait_ld();
+                if (hrow == 1) {                                 // last TMEM read of this tile: release the accumulator
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_cluster(acc_empty_bar(a), 0));
+                }
+                if (live) epi_frag_dispatch<8>(e, r, lane, row_base + 16 * hrow, m_eff, col0, N);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                          // the peer's smem / barriers stay alive until both are done
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(ACC_STAGES * BN2)) : "memory");
     }
 }
 
@@ -558,6 +792,30 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtens
     return 0;
 }
 
+template <int TERMS>
+static int launch_2cta(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
+                       long long M, int N, int K, const EpiParams& e, const int* m_count, cudaStream_t st) {
+    using P = SmemPlan2<TERMS>;
+    auto kern = gemm_tf32_2cta_kernel<TERMS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        IDRK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL));
+        attr_done = true;
+    }
+    const long long items = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2);
+    long long pairs = sm_count() / 2;
+    if (pairs > items) pairs = items;
+    kern<<<(unsigned)(2 * pairs), GEMM_THREADS_V2, P::TOTAL, st>>>(tA, tAl, tB, tBl, M, N, K, e, m_count);
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+static bool use_2cta() {
+    static int v = -1;
+    if (v < 0) { const char* s = getenv("IDRK_GEMM_2CTA"); v = (s == nullptr || s[0] != '0') ? 1 : 0; }
+    return v == 1;
+}
+
 }  // namespace idrk
 
 using namespace idrk;
@@ -597,6 +855,19 @@ extern "C" int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N
 
     const int terms = precision == IDRK_PREC_3XTF32 ? 3 : 1;
     if (terms == 3 && (!A_lo || !B_lo)) return IDRK_E_ARG;
+    if (layout == IDRK_GEMM_NT && M >= 8192 && N >= 256 && split_k == 1 && use_2cta()) {
+        // large forward / inference batches: CTA-pair kernel (256 x 256 tiles, half the B ingress per SM)
+        CUtensorMap tA, tAl, tB, tBl;
+        int rc;
+        if ((rc = make_tmap(&tA, A, (uint64_t)K, (uint64_t)M, lda, BM))) return rc;
+        if ((rc = make_tmap(&tB, B, (uint64_t)K, (uint64_t)N, ldb, BN2 / 2))) return rc;
+        if (terms == 3) {
+            if ((rc = make_tmap(&tAl, A_lo, (uint64_t)K, (uint64_t)M, lda, BM))) return rc;
+            if ((rc = make_tmap(&tBl, B_lo, (uint64_t)K, (uint64_t)N, ldb, BN2 / 2))) return rc;
+            return launch_2cta<3>(tA, tAl, tB, tBl, M, N, K, e, m_count, st);
+        }
+        return launch_2cta<1>(tA, tA, tB, tB, M, N, K, e, m_count, st);
+    }
     const int bn = (N <= 64 || M <= 4096) ? 64 : 128;      // small row counts: more, shorter tiles
     CUtensorMap tA, tAl, tB, tBl;
     int rc;

@@ -26,7 +26,11 @@ from .. import kernels as K
 from .._lib import RayStateDesc, check, lib, ptr, stream_ptr
 from ..utils import rend_util
 
-_SDF_CHUNK_POINTS = 32768          # points per SDF call in the sampler / min-SDF sweeps
+import os as _os
+
+# points per SDF call in the sampler / min-SDF sweeps: small enough that a layer's input + output operand pairs
+# (2 x rows x 512 x 8 B) stay resident in the 126 MB L2 instead of round-tripping through HBM
+_SDF_CHUNK_POINTS = int(_os.environ.get("IDRK_SDF_CHUNK", "32768"))
 
 
 class _Evaluator:

@@ -110,3 +110,31 @@ def test_weight_norm_and_helpers():
     rho = (1 / beta) * (0.5 + 0.5 * s.sign() * torch.expm1(-s.abs() / beta))
     assert torch.allclose(sq, torch.tanh(s / (2 + rho)), atol=1e-6)
     assert torch.allclose(d, (1 - sq * sq) / (2 + rho), atol=1e-6)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "3xtf32"])
+@pytest.mark.parametrize("shape", [(8192, 512, 512), (20000, 445, 67), (33000, 257, 512), (9000, 512, 40)])
+def test_gemm_cta_pair_kernel(prec, shape):
+    """Large NT launches take the cta_group::2 kernel (256 x 256 tiles per CTA pair)."""
+    M, N, Kc = shape
+    C, ref, mag = _run(0, prec, M, N, Kc)
+    err = ((C.double() - ref).abs() / (mag + 1e-30)).max().item()
+    assert err < TOL[prec], err
+
+
+def test_gemm_cta_pair_epilogue_and_count():
+    from idrk import kernels as K
+    M, N, Kc = 16384, 512, 512
+    A, W, b = _mk((M, Kc), 15) * 0.05, _mk((N, Kc), 16) * 0.05, _mk((N,), 17) * 0.01
+    Au, A_lo = K.split_tf32(A)
+    Wu, W_lo = K.split_tf32(W)
+    Hh, Hl = K.empty_padded(M, N, DEV), K.empty_padded(M, N, DEV)
+    Hh.fill_(-3.0)
+    Hl.zero_()
+    cnt = torch.tensor([9001], device=DEV, dtype=torch.int32)
+    K.gemm(K.GEMM_NT, Au, Wu, M, N, Kc, precision=K.PREC_3XTF32, A_lo=A_lo, B_lo=W_lo, C_hi=Hh, C_lo=Hl, bias=b,
+           mode=K.EPI_SOFTPLUS, act=100.0, scale=0.70710678, m_count=cnt)
+    z = (A[:9001].double() @ W.double().t() + b.double())
+    ref = torch.nn.functional.softplus(z, beta=100) * 0.70710678
+    assert torch.allclose((Hh + Hl)[:9001].double(), ref, atol=1e-6, rtol=1e-5)
+    assert (Hh[9216:] == -3.0).all()            # rows of tiles entirely beyond the count are untouched
