@@ -106,7 +106,7 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_rt_init", "idrk_rt_top", "idrk_rt_step", "idrk_rt_linesearch", "idrk_rt_end",
            "idrk_rt_select_sampler", "idrk_rt_sampler_points", "idrk_rt_sampler_resolve", "idrk_rt_secant",
            "idrk_rt_select_minsdf", "idrk_rt_minsdf_points", "idrk_rt_minsdf_resolve", "idrk_rt_chunk_counts",
-           "idrk_sumsq", "idrk_clip_adam"]
+           "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd"]
 
 
 class RayStateDesc(ctypes.Structure):
@@ -179,6 +179,7 @@ def _declare(L):
     L.idrk_rt_select_minsdf.argtypes = [rs, vp, vp, vp, vp, vp, vp, vp]
     L.idrk_rt_minsdf_points.argtypes = [rs, vp, i32, i32, i32, vp, vp, vp, vp]
     L.idrk_rt_minsdf_resolve.argtypes = [rs, vp, i32, i32, vp, vp, vp, vp]
+    L.idrk_act_bwd.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, i32, vp]
     L.idrk_sumsq.argtypes = [vp, i64, vp, vp]
     L.idrk_clip_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp, f32, vp]
     for fn in EXPORTS:

@@ -135,6 +135,32 @@ __global__ void sdf_squash_kernel(const float* __restrict__ s, long long n, floa
     }
 }
 
+// backward of H = scale * act(Z), S = act'(Z):  dZ = dH * S * scale + dS * act''(Z), also written as a 3xTF32 operand pair
+__global__ void act_bwd_kernel(const float* __restrict__ dH, int ld_dh, const float* __restrict__ dS, int ld_ds,
+                               const float* __restrict__ S, int ld_s, const float* __restrict__ H, int ld_h,
+                               long long rows, int cols, int mode, float act, float scale,
+                               float* __restrict__ dZ, float* __restrict__ hi, float* __restrict__ lo, int ld_out) {
+    const long long total = rows * (long long)ld_out;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / ld_out;
+        const int c = (int)(i - r * ld_out);
+        float v = 0.f;
+        if (c < cols) {
+            const float s = S[r * ld_s + c];
+            if (dH) v = dH[r * ld_dh + c] * s * scale;
+            if (dS) {
+                float s2 = 0.f;
+                if (mode == IDRK_EPI_SOFTPLUS) s2 = act * s * (1.f - s);
+                else if (mode == IDRK_EPI_SINE) s2 = -(act * act) * H[r * ld_h + c] / scale;
+                else if (mode == IDRK_EPI_TANH) s2 = -2.f * H[r * ld_h + c] * s / scale;
+                v = fmaf(dS[r * ld_ds + c], s2, v);
+            }
+        }
+        dZ[i] = v;
+        if (hi) { const float h = tf32_round(v); hi[i] = h; lo[i] = tf32_round(v - h); }
+    }
+}
+
 static inline int ew_blocks(long long total, int threads) {
     long long b = (total + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
@@ -179,9 +205,9 @@ extern "C" int idrk_weight_norm_bwd(const float* g, const float* v, const float*
 extern "C" int idrk_colsum(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* out, void* stream) {
     if (!x || !out || rows < 0 || cols < 1 || ldx < cols) return IDRK_E_ARG;
     if (rows == 0) return 0;
-    long long ysplit = rows / 512;
+    long long ysplit = rows / 64;                 // ~8 rows per thread: enough CTAs to cover the SMs
     if (ysplit < 1) ysplit = 1;
-    if (ysplit > 64) ysplit = 64;
+    if (ysplit > 128) ysplit = 128;
     dim3 grid((cols + 31) / 32, (unsigned)ysplit);
     colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, out);
     IDRK_LAUNCH_CHECK();
@@ -204,6 +230,19 @@ extern "C" int idrk_sdf_squash(const float* s, int64_t n, float beta, float* out
     if (!s || !out || n < 0 || !(beta > 0.f)) return IDRK_E_ARG;
     if (n == 0) return 0;
     sdf_squash_kernel<<<ew_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(s, n, beta, out, dout);
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_act_bwd(const float* dH, int32_t ld_dh, const float* dS, int32_t ld_ds, const float* S, int32_t ld_s,
+                            const float* H, int32_t ld_h, int64_t rows, int32_t cols, int32_t mode, float act, float scale,
+                            float* dZ, float* dZ_hi, float* dZ_lo, int32_t ld_out, void* stream) {
+    if (!S || !dZ || (!dH && !dS) || rows < 0 || cols < 1 || ld_out < cols || ld_s < cols) return IDRK_E_ARG;
+    if ((dZ_hi == nullptr) != (dZ_lo == nullptr)) return IDRK_E_ARG;
+    if (dS && (mode == IDRK_EPI_SINE || mode == IDRK_EPI_TANH) && !H) return IDRK_E_ARG;
+    if (rows == 0) return 0;
+    act_bwd_kernel<<<ew_blocks(rows * (long long)ld_out, 256), 256, 0, (cudaStream_t)stream>>>(
+        dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, dZ_hi, dZ_lo, ld_out);
     IDRK_LAUNCH_CHECK();
     return 0;
 }

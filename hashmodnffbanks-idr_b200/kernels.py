@@ -304,3 +304,22 @@ def sumsq(g: torch.Tensor, out: torch.Tensor):
 def clip_adam(p, g, m, v, lr, beta1, beta2, eps, step, max_norm, sumsq_buf, grad_scale):
     check(lib().idrk_clip_adam(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
                                int(step), float(max_norm), ptr(sumsq_buf), float(grad_scale), stream_ptr()), "idrk_clip_adam")
+
+
+def act_bwd(dH, dS, S, H, mode: int, act: float, scale: float, want_split: bool):
+    """dZ = dH * S * scale + dS * act''(Z) (+ its hi/lo operand pair)."""
+    S = rows2d(S, "S")
+    rows, cols = S.shape
+    dev = S.device
+    dZ = empty_padded(rows, cols, dev)
+    hi = empty_padded(rows, cols, dev) if want_split else None
+    lo = empty_padded(rows, cols, dev) if want_split else None
+    if rows == 0:
+        return dZ, hi, lo
+    dH = rows2d(dH, "dH") if dH is not None else None
+    dS = rows2d(dS, "dS") if dS is not None else None
+    H = rows2d(H, "H") if H is not None else None
+    check(lib().idrk_act_bwd(ptr(dH), ld_of(dH) if dH is not None else 0, ptr(dS), ld_of(dS) if dS is not None else 0,
+                             ptr(S), ld_of(S), ptr(H), ld_of(H) if H is not None else 0, rows, cols, mode, float(act),
+                             float(scale), ptr(dZ), ptr(hi), ptr(lo), pad4(cols), stream_ptr()), "idrk_act_bwd")
+    return dZ, hi, lo

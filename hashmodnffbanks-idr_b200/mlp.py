@@ -240,6 +240,17 @@ class _LinearAct(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dH, dS):
         X, W, H, S = ctx.saved_tensors
+        if dH is None and dS is None:
+            return None, None, None, None, None, None
+        if not torch.is_grad_enabled():
+            # plain (first-order) backward: one fused kernel forms dZ and its 3xTF32 operand pair
+            dZ, hi, lo = K.act_bwd(dH, dS if ctx.mode != "relu" else None, S, H, _ACT_MODES[ctx.mode], ctx.act, ctx.scale,
+                                   _three_pass()) if (dH is not None or ctx.mode != "relu") else (None, None, None)
+            if dZ is None:
+                return None, None, None, None, None, None
+            if hi is not None:
+                tag_split(dZ, hi, lo)
+            return (*_layer_backward(ctx, dZ, X, W), None, None, None)
         dZ = None
         if dH is not None:
             dZ = dH * S if ctx.scale == 1.0 else dH * (S * ctx.scale)
@@ -289,11 +300,34 @@ def weight_norm(g, v):
     return _WeightNorm.apply(g, v)
 
 
+_WEIGHT_SCOPE = []      # stack of per-step caches opened by `shared_weights()`
+
+
+class shared_weights:
+    """Within this context every layer's effective weight W = g v / ||v|| is computed ONCE and shared by all
+    forward calls (IDRNetwork.shade evaluates the implicit network three times per step): autograd sums the
+    weight gradients of all uses and runs the weight-norm backward once."""
+
+    def __enter__(self):
+        _WEIGHT_SCOPE.append({})
+        return self
+
+    def __exit__(self, *exc):
+        _WEIGHT_SCOPE.pop()
+        return False
+
+
 def layer_weight(lin: torch.nn.Module) -> torch.Tensor:
     """Effective weight of a (possibly weight-normalised) nn.Linear, differentiable."""
-    if hasattr(lin, "weight_g"):
-        return weight_norm(lin.weight_g, lin.weight_v)
-    return lin.weight
+    if not hasattr(lin, "weight_g"):
+        return lin.weight
+    if _WEIGHT_SCOPE and torch.is_grad_enabled():
+        cache = _WEIGHT_SCOPE[-1]
+        W = cache.get(id(lin))
+        if W is None:
+            W = cache[id(lin)] = weight_norm(lin.weight_g, lin.weight_v)
+        return W
+    return weight_norm(lin.weight_g, lin.weight_v)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -92,9 +92,7 @@ class ImplicitNetwork(nn.Module):
 
     def supports_device_count(self) -> bool:
         """True when the encoder can take its row count from device memory (no host sync in the tracer)."""
-        if self.embed_fn is None:
-            return True
-        return getattr(self.embed_model, "embed_type", None) == "HashGrid"
+        return True
 
     @torch.no_grad()
     def sdf_compacted(self, pts: torch.Tensor, rows: int, m_count, out: torch.Tensor) -> None:
@@ -108,8 +106,9 @@ class ImplicitNetwork(nn.Module):
             emb = pipe._buf("emb", rows, grid.embeddings_dim, pts.device)
             K.hash_encode_fwd(grid.spec(), pts, grid.tables(), grid.freq_encoding.B, out=emb, m_count=m_count, rows=rows)
         else:
-            if m_count is not None:
-                raise K._lib.IdrkError("this encoder needs a host-side row count")
+            # filter-bank / positional encoders: evaluated on the whole (fixed-capacity) buffer with their module
+            # kernels - rows beyond the device-side count hold stale points and are never consumed - so the call
+            # sequence stays free of host syncs and can live in a CUDA graph
             emb = K.operand(self._embed(pts[:rows]))
         pipe.run(emb, rows, want="sdf", m_count=m_count, out=out)
 
@@ -246,6 +245,10 @@ class IDRNetwork(nn.Module):
 
     def shade(self, traced, eikonal_points=None):
         """Differentiable part of the forward (reference :262-319) given the traced distances."""
+        with mlp.shared_weights():
+            return self._shade(traced, eikonal_points)
+
+    def _shade(self, traced, eikonal_points=None):
         ray_dirs, cam_loc, dists = traced["ray_dirs"], traced["cam_loc"], traced["dists"]
         network_object_mask, object_mask = traced["network_object_mask"], traced["object_mask"]
         batch_size, num_pixels, _ = ray_dirs.shape

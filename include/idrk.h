@@ -147,6 +147,12 @@ int idrk_colsum(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* 
 int idrk_sdf_head(const float* h, int64_t rows, int32_t K, int32_t ldh, const float* w, const float* bias,
                   float beta, float* out, const int32_t* m_count, void* stream);
 int idrk_sdf_squash(const float* s, int64_t n, float beta, float* out, float* dout, void* stream);
+/* idrk_act_bwd: backward of the fused activation epilogue H = scale * act(Z), S = act'(Z) (autograd of the
+ * Softplus / ReLU / Sine / Tanh layers):  dZ = dH * S * scale + dS * act''(Z)  (dH or dS may be NULL); dZ is also
+ * written as a 3xTF32 operand pair when dZ_hi / dZ_lo are given.  Columns [cols, ld_out) are zero-filled. */
+int idrk_act_bwd(const float* dH, int32_t ld_dh, const float* dS, int32_t ld_ds, const float* S, int32_t ld_s,
+                 const float* H, int32_t ld_h, int64_t rows, int32_t cols, int32_t mode, float act, float scale,
+                 float* dZ, float* dZ_hi, float* dZ_lo, int32_t ld_out, void* stream);
 
 /* -- K5: ray-state kernels of RayTracing ----------------------------------------------------
  * Replace model/ray_tracing.py (forward :26-95, sphere_tracing :98-187, ray_sampler :189-249,
