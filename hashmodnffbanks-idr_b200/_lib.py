@@ -106,7 +106,14 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_rt_init", "idrk_rt_top", "idrk_rt_step", "idrk_rt_linesearch", "idrk_rt_end",
            "idrk_rt_select_sampler", "idrk_rt_sampler_points", "idrk_rt_sampler_resolve", "idrk_rt_secant",
            "idrk_rt_select_minsdf", "idrk_rt_minsdf_points", "idrk_rt_minsdf_resolve", "idrk_rt_chunk_counts",
-           "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd"]
+           "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd", "idrk_gemm_f16s", "idrk_split_f16"]
+
+
+class EpilogueH(ctypes.Structure):
+    """Mirror of idrk_epilogue_f16_t."""
+    _fields_ = [("C", ctypes.c_void_p), ("C_h", ctypes.c_void_p), ("C_l", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+                ("ldc", ctypes.c_int32), ("ldh", ctypes.c_int32), ("mode", ctypes.c_int32),
+                ("act_param", ctypes.c_float), ("scale", ctypes.c_float)]
 
 
 class RayStateDesc(ctypes.Structure):
@@ -180,6 +187,8 @@ def _declare(L):
     L.idrk_rt_minsdf_points.argtypes = [rs, vp, i32, i32, i32, vp, vp, vp, vp]
     L.idrk_rt_minsdf_resolve.argtypes = [rs, vp, i32, i32, vp, vp, vp, vp]
     L.idrk_act_bwd.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, i32, vp]
+    L.idrk_gemm_f16s.argtypes = [i64, i32, i32, vp, vp, i32, vp, vp, i32, c.POINTER(EpilogueH), vp, vp]
+    L.idrk_split_f16.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp]
     L.idrk_sumsq.argtypes = [vp, i64, vp, vp]
     L.idrk_clip_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp, f32, vp]
     for fn in EXPORTS:

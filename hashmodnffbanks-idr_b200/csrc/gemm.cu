@@ -16,6 +16,7 @@
 // K-major operands use the canonical K-major SW128 smem layout, MN-major operands SW128 with a 32-byte base
 // (cute/atom/mma_traits_sm100.hpp make_umma_desc documents both), so no transposes are ever materialised.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include "common.cuh"
 
@@ -669,6 +670,239 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------
+// FP16-pair variant for the no-grad SDF path ("fp16x2"): every operand is stored as two halves
+//     x ~= h + l * 2^-11,   h = fp16(x),  l = fp16((x - h) * 2^11)        (relative error ~2^-22, like 3xTF32)
+// so it is 4 bytes per element instead of the 8 of the TF32 hi/lo pair, and the three product terms run on the
+// kind::f16 pipe at twice the TF32 rate:   D0 += Ah.Bh,   D1 += Ah.Bl + Al.Bh,   result = D0 + 2^-11 * D1
+// (two TMEM accumulators per tile; the scaled low halves stay in fp16's normal range).  Valid where magnitudes are
+// benign (|x| < 65504: weights, embeddings and softplus activations of the SDF network), i.e. inference only.
+// NT layout, 128 x 128 tiles, BK = 64 halves (128-byte swizzle rows), same warp roles as gemm_tf32_kernel.
+// ------------------------------------------------------------------------------------------
+
+constexpr int BKH = 64;
+constexpr int BNH = 128;
+constexpr float F16S_SCALE = 2048.f;
+
+struct EpiParamsH {
+    float* C; __half* C_h; __half* C_l;
+    const float* bias;
+    int ldc, ldh;
+    int mode; float act; float scale;
+};
+
+struct SmemPlanH {
+    static constexpr int A_BYTES = BM * BKH * 2;
+    static constexpr int B_BYTES = BNH * BKH * 2;
+    static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = 3;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_frag_h(const EpiParamsH& e, const uint32_t* r0, const uint32_t* r1, int lane, long long row0,
+                                           long long m_eff, int col0, int N) {
+    constexpr int NB = 4;
+    const int t = lane & 3, g = lane >> 2;
+    const long long ra = row0 + g, rb = ra + 8;
+    const bool va = ra < m_eff, vb = rb < m_eff;
+    const float inv_act = MODE == IDRK_EPI_SOFTPLUS ? 1.f / e.act : 0.f;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const int col = col0 + 8 * i + 2 * t;
+        if (col >= N) continue;
+        const bool both = col + 1 < N;
+        float b0 = 0.f, b1 = 0.f;
+        if (e.bias != nullptr) { b0 = __ldg(e.bias + col); b1 = both ? __ldg(e.bias + col + 1) : 0.f; }
+        float v[4], sd;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float z = fmaf(__uint_as_float(r1[4 * i + k]), 1.f / F16S_SCALE, __uint_as_float(r0[4 * i + k])) + ((k & 1) ? b1 : b0);
+            v[k] = epi_fast<MODE>(z, e.act, inv_act, e.scale, sd);
+        }
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const long long row = hrow ? rb : ra;
+            if (!(hrow ? vb : va)) continue;
+            const float x0 = v[2 * hrow], x1 = v[2 * hrow + 1];
+            if (e.C) {
+                if (both) *reinterpret_cast<float2*>(e.C + row * e.ldc + col) = make_float2(x0, x1);
+                else e.C[row * e.ldc + col] = x0;
+            }
+            if (e.C_h) {
+                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                const __half l0 = __float2half_rn((x0 - __half2float(h0)) * F16S_SCALE);
+                const __half l1 = __float2half_rn((x1 - __half2float(h1)) * F16S_SCALE);
+                const long long o = row * e.ldh + col;
+                if (both) {
+                    *reinterpret_cast<__half2*>(e.C_h + o) = __halves2half2(h0, h1);
+                    *reinterpret_cast<__half2*>(e.C_l + o) = __halves2half2(l0, l1);
+                } else { e.C_h[o] = h0; e.C_l[o] = l0; }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS_V2, 1)
+gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl,
+                 long long M, int N, int K, EpiParamsH e, const int* __restrict__ m_count) {
+    using P = SmemPlanH;
+    long long m_eff = M;
+    if (m_count != nullptr) { const long long c = *m_count; m_eff = c < M ? c : M; }
+    const int m_tiles = (int)((m_eff + BM - 1) / BM);
+    const int n_tiles = (N + BNH - 1) / BNH;
+    const int items = m_tiles * n_tiles;
+    if ((int)blockIdx.x >= items) return;
+    const int kb_total = (K + BKH - 1) / BKH;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::STAGES * P::STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P::STAGES + 2 * ACC_STAGES);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (P::STAGES + s); };
+    auto acc_full_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + a); };
+    auto acc_empty_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + ACC_STAGES + a); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(acc_full_bar(a), 1); mbar_init(acc_empty_bar(a), EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    constexpr uint32_t TMEM_COLS = ACC_STAGES * 2 * BNH;         // two accumulators (D0, D1) per stage = 512 columns
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int n0 = (item % n_tiles) * BNH;
+                const int m0 = (item / n_tiles) * BM;
+                for (int kb = 0; kb < kb_total; ++kb, ++it) {
+                    const int s = it % P::STAGES;
+                    const uint32_t ph = (it / P::STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), P::STAGE_BYTES);
+                    const uint32_t st = smem_base + s * P::STAGE_BYTES;
+                    const int k0 = kb * BKH;
+                    tma_load_2d(st, &tmA, full_bar(s), k0, m0);
+                    tma_load_2d(st + P::A_BYTES, &tmB, full_bar(s), k0, n0);
+                    tma_load_2d(st + P::A_BYTES + P::B_BYTES, &tmAl, full_bar(s), k0, m0);
+                    tma_load_2d(st + 2 * P::A_BYTES + P::B_BYTES, &tmBl, full_bar(s), k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // kind::f16: A, B fp16 (format 0), f32 accumulate, K-major, M = 128, N = 128, K = 16 per instruction
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BNH >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int it = 0, ti = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
+                const int a = ti & 1;
+                mbar_wait(acc_empty_bar(a), ((ti >> 1) & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(a * 2 * BNH);
+                const uint32_t d1 = d0 + BNH;
+                for (int kb = 0; kb < kb_total; ++kb, ++it) {
+                    const int s = it % P::STAGES;
+                    const uint32_t ph = (it / P::STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + s * P::STAGE_BYTES;
+                    const uint64_t a_h = umma_desc(st, 16, 1024, 2);
+                    const uint64_t b_h = umma_desc(st + P::A_BYTES, 16, 1024, 2);
+                    const uint64_t a_l = umma_desc(st + P::A_BYTES + P::B_BYTES, 16, 1024, 2);
+                    const uint64_t b_l = umma_desc(st + 2 * P::A_BYTES + P::B_BYTES, 16, 1024, 2);
+#pragma unroll
+                    for (int k = 0; k < BKH / 16; ++k) {
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        tc_mma_f16(d0, a_h + 2 * k, b_h + 2 * k, idesc, acc);
+                        tc_mma_f16(d1, a_h + 2 * k, b_l + 2 * k, idesc, acc);
+                        tc_mma_f16(d1, a_l + 2 * k, b_h + 2 * k, idesc, 1u);
+                    }
+                    tc_commit(empty_bar(s));
+                }
+                tc_commit(acc_full_bar(a));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;                        // 32-column group of this warp
+        int ti = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
+            const int n0 = (item % n_tiles) * BNH;
+            const long long m0 = (long long)(item / n_tiles) * BM;
+            const int a = ti & 1;
+            mbar_wait(acc_full_bar(a), (ti >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 2 * BNH + grp * 32);
+            uint32_t a0[16], a1[16], b0[16], b1[16];            // D0 / D1 fragments of rows +0..15 and +16..31
+            tc_ld_16x256b_x4(t0, a0);
+            tc_ld_16x256b_x4(t0 + BNH, a1);
+            tc_ld_16x256b_x4(t0 + (16u << 16), b0);
+            tc_ld_16x256b_x4(t0 + (16u << 16) + BNH, b1);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty_bar(a));
+            const long long row_base = m0 + q * 32;
+            const int col0 = n0 + grp * 32;
+            if (col0 >= N || row_base >= m_eff) continue;
+            if (e.mode == IDRK_EPI_SOFTPLUS) {
+                epi_frag_h<IDRK_EPI_SOFTPLUS>(e, a0, a1, lane, row_base, m_eff, col0, N);
+                epi_frag_h<IDRK_EPI_SOFTPLUS>(e, b0, b1, lane, row_base + 16, m_eff, col0, N);
+            } else {
+                epi_frag_h<IDRK_EPI_NONE>(e, a0, a1, lane, row_base, m_eff, col0, N);
+                epi_frag_h<IDRK_EPI_NONE>(e, b0, b1, lane, row_base + 16, m_eff, col0, N);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+__global__ void split_f16_kernel(const float* __restrict__ x, long long rows, int cols, int ldx, float scale,
+                                 __half* __restrict__ h, __half* __restrict__ l, int ldo, int pad_cols, const int* __restrict__ m_count) {
+    long long r_eff = rows;
+    if (m_count) { const long long c = *m_count; r_eff = c < rows ? c : rows; }
+    const int w = cols + pad_cols;
+    const long long total = r_eff * (long long)w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / w;
+        const int c = (int)(i - r * w);
+        __half hv = __float2half_rn(0.f), lv = hv;
+        if (c < cols) {
+            const float v = fminf(fmaxf(x[r * ldx + c] * scale, -65504.f), 65504.f);
+            hv = __float2half_rn(v);
+            lv = __float2half_rn((v - __half2float(hv)) * F16S_SCALE);
+        }
+        h[r * ldo + c] = hv;
+        l[r * ldo + c] = lv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // plain fp32 FFMA tiles: exact-fp32 mode (parity debugging, tiny shapes) - same epilogue
 // ------------------------------------------------------------------------------------------
 template <int TM, int TN>
@@ -792,6 +1026,20 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtens
     return 0;
 }
 
+static int make_tmap_h(CUtensorMap* tm, const void* base, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return IDRK_E_DRIVER;
+    if (!aligned16(base) || (ld & 7)) return IDRK_E_ALIGN;
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : IDRK_E_ARG;
+}
+
 template <int TERMS>
 static int launch_2cta(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
                        long long M, int N, int K, const EpiParams& e, const int* m_count, cudaStream_t st) {
@@ -890,4 +1138,47 @@ extern "C" int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N
     if (layout == IDRK_GEMM_NN) IDRK_TC(false, true);
     IDRK_TC(true, true);
 #undef IDRK_TC
+}
+
+extern "C" int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, const void* A_l, int32_t lda,
+                              const void* B_h, const void* B_l, int32_t ldb, const idrk_epilogue_f16_t* h_epi,
+                              const int32_t* m_count, void* stream) {
+    if (!A_h || !A_l || !B_h || !B_l || !h_epi || M < 0 || N < 1 || K < 1) return IDRK_E_ARG;
+    if (M == 0) return 0;
+    EpiParamsH e;
+    e.C = h_epi->C; e.C_h = (__half*)h_epi->C_h; e.C_l = (__half*)h_epi->C_l; e.bias = h_epi->bias;
+    e.ldc = h_epi->ldc; e.ldh = h_epi->ldh; e.mode = h_epi->mode; e.act = h_epi->act_param; e.scale = h_epi->scale;
+    if (!e.C && !e.C_h) return IDRK_E_ARG;
+    if ((e.C_h == nullptr) != (e.C_l == nullptr)) return IDRK_E_ARG;
+    if (e.mode != IDRK_EPI_NONE && e.mode != IDRK_EPI_SOFTPLUS) return IDRK_E_UNSUP;
+    if ((e.C && (e.ldc < N || (e.ldc & 1))) || (e.C_h && (e.ldh < N || (e.ldh & 1)))) return IDRK_E_ARG;
+    CUtensorMap tA, tAl, tB, tBl;
+    int rc;
+    if ((rc = make_tmap_h(&tA, A_h, (uint64_t)K, (uint64_t)M, lda, BM))) return rc;
+    if ((rc = make_tmap_h(&tAl, A_l, (uint64_t)K, (uint64_t)M, lda, BM))) return rc;
+    if ((rc = make_tmap_h(&tB, B_h, (uint64_t)K, (uint64_t)N, ldb, BNH))) return rc;
+    if ((rc = make_tmap_h(&tBl, B_l, (uint64_t)K, (uint64_t)N, ldb, BNH))) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        IDRK_CUDA_TRY(cudaFuncSetAttribute(gemm_f16s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlanH::TOTAL));
+        attr_done = true;
+    }
+    const long long items = ((M + BM - 1) / BM) * ((N + BNH - 1) / BNH);
+    const long long grid = items < sm_count() ? items : sm_count();
+    gemm_f16s_kernel<<<(unsigned)grid, GEMM_THREADS_V2, SmemPlanH::TOTAL, (cudaStream_t)stream>>>(tA, tAl, tB, tBl, M, N, K, e, m_count);
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_split_f16(const float* x, int64_t rows, int32_t cols, int32_t ldx, float scale, void* h, void* l,
+                              int32_t ld_out, int32_t pad_cols, const int32_t* m_count, void* stream) {
+    if (!x || !h || !l || rows < 0 || cols < 1 || ldx < cols || pad_cols < 0 || ld_out < cols + pad_cols) return IDRK_E_ARG;
+    if (rows == 0) return 0;
+    long long total = rows * (long long)(cols + pad_cols);
+    long long b = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (b > cap) b = cap;
+    split_f16_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, scale, (__half*)h, (__half*)l, ld_out, pad_cols, m_count);
+    IDRK_LAUNCH_CHECK();
+    return 0;
 }

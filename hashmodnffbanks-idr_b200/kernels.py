@@ -323,3 +323,73 @@ def act_bwd(dH, dS, S, H, mode: int, act: float, scale: float, want_split: bool)
                              ptr(S), ld_of(S), ptr(H), ld_of(H) if H is not None else 0, rows, cols, mode, float(act),
                              float(scale), ptr(dZ), ptr(hi), ptr(lo), pad4(cols), stream_ptr()), "idrk_act_bwd")
     return dZ, hi, lo
+
+
+# ---------------------------------------------------------------------------------------------
+# fp16-pair contraction (no-grad SDF path)
+# ---------------------------------------------------------------------------------------------
+from ._lib import EpilogueH  # noqa: E402
+
+_inference_fp16x2 = True
+
+
+def set_inference_precision(name: str):
+    """Operand format of the no-grad SDF pipeline (ray tracer / eval queries): "fp16x2" = fp16 pairs
+    x ~= h + l * 2^-11 (default, 3xTF32-class accuracy at half the bytes and MMA time), "default" = follow
+    set_precision()."""
+    global _inference_fp16x2
+    if name not in ("fp16x2", "default"):
+        raise ValueError(name)
+    _inference_fp16x2 = name == "fp16x2"
+
+
+def inference_fp16x2() -> bool:
+    return _inference_fp16x2 and _default_precision == PREC_3XTF32
+
+
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def empty_half(rows: int, cols: int, device) -> torch.Tensor:
+    return torch.empty((rows, pad8(cols)), device=device, dtype=torch.float16)[:, :cols]
+
+
+def split_f16_into(x: torch.Tensor, rows: int, cols: int, scale: float, h: torch.Tensor, l: torch.Tensor, ld_out: int,
+                   pad_cols: int = 0, m_count: Optional[torch.Tensor] = None):
+    check(lib().idrk_split_f16(ptr(x), rows, cols, ld_of(x), float(scale), ptr(h), ptr(l), ld_out, pad_cols, ptr(m_count),
+                               stream_ptr()), "idrk_split_f16")
+
+
+def split_f16(x: torch.Tensor, m_count: Optional[torch.Tensor] = None):
+    x = rows2d(x, "x")
+    r, c = x.shape
+    h, l = empty_half(r, c, x.device), empty_half(r, c, x.device)
+    if r:
+        split_f16_into(x, r, c, 1.0, h, l, pad8(c), pad8(c) - c, m_count)
+    return h, l
+
+
+def half_ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else pad8(t.shape[1])
+
+
+def gemm_f16s(A_h, A_l, B_h, B_l, M: int, N: int, Kc: int, *, C=None, C_h=None, C_l=None, bias=None, mode=EPI_NONE,
+              act=0.0, scale=1.0, m_count=None):
+    e = EpilogueH()
+    e.C = C.data_ptr() if C is not None else None
+    e.C_h = C_h.data_ptr() if C_h is not None else None
+    e.C_l = C_l.data_ptr() if C_l is not None else None
+    e.bias = bias.data_ptr() if bias is not None else None
+    e.ldc = op_ld(C) if C is not None else 0
+    e.ldh = half_ld(C_h) if C_h is not None else 0
+    e.mode, e.act_param, e.scale = mode, float(act), float(scale)
+    if PROFILE.enabled:
+        PROFILE.pending_tag = "[f16s M=%d N=%d K=%d mode=%d%s]" % (M, N, Kc, mode, " cnt" if m_count is not None else "")
+        if m_count is not None:
+            cnt = m_count.clone()
+            PROFILE.pending_flops = lambda cnt=cnt, M=M, N=N, Kc=Kc: 2.0 * min(M, int(cnt.item())) * N * Kc
+        else:
+            PROFILE.pending_flops = 2.0 * M * N * Kc
+    check(lib().idrk_gemm_f16s(M, N, Kc, ptr(A_h), ptr(A_l), half_ld(A_h), ptr(B_h), ptr(B_l), half_ld(B_h),
+                               ctypes.byref(e), ptr(m_count), stream_ptr()), "idrk_gemm_f16s")

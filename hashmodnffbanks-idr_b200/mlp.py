@@ -335,12 +335,13 @@ def layer_weight(lin: torch.nn.Module) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 class FoldedLayer:
     """Effective (weight-norm folded) weight of one Linear, optionally hi/lo split, in persistent buffers."""
-    __slots__ = ("lin", "split", "bufs", "W", "W_lo", "Wfull", "bias", "n_out", "n_in")
+    __slots__ = ("lin", "split", "bufs", "W", "W_lo", "Wfull", "bias", "n_out", "n_in", "W_h16", "W_l16")
 
     def __init__(self, lin: torch.nn.Module, split: bool):
         self.lin, self.split, self.bufs = lin, split, None
-        self.refresh()
+        self.W_h16 = self.W_l16 = None
         self.n_out, self.n_in = (lin.weight_v if hasattr(lin, "weight_v") else lin.weight).shape
+        self.refresh()
 
     @torch.no_grad()
     def refresh(self):
@@ -353,6 +354,12 @@ class FoldedLayer:
         self.W_lo = self.bufs.get("W_lo")
         self.Wfull = self.bufs["W"]
         self.bias = lin.bias.detach()
+        if K.inference_fp16x2():                    # fp16 pair of the folded weight (persistent buffers)
+            if self.W_h16 is None:
+                self.W_h16 = K.empty_half(self.n_out, self.n_in, self.Wfull.device)
+                self.W_l16 = K.empty_half(self.n_out, self.n_in, self.Wfull.device)
+            K.split_f16_into(self.Wfull, self.n_out, self.n_in, 1.0, self.W_h16, self.W_l16, K.pad8(self.n_in),
+                             K.pad8(self.n_in) - self.n_in)
 
 
 def params_version(params: Sequence[torch.Tensor]) -> Tuple:
@@ -414,6 +421,53 @@ class SdfPipeline:
             self._bufs[key] = b
         return b
 
+    def _hbuf(self, name, rows, cols, device):
+        key = ("h16", name, cols)
+        b = self._bufs.get(key)
+        if b is None or b.shape[0] < rows or b.device != device:
+            b = torch.empty((max(rows, 1), K.pad8(cols)), device=device, dtype=torch.float16)
+            self._bufs[key] = b
+        return b
+
+    def _run_f16(self, emb, rows, want, m_count, out, fl):
+        """Same pipeline with fp16-pair operands (csrc/gemm.cu gemm_f16s_kernel): half the operand bytes and half the
+        tensor-pipe time of the 3xTF32 pair at the same accuracy class; used only here (no autograd)."""
+        net = self.net
+        dev = emb.device
+        E = fl[0].n_in
+        cur_h, cur_l = self._hbuf("emb_h", rows, E, dev), self._hbuf("emb_l", rows, E, dev)
+        K.split_f16_into(emb, rows, E, 1.0, cur_h, cur_l, K.pad8(E), K.pad8(E) - E, m_count)
+        cur_dim = E
+        n = self.n_lin
+        for l, f in enumerate(fl):
+            last = l == n - 1
+            if last:
+                C = self._buf("full_out", rows, f.n_out, dev) if out is None else out
+                K.gemm_f16s(cur_h, cur_l, f.W_h16, f.W_l16, rows, f.n_out, cur_dim, C=C, bias=f.bias, m_count=m_count)
+                res = C[:rows, :f.n_out]
+                sq, _ = K.sdf_squash(res[:, 0].contiguous(), self.beta(), False)
+                res[:, 0] = sq
+                return res
+            feeds_skip = (l + 1) in net.skip_in
+            width = f.n_out + (E if feeds_skip else 0)
+            head_next = (l == n - 2) and want == "sdf"
+            scale = SQRT2_INV if feeds_skip else 1.0
+            if head_next:                                         # last hidden layer: fp32 activations for the SDF head
+                h32 = self._buf("h_last", rows, width, dev)
+                K.gemm_f16s(cur_h, cur_l, f.W_h16, f.W_l16, rows, f.n_out, cur_dim, C=h32, bias=f.bias,
+                            mode=K.EPI_SOFTPLUS, act=100.0, scale=scale, m_count=m_count)
+                res = out if out is not None else torch.empty(rows, device=dev, dtype=torch.float32)
+                K.sdf_head(h32, fl[n - 1].Wfull[0], fl[n - 1].bias, self.beta(), res, rows, m_count)
+                return res
+            nxt_h, nxt_l = self._hbuf(("h", l & 1), rows, width, dev), self._hbuf(("l", l & 1), rows, width, dev)
+            K.gemm_f16s(cur_h, cur_l, f.W_h16, f.W_l16, rows, f.n_out, cur_dim, C_h=nxt_h, C_l=nxt_l, bias=f.bias,
+                        mode=K.EPI_SOFTPLUS, act=100.0, scale=scale, m_count=m_count)
+            if feeds_skip:
+                ldw = K.pad8(width)
+                K.split_f16_into(emb, rows, E, SQRT2_INV, nxt_h[:, f.n_out:], nxt_l[:, f.n_out:], ldw, ldw - width, m_count)
+            cur_h, cur_l, cur_dim = nxt_h, nxt_l, width
+        raise IdrkError("unreachable")
+
     # -- execution -----------------------------------------------------------------------
     @torch.no_grad()
     def run(self, emb: torch.Tensor, rows: int, want: str = "sdf", m_count: Optional[torch.Tensor] = None,
@@ -421,6 +475,10 @@ class SdfPipeline:
         """emb: fp32 embedding buffer [>=rows, ld] (padded operand), width = net input width."""
         net = self.net
         fl = self.folded()
+        if K.inference_fp16x2():
+            if fl[0].W_h16 is None:
+                fl = self.folded(force=True)
+            return self._run_f16(emb, rows, want, m_count, out, fl)
         split = K.get_precision() == K.PREC_3XTF32
         dev = emb.device
         E = fl[0].n_in

@@ -124,6 +124,26 @@ int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N, int32_t K
               const float* A, const float* A_lo, int32_t lda, const float* B, const float* B_lo, int32_t ldb,
               const idrk_epilogue_t* h_epi, const int32_t* m_count, int32_t split_k, void* stream);
 
+/* -- K4c: fp16-pair contraction for the no-grad SDF path ------------------------------------
+ * Operands are pairs of IEEE halves  x ~= h + l * 2^-11  (h = fp16(x), l = fp16((x - h) * 2^11)): 4 bytes per element,
+ * three kind::f16 MMAs per product (Ah.Bh | Ah.Bl + Al.Bh) into two TMEM accumulators, result = D0 + 2^-11 D1.
+ * Same use as idrk_gemm NT (ImplicitNetwork.forward under no_grad, ray_tracing.py SDF queries); needs |x| < 65504.
+ * A [M, K], B [N, K] row-major halves with lda, ldb % 8 == 0.  Outputs: fp32 C and/or the half pair (C_h, C_l). */
+typedef struct idrk_epilogue_f16 {
+    float* C;            /* [M, ldc] fp32 (nullable)                      */
+    void* C_h;           /* [M, ldh] fp16 high halves (nullable, with C_l) */
+    void* C_l;           /* [M, ldh] fp16 scaled low halves                */
+    const float* bias;   /* [N] (nullable)                                 */
+    int32_t ldc, ldh;
+    int32_t mode;        /* IDRK_EPI_NONE or IDRK_EPI_SOFTPLUS             */
+    float act_param, scale;
+} idrk_epilogue_f16_t;
+int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, const void* A_l, int32_t lda,
+                   const void* B_h, const void* B_l, int32_t ldb, const idrk_epilogue_f16_t* h_epi,
+                   const int32_t* m_count, void* stream);
+int idrk_split_f16(const float* x, int64_t rows, int32_t cols, int32_t ldx, float scale, void* h, void* l,
+                   int32_t ld_out, int32_t pad_cols, const int32_t* m_count, void* stream);
+
 /* -- helpers around the MLP tiles ----------------------------------------------------------
  * idrk_split_tf32: v = scale * x; hi = tf32(v), lo = tf32(v - hi) for 3xTF32 operands (lo nullable -> plain
  *   scaled copy rounded to tf32 is NOT applied: hi then receives v itself); columns [cols, cols+pad_cols)

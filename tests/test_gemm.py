@@ -138,3 +138,28 @@ def test_gemm_cta_pair_epilogue_and_count():
     ref = torch.nn.functional.softplus(z, beta=100) * 0.70710678
     assert torch.allclose((Hh + Hl)[:9001].double(), ref, atol=1e-6, rtol=1e-5)
     assert (Hh[9216:] == -3.0).all()            # rows of tiles entirely beyond the count are untouched
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (300, 445, 67), (4096, 512, 512), (33000, 512, 27), (20000, 512, 512)])
+def test_gemm_fp16_pair(shape):
+    """fp16-pair operands (x ~= h + l 2^-11): same accuracy class as 3xTF32 (rel 2e-5 of sum|a||b|)."""
+    from idrk import kernels as K
+    M, N, Kc = shape
+    A, W, b = _mk((M, Kc), 21) * 0.3, _mk((N, Kc), 22) * 0.1, _mk((N,), 23) * 0.01
+    Ah, Al = K.split_f16(A)
+    Wh, Wl = K.split_f16(W)
+    C = K.empty_padded(M, N, DEV)
+    Ch, Cl = K.empty_half(M, N, DEV), K.empty_half(M, N, DEV)
+    K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, C=C, C_h=Ch, C_l=Cl, bias=b)
+    ref = A.double() @ W.double().t() + b.double()
+    mag = A.double().abs() @ W.double().abs().t() + 1e-30
+    assert ((C.double() - ref).abs() / mag).max().item() < 2e-5
+    rec = Ch.double() + Cl.double() / 2048.0
+    assert ((rec - ref).abs() / mag).max().item() < 3e-5
+    cnt = torch.tensor([min(M, 77)], device=DEV, dtype=torch.int32)
+    C2 = K.empty_padded(M, N, DEV)
+    C2.fill_(5.0)
+    K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, C=C2, bias=b, mode=K.EPI_SOFTPLUS, act=100.0, scale=0.5, m_count=cnt)
+    k = int(cnt.item())
+    assert torch.allclose(C2[:k].double(), torch.nn.functional.softplus(ref[:k], beta=100) * 0.5, atol=2e-6, rtol=2e-5)
+    assert (C2[((k + 127) // 128) * 128:] == 5.0).all()
