@@ -89,7 +89,8 @@ class _Proxy:
                     if PROFILE.detail:
                         key = _name + (tag or "")
                     else:
-                        key = _name + "_2cta" if (tag or "").startswith("_2cta") else _name
+                        t = tag or ""
+                        key = _name + "_2cta" if t.startswith("_2cta") else (_name + "_big" if t.startswith("_big") else _name)
                     PROFILE.records.append((key, s, e, flops))
                 else:
                     rc = _raw(*args)

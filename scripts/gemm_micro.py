@@ -33,3 +33,30 @@ if __name__ == "__main__":
     run(32768, 512, 512, prec="tf32", split_out=False)
     run(2048, 512, 512)
     run(2048, 512, 512, prec="tf32", split_out=False)
+
+
+def run_h(M, N, Kc, reps=4, mode=K.EPI_SOFTPLUS, fp32_out=False):
+    A = torch.randn(M, Kc, device="cuda") * 0.05
+    W = torch.randn(N, Kc, device="cuda") * 0.05
+    b = torch.randn(N, device="cuda") * 0.01
+    Ah, Al = K.split_f16(A); Wh, Wl = K.split_f16(W)
+    Ch, Cl = K.empty_half(M, N, "cuda"), K.empty_half(M, N, "cuda")
+    C = K.empty_padded(M, N, "cuda")
+    ts = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        if fp32_out:
+            K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, C=C, bias=b, mode=mode, act=100.0)
+        else:
+            K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, C_h=Ch, C_l=Cl, bias=b, mode=mode, act=100.0)
+        e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e) * 1e3)
+    print("f16s M=%d N=%d K=%d fp32_out=%s: %s us  (%.1f TF/s alg)" % (M, N, Kc, fp32_out, ["%.1f" % t for t in ts], 2.0 * M * N * Kc / min(ts) / 1e6))
+
+
+if __name__ == "__main__":
+    run_h(32768, 512, 512)
+    run_h(32768, 512, 64)
+    run_h(32768, 512, 512, fp32_out=True)
+    run_h(2048, 512, 512)
