@@ -113,3 +113,50 @@ def test_device_count_path_equals_callable_path():
     agree = a[1].cpu() == m_ref
     bad = ((a[2].cpu() - d_ref).abs()[agree] > 1e-3).sum().item()
     assert bad <= 2048 // 20, bad
+
+
+def test_full_size_analytic_sphere_closed_form():
+    """BASELINE-sized ray batch (65536 rays): with the exact sphere SDF the traced distance must equal the closed-form
+    ray / sphere intersection (size-independent property, no oracle run needed)."""
+    from idrk.model.ray_tracing import RayTracing
+    n, R = 65536, 0.5
+    dirs, cam, mask = rays(n, 11, f=300.0)
+    dirs, cam, mask = dirs.to(DEV), cam.to(DEV), mask.to(DEV)
+    tr = RayTracing(**CONF)
+    tr.eval()
+    p, m, d = tr(lambda q: q.norm(2, dim=1) - R, cam, torch.ones_like(mask), dirs)
+    dd = dirs.reshape(-1, 3).double()
+    c = cam.double()[0]
+    b = (dd * c).sum(-1)
+    disc = b * b - (c.dot(c) - R * R)
+    hit = disc > 1e-6
+    t_exact = -b - torch.sqrt(disc.clamp_min(0))
+    assert (m[hit]).float().mean().item() > 0.999                 # rays that hit the sphere are classified as hits
+    assert (~m[disc < -1e-6]).all()                               # rays that miss are not
+    err = (d.double() - t_exact).abs()[hit & m]
+    assert err.max().item() < 2e-4, err.max().item()
+    assert (p.double() - (c + d.double().unsqueeze(-1) * dd)).abs().max().item() < 1e-5
+
+
+def test_device_count_path_at_32768_rays():
+    """Sync-free CUDA-graph trace == eager device-count trace == callable path on a large batch (MLP SDF)."""
+    from idrk.model.implicit_differentiable_renderer import ImplicitNetwork
+    from idrk.model.ray_tracing import RayTracing
+    from tests_support import load_sd_into, quiet_build
+    cfg = O.EmbedCfg("HashGrid", 16, 14, 2, 16, 2048, 1.0)
+    sd = O.make_implicit_sd(cfg, torch.Generator().manual_seed(4), perturb=0.02)
+    net = quiet_build(ImplicitNetwork, 256, 3, 1, [512] * 8, True, 0.6, (4,), True, 16, "HashGrid", 14, 2, 16, 2048, 1.0)
+    load_sd_into(net, sd, "implicit_network.")
+    net = net.to(DEV)
+    dirs, cam, mask = rays(32768, 8)
+    u = torch.rand(100, generator=torch.Generator().manual_seed(6))
+    args = (cam.to(DEV), mask.to(DEV), dirs.to(DEV))
+    tr = RayTracing(**CONF)
+    a = tr(net.sdf, *args, min_sdf_steps=u)
+    tr.use_cuda_graph = True
+    for _ in range(3):                       # warm-up call, capture call, replay call
+        g = tr(net.sdf, *args, min_sdf_steps=u)
+    b = tr(lambda x: net.sdf(x), *args, min_sdf_steps=u)
+    for x, y, z in zip(a, g, b):
+        assert torch.equal(x, y) and torch.equal(x, z)
+    assert "n_sampler" in tr.last_stats
