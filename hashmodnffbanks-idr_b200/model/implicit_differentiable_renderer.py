@@ -139,14 +139,21 @@ class ImplicitNetwork(nn.Module):
         s = torch.tanh(s / (2 + rho))
         return torch.cat([s.unsqueeze(1), x[:, 1:]], dim=1)
 
-    def gradient(self, x):
-        """d sdf / d x, [P, 1, 3], recorded on the tape (create_graph) like the reference (:116-128)."""
+    def forward_with_gradient(self, x):
+        """(forward(x), d sdf / d x) from ONE network evaluation.  The reference evaluates `implicit_network(p)` and
+        `implicit_network.gradient(p)` separately on the same points (:321-324); `gradient` runs the same forward
+        internally, so sharing it yields identical values for half the work."""
         x.requires_grad_(True)
         with torch.enable_grad():
-            y = self.forward(x)[:, :1]
+            out = self.forward(x)
+            y = out[:, :1]
             g = torch.autograd.grad(outputs=y, inputs=x, grad_outputs=torch.ones_like(y), create_graph=True,
                                     retain_graph=True, only_inputs=True)[0]
-        return g.unsqueeze(1)
+        return out, g.unsqueeze(1)
+
+    def gradient(self, x):
+        """d sdf / d x, [P, 1, 3], recorded on the tape (create_graph) like the reference (:116-128)."""
+        return self.forward_with_gradient(x)[1]
 
 
 class RenderingNetwork(nn.Module):
@@ -254,16 +261,16 @@ class IDRNetwork(nn.Module):
         batch_size, num_pixels, _ = ray_dirs.shape
         device = ray_dirs.device
         points = (cam_loc.unsqueeze(1) + dists.reshape(batch_size, num_pixels, 1) * ray_dirs).reshape(-1, 3)
-        sdf_output = self.implicit_network(points)[:, 0:1]
         ray_dirs = ray_dirs.reshape(-1, 3)
 
         if self.training:
             if eikonal_points is None:
                 eikonal_points = self._draw_eikonal(batch_size * num_pixels, device)
             cam_rep = cam_loc.unsqueeze(1).repeat(1, num_pixels, 1).reshape(-1, 3)
-            rgb_values, grad_theta = self.render_training(points, dists, ray_dirs, cam_rep, sdf_output,
-                                                          network_object_mask & object_mask, eikonal_points)
+            rgb_values, grad_theta, sdf_output = self.render_training(points, dists, ray_dirs, cam_rep,
+                                                                      network_object_mask & object_mask, eikonal_points)
         else:
+            sdf_output = self.implicit_network(points)[:, 0:1]
             surface_mask = network_object_mask
             differentiable_surface_points = points[surface_mask]
             grad_theta = None
@@ -281,18 +288,25 @@ class IDRNetwork(nn.Module):
         r = self.object_bounding_sphere      # drawn on the host generator, like the reference (:279)
         return torch.empty(n_rays // 2, 3).uniform_(-r, r).to(device)
 
-    def render_training(self, points, dists, ray_dirs, cam_rep, sdf_output, surface_mask, eik):
-        """Training branch of the reference forward (:268-308) on FIXED shapes.
+    def render_training(self, points, dists, ray_dirs, cam_rep, surface_mask, eik):
+        """Training branch of the reference forward (:264-308) on FIXED shapes, without its duplicate evaluations.
 
-        The reference gathers the N_s surface rays with boolean masks and evaluates the network on
-        [surface | eikonal | all] points.  Surface points are a subset of `points`, so the same numbers are
-        obtained by evaluating ONE gradient() on [eikonal | all points] and reading the surface rows out of
-        it, and by running sample network + rendering on all N rays with the non-surface rows masked out
-        afterwards (their rgb is the constant 1 and they receive zero gradient, exactly as in the reference).
-        Fixed shapes keep the step free of host syncs and capturable in a CUDA graph."""
-        n = points.shape[0]
+        The reference gathers the N_s surface rays with boolean masks and evaluates the network on `points`,
+        on `surface_points`, and on [surface | eikonal | points] for the gradient.  Surface points are a subset of
+        `points`, and `gradient()` runs a forward pass internally, so the same numbers come out of ONE
+        forward-with-gradient on [eikonal | points]: its SDF column on the `points` rows is `sdf_output`, its gradient
+        rows are `grad_theta`, and the surface rows of both are read out by mask.  Sample network + rendering then
+        run on all N rays with the non-surface rows masked afterwards (their rgb is the constant 1 and they receive
+        zero gradient, exactly as in the reference).  Fixed shapes keep the step free of host syncs and capturable in
+        a CUDA graph.  When `points` itself carries gradient (trainable cameras) the separate evaluation of the
+        reference is kept so that d sdf / d pose is preserved."""
         n_eik = eik.shape[0]
-        g = self.implicit_network.gradient(torch.cat([eik, points.clone().detach()], 0))
+        if points.requires_grad:
+            sdf_output = self.implicit_network(points)[:, 0:1]
+            g = self.implicit_network.gradient(torch.cat([eik, points.clone().detach()], 0))
+        else:
+            out_all, g = self.implicit_network.forward_with_gradient(torch.cat([eik, points], 0))
+            sdf_output = out_all[n_eik:, 0:1]
         grad_theta = g[:, 0, :]
         normals0 = g[n_eik:, 0, :].clone().detach()
         sdf0 = sdf_output.detach()
@@ -303,11 +317,10 @@ class IDRNetwork(nn.Module):
         diff_points = cam_rep + t_theta * ray_dirs
         rgb = self.get_rbg_value(diff_points, -ray_dirs)
         rgb_values = torch.where(mask, rgb, torch.ones_like(rgb))
-        return rgb_values, grad_theta
+        return rgb_values, grad_theta, sdf_output
 
     def get_rbg_value(self, points, view_dirs):
-        output = self.implicit_network(points)
-        g = self.implicit_network.gradient(points)
+        output, g = self.implicit_network.forward_with_gradient(points)
         normals = g[:, 0, :]
         feature_vectors = output[:, 1:]
         return self.rendering_network(points, normals, view_dirs, feature_vectors)
