@@ -175,6 +175,7 @@ def hash_encode_section(torch, hbm, src):
         r = run(1 << 24, 19, mode, flush=flush)
         out[mode] = {"fwd_mpts_per_s": round(r["fwd_mpts"], 1), "bwd_mpts_per_s": round(r["bwd_mpts"], 1),
                      "fwd_frac_of_hbm_peak": round(r["fwd_frac"], 4), "bwd_frac_of_hbm_peak": round(r["bwd_frac"], 4),
+                     "bwd_with_dx_mpts_per_s": round(r["bwd_with_dx_mpts"], 1),
                      "algorithmic_bytes_per_point": r["bytes_per_pt"]}
     out["points"] = 1 << 24
     out["table"] = "L=16, F=2, T=2^19 (48.5 MB)"

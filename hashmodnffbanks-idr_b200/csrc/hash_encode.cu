@@ -104,9 +104,10 @@ __device__ __forceinline__ void scatter_add(float* table, uint32_t idx, const fl
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
+// Reference mode (one gather per level): whole-row block staging, one float4 write-back per row.
 template <int F, int MODE, int ROWS>
 __global__ void __launch_bounds__(ROWS)
-hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
+hash_encode_fwd_block_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
                        float* __restrict__ out, int ld_out, uint32_t* __restrict__ idx_dbg,
                        const int* __restrict__ m_count) {
     extern __shared__ float smem[];
@@ -220,6 +221,146 @@ hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n
             }
         }
         __syncthreads();
+    }
+}
+
+
+// Writes columns [coloff, coloff + ncols) of `rows_here` consecutive output rows from a warp-private tile.
+// The 16-byte aligned middle of each row segment goes out as float4 (8 lanes per row, 4 rows per instruction),
+// the unaligned head / tail columns as scalars.
+__device__ __forceinline__ void flush_tile(const float* tile, int tws, float* __restrict__ out, long long row0, int rows_here,
+                                           int ld_out, int coloff, int ncols, int lane, bool vec_ok) {
+    int head = 0, nv = 0;
+    if (vec_ok) { head = (4 - (coloff & 3)) & 3; if (head > ncols) head = ncols; nv = (ncols - head) >> 2; }
+    const int tail0 = head + 4 * nv;
+    if (nv > 0) {
+        int lanes_per_row = 1;
+        while (lanes_per_row < nv) lanes_per_row <<= 1;              // 8 for a 32..35-column pass
+        if (lanes_per_row > 32) lanes_per_row = 32;
+        const int rows_per_it = 32 / lanes_per_row;
+        const int lr = lane / lanes_per_row, lc = lane % lanes_per_row;
+        for (int r = lr; r < rows_here; r += rows_per_it) {
+            const float* src = tile + r * tws + head;
+            float* dst = out + (row0 + r) * (long long)ld_out + coloff + head;
+            for (int c4 = lc; c4 < nv; c4 += lanes_per_row)
+                st_stream4(reinterpret_cast<float4*>(dst) + c4,
+                           make_float4(src[4 * c4], src[4 * c4 + 1], src[4 * c4 + 2], src[4 * c4 + 3]));
+        }
+    }
+    for (int c = 0; c < head; ++c)
+        for (int r = lane; r < rows_here; r += 32) out[(row0 + r) * (long long)ld_out + coloff + c] = tile[r * tws + c];
+    for (int c = tail0; c < ncols; ++c)
+        for (int r = lane; r < rows_here; r += 32) out[(row0 + r) * (long long)ld_out + coloff + c] = tile[r * tws + c];
+}
+
+// Warp-private staging: each warp owns 32 points and a [32][TW+1] shared tile (TW = max(prefix width, level width)),
+// used twice per tile of points - once for the Fourier prefix columns, once for the level columns - so the shared
+// footprint is ~4.7 KB per warp (48+ resident warps per SM instead of 24 with whole-row staging), there is no
+// block-wide barrier in the point loop, and global traffic stays coalesced (row segments of 128 bytes).
+template <int F, int MODE, int ROWS>
+__global__ void __launch_bounds__(ROWS)
+hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
+                       float* __restrict__ out, int ld_out, uint32_t* __restrict__ idx_dbg,
+                       const int* __restrict__ m_count, int tw) {
+    extern __shared__ float smem[];
+    if (m_count != nullptr) { const long long c = *m_count; n = c < n ? c : n; }
+    const int C = g.n_fourier, L = g.n_levels;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tws = tw + 1;                              // odd-ish stride: row writes and column reads conflict free
+    float* s_B = smem;                                   // [3][C]
+    float* tile = smem + 3 * C + warp * (32 * tws);      // [32][tws], private to this warp
+    for (int i = threadIdx.x; i < 3 * C; i += ROWS) s_B[i] = g.B[i];
+    __syncthreads();
+    const int pre = C > 0 ? 3 + 2 * C : 0;
+    const int lev = ld_out - pre;                        // level columns + zero padding up to ld_out
+    float* my = tile + lane * tws;
+    const bool vec_ok = (ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+
+    const long long n_wtiles = (n + 31) / 32;
+    const long long wstride = (long long)gridDim.x * (ROWS / 32);
+    for (long long wt = (long long)blockIdx.x * (ROWS / 32) + warp; wt < n_wtiles; wt += wstride) {
+        const long long p0 = wt * 32, p = p0 + lane;
+        const bool valid = p < n;
+        const int rows_here = (int)min(32LL, n - p0);
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+        if (valid) { x0 = x[p * ldx + 0]; x1 = x[p * ldx + 1]; x2 = x[p * ldx + 2]; }
+        if (C > 0) {
+            my[0] = x0; my[1] = x1; my[2] = x2;
+            const float t0 = __fmul_rn(x0, 6.283185307179586f);
+            const float t1 = __fmul_rn(x1, 6.283185307179586f);
+            const float t2 = __fmul_rn(x2, 6.283185307179586f);
+            for (int c = 0; c < C; ++c) {
+                float xp = __fmul_rn(t0, s_B[c]);
+                xp = __fmaf_rn(t1, s_B[C + c], xp);
+                xp = __fmaf_rn(t2, s_B[2 * C + c], xp);
+                float sn, cs;
+                sincos_fast(xp, &sn, &cs);
+                my[3 + c] = sn;
+                my[3 + C + c] = cs;
+            }
+            __syncwarp();
+            flush_tile(tile, tws, out, p0, rows_here, ld_out, 0, pre, lane, vec_ok);
+            __syncwarp();
+        }
+        if constexpr (MODE == IDRK_HASH_REFERENCE) {
+#pragma unroll 4
+            for (int l = 0; l < L; ++l) {
+                const float r = g.res[l];
+                const uint32_t h = hash3(trunc_u32(__fmul_rn(x0, r)), trunc_u32(__fmul_rn(x1, r)),
+                                         trunc_u32(__fmul_rn(x2, r)));
+                float v[F];
+                gather<F>(g.tables[l], wrap(h, g.rows[l], g.pow2mask[l], g.magic[l]), v);
+#pragma unroll
+                for (int f = 0; f < F; ++f) my[l * F + f] = v[f];
+            }
+        } else {
+#pragma unroll 2
+            for (int l = 0; l < L; ++l) {
+                const float r = g.res[l];
+                const float s0 = __fmul_rn(x0, r), s1 = __fmul_rn(x1, r), s2 = __fmul_rn(x2, r);
+                const float f0 = floorf(s0), f1 = floorf(s1), f2 = floorf(s2);
+                const float w0 = s0 - f0, w1 = s1 - f1, w2 = s2 - f2;
+                const uint32_t c0 = trunc_u32(f0), c1 = trunc_u32(f1), c2 = trunc_u32(f2);
+                const uint32_t rows = g.rows[l], mask = g.pow2mask[l];
+                const unsigned long long magic = g.magic[l];
+                const float* tab = g.tables[l];
+                float v[8][F];
+                // hash3 is an xor of three per-dimension terms: form the 2 x 3 terms once, xor per corner
+                const uint32_t hx0 = c0, hx1 = c0 + 1u, hy0 = c1 * 3u, hy1 = hy0 + 3u;
+                const uint32_t hz0 = c2 * 2654435761u, hz1 = hz0 + 2654435761u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    gather<F>(tab, wrap(((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0), rows, mask, magic), v[k]);
+                float acc[F];
+#pragma unroll
+                for (int f = 0; f < F; ++f) acc[f] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float wk = ((k & 1) ? w0 : 1.f - w0) * ((k & 2) ? w1 : 1.f - w1) * ((k & 4) ? w2 : 1.f - w2);
+#pragma unroll
+                    for (int f = 0; f < F; ++f) acc[f] = fmaf(wk, v[k][f], acc[f]);
+                }
+#pragma unroll
+                for (int f = 0; f < F; ++f) my[l * F + f] = acc[f];
+            }
+        }
+        for (int c = L * F; c < lev; ++c) my[c] = 0.f;
+        __syncwarp();
+        flush_tile(tile, tws, out, p0, rows_here, ld_out, pre, lev, lane, vec_ok);
+        __syncwarp();
+
+        if (idx_dbg != nullptr && valid) {      // debug / parity output: table row of all 8 corners
+            for (int l = 0; l < L; ++l) {
+                const float r = g.res[l];
+                const float s0 = __fmul_rn(x0, r), s1 = __fmul_rn(x1, r), s2 = __fmul_rn(x2, r);
+                uint32_t c0, c1, c2;
+                if constexpr (MODE == IDRK_HASH_REFERENCE) { c0 = trunc_u32(s0); c1 = trunc_u32(s1); c2 = trunc_u32(s2); }
+                else { c0 = trunc_u32(floorf(s0)); c1 = trunc_u32(floorf(s1)); c2 = trunc_u32(floorf(s2)); }
+                for (int k = 0; k < 8; ++k)
+                    idx_dbg[(p * L + l) * 8 + k] =
+                        wrap(hash3(c0 + (k & 1), c1 + ((k >> 1) & 1), c2 + ((k >> 2) & 1)), g.rows[l], g.pow2mask[l], g.magic[l]);
+            }
+        }
     }
 }
 
@@ -395,11 +536,24 @@ static int persistent_grid(K kernel, int threads, size_t smem, long long n_tiles
 template <int F, int MODE, int ROWS>
 static int launch_fwd(const GridDev& g, const float* x, long long n, int ldx, float* out, int ld_out,
                       uint32_t* idx_dbg, const int* m_count, cudaStream_t st) {
-    const size_t smem = ((size_t)ROWS * (ld_out | 1) + 3 * g.n_fourier) * sizeof(float);
+    if (MODE == IDRK_HASH_REFERENCE && (size_t)ROWS * (ld_out | 1) * sizeof(float) <= 72 * 1024) {
+        // one gather per level: issue-bound, whole-row staging with a single float4 write-back wins
+        const size_t smem_b = ((size_t)ROWS * (ld_out | 1) + 3 * g.n_fourier) * sizeof(float);
+        auto kb = hash_encode_fwd_block_kernel<F, MODE, ROWS>;
+        IDRK_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        const int grid_b = persistent_grid(kb, ROWS, smem_b, (n + ROWS - 1) / ROWS);
+        kb<<<grid_b, ROWS, smem_b, st>>>(g, x, n, ldx, out, ld_out, idx_dbg, m_count);
+        IDRK_LAUNCH_CHECK();
+        return 0;
+    }
+    // 8 gathers per level: latency-bound, warp-private staging doubles the resident warps
+    const int pre = g.n_fourier > 0 ? 3 + 2 * g.n_fourier : 0;
+    const int tw = (pre > ld_out - pre ? pre : ld_out - pre) | 1;
+    const size_t smem = ((size_t)(ROWS / 32) * 32 * (tw + 1) + 3 * g.n_fourier) * sizeof(float);
     auto kern = hash_encode_fwd_kernel<F, MODE, ROWS>;
     IDRK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = persistent_grid(kern, ROWS, smem, (n + ROWS - 1) / ROWS);
-    kern<<<grid, ROWS, smem, st>>>(g, x, n, ldx, out, ld_out, idx_dbg, m_count);
+    kern<<<grid, ROWS, smem, st>>>(g, x, n, ldx, out, ld_out, idx_dbg, m_count, tw);
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -454,17 +608,9 @@ extern "C" int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* 
     if ((ld_out & 3) == 0 && !aligned16(out)) return IDRK_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = h_grid->frac_mode;
-    const size_t row_bytes = (size_t)(ld_out | 1) * sizeof(float);
-    if (row_bytes * 128 <= 72 * 1024) {
 #define CALL(F, M) launch_fwd<F, M, 128>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
-        IDRK_DISPATCH_F_MODE(CALL)
+    IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
-    } else if (row_bytes * 64 <= 200 * 1024) {
-#define CALL(F, M) launch_fwd<F, M, 64>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
-        IDRK_DISPATCH_F_MODE(CALL)
-#undef CALL
-    }
-    return IDRK_E_UNSUP;
 }
 
 extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,

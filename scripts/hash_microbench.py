@@ -46,14 +46,16 @@ def run(n, log2T, mode, L=16, F=2, flush=None):
     grads = [torch.zeros_like(t) for t in tables]
     G = 1 if mode == "reference" else 8
     t_f = time_cuda(lambda: K.hash_encode_fwd(spec, x, tables, B, out=out), flush=flush)
-    t_b = time_cuda(lambda: K.hash_encode_bwd(spec, x, tables, B, dy, grads, True), flush=flush)
+    t_b = time_cuda(lambda: K.hash_encode_bwd(spec, x, tables, B, dy, grads, False), flush=flush)      # table gradients
+    t_bx = time_cuda(lambda: K.hash_encode_bwd(spec, x, tables, B, dy, grads, True), flush=flush)     # + dL/dx
     pre = 4 * (3 + 2 * L)
     bf = 12 + 4 * L * F + G * L * 4 * F + pre
-    bb = 12 + 4 * L * F + 2 * G * L * 4 * F + pre + 12
+    bb = 12 + 4 * L * F + 2 * G * L * 4 * F + pre
     hbm, src = peaks()
     return {"n": n, "log2T": log2T, "mode": mode,
             "fwd_ms": t_f, "fwd_mpts": n / t_f / 1e3, "fwd_frac": n * bf / (t_f * 1e-3) / (hbm * 1e9),
             "bwd_ms": t_b, "bwd_mpts": n / t_b / 1e3, "bwd_frac": n * bb / (t_b * 1e-3) / (hbm * 1e9),
+            "bwd_with_dx_ms": t_bx, "bwd_with_dx_mpts": n / t_bx / 1e3,
             "bytes_per_pt": [bf, bb], "peak": src}
 
 
