@@ -176,7 +176,8 @@ def hash_encode_section(torch, hbm, src):
         out[mode] = {"fwd_mpts_per_s": round(r["fwd_mpts"], 1), "bwd_mpts_per_s": round(r["bwd_mpts"], 1),
                      "fwd_frac_of_hbm_peak": round(r["fwd_frac"], 4), "bwd_frac_of_hbm_peak": round(r["bwd_frac"], 4),
                      "bwd_with_dx_mpts_per_s": round(r["bwd_with_dx_mpts"], 1),
-                     "algorithmic_bytes_per_point": r["bytes_per_pt"]}
+                     "bwd_with_dx_frac_of_hbm_peak": round(r["bwd_with_dx_frac"], 4),
+                     "algorithmic_bytes_per_point": dict(zip(("fwd", "bwd_tables", "bwd_tables_dx"), r["bytes_per_pt"]))}
     out["points"] = 1 << 24
     out["table"] = "L=16, F=2, T=2^19 (48.5 MB)"
     out["peak_gbs"] = hbm
@@ -249,6 +250,17 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    # The hash-encode microbench (its own workload, own buffers) runs before the training loop: measured on this
+    # pool, 4.5 GB buffers cudaMalloc'ed late in the process (after the step's graphs and pools exist) make the same
+    # kernels 15-35 % slower than buffers allocated early - a physical-placement effect outside the kernels' control.
+    hash_line = None
+    if rank == 0:
+        try:
+            hash_line = hash_encode_section(torch, *[peaks()[i] for i in (0, 3)])
+        except Exception as exc:      # the microbench must never take the headline down
+            hash_line = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+    barrier()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     clocks = ClockSampler(local)
@@ -335,10 +347,7 @@ def run_ours(args):
                          "sample": "1 full train step on 512 of the 2048 rays, oracle port of the reference's "
                                    "PyTorch path, %d threads" % cores},
     }
-    try:
-        line["hash_encode"] = hash_encode_section(torch, hbm, src)
-    except Exception as exc:      # the microbench must never take the headline down
-        line["hash_encode"] = {"error": repr(exc)}
+    line["hash_encode"] = hash_line
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -8,17 +8,18 @@
 // IDRK_HASH_REFERENCE reproduces it bit-exactly (the reference's fractional part is identically 0, so a
 // level's output is the floor-corner row); IDRK_HASH_TRILINEAR is the 8-corner interpolation.
 //
-// Design (HBM/L2-bound gather):
-//   * one thread owns one point and walks all levels, so L (or 8L) independent gathers are in flight
-//     per thread and the [n, width] output row is produced once, in its final layout;
-//   * rows are staged in shared memory (odd row stride -> conflict free) and written back with
-//     fully coalesced 128-byte stores; the input is read once, the output written once;
-//   * tables are read through the read-only path (ld.global.nc): coarse levels live in L1, the
-//     rest in the 126 MB L2;  persistent grid = (resident CTAs per SM) x (SM count);
-//   * backward: dL/dy tile staged the same way; table gradients go out as vector reductions
-//     (red.global.add.v2.f32).  Levels whose whole table fits a shared-memory budget are first
-//     accumulated per CTA in shared memory and flushed once (kills the contention on tiny tables
-//     such as the reference configs' T = 32).
+// Design (bound by the SM <-> L2 request rate: every random 8-byte table read or reduction costs a full 32-byte
+// sector request, so the lever is requests per point, not bytes):
+//   * a warp owns 32 consecutive points, a lane one (point, level) element at a time; every output float is
+//     produced by the lane that stores it, in row-major order -> coalesced row segments with no shared-memory
+//     staging, no block barrier, occupancy limited by registers only;
+//   * stores are re-aligned to 8-byte words with one shuffle (the level columns start on an odd column), so each
+//     output sector is written by one full request; KB independent gathers are issued before the first store;
+//   * tables are read through the read-only path (ld.global.nc): coarse levels live in L1, the rest in the 126 MB L2;
+//     persistent grid = (resident CTAs per SM) x (SM count);
+//   * backward: table gradients go out as vector reductions (red.global.add.v2/v4.f32).  Levels whose whole table
+//     fits a shared-memory budget are first accumulated per CTA in shared memory and flushed once (kills the
+//     contention on tiny tables such as the reference configs' T = 32); dL/dx partials are shuffle-reduced per row.
 #include "common.cuh"
 
 namespace idrk {
@@ -37,6 +38,7 @@ struct GradDev {
     float* grad[IDRK_MAX_LEVELS];
     int small_off[IDRK_MAX_LEVELS];         // offset (floats) into the CTA's shared accumulator, -1 = global
     int small_total;                        // floats
+    int any_grad;                           // 0 when only dL/dx is wanted
 };
 
 __device__ __forceinline__ uint32_t hash3(uint32_t c0, uint32_t c1, uint32_t c2) {
@@ -102,262 +104,249 @@ __device__ __forceinline__ void scatter_add(float* table, uint32_t idx, const fl
 }
 
 // ------------------------------------------------------------------------------------------
-// forward
+// element-per-lane kernels
 // ------------------------------------------------------------------------------------------
-// Reference mode (one gather per level): whole-row block staging, one float4 write-back per row.
-template <int F, int MODE, int ROWS>
-__global__ void __launch_bounds__(ROWS)
-hash_encode_fwd_block_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
-                       float* __restrict__ out, int ld_out, uint32_t* __restrict__ idx_dbg,
-                       const int* __restrict__ m_count) {
-    extern __shared__ float smem[];
-    if (m_count != nullptr) { const long long c = *m_count; n = c < n ? c : n; }
-    const int lds = ld_out | 1;                 // odd stride: per-thread row writes hit distinct banks
-    float* s_rows = smem;                       // [ROWS][lds]
-    float* s_B = smem + ROWS * lds;             // [3][C]
-    const int C = g.n_fourier, L = g.n_levels;
-    for (int i = threadIdx.x; i < 3 * C; i += ROWS) s_B[i] = g.B[i];
-    __syncthreads();
+// A warp owns 32 consecutive points; a lane owns one (point, level) element at a time (flat index e = lane,
+// lane + 32, ... over [32 points][L levels]; the Fourier prefix likewise over [32 points][C frequencies]).
+// Every output float is produced by the lane that stores it, in row-major order, so the stores (and the dL/dy
+// loads of the backward) are coalesced 128-byte row segments WITHOUT shared-memory staging: no block barrier,
+// ~0.7 KB of shared memory per warp, occupancy limited by registers only.  When L (or C) divides 32 a lane's
+// level (frequency) never changes, so its constants - resolution, rows, fastmod magic, table pointer, B column -
+// live in registers for the whole kernel.
+struct LevelC {                      // 32 bytes, read as two 16-byte shared loads
+    float res; uint32_t rows, mask, soff;
+    unsigned long long magic; const float* tab;
+};
 
-    const long long n_tiles = (n + ROWS - 1) / ROWS;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long p = tile * ROWS + threadIdx.x;
-        float* row = s_rows + threadIdx.x * lds;
-        if (p < n) {
-            const float x0 = x[p * ldx + 0], x1 = x[p * ldx + 1], x2 = x[p * ldx + 2];
-            int col = 0;
-            if (C > 0) {
-                row[0] = x0; row[1] = x1; row[2] = x2;
-                const float t0 = __fmul_rn(x0, 6.283185307179586f);
-                const float t1 = __fmul_rn(x1, 6.283185307179586f);
-                const float t2 = __fmul_rn(x2, 6.283185307179586f);
-                for (int c = 0; c < C; ++c) {
-                    float xp = __fmul_rn(t0, s_B[c]);
-                    xp = __fmaf_rn(t1, s_B[C + c], xp);
-                    xp = __fmaf_rn(t2, s_B[2 * C + c], xp);
-                    float sn, cs;
-                    sincos_fast(xp, &sn, &cs);
-                    row[3 + c] = sn;
-                    row[3 + C + c] = cs;
-                }
-                col = 3 + 2 * C;
-            }
-            if constexpr (MODE == IDRK_HASH_REFERENCE) {
-#pragma unroll 4
-                for (int l = 0; l < L; ++l) {
-                    const float r = g.res[l];
-                    const uint32_t h = hash3(trunc_u32(__fmul_rn(x0, r)), trunc_u32(__fmul_rn(x1, r)),
-                                             trunc_u32(__fmul_rn(x2, r)));
-                    float v[F];
-                    gather<F>(g.tables[l], wrap(h, g.rows[l], g.pow2mask[l], g.magic[l]), v);
+__device__ __forceinline__ LevelC load_level(const LevelC* s_lev, int l) {
+    const uint4 a = reinterpret_cast<const uint4*>(s_lev)[2 * l], b = reinterpret_cast<const uint4*>(s_lev)[2 * l + 1];
+    LevelC c;
+    c.res = __uint_as_float(a.x); c.rows = a.y; c.mask = a.z; c.soff = a.w;
+    c.magic = ((unsigned long long)b.y << 32) | b.x;
+    c.tab = reinterpret_cast<const float*>(((unsigned long long)b.w << 32) | b.z);
+    return c;
+}
+template <bool FAST> __device__ __forceinline__ uint32_t trunc_sel(float v) {
+    if constexpr (FAST) return (uint32_t)__float2int_rz(v); else return trunc_u32(v);
+}
+
+// one (point, level) element of the forward
+template <int F, int MODE, bool FAST>
+__device__ __forceinline__ void fwd_element(const LevelC& lc, float x0, float x1, float x2, float (&acc)[F]) {
+    const float s0 = __fmul_rn(x0, lc.res), s1 = __fmul_rn(x1, lc.res), s2 = __fmul_rn(x2, lc.res);
+    if constexpr (MODE == IDRK_HASH_REFERENCE) {
+        const uint32_t h = hash3(trunc_sel<FAST>(s0), trunc_sel<FAST>(s1), trunc_sel<FAST>(s2));
+        gather<F>(lc.tab, wrap(h, lc.rows, lc.mask, lc.magic), acc);
+    } else {
+        const float f0 = floorf(s0), f1 = floorf(s1), f2 = floorf(s2);
+        const float w0 = s0 - f0, w1 = s1 - f1, w2 = s2 - f2;
+        const uint32_t c0 = trunc_sel<FAST>(f0), c1 = trunc_sel<FAST>(f1), c2 = trunc_sel<FAST>(f2);
+        // hash3 is an xor of three per-dimension terms: form the 2 x 3 terms once, xor per corner
+        const uint32_t hx0 = c0, hx1 = c0 + 1u, hy0 = c1 * 3u, hy1 = hy0 + 3u;
+        const uint32_t hz0 = c2 * 2654435761u, hz1 = hz0 + 2654435761u;
+        float v[8][F];
 #pragma unroll
-                    for (int f = 0; f < F; ++f) row[col + l * F + f] = v[f];
+        for (int k = 0; k < 8; ++k)
+            gather<F>(lc.tab, wrap(((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0), lc.rows, lc.mask, lc.magic), v[k]);
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float wk = ((k & 1) ? w0 : 1.f - w0) * ((k & 2) ? w1 : 1.f - w1) * ((k & 4) ? w2 : 1.f - w2);
+#pragma unroll
+            for (int f = 0; f < F; ++f) acc[f] = fmaf(wk, v[k][f], acc[f]);
+        }
+    }
+}
+
+template <int F>
+__device__ __forceinline__ void store_feat(float* o, const float (&v)[F], bool vec) {
+    if (vec) {
+        if constexpr (F == 2) { __stcs(reinterpret_cast<float2*>(o), make_float2(v[0], v[1])); return; }
+        if constexpr (F == 4) { __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3])); return; }
+        if constexpr (F == 8) {
+            __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+            __stcs(reinterpret_cast<float4*>(o) + 1, make_float4(v[4], v[5], v[6], v[7]));
+            return;
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) __stcs(o + f, v[f]);
+}
+
+// Walks the tile's [rows][L] elements KB at a time: KB independent gathers (8 * KB in the 8-corner mode) are issued
+// before the first store waits on one, which is what hides the L2 / HBM latency of the random table reads.
+// SHIFT (F == 2, level columns starting on an odd column, L | 32): a lane's two features straddle an 8-byte
+// boundary, so it stores (own f1, next level's f0) as one aligned float2 instead of two scalars - every 32-byte
+// sector of the row is then written by one request instead of two half-filled ones.
+template <int F, int MODE, bool FAST, bool SHIFT>
+__device__ __forceinline__ void fwd_levels(const LevelC* s_lev, const float4* xs, int L, int lane, int rows_here,
+                                           float* __restrict__ orow0, int ld_out, bool vec, bool has_pad) {
+    constexpr int KB = !FAST ? 1 : (MODE == IDRK_HASH_REFERENCE) ? (F <= 2 ? 8 : 4) : (F <= 2 ? 2 : 1);
+    const int lstep = 32 % L, rstep = 32 / L;
+    int row = lane / L, l = lane - row * L;
+    LevelC lc = load_level(s_lev, l);
+    const int total = rows_here * L;
+    for (int base = 0; base < total; base += 32 * KB) {
+        float acc[KB][F];
+        int dst[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            dst[k] = -1;
+            if constexpr (SHIFT) acc[k][0] = 0.f;
+            if (base + 32 * k + lane < total) {
+                const float4 xv = xs[row];
+                fwd_element<F, MODE, FAST>(lc, xv.x, xv.y, xv.z, acc[k]);
+                dst[k] = row * ld_out + l * F;
+                row += rstep;
+                if (lstep != 0) {                        // warp-uniform: a lane's level changes only when L does not divide 32
+                    l += lstep;
+                    if (l >= L) { l -= L; ++row; }
+                    lc = load_level(s_lev, l);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            if constexpr (SHIFT) {
+                const float nx = __shfl_down_sync(0xffffffffu, acc[k][0], 1);
+                if (dst[k] >= 0) {
+                    float* o = orow0 + dst[k];
+                    if (l == 0) __stcs(o, acc[k][0]);
+                    if (l != L - 1) __stcs(reinterpret_cast<float2*>(o + 1), make_float2(acc[k][1], nx));
+                    else if (has_pad) __stcs(reinterpret_cast<float2*>(o + 1), make_float2(acc[k][1], 0.f));
+                    else __stcs(o + 1, acc[k][1]);
                 }
             } else {
-#pragma unroll 2
-                for (int l = 0; l < L; ++l) {
-                    const float r = g.res[l];
-                    const float s0 = __fmul_rn(x0, r), s1 = __fmul_rn(x1, r), s2 = __fmul_rn(x2, r);
-                    const float f0 = floorf(s0), f1 = floorf(s1), f2 = floorf(s2);
-                    const float w0 = s0 - f0, w1 = s1 - f1, w2 = s2 - f2;
-                    const uint32_t c0 = trunc_u32(f0), c1 = trunc_u32(f1), c2 = trunc_u32(f2);
-                    const uint32_t rows = g.rows[l], mask = g.pow2mask[l];
-                    const unsigned long long magic = g.magic[l];
-                    const float* tab = g.tables[l];
-                    float v[8][F];
-                    // hash3 is an xor of three per-dimension terms: form the 2 x 3 terms once, xor per corner
-                    const uint32_t hx0 = c0, hx1 = c0 + 1u, hy0 = c1 * 3u, hy1 = hy0 + 3u;
-                    const uint32_t hz0 = c2 * 2654435761u, hz1 = hz0 + 2654435761u;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        gather<F>(tab, wrap(((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0), rows, mask, magic), v[k]);
-                    float acc[F];
-#pragma unroll
-                    for (int f = 0; f < F; ++f) acc[f] = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float wk = ((k & 1) ? w0 : 1.f - w0) * ((k & 2) ? w1 : 1.f - w1) * ((k & 4) ? w2 : 1.f - w2);
-#pragma unroll
-                        for (int f = 0; f < F; ++f) acc[f] = fmaf(wk, v[k][f], acc[f]);
-                    }
-#pragma unroll
-                    for (int f = 0; f < F; ++f) row[col + l * F + f] = acc[f];
-                }
-            }
-            for (int c = g.width; c < ld_out; ++c) row[c] = 0.f;
-
-            if (idx_dbg != nullptr) {           // debug / parity output: table row of all 8 corners
-                for (int l = 0; l < L; ++l) {
-                    const float r = g.res[l];
-                    const float s0 = __fmul_rn(x0, r), s1 = __fmul_rn(x1, r), s2 = __fmul_rn(x2, r);
-                    uint32_t c0, c1, c2;
-                    if constexpr (MODE == IDRK_HASH_REFERENCE) { c0 = trunc_u32(s0); c1 = trunc_u32(s1); c2 = trunc_u32(s2); }
-                    else { c0 = trunc_u32(floorf(s0)); c1 = trunc_u32(floorf(s1)); c2 = trunc_u32(floorf(s2)); }
-                    for (int k = 0; k < 8; ++k)
-                        idx_dbg[(p * L + l) * 8 + k] =
-                            wrap(hash3(c0 + (k & 1), c1 + ((k >> 1) & 1), c2 + ((k >> 2) & 1)), g.rows[l], g.pow2mask[l], g.magic[l]);
-                }
+                if (dst[k] >= 0) store_feat<F>(orow0 + dst[k], acc[k], vec);
             }
         }
-        __syncthreads();
-        // coalesced write-back: the tile's rows are contiguous in global memory (ld_out floats each)
-        const long long rows_here = min((long long)ROWS, n - tile * ROWS);
-        float* gdst = out + tile * ROWS * (long long)ld_out;
-        // the tile's rows are contiguous in global memory: lanes walk consecutive floats (conflict-free smem
-        // reads with the odd row stride, 128-byte coalesced stores)
-        if ((ld_out & 3) == 0) {
-            const int ld4 = ld_out >> 2;
-            for (int r = threadIdx.x >> 5; r < rows_here; r += ROWS / 32) {
-                const float* src = s_rows + r * lds;
-                float4* dst = reinterpret_cast<float4*>(gdst + (long long)r * ld_out);
-                for (int c4 = threadIdx.x & 31; c4 < ld4; c4 += 32)
-                    st_stream4(dst + c4, make_float4(src[4 * c4], src[4 * c4 + 1], src[4 * c4 + 2], src[4 * c4 + 3]));
-            }
-        } else {
-            for (int r = threadIdx.x >> 5; r < rows_here; r += ROWS / 32) {
-                const float* src = s_rows + r * lds;
-                float* dst = gdst + (long long)r * ld_out;
-                for (int c = threadIdx.x & 31; c < ld_out; c += 32) dst[c] = src[c];
-            }
-        }
-        __syncthreads();
     }
 }
 
-
-// Writes columns [coloff, coloff + ncols) of `rows_here` consecutive output rows from a warp-private tile.
-// The 16-byte aligned middle of each row segment goes out as float4 (8 lanes per row, 4 rows per instruction),
-// the unaligned head / tail columns as scalars.
-__device__ __forceinline__ void flush_tile(const float* tile, int tws, float* __restrict__ out, long long row0, int rows_here,
-                                           int ld_out, int coloff, int ncols, int lane, bool vec_ok) {
-    int head = 0, nv = 0;
-    if (vec_ok) { head = (4 - (coloff & 3)) & 3; if (head > ncols) head = ncols; nv = (ncols - head) >> 2; }
-    const int tail0 = head + 4 * nv;
-    if (nv > 0) {
-        int lanes_per_row = 1;
-        while (lanes_per_row < nv) lanes_per_row <<= 1;              // 8 for a 32..35-column pass
-        if (lanes_per_row > 32) lanes_per_row = 32;
-        const int rows_per_it = 32 / lanes_per_row;
-        const int lr = lane / lanes_per_row, lc = lane % lanes_per_row;
-        for (int r = lr; r < rows_here; r += rows_per_it) {
-            const float* src = tile + r * tws + head;
-            float* dst = out + (row0 + r) * (long long)ld_out + coloff + head;
-            for (int c4 = lc; c4 < nv; c4 += lanes_per_row)
-                st_stream4(reinterpret_cast<float4*>(dst) + c4,
-                           make_float4(src[4 * c4], src[4 * c4 + 1], src[4 * c4 + 2], src[4 * c4 + 3]));
-        }
-    }
-    for (int c = 0; c < head; ++c)
-        for (int r = lane; r < rows_here; r += 32) out[(row0 + r) * (long long)ld_out + coloff + c] = tile[r * tws + c];
-    for (int c = tail0; c < ncols; ++c)
-        for (int r = lane; r < rows_here; r += 32) out[(row0 + r) * (long long)ld_out + coloff + c] = tile[r * tws + c];
-}
-
-// Warp-private staging: each warp owns 32 points and a [32][TW+1] shared tile (TW = max(prefix width, level width)),
-// used twice per tile of points - once for the Fourier prefix columns, once for the level columns - so the shared
-// footprint is ~4.7 KB per warp (48+ resident warps per SM instead of 24 with whole-row staging), there is no
-// block-wide barrier in the point loop, and global traffic stays coalesced (row segments of 128 bytes).
-template <int F, int MODE, int ROWS>
-__global__ void __launch_bounds__(ROWS)
-hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
-                       float* __restrict__ out, int ld_out, uint32_t* __restrict__ idx_dbg,
-                       const int* __restrict__ m_count, int tw) {
-    extern __shared__ float smem[];
+template <int F, int MODE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
+                            float* __restrict__ out, int ld_out, uint32_t* __restrict__ idx_dbg,
+                            const int* __restrict__ m_count) {
+    extern __shared__ uint4 smem_u4[];
     if (m_count != nullptr) { const long long c = *m_count; n = c < n ? c : n; }
     const int C = g.n_fourier, L = g.n_levels;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tws = tw + 1;                              // odd-ish stride: row writes and column reads conflict free
-    float* s_B = smem;                                   // [3][C]
-    float* tile = smem + 3 * C + warp * (32 * tws);      // [32][tws], private to this warp
-    for (int i = threadIdx.x; i < 3 * C; i += ROWS) s_B[i] = g.B[i];
+    LevelC* s_lev = reinterpret_cast<LevelC*>(smem_u4);                               // [L]
+    float4* xs = reinterpret_cast<float4*>(smem_u4 + 2 * L) + warp * 32;              // [32] per warp
+    float* s_B = reinterpret_cast<float*>(smem_u4 + 2 * L + WARPS * 32);              // [3][C]
+    for (int i = threadIdx.x; i < L; i += WARPS * 32) {
+        LevelC c; c.res = g.res[i]; c.rows = g.rows[i]; c.mask = g.pow2mask[i]; c.soff = 0; c.magic = g.magic[i]; c.tab = g.tables[i];
+        s_lev[i] = c;
+    }
+    for (int i = threadIdx.x; i < 3 * C; i += WARPS * 32) s_B[i] = g.B[i];
     __syncthreads();
     const int pre = C > 0 ? 3 + 2 * C : 0;
-    const int lev = ld_out - pre;                        // level columns + zero padding up to ld_out
-    float* my = tile + lane * tws;
-    const bool vec_ok = (ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    const int fa = F >= 4 ? 4 : F;                          // floats a vector store must be aligned to
+    const bool vec = F > 1 && (pre % fa) == 0 && (ld_out % fa) == 0 && (reinterpret_cast<uintptr_t>(out) % (4 * fa)) == 0;
+    const bool has_pad = ld_out > g.width;
+    const bool pshift = C >= 2 && (32 % C) == 0 && (ld_out & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
+    const bool shift = F == 2 && L > 0 && (32 % L) == 0 && (pre & 1) && (ld_out & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
+    float res_max = 0.f;
+    for (int l = 0; l < L; ++l) res_max = fmaxf(res_max, fabsf(g.res[l]));
+    // Fourier: lane's frequency is fixed when C divides 32
+    const int jstep = C > 0 ? 32 % C : 0, jrstep = C > 0 ? 32 / C : 0;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    if (C > 0) { const int j = lane % C; b0 = s_B[j]; b1 = s_B[C + j]; b2 = s_B[2 * C + j]; }
 
     const long long n_wtiles = (n + 31) / 32;
-    const long long wstride = (long long)gridDim.x * (ROWS / 32);
-    for (long long wt = (long long)blockIdx.x * (ROWS / 32) + warp; wt < n_wtiles; wt += wstride) {
+    const long long wstride = (long long)gridDim.x * WARPS;
+    for (long long wt = (long long)blockIdx.x * WARPS + warp; wt < n_wtiles; wt += wstride) {
         const long long p0 = wt * 32, p = p0 + lane;
-        const bool valid = p < n;
         const int rows_here = (int)min(32LL, n - p0);
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-        if (valid) { x0 = x[p * ldx + 0]; x1 = x[p * ldx + 1]; x2 = x[p * ldx + 2]; }
-        if (C > 0) {
-            my[0] = x0; my[1] = x1; my[2] = x2;
-            const float t0 = __fmul_rn(x0, 6.283185307179586f);
-            const float t1 = __fmul_rn(x1, 6.283185307179586f);
-            const float t2 = __fmul_rn(x2, 6.283185307179586f);
-            for (int c = 0; c < C; ++c) {
-                float xp = __fmul_rn(t0, s_B[c]);
-                xp = __fmaf_rn(t1, s_B[C + c], xp);
-                xp = __fmaf_rn(t2, s_B[2 * C + c], xp);
+        if (lane < rows_here) { x0 = x[p * ldx + 0]; x1 = x[p * ldx + 1]; x2 = x[p * ldx + 2]; }
+        __syncwarp();
+        xs[lane] = make_float4(x0, x1, x2, 0.f);
+        __syncwarp();
+        float* orow0 = out + p0 * (long long)ld_out;
+        if (C > 0 && pshift) {
+            // C | 32: the lane's frequency j is fixed.  Column 3 + j is even for odd j, so odd lanes store the aligned
+            // pairs (s_j, s_j+1) and (c_j, c_j+1) - the partner value comes from the next lane - lane 0 stores
+            // (x2, s_0) and one even lane (x0, x1): every sector of the prefix is written by full 8-byte words.
+            const int j = lane & (C - 1), jx = C > 2 ? 2 : 1;
+            for (int row0 = 0; row0 < rows_here; row0 += jrstep) {
+                const int row = row0 + lane / C;
+                const float4 xv = xs[row & 31];
+                float xp = __fmul_rn(__fmul_rn(xv.x, 6.283185307179586f), b0);
+                xp = __fmaf_rn(__fmul_rn(xv.y, 6.283185307179586f), b1, xp);
+                xp = __fmaf_rn(__fmul_rn(xv.z, 6.283185307179586f), b2, xp);
                 float sn, cs;
                 sincos_fast(xp, &sn, &cs);
-                my[3 + c] = sn;
-                my[3 + C + c] = cs;
-            }
-            __syncwarp();
-            flush_tile(tile, tws, out, p0, rows_here, ld_out, 0, pre, lane, vec_ok);
-            __syncwarp();
-        }
-        if constexpr (MODE == IDRK_HASH_REFERENCE) {
-#pragma unroll 4
-            for (int l = 0; l < L; ++l) {
-                const float r = g.res[l];
-                const uint32_t h = hash3(trunc_u32(__fmul_rn(x0, r)), trunc_u32(__fmul_rn(x1, r)),
-                                         trunc_u32(__fmul_rn(x2, r)));
-                float v[F];
-                gather<F>(g.tables[l], wrap(h, g.rows[l], g.pow2mask[l], g.magic[l]), v);
-#pragma unroll
-                for (int f = 0; f < F; ++f) my[l * F + f] = v[f];
-            }
-        } else {
-#pragma unroll 2
-            for (int l = 0; l < L; ++l) {
-                const float r = g.res[l];
-                const float s0 = __fmul_rn(x0, r), s1 = __fmul_rn(x1, r), s2 = __fmul_rn(x2, r);
-                const float f0 = floorf(s0), f1 = floorf(s1), f2 = floorf(s2);
-                const float w0 = s0 - f0, w1 = s1 - f1, w2 = s2 - f2;
-                const uint32_t c0 = trunc_u32(f0), c1 = trunc_u32(f1), c2 = trunc_u32(f2);
-                const uint32_t rows = g.rows[l], mask = g.pow2mask[l];
-                const unsigned long long magic = g.magic[l];
-                const float* tab = g.tables[l];
-                float v[8][F];
-                // hash3 is an xor of three per-dimension terms: form the 2 x 3 terms once, xor per corner
-                const uint32_t hx0 = c0, hx1 = c0 + 1u, hy0 = c1 * 3u, hy1 = hy0 + 3u;
-                const uint32_t hz0 = c2 * 2654435761u, hz1 = hz0 + 2654435761u;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    gather<F>(tab, wrap(((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0), rows, mask, magic), v[k]);
-                float acc[F];
-#pragma unroll
-                for (int f = 0; f < F; ++f) acc[f] = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float wk = ((k & 1) ? w0 : 1.f - w0) * ((k & 2) ? w1 : 1.f - w1) * ((k & 4) ? w2 : 1.f - w2);
-#pragma unroll
-                    for (int f = 0; f < F; ++f) acc[f] = fmaf(wk, v[k][f], acc[f]);
+                const float sn_n = __shfl_down_sync(0xffffffffu, sn, 1), cs_n = __shfl_down_sync(0xffffffffu, cs, 1);
+                const float cs_0 = __shfl_sync(0xffffffffu, cs, lane & ~(C - 1));
+                if (row < rows_here) {
+                    float* o = orow0 + (long long)row * ld_out;
+                    if (j & 1) {
+                        __stcs(reinterpret_cast<float2*>(o + 3 + j), make_float2(sn, j == C - 1 ? cs_0 : sn_n));
+                        if (j != C - 1) __stcs(reinterpret_cast<float2*>(o + 3 + C + j), make_float2(cs, cs_n));
+                        else __stcs(o + 3 + C + j, cs);
+                    }
+                    if (j == 0) __stcs(reinterpret_cast<float2*>(o + 2), make_float2(xv.z, sn));
+                    if (j == jx) __stcs(reinterpret_cast<float2*>(o), make_float2(xv.x, xv.y));
                 }
-#pragma unroll
-                for (int f = 0; f < F; ++f) my[l * F + f] = acc[f];
+            }
+        } else if (C > 0) {
+            for (int i = lane; i < 3 * rows_here; i += 32) {
+                const int r = i / 3, c = i - 3 * r;
+                __stcs(orow0 + (long long)r * ld_out + c, reinterpret_cast<const float*>(xs + r)[c]);
+            }
+            int row = lane / C, j = lane - row * C;
+            const int total = rows_here * C;
+#pragma unroll 2
+            for (int e = lane; e < total; e += 32) {
+                const float4 xv = xs[row];
+                float xp = __fmul_rn(__fmul_rn(xv.x, 6.283185307179586f), b0);
+                xp = __fmaf_rn(__fmul_rn(xv.y, 6.283185307179586f), b1, xp);
+                xp = __fmaf_rn(__fmul_rn(xv.z, 6.283185307179586f), b2, xp);
+                float sn, cs;
+                sincos_fast(xp, &sn, &cs);
+                float* o = orow0 + (long long)row * ld_out + 3 + j;
+                __stcs(o, sn);
+                __stcs(o + C, cs);
+                row += jrstep;
+                if (jstep != 0) {
+                    j += jstep;
+                    if (j >= C) { j -= C; ++row; }
+                    b0 = s_B[j]; b1 = s_B[C + j]; b2 = s_B[2 * C + j];
+                }
+            }
+            if (jstep != 0) { const int j0 = lane % C; b0 = s_B[j0]; b1 = s_B[C + j0]; b2 = s_B[2 * C + j0]; }
+        }
+        bool fast_tile = true;
+        if (L > 0) {
+            // .long() of a coordinate fits 32 bits for every level unless a point is astronomically far out
+            const float amax = fmaxf(fabsf(x0), fmaxf(fabsf(x1), fabsf(x2))) * res_max;
+            const bool fast = __all_sync(0xffffffffu, amax < 2147483520.f);
+            fast_tile = fast;
+            if (!fast) {
+                fwd_levels<F, MODE, false, false>(s_lev, xs, L, lane, rows_here, orow0 + pre, ld_out, vec, has_pad);
+            } else if (F == 2 && shift) {
+                fwd_levels<F, MODE, true, F == 2>(s_lev, xs, L, lane, rows_here, orow0 + pre, ld_out, vec, has_pad);
+            } else {
+                fwd_levels<F, MODE, true, false>(s_lev, xs, L, lane, rows_here, orow0 + pre, ld_out, vec, has_pad);
             }
         }
-        for (int c = L * F; c < lev; ++c) my[c] = 0.f;
-        __syncwarp();
-        flush_tile(tile, tws, out, p0, rows_here, ld_out, pre, lev, lane, vec_ok);
-        __syncwarp();
+        if (lane < rows_here)
+            for (int c = g.width + (shift && fast_tile && has_pad ? 1 : 0); c < ld_out; ++c) __stcs(orow0 + (long long)lane * ld_out + c, 0.f);
 
-        if (idx_dbg != nullptr && valid) {      // debug / parity output: table row of all 8 corners
-            for (int l = 0; l < L; ++l) {
+        if (idx_dbg != nullptr) {               // debug / parity output: table row of all 8 corners
+            for (int e = lane; e < rows_here * L; e += 32) {
+                const int row = e / L, l = e - row * L;
+                const float4 xv = xs[row];
                 const float r = g.res[l];
-                const float s0 = __fmul_rn(x0, r), s1 = __fmul_rn(x1, r), s2 = __fmul_rn(x2, r);
+                const float s0 = __fmul_rn(xv.x, r), s1 = __fmul_rn(xv.y, r), s2 = __fmul_rn(xv.z, r);
                 uint32_t c0, c1, c2;
                 if constexpr (MODE == IDRK_HASH_REFERENCE) { c0 = trunc_u32(s0); c1 = trunc_u32(s1); c2 = trunc_u32(s2); }
                 else { c0 = trunc_u32(floorf(s0)); c1 = trunc_u32(floorf(s1)); c2 = trunc_u32(floorf(s2)); }
                 for (int k = 0; k < 8; ++k)
-                    idx_dbg[(p * L + l) * 8 + k] =
+                    idx_dbg[((p0 + row) * L + l) * 8 + k] =
                         wrap(hash3(c0 + (k & 1), c1 + ((k >> 1) & 1), c2 + ((k >> 2) & 1)), g.rows[l], g.pow2mask[l], g.magic[l]);
             }
         }
@@ -367,131 +356,256 @@ hash_encode_fwd_kernel(const GridDev g, const float* __restrict__ x, long long n
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
-template <int F, int MODE, int ROWS>
-__global__ void __launch_bounds__(ROWS)
-hash_encode_bwd_kernel(const GridDev g, const GradDev gd, const float* __restrict__ x, long long n, int ldx,
-                       const float* __restrict__ dy, int ld_dy, float* __restrict__ dx) {
-    extern __shared__ float smem[];
-    const int lds = ld_dy | 1;
-    float* s_rows = smem;                        // [ROWS][lds]
-    float* s_B = smem + ROWS * lds;              // [3][C]
-    float* s_acc = s_B + 3 * g.n_fourier;        // [small_total]
-    const int C = g.n_fourier, L = g.n_levels;
-    for (int i = threadIdx.x; i < 3 * C; i += ROWS) s_B[i] = g.B[i];
-    for (int i = threadIdx.x; i < gd.small_total; i += ROWS) s_acc[i] = 0.f;
-    __syncthreads();
+// Backward, element-per-lane (see the forward above): lane (row, l) reads its dL/dy features straight from the row
+// (aligned float2 + one shuffle when the level columns start on an odd column), forms the table row(s) again and
+// issues the vector reductions.  dL/dx partials are reduced across a row's lanes with xor-shuffles when L (C)
+// divides 32, otherwise through shared-memory float atomics on a per-warp [32][3] tile.
+template <int F>
+__device__ __forceinline__ void scatter_sel(float* gtab, float* s_acc, uint32_t soff, uint32_t idx, const float (&v)[F]) {
+    if (soff != 0xffffffffu) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) atomicAdd(s_acc + soff + idx * F + f, v[f]);
+    } else {
+        scatter_add<F>(gtab, idx, v);
+    }
+}
 
-    const int col0 = (C > 0) ? 3 + 2 * C : 0;
-    const long long n_tiles = (n + ROWS - 1) / ROWS;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long rows_here = min((long long)ROWS, n - tile * ROWS);
-        const float* gsrc = dy + tile * ROWS * (long long)ld_dy;
-        if ((ld_dy & 3) == 0 && ((reinterpret_cast<uintptr_t>(dy) & 15u) == 0)) {
-            const int ld4 = ld_dy >> 2;
-            for (int r = threadIdx.x >> 5; r < rows_here; r += ROWS / 32) {
-                float* dst = s_rows + r * lds;
-                for (int c4 = threadIdx.x & 31; c4 < ld4; c4 += 32) {
-                    float4 v = ld_stream4(reinterpret_cast<const float4*>(gsrc + (long long)r * ld_dy) + c4);
-                    dst[4 * c4] = v.x; dst[4 * c4 + 1] = v.y; dst[4 * c4 + 2] = v.z; dst[4 * c4 + 3] = v.w;
-                }
+template <int F, int MODE, bool FAST, bool WANT_DX>
+__device__ __forceinline__ void bwd_element(const LevelC& lc, float* gtab, float* s_acc, float x0, float x1, float x2,
+                                            const float (&gy)[F], float (&d)[3]) {
+    const float s0 = __fmul_rn(x0, lc.res), s1 = __fmul_rn(x1, lc.res), s2 = __fmul_rn(x2, lc.res);
+    if constexpr (MODE == IDRK_HASH_REFERENCE) {
+        if (gtab == nullptr) return;
+        const uint32_t h = hash3(trunc_sel<FAST>(s0), trunc_sel<FAST>(s1), trunc_sel<FAST>(s2));
+        scatter_sel<F>(gtab, s_acc, lc.soff, wrap(h, lc.rows, lc.mask, lc.magic), gy);
+    } else {
+        const float f0 = floorf(s0), f1 = floorf(s1), f2 = floorf(s2);
+        const float w0 = s0 - f0, w1 = s1 - f1, w2 = s2 - f2;
+        const uint32_t c0 = trunc_sel<FAST>(f0), c1 = trunc_sel<FAST>(f1), c2 = trunc_sel<FAST>(f2);
+        const uint32_t hx0 = c0, hx1 = c0 + 1u, hy0 = c1 * 3u, hy1 = hy0 + 3u;
+        const uint32_t hz0 = c2 * 2654435761u, hz1 = hz0 + 2654435761u;
+        uint32_t idx[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            idx[k] = wrap(((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0), lc.rows, lc.mask, lc.magic);
+        float t[8][F];
+        if constexpr (WANT_DX) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gather<F>(lc.tab, idx[k], t[k]);
+        }
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float a0 = (k & 1) ? w0 : 1.f - w0, a1 = (k & 2) ? w1 : 1.f - w1, a2 = (k & 4) ? w2 : 1.f - w2;
+            if (gtab != nullptr) {
+                const float wk = a0 * a1 * a2;
+                float v[F];
+#pragma unroll
+                for (int f = 0; f < F; ++f) v[f] = wk * gy[f];
+                scatter_sel<F>(gtab, s_acc, lc.soff, idx[k], v);
             }
-        } else {
-            const int total = (int)rows_here * ld_dy;
-            for (int i = threadIdx.x; i < total; i += ROWS) {
-                const int r = i / ld_dy, c = i - r * ld_dy;
-                s_rows[r * lds + c] = gsrc[i];
+            if constexpr (WANT_DX) {
+                float dot = 0.f;
+#pragma unroll
+                for (int f = 0; f < F; ++f) dot = fmaf(t[k][f], gy[f], dot);
+                d0 = fmaf(((k & 1) ? 1.f : -1.f) * a1 * a2, dot, d0);
+                d1 = fmaf(((k & 2) ? 1.f : -1.f) * a0 * a2, dot, d1);
+                d2 = fmaf(((k & 4) ? 1.f : -1.f) * a0 * a1, dot, d2);
             }
         }
-        __syncthreads();
-        const long long p = tile * ROWS + threadIdx.x;
-        if (p < n) {
-            const float* row = s_rows + threadIdx.x * lds;
-            const float x0 = x[p * ldx + 0], x1 = x[p * ldx + 1], x2 = x[p * ldx + 2];
-            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-            if (C > 0 && dx != nullptr) {
-                g0 = row[0]; g1 = row[1]; g2 = row[2];
-                const float t0 = __fmul_rn(x0, 6.283185307179586f);
-                const float t1 = __fmul_rn(x1, 6.283185307179586f);
-                const float t2 = __fmul_rn(x2, 6.283185307179586f);
-                for (int c = 0; c < C; ++c) {
-                    float xp = __fmul_rn(t0, s_B[c]);
-                    xp = __fmaf_rn(t1, s_B[C + c], xp);
-                    xp = __fmaf_rn(t2, s_B[2 * C + c], xp);
+        if constexpr (WANT_DX) { d[0] = d0 * lc.res; d[1] = d1 * lc.res; d[2] = d2 * lc.res; }
+    }
+}
+
+// adds (v0, v1, v2) of every lane into dxs[row]: xor-shuffle over the aligned group of `grp` lanes that share the row
+// (grp = L or C when it divides 32), else shared-memory atomics.
+__device__ __forceinline__ void row_reduce_add(float* dxs, int row, bool active, int grp, bool grp_ok, int lane,
+                                               float v0, float v1, float v2) {
+    if (grp_ok) {
+        for (int off = grp >> 1; off > 0; off >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, off);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, off);
+        }
+        if (active && (lane & (grp - 1)) == 0) { dxs[4 * row] += v0; dxs[4 * row + 1] += v1; dxs[4 * row + 2] += v2; }
+    } else if (active) {
+        atomicAdd(dxs + 4 * row, v0); atomicAdd(dxs + 4 * row + 1, v1); atomicAdd(dxs + 4 * row + 2, v2);
+    }
+}
+
+template <int F, int MODE, bool FAST, bool WANT_DX>
+__device__ __forceinline__ void bwd_levels(const LevelC* s_lev, float* const* s_grad, float* s_acc, const float4* xs, float* dxs,
+                                           int L, int lane, int rows_here, const float* __restrict__ drow0, int ld_dy,
+                                           bool shift, bool has_pad) {
+    constexpr int KB = !FAST ? 1 : (MODE == IDRK_HASH_REFERENCE) ? 4 : (WANT_DX ? 1 : 2);
+    const int lstep = 32 % L, rstep = 32 / L;
+    const bool l_ok = lstep == 0;
+    int row = lane / L, l = lane - row * L;
+    LevelC lc = load_level(s_lev, l);
+    float* gtab = s_grad[l];
+    const int total = rows_here * L;
+    for (int base = 0; base < total; base += 32 * KB) {
+        float gy[KB][F];
+        // phase 1: the dL/dy loads of KB elements
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const bool act = base + 32 * k + lane < total;
+            if constexpr (F == 2) {
+                if (shift) {
+                    // aligned pair (own f1, next level's f0); own f0 arrives from the previous lane
+                    float2 pr = make_float2(0.f, 0.f);
+                    float first = 0.f;
+                    if (act) {
+                        const float* o = drow0 + (long long)(row + k * rstep) * ld_dy + 2 * l;
+                        if (l != L - 1 || has_pad) pr = __ldcs(reinterpret_cast<const float2*>(o + 1));
+                        else pr.x = __ldcs(o + 1);
+                        if (l == 0) first = __ldcs(o);
+                    }
+                    const float up = __shfl_up_sync(0xffffffffu, pr.y, 1);
+                    gy[k][0] = (l == 0) ? first : up;
+                    gy[k][1] = pr.x;
+                    continue;
+                }
+            }
+            if (lstep == 0 && act) {
+                const float* o = drow0 + (long long)(row + k * rstep) * ld_dy + l * F;
+#pragma unroll
+                for (int f = 0; f < F; ++f) gy[k][f] = __ldg(o + f);
+            }
+        }
+        // phase 2: table rows, reductions, dL/dx partials
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const bool act = base + 32 * k + lane < total;
+            if (lstep != 0 && act) {
+                const float* o = drow0 + (long long)row * ld_dy + l * F;
+#pragma unroll
+                for (int f = 0; f < F; ++f) gy[k][f] = __ldg(o + f);
+            }
+            float d[3] = {0.f, 0.f, 0.f};
+            const int r_here = row;
+            if (act) {
+                const float4 xv = xs[row];
+                bwd_element<F, MODE, FAST, WANT_DX>(lc, gtab, s_acc, xv.x, xv.y, xv.z, gy[k], d);
+            }
+            if constexpr (WANT_DX && MODE == IDRK_HASH_TRILINEAR) row_reduce_add(dxs, r_here & 31, act, L, l_ok, lane, d[0], d[1], d[2]);
+            row += rstep;
+            if (lstep != 0 && act) {
+                l += lstep;
+                if (l >= L) { l -= L; ++row; }
+                lc = load_level(s_lev, l);
+                gtab = s_grad[l];
+            }
+        }
+    }
+}
+
+template <int F, int MODE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __restrict__ x, long long n, int ldx,
+                            const float* __restrict__ dy, int ld_dy, float* __restrict__ dx) {
+    extern __shared__ uint4 smem_u4[];
+    const int C = g.n_fourier, L = g.n_levels;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    LevelC* s_lev = reinterpret_cast<LevelC*>(smem_u4);                               // [L]
+    float4* xs = reinterpret_cast<float4*>(smem_u4 + 2 * L) + warp * 32;              // [32] per warp
+    float* dxs = reinterpret_cast<float*>(smem_u4 + 2 * L + WARPS * 32) + warp * 128; // [32][4] per warp
+    float** s_grad = reinterpret_cast<float**>(smem_u4 + 2 * L + 2 * WARPS * 32);     // [L] (padded to even)
+    float* s_B = reinterpret_cast<float*>(s_grad + ((L + 1) & ~1));                   // [3][C]
+    float* s_acc = s_B + ((3 * C + 3) & ~3);                                          // [small_total]
+    for (int i = threadIdx.x; i < L; i += WARPS * 32) {
+        LevelC c; c.res = g.res[i]; c.rows = g.rows[i]; c.mask = g.pow2mask[i];
+        c.soff = gd.small_off[i] >= 0 ? (uint32_t)gd.small_off[i] : 0xffffffffu; c.magic = g.magic[i]; c.tab = g.tables[i];
+        s_lev[i] = c;
+        s_grad[i] = gd.grad[i];
+    }
+    for (int i = threadIdx.x; i < 3 * C; i += WARPS * 32) s_B[i] = g.B[i];
+    for (int i = threadIdx.x; i < gd.small_total; i += WARPS * 32) s_acc[i] = 0.f;
+    __syncthreads();
+    const int pre = C > 0 ? 3 + 2 * C : 0;
+    const bool has_pad = ld_dy > g.width;
+    const bool shift = F == 2 && L > 0 && (32 % L) == 0 && (pre & 1) && (ld_dy & 1) == 0 && (reinterpret_cast<uintptr_t>(dy) & 7u) == 0;
+    const bool want_dx = dx != nullptr;
+    float res_max = 0.f;
+    for (int l = 0; l < L; ++l) res_max = fmaxf(res_max, fabsf(g.res[l]));
+    const int jstep = C > 0 ? 32 % C : 0, jrstep = C > 0 ? 32 / C : 0;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    if (C > 0) { const int j = lane % C; b0 = s_B[j]; b1 = s_B[C + j]; b2 = s_B[2 * C + j]; }
+
+    const long long n_wtiles = (n + 31) / 32;
+    const long long wstride = (long long)gridDim.x * WARPS;
+    for (long long wt = (long long)blockIdx.x * WARPS + warp; wt < n_wtiles; wt += wstride) {
+        const long long p0 = wt * 32, p = p0 + lane;
+        const int rows_here = (int)min(32LL, n - p0);
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+        if (lane < rows_here) { x0 = x[p * ldx + 0]; x1 = x[p * ldx + 1]; x2 = x[p * ldx + 2]; }
+        const float* drow0 = dy + p0 * (long long)ld_dy;
+        __syncwarp();
+        xs[lane] = make_float4(x0, x1, x2, 0.f);
+        if (want_dx) {
+            float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (C > 0 && lane < rows_here) {           // identity columns of the prefix
+                const float* o = drow0 + (long long)lane * ld_dy;
+                d0.x = __ldg(o); d0.y = __ldg(o + 1); d0.z = __ldg(o + 2);
+            }
+            reinterpret_cast<float4*>(dxs)[lane] = d0;
+        }
+        __syncwarp();
+        if (want_dx && C > 0) {
+            // d/dx of [sin(2 pi x B), cos(2 pi x B)]
+            int row = lane / C, j = lane - row * C;
+            const int total = rows_here * C;
+            for (int base = 0; base < total; base += 32) {
+                const bool act = base + lane < total;
+                float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                const int r_here = row;
+                if (act) {
+                    const float4 xv = xs[row];
+                    float xp = __fmul_rn(__fmul_rn(xv.x, 6.283185307179586f), b0);
+                    xp = __fmaf_rn(__fmul_rn(xv.y, 6.283185307179586f), b1, xp);
+                    xp = __fmaf_rn(__fmul_rn(xv.z, 6.283185307179586f), b2, xp);
                     float sn, cs;
                     sincos_fast(xp, &sn, &cs);
-                    const float dxp = (row[3 + c] * cs - row[3 + C + c] * sn) * 6.283185307179586f;
-                    g0 = fmaf(dxp, s_B[c], g0);
-                    g1 = fmaf(dxp, s_B[C + c], g1);
-                    g2 = fmaf(dxp, s_B[2 * C + c], g2);
+                    const float* o = drow0 + (long long)row * ld_dy + 3 + j;
+                    const float dxp = (__ldg(o) * cs - __ldg(o + C) * sn) * 6.283185307179586f;
+                    v0 = dxp * b0; v1 = dxp * b1; v2 = dxp * b2;
+                }
+                row_reduce_add(dxs, r_here & 31, act, C, jstep == 0, lane, v0, v1, v2);
+                row += jrstep;
+                if (jstep != 0) {
+                    j += jstep;
+                    if (j >= C) { j -= C; ++row; }
+                    b0 = s_B[j]; b1 = s_B[C + j]; b2 = s_B[2 * C + j];
                 }
             }
-#pragma unroll 2
-            for (int l = 0; l < L; ++l) {
-                const float r = g.res[l];
-                const uint32_t rows = g.rows[l], mask = g.pow2mask[l];
-                const unsigned long long magic = g.magic[l];
-                float gy[F];
-#pragma unroll
-                for (int f = 0; f < F; ++f) gy[f] = row[col0 + l * F + f];
-                const int soff = gd.small_off[l];
-                const bool do_scatter = gd.grad[l] != nullptr;
-                if constexpr (MODE == IDRK_HASH_REFERENCE) {
-                    if (!do_scatter) continue;
-                    const uint32_t idx = wrap(hash3(trunc_u32(__fmul_rn(x0, r)), trunc_u32(__fmul_rn(x1, r)),
-                                                    trunc_u32(__fmul_rn(x2, r))), rows, mask, magic);
-                    if (soff >= 0) {
-#pragma unroll
-                        for (int f = 0; f < F; ++f) atomicAdd(s_acc + soff + idx * F + f, gy[f]);
-                    } else {
-                        scatter_add<F>(gd.grad[l], idx, gy);
-                    }
-                } else {
-                    const float s0 = __fmul_rn(x0, r), s1 = __fmul_rn(x1, r), s2 = __fmul_rn(x2, r);
-                    const float f0 = floorf(s0), f1 = floorf(s1), f2 = floorf(s2);
-                    const float w0 = s0 - f0, w1 = s1 - f1, w2 = s2 - f2;
-                    const uint32_t c0 = trunc_u32(f0), c1 = trunc_u32(f1), c2 = trunc_u32(f2);
-                    const float* tab = g.tables[l];
-                    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t idx = wrap(hash3(c0 + (k & 1), c1 + ((k >> 1) & 1), c2 + ((k >> 2) & 1)), rows, mask, magic);
-                        const float a0 = (k & 1) ? w0 : 1.f - w0, a1 = (k & 2) ? w1 : 1.f - w1, a2 = (k & 4) ? w2 : 1.f - w2;
-                        const float wk = a0 * a1 * a2;
-                        float v[F];
-#pragma unroll
-                        for (int f = 0; f < F; ++f) v[f] = wk * gy[f];
-                        if (!do_scatter) {
-                        } else if (soff >= 0) {
-#pragma unroll
-                            for (int f = 0; f < F; ++f) atomicAdd(s_acc + soff + idx * F + f, v[f]);
-                        } else {
-                            scatter_add<F>(gd.grad[l], idx, v);
-                        }
-                        if (dx != nullptr) {
-                            float t[F];
-                            gather<F>(tab, idx, t);
-                            float dot = 0.f;
-#pragma unroll
-                            for (int f = 0; f < F; ++f) dot = fmaf(t[f], gy[f], dot);
-                            d0 = fmaf(((k & 1) ? 1.f : -1.f) * a1 * a2, dot, d0);
-                            d1 = fmaf(((k & 2) ? 1.f : -1.f) * a0 * a2, dot, d1);
-                            d2 = fmaf(((k & 4) ? 1.f : -1.f) * a0 * a1, dot, d2);
-                        }
-                    }
-                    g0 = fmaf(d0, r, g0); g1 = fmaf(d1, r, g1); g2 = fmaf(d2, r, g2);
-                }
-            }
-            if (dx != nullptr) { dx[p * 3 + 0] = g0; dx[p * 3 + 1] = g1; dx[p * 3 + 2] = g2; }
+            if (jstep != 0) { const int j0 = lane % C; b0 = s_B[j0]; b1 = s_B[C + j0]; b2 = s_B[2 * C + j0]; }
         }
-        __syncthreads();
+        __syncwarp();
+        if (L > 0 && (MODE == IDRK_HASH_TRILINEAR || gd.any_grad)) {
+            const float amax = fmaxf(fabsf(x0), fmaxf(fabsf(x1), fabsf(x2))) * res_max;
+            const bool fast = __all_sync(0xffffffffu, amax < 2147483520.f);
+            if (!fast) {
+                if (want_dx) bwd_levels<F, MODE, false, true>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy, false, has_pad);
+                else         bwd_levels<F, MODE, false, false>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy, false, has_pad);
+            } else if (want_dx) {
+                bwd_levels<F, MODE, true, true>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy, shift, has_pad);
+            } else {
+                bwd_levels<F, MODE, true, false>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy, shift, has_pad);
+            }
+        }
+        if (want_dx) {
+            __syncwarp();
+            if (lane < rows_here) { dx[p * 3 + 0] = dxs[4 * lane]; dx[p * 3 + 1] = dxs[4 * lane + 1]; dx[p * 3 + 2] = dxs[4 * lane + 2]; }
+        }
     }
     // flush the CTA-local accumulators of the small tables
     if (gd.small_total > 0) {
+        __syncthreads();
         for (int l = 0; l < L; ++l) {
             const int soff = gd.small_off[l];
             if (soff < 0) continue;
             const int cnt = (int)g.rows[l] * F;
-            for (int i = threadIdx.x; i < cnt; i += ROWS) {
+            for (int i = threadIdx.x; i < cnt; i += WARPS * 32) {
                 const float v = s_acc[soff + i];
                 if (v != 0.f) atomicAdd(gd.grad[l] + i, v);
             }
@@ -523,49 +637,43 @@ static int fill_grid(const idrk_hashgrid_t* h, GridDev& g) {
     return 0;
 }
 
+// Persistent grid = resident CTAs per SM x SM count.  Also pins the L1 / shared-memory split to what the kernel
+// needs: the random table reads live off L1 + L2, and with the default preference the driver keeps the large
+// shared-memory carve-out left behind by a preceding GEMM launch (measured: -35 % on the 8-corner forward).
 template <typename K>
 static int persistent_grid(K kernel, int threads, size_t smem, long long n_tiles) {
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int pct = (int)(((smem + 1024) * (size_t)per_sm * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     long long g = (long long)per_sm * sm_count();
     if (g > n_tiles) g = n_tiles;
     if (g < 1) g = 1;
     return (int)g;
 }
 
-template <int F, int MODE, int ROWS>
+template <int F, int MODE, int WARPS>
 static int launch_fwd(const GridDev& g, const float* x, long long n, int ldx, float* out, int ld_out,
                       uint32_t* idx_dbg, const int* m_count, cudaStream_t st) {
-    if (MODE == IDRK_HASH_REFERENCE && (size_t)ROWS * (ld_out | 1) * sizeof(float) <= 72 * 1024) {
-        // one gather per level: issue-bound, whole-row staging with a single float4 write-back wins
-        const size_t smem_b = ((size_t)ROWS * (ld_out | 1) + 3 * g.n_fourier) * sizeof(float);
-        auto kb = hash_encode_fwd_block_kernel<F, MODE, ROWS>;
-        IDRK_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-        const int grid_b = persistent_grid(kb, ROWS, smem_b, (n + ROWS - 1) / ROWS);
-        kb<<<grid_b, ROWS, smem_b, st>>>(g, x, n, ldx, out, ld_out, idx_dbg, m_count);
-        IDRK_LAUNCH_CHECK();
-        return 0;
-    }
-    // 8 gathers per level: latency-bound, warp-private staging doubles the resident warps
-    const int pre = g.n_fourier > 0 ? 3 + 2 * g.n_fourier : 0;
-    const int tw = (pre > ld_out - pre ? pre : ld_out - pre) | 1;
-    const size_t smem = ((size_t)(ROWS / 32) * 32 * (tw + 1) + 3 * g.n_fourier) * sizeof(float);
-    auto kern = hash_encode_fwd_kernel<F, MODE, ROWS>;
-    IDRK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = persistent_grid(kern, ROWS, smem, (n + ROWS - 1) / ROWS);
-    kern<<<grid, ROWS, smem, st>>>(g, x, n, ldx, out, ld_out, idx_dbg, m_count, tw);
+    const size_t smem = ((size_t)2 * g.n_levels + WARPS * 32) * 16 + (size_t)3 * g.n_fourier * sizeof(float);
+    auto kern = hash_encode_fwd_elem_kernel<F, MODE, WARPS>;
+    const int grid = persistent_grid(kern, WARPS * 32, smem, (n + WARPS * 32 - 1) / (WARPS * 32));
+    kern<<<grid, WARPS * 32, smem, st>>>(g, x, n, ldx, out, ld_out, idx_dbg, m_count);
     IDRK_LAUNCH_CHECK();
     return 0;
 }
 
-template <int F, int MODE, int ROWS>
+template <int F, int MODE, int WARPS>
 static int launch_bwd(const GridDev& g, const GradDev& gd, const float* x, long long n, int ldx, const float* dy,
                       int ld_dy, float* dx, cudaStream_t st) {
-    const size_t smem = ((size_t)ROWS * (ld_dy | 1) + 3 * g.n_fourier + gd.small_total) * sizeof(float);
-    auto kern = hash_encode_bwd_kernel<F, MODE, ROWS>;
+    const int L = g.n_levels, C = g.n_fourier;
+    const size_t smem = ((size_t)2 * L + 2 * WARPS * 32) * 16 + (size_t)((L + 1) & ~1) * 8 +
+                        (size_t)((3 * C + 3) & ~3) * 4 + (size_t)gd.small_total * 4;
+    auto kern = hash_encode_bwd_elem_kernel<F, MODE, WARPS>;
     IDRK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = persistent_grid(kern, ROWS, smem, (n + ROWS - 1) / ROWS);
-    kern<<<grid, ROWS, smem, st>>>(g, gd, x, n, ldx, dy, ld_dy, dx);
+    const int grid = persistent_grid(kern, WARPS * 32, smem, (n + WARPS * 32 - 1) / (WARPS * 32));
+    kern<<<grid, WARPS * 32, smem, st>>>(g, gd, x, n, ldx, dy, ld_dy, dx);
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -608,7 +716,7 @@ extern "C" int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* 
     if ((ld_out & 3) == 0 && !aligned16(out)) return IDRK_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = h_grid->frac_mode;
-#define CALL(F, M) launch_fwd<F, M, 128>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
+#define CALL(F, M) launch_fwd<F, M, 4>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
     IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
 }
@@ -624,6 +732,7 @@ extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* 
     if (n == 0) return 0;
     GradDev gd;
     gd.small_total = 0;
+    gd.any_grad = h_grad_tables != nullptr ? 1 : 0;
     const int budget = 8192;                    // floats of CTA-local accumulators (32 KB)
     const size_t align = (g.n_feat >= 4) ? 16 : 4 * (size_t)g.n_feat;
     for (int l = 0; l < IDRK_MAX_LEVELS; ++l) { gd.grad[l] = nullptr; gd.small_off[l] = -1; }
@@ -636,15 +745,7 @@ extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* 
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = h_grid->frac_mode;
-    const size_t row_bytes = (size_t)(ld_dy | 1) * sizeof(float);
-    if (row_bytes * 128 <= 72 * 1024) {
-#define CALL(F, M) launch_bwd<F, M, 128>(g, gd, x, n, ldx, dy, ld_dy, dx, st)
-        IDRK_DISPATCH_F_MODE(CALL)
+#define CALL(F, M) launch_bwd<F, M, 4>(g, gd, x, n, ldx, dy, ld_dy, dx, st)
+    IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
-    } else if (row_bytes * 64 <= 160 * 1024) {
-#define CALL(F, M) launch_bwd<F, M, 64>(g, gd, x, n, ldx, dy, ld_dy, dx, st)
-        IDRK_DISPATCH_F_MODE(CALL)
-#undef CALL
-    }
-    return IDRK_E_UNSUP;
 }

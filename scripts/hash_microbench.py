@@ -48,15 +48,21 @@ def run(n, log2T, mode, L=16, F=2, flush=None):
     t_f = time_cuda(lambda: K.hash_encode_fwd(spec, x, tables, B, out=out), flush=flush)
     t_b = time_cuda(lambda: K.hash_encode_bwd(spec, x, tables, B, dy, grads, False), flush=flush)      # table gradients
     t_bx = time_cuda(lambda: K.hash_encode_bwd(spec, x, tables, B, dy, grads, True), flush=flush)     # + dL/dx
-    pre = 4 * (3 + 2 * L)
-    bf = 12 + 4 * L * F + G * L * 4 * F + pre
-    bb = 12 + 4 * L * F + 2 * G * L * 4 * F + pre
+    # algorithmic bytes per point.  fwd: x + prefix columns + level columns written, one F-float table row read per
+    # gather.  bwd (table gradients): x + the level columns of dL/dy read (the prefix columns are not needed), one
+    # read-modify-write of a table row per reduction.  bwd + dL/dx additionally reads the prefix columns of dL/dy and
+    # the table rows, and writes dx.
+    pre = 4 * (3 + 2 * spec.n_fourier)
+    bf = 12 + pre + 4 * L * F + G * L * 4 * F
+    bb = 12 + 4 * L * F + 2 * G * L * 4 * F
+    bbx = bb + pre + 12 + (G * L * 4 * F if mode != "reference" else 0)
     hbm, src = peaks()
     return {"n": n, "log2T": log2T, "mode": mode,
             "fwd_ms": t_f, "fwd_mpts": n / t_f / 1e3, "fwd_frac": n * bf / (t_f * 1e-3) / (hbm * 1e9),
             "bwd_ms": t_b, "bwd_mpts": n / t_b / 1e3, "bwd_frac": n * bb / (t_b * 1e-3) / (hbm * 1e9),
             "bwd_with_dx_ms": t_bx, "bwd_with_dx_mpts": n / t_bx / 1e3,
-            "bytes_per_pt": [bf, bb], "peak": src}
+            "bwd_with_dx_frac": n * bbx / (t_bx * 1e-3) / (hbm * 1e9),
+            "bytes_per_pt": [bf, bb, bbx], "peak": src}
 
 
 if __name__ == "__main__":

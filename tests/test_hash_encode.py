@@ -107,6 +107,57 @@ def test_backward_tables_and_dx(mode):
         assert torch.allclose(xd.grad.cpu(), xo.grad, atol=2e-5 * xo.grad.abs().max().item(), rtol=1e-4)
 
 
+@pytest.mark.parametrize("mode", ["reference", "trilinear"])
+def test_aligned_store_paths_l16(mode):
+    """L = C = 16, F = 2: a lane's level is fixed and the level columns start on an odd column, so the forward
+    stores / backward loads take the shuffle-realigned float2 path.  Forward, table grads and dL/dx vs the oracle,
+    at a ragged size (last warp tile partially filled)."""
+    L, F, n = 16, 2, 4099
+    m, sd = make_grid(L, F, 12, 16, 512, mode=mode, seed=11)
+    gen = torch.Generator().manual_seed(6)
+    x = torch.rand(n, 3, generator=gen) * 2 - 1
+    w = torch.randn(n, 3 + 2 * L + L * F, generator=gen)
+    xd = x.to(DEV).requires_grad_(True)
+    y = m(xd)
+    (y * w.to(DEV)).sum().backward()
+    for v in sd.values():
+        v.requires_grad_(v.dim() == 2 and v.shape[0] != 3)
+    xo = x.clone().requires_grad_(True)
+    ref = O.hashgrid_embed(xo, sd, "", L, 16, 512, mode)
+    (ref * w).sum().backward()
+    pre = 3 + 2 * L
+    assert torch.allclose(y[:, :pre].detach().cpu(), ref[:, :pre].detach(), atol=4e-6, rtol=0)
+    if mode == "reference":
+        assert torch.equal(y[:, pre:].detach().cpu(), ref[:, pre:].detach())
+    else:
+        assert torch.allclose(y[:, pre:].detach().cpu(), ref[:, pre:].detach(), atol=2e-6, rtol=1e-5)
+    for l, lvl in enumerate(m.levels):
+        r = sd["levels.%d.embedding.weight" % l].grad
+        assert torch.allclose(lvl.embedding.weight.grad.cpu(), r, atol=1e-5 * r.abs().max().item(), rtol=1e-4), l
+    if mode == "reference":     # trilinear dL/dx is discontinuous at cell faces; covered by test_feature_widths_and_modes
+        assert torch.allclose(xd.grad.cpu(), xo.grad, atol=2e-5 * xo.grad.abs().max().item(), rtol=1e-4)
+    else:
+        bad = ~torch.isclose(xd.grad.cpu(), xo.grad, atol=1e-3 * xo.grad.abs().max().item(), rtol=1e-3)
+        assert bad.sum().item() <= 3
+
+
+def test_unpadded_rows_and_huge_coordinates():
+    """ld_out == width (odd: no vector path, no pad column) and coordinates whose scaled value leaves the int32
+    range (the .long() emulation has to take the 64-bit conversion): indices stay bit-exact."""
+    from idrk import kernels as K
+    L, F = 16, 2
+    m, sd = make_grid(L, F, 12, 16, 512, seed=13)
+    x = torch.rand(1000, 3, generator=torch.Generator().manual_seed(8)) * 2 - 1
+    x[::7] *= 3.0e7
+    x[5, 1] = -2.5e9
+    spec, tables, B = m.spec(), tuple(t.detach() for t in m.tables()), m.freq_encoding.B
+    out = torch.full((1000, spec.width), float("nan"), device=DEV)
+    K.hash_encode_fwd(spec, x.to(DEV), tables, B, out=out)
+    ref = O.hashgrid_embed(x, sd, "", L, 16, 512)
+    assert torch.equal(out[:, 35:].cpu(), ref[:, 35:])
+    assert torch.equal(out[:, :3].cpu(), x)
+
+
 def test_tiny_tables_shared_accumulation():
     """Reference configs use T = 32 rows per level: every point collides (CTA-local accumulators)."""
     L, F = 6, 2
