@@ -174,51 +174,55 @@ __device__ __forceinline__ void store_feat(float* o, const float (&v)[F], bool v
     for (int f = 0; f < F; ++f) __stcs(o + f, v[f]);
 }
 
-// Walks the tile's [rows][L] elements KB at a time: KB independent gathers (8 * KB in the 8-corner mode) are issued
-// before the first store waits on one, which is what hides the L2 / HBM latency of the random table reads.
-// SHIFT (F == 2, level columns starting on an odd column, L | 32): a lane's two features straddle an 8-byte
-// boundary, so it stores (own f1, next level's f0) as one aligned float2 instead of two scalars - every 32-byte
-// sector of the row is then written by one request instead of two half-filled ones.
-template <int F, int MODE, bool FAST, bool SHIFT>
-__device__ __forceinline__ void fwd_levels(const LevelC* s_lev, const float4* xs, int L, int lane, int rows_here,
-                                           float* __restrict__ orow0, int ld_out, bool vec, bool has_pad) {
-    constexpr int KB = !FAST ? 1 : (MODE == IDRK_HASH_REFERENCE) ? (F <= 2 ? 8 : 4) : (F <= 2 ? 2 : 1);
-    const int lstep = 32 % L, rstep = 32 / L;
-    int row = lane / L, l = lane - row * L;
-    LevelC lc = load_level(s_lev, l);
+// Generic tile walk (any L, ragged tiles, coordinates outside the int32 range): one element at a time.
+template <int F, int MODE>
+__device__ __forceinline__ void fwd_levels_generic(const LevelC* s_lev, const float4* xs, int L, int lane, int rows_here,
+                                                   float* __restrict__ orow0, int ld_out, bool vec) {
     const int total = rows_here * L;
-    for (int base = 0; base < total; base += 32 * KB) {
+    for (int e = lane; e < total; e += 32) {
+        const int row = e / L, l = e - row * L;
+        const LevelC lc = load_level(s_lev, l);
+        const float4 xv = xs[row];
+        float acc[F];
+        fwd_element<F, MODE, false>(lc, xv.x, xv.y, xv.z, acc);
+        store_feat<F>(orow0 + row * ld_out + l * F, acc, vec);
+    }
+}
+
+// Full 32-row tile with L | 32: the lane's level l = lane % L and its constants are fixed for the whole kernel; the
+// tile takes L passes of 32 / L rows.  KB passes are batched so that KB (8 * KB in the 8-corner mode) independent
+// gathers are in flight before the first store waits on one - that is what hides the L2 / HBM latency.
+// SHIFT (F == 2, level columns starting on an odd column, a pad column after the last level): a lane's two features
+// straddle an 8-byte boundary, so it stores (own f1, next level's f0) as one aligned float2 - every 32-byte sector
+// of the row is then written by one full request instead of two half-filled ones.
+template <int F, int MODE, bool SHIFT>
+__device__ __forceinline__ void fwd_levels_full(const LevelC& lc, const float4* xs, int L, int lane,
+                                                float* __restrict__ orow0, int ld_out, bool vec) {
+    constexpr int KB = (MODE == IDRK_HASH_REFERENCE) ? (F <= 2 ? 4 : 2) : (F <= 2 ? 2 : 1);
+    const int rstep = 32 / L, row0 = lane / L, l = lane - row0 * L;
+    float* __restrict__ o0 = orow0 + row0 * ld_out + l * F;
+    const int step = rstep * ld_out;
+    for (int pass = 0; pass < L; pass += KB) {
         float acc[KB][F];
-        int dst[KB];
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
-            dst[k] = -1;
-            if constexpr (SHIFT) acc[k][0] = 0.f;
-            if (base + 32 * k + lane < total) {
-                const float4 xv = xs[row];
-                fwd_element<F, MODE, FAST>(lc, xv.x, xv.y, xv.z, acc[k]);
-                dst[k] = row * ld_out + l * F;
-                row += rstep;
-                if (lstep != 0) {                        // warp-uniform: a lane's level changes only when L does not divide 32
-                    l += lstep;
-                    if (l >= L) { l -= L; ++row; }
-                    lc = load_level(s_lev, l);
-                }
+            if (pass + k < L) {
+                const float4 xv = xs[row0 + (pass + k) * rstep];
+                fwd_element<F, MODE, true>(lc, xv.x, xv.y, xv.z, acc[k]);
             }
         }
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
-            if constexpr (SHIFT) {
-                const float nx = __shfl_down_sync(0xffffffffu, acc[k][0], 1);
-                if (dst[k] >= 0) {
-                    float* o = orow0 + dst[k];
+            if (pass + k < L) {
+                float* o = o0 + (pass + k) * step;
+                if constexpr (SHIFT) {
+                    float nx = __shfl_down_sync(0xffffffffu, acc[k][0], 1);
+                    if (l == L - 1) nx = 0.f;                                  // the pad column
+                    __stcs(reinterpret_cast<float2*>(o + 1), make_float2(acc[k][1], nx));
                     if (l == 0) __stcs(o, acc[k][0]);
-                    if (l != L - 1) __stcs(reinterpret_cast<float2*>(o + 1), make_float2(acc[k][1], nx));
-                    else if (has_pad) __stcs(reinterpret_cast<float2*>(o + 1), make_float2(acc[k][1], 0.f));
-                    else __stcs(o + 1, acc[k][1]);
+                } else {
+                    store_feat<F>(o, acc[k], vec);
                 }
-            } else {
-                if (dst[k] >= 0) store_feat<F>(orow0 + dst[k], acc[k], vec);
             }
         }
     }
@@ -244,16 +248,24 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
     __syncthreads();
     const int pre = C > 0 ? 3 + 2 * C : 0;
     const int fa = F >= 4 ? 4 : F;                          // floats a vector store must be aligned to
+    const bool al8 = (ld_out & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
     const bool vec = F > 1 && (pre % fa) == 0 && (ld_out % fa) == 0 && (reinterpret_cast<uintptr_t>(out) % (4 * fa)) == 0;
     const bool has_pad = ld_out > g.width;
-    const bool pshift = C >= 2 && (32 % C) == 0 && (ld_out & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
-    const bool shift = F == 2 && L > 0 && (32 % L) == 0 && (pre & 1) && (ld_out & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
+    const bool l_fixed = L > 0 && (32 % L) == 0;            // lane <-> level is fixed
+    const bool shift = F == 2 && l_fixed && (pre & 1) && has_pad && al8;
+    const bool c_fixed = C >= 2 && (32 % C) == 0 && al8;    // lane <-> frequency is fixed, aligned pair stores
     float res_max = 0.f;
     for (int l = 0; l < L; ++l) res_max = fmaxf(res_max, fabsf(g.res[l]));
-    // Fourier: lane's frequency is fixed when C divides 32
-    const int jstep = C > 0 ? 32 % C : 0, jrstep = C > 0 ? 32 / C : 0;
+    LevelC lc = load_level(s_lev, L > 0 ? lane % L : 0);
+    // Fourier prefix, c_fixed: column 3 + j is even for odd j, so odd lanes store the aligned pairs (s_j, s_j+1) and
+    // (c_j, c_j+1) - the partner value comes from the next lane - lane j = 0 stores (x2, s_0) and one even lane
+    // (x0, x1): every sector of the prefix is written in full 8-byte words.
+    const int j = C > 0 ? lane % C : 0, jr0 = C > 0 ? lane / C : 0, jrstep = C > 0 ? 32 / C : 0;
     float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-    if (C > 0) { const int j = lane % C; b0 = s_B[j]; b1 = s_B[C + j]; b2 = s_B[2 * C + j]; }
+    if (C > 0) { b0 = s_B[j]; b1 = s_B[C + j]; b2 = s_B[2 * C + j]; }
+    const bool j_odd = j & 1, j_last = j == C - 1, j_zero = j == 0, j_x = j == (C > 2 ? 2 : 1);
+    const bool st_a = j_odd || j_zero || j_x, st_b = j_odd && !j_last;
+    const int off_a = j_odd ? 3 + j : (j_zero ? 2 : 0);
 
     const long long n_wtiles = (n + 31) / 32;
     const long long wstride = (long long)gridDim.x * WARPS;
@@ -266,14 +278,12 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
         xs[lane] = make_float4(x0, x1, x2, 0.f);
         __syncwarp();
         float* orow0 = out + p0 * (long long)ld_out;
-        if (C > 0 && pshift) {
-            // C | 32: the lane's frequency j is fixed.  Column 3 + j is even for odd j, so odd lanes store the aligned
-            // pairs (s_j, s_j+1) and (c_j, c_j+1) - the partner value comes from the next lane - lane 0 stores
-            // (x2, s_0) and one even lane (x0, x1): every sector of the prefix is written by full 8-byte words.
-            const int j = lane & (C - 1), jx = C > 2 ? 2 : 1;
-            for (int row0 = 0; row0 < rows_here; row0 += jrstep) {
-                const int row = row0 + lane / C;
-                const float4 xv = xs[row & 31];
+        const bool full = rows_here == 32;
+        if (C > 0 && c_fixed && full) {
+#pragma unroll 2
+            for (int pass = 0; pass < C; ++pass) {
+                const int row = jr0 + pass * jrstep;
+                const float4 xv = xs[row];
                 float xp = __fmul_rn(__fmul_rn(xv.x, 6.283185307179586f), b0);
                 xp = __fmaf_rn(__fmul_rn(xv.y, 6.283185307179586f), b1, xp);
                 xp = __fmaf_rn(__fmul_rn(xv.z, 6.283185307179586f), b2, xp);
@@ -281,60 +291,47 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
                 sincos_fast(xp, &sn, &cs);
                 const float sn_n = __shfl_down_sync(0xffffffffu, sn, 1), cs_n = __shfl_down_sync(0xffffffffu, cs, 1);
                 const float cs_0 = __shfl_sync(0xffffffffu, cs, lane & ~(C - 1));
-                if (row < rows_here) {
-                    float* o = orow0 + (long long)row * ld_out;
-                    if (j & 1) {
-                        __stcs(reinterpret_cast<float2*>(o + 3 + j), make_float2(sn, j == C - 1 ? cs_0 : sn_n));
-                        if (j != C - 1) __stcs(reinterpret_cast<float2*>(o + 3 + C + j), make_float2(cs, cs_n));
-                        else __stcs(o + 3 + C + j, cs);
-                    }
-                    if (j == 0) __stcs(reinterpret_cast<float2*>(o + 2), make_float2(xv.z, sn));
-                    if (j == jx) __stcs(reinterpret_cast<float2*>(o), make_float2(xv.x, xv.y));
-                }
+                float* o = orow0 + row * ld_out;
+                const float a0 = j_odd ? sn : (j_zero ? xv.z : xv.x);
+                const float a1 = j_odd ? (j_last ? cs_0 : sn_n) : (j_zero ? sn : xv.y);
+                if (st_a) __stcs(reinterpret_cast<float2*>(o + off_a), make_float2(a0, a1));
+                if (st_b) __stcs(reinterpret_cast<float2*>(o + 3 + C + j), make_float2(cs, cs_n));
+                if (j_last) __stcs(o + 3 + C + j, cs);
+                if (C == 2 && j_zero) __stcs(reinterpret_cast<float2*>(o), make_float2(xv.x, xv.y));   // C == 2: lane 1 is both "odd" and j_x
             }
         } else if (C > 0) {
             for (int i = lane; i < 3 * rows_here; i += 32) {
                 const int r = i / 3, c = i - 3 * r;
-                __stcs(orow0 + (long long)r * ld_out + c, reinterpret_cast<const float*>(xs + r)[c]);
+                __stcs(orow0 + r * ld_out + c, reinterpret_cast<const float*>(xs + r)[c]);
             }
-            int row = lane / C, j = lane - row * C;
             const int total = rows_here * C;
-#pragma unroll 2
             for (int e = lane; e < total; e += 32) {
+                const int row = e / C, jj = e - row * C;
                 const float4 xv = xs[row];
-                float xp = __fmul_rn(__fmul_rn(xv.x, 6.283185307179586f), b0);
-                xp = __fmaf_rn(__fmul_rn(xv.y, 6.283185307179586f), b1, xp);
-                xp = __fmaf_rn(__fmul_rn(xv.z, 6.283185307179586f), b2, xp);
+                float xp = __fmul_rn(__fmul_rn(xv.x, 6.283185307179586f), s_B[jj]);
+                xp = __fmaf_rn(__fmul_rn(xv.y, 6.283185307179586f), s_B[C + jj], xp);
+                xp = __fmaf_rn(__fmul_rn(xv.z, 6.283185307179586f), s_B[2 * C + jj], xp);
                 float sn, cs;
                 sincos_fast(xp, &sn, &cs);
-                float* o = orow0 + (long long)row * ld_out + 3 + j;
+                float* o = orow0 + row * ld_out + 3 + jj;
                 __stcs(o, sn);
                 __stcs(o + C, cs);
-                row += jrstep;
-                if (jstep != 0) {
-                    j += jstep;
-                    if (j >= C) { j -= C; ++row; }
-                    b0 = s_B[j]; b1 = s_B[C + j]; b2 = s_B[2 * C + j];
-                }
             }
-            if (jstep != 0) { const int j0 = lane % C; b0 = s_B[j0]; b1 = s_B[C + j0]; b2 = s_B[2 * C + j0]; }
         }
-        bool fast_tile = true;
+        bool pad_done = false;
         if (L > 0) {
-            // .long() of a coordinate fits 32 bits for every level unless a point is astronomically far out
+            // .long() of a scaled coordinate fits 32 bits for every level unless a point is astronomically far out
             const float amax = fmaxf(fabsf(x0), fmaxf(fabsf(x1), fabsf(x2))) * res_max;
             const bool fast = __all_sync(0xffffffffu, amax < 2147483520.f);
-            fast_tile = fast;
-            if (!fast) {
-                fwd_levels<F, MODE, false, false>(s_lev, xs, L, lane, rows_here, orow0 + pre, ld_out, vec, has_pad);
-            } else if (F == 2 && shift) {
-                fwd_levels<F, MODE, true, F == 2>(s_lev, xs, L, lane, rows_here, orow0 + pre, ld_out, vec, has_pad);
+            if (fast && full && l_fixed) {
+                if (F == 2 && shift) { fwd_levels_full<F, MODE, F == 2>(lc, xs, L, lane, orow0 + pre, ld_out, vec); pad_done = true; }
+                else fwd_levels_full<F, MODE, false>(lc, xs, L, lane, orow0 + pre, ld_out, vec);
             } else {
-                fwd_levels<F, MODE, true, false>(s_lev, xs, L, lane, rows_here, orow0 + pre, ld_out, vec, has_pad);
+                fwd_levels_generic<F, MODE>(s_lev, xs, L, lane, rows_here, orow0 + pre, ld_out, vec);
             }
         }
         if (lane < rows_here)
-            for (int c = g.width + (shift && fast_tile && has_pad ? 1 : 0); c < ld_out; ++c) __stcs(orow0 + (long long)lane * ld_out + c, 0.f);
+            for (int c = g.width + (pad_done ? 1 : 0); c < ld_out; ++c) __stcs(orow0 + lane * ld_out + c, 0.f);
 
         if (idx_dbg != nullptr) {               // debug / parity output: table row of all 8 corners
             for (int e = lane; e < rows_here * L; e += 32) {
@@ -433,68 +430,64 @@ __device__ __forceinline__ void row_reduce_add(float* dxs, int row, bool active,
     }
 }
 
-template <int F, int MODE, bool FAST, bool WANT_DX>
-__device__ __forceinline__ void bwd_levels(const LevelC* s_lev, float* const* s_grad, float* s_acc, const float4* xs, float* dxs,
-                                           int L, int lane, int rows_here, const float* __restrict__ drow0, int ld_dy,
-                                           bool shift, bool has_pad) {
-    constexpr int KB = !FAST ? 1 : (MODE == IDRK_HASH_REFERENCE) ? 4 : (WANT_DX ? 1 : 2);
-    const int lstep = 32 % L, rstep = 32 / L;
-    const bool l_ok = lstep == 0;
-    int row = lane / L, l = lane - row * L;
-    LevelC lc = load_level(s_lev, l);
-    float* gtab = s_grad[l];
+// Generic tile walk (any L, ragged tiles, coordinates outside the int32 range): one element at a time.
+template <int F, int MODE, bool WANT_DX>
+__device__ __forceinline__ void bwd_levels_generic(const LevelC* s_lev, float* const* s_grad, float* s_acc, const float4* xs,
+                                                   float* dxs, int L, int lane, int rows_here,
+                                                   const float* __restrict__ drow0, int ld_dy) {
     const int total = rows_here * L;
-    for (int base = 0; base < total; base += 32 * KB) {
+    for (int e = lane; e < total; e += 32) {
+        const int row = e / L, l = e - row * L;
+        const LevelC lc = load_level(s_lev, l);
+        const float* o = drow0 + row * ld_dy + l * F;
+        float gy[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) gy[f] = __ldg(o + f);
+        float d[3] = {0.f, 0.f, 0.f};
+        const float4 xv = xs[row];
+        bwd_element<F, MODE, false, WANT_DX>(lc, s_grad[l], s_acc, xv.x, xv.y, xv.z, gy, d);
+        if constexpr (WANT_DX && MODE == IDRK_HASH_TRILINEAR) {
+            atomicAdd(dxs + 4 * row, d[0]); atomicAdd(dxs + 4 * row + 1, d[1]); atomicAdd(dxs + 4 * row + 2, d[2]);
+        }
+    }
+}
+
+// Full 32-row tile with L | 32 (see fwd_levels_full).  SHIFT: dL/dy features are read as the aligned pair
+// (own f1, next level's f0); the lane's f0 arrives from the previous lane by shuffle.
+template <int F, int MODE, bool WANT_DX, bool SHIFT>
+__device__ __forceinline__ void bwd_levels_full(const LevelC& lc, float* gtab, float* s_acc, const float4* xs, float* dxs,
+                                                int L, int lane, const float* __restrict__ drow0, int ld_dy) {
+    constexpr int KB = (MODE == IDRK_HASH_REFERENCE) ? (F <= 2 ? 4 : 2) : (WANT_DX ? 1 : 2);
+    const int rstep = 32 / L, row0 = lane / L, l = lane - row0 * L;
+    const float* __restrict__ o0 = drow0 + row0 * ld_dy + l * F;
+    const int step = rstep * ld_dy;
+    for (int pass = 0; pass < L; pass += KB) {
         float gy[KB][F];
-        // phase 1: the dL/dy loads of KB elements
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
-            const bool act = base + 32 * k + lane < total;
-            if constexpr (F == 2) {
-                if (shift) {
-                    // aligned pair (own f1, next level's f0); own f0 arrives from the previous lane
-                    float2 pr = make_float2(0.f, 0.f);
+            if (pass + k < L) {
+                const float* o = o0 + (pass + k) * step;
+                if constexpr (SHIFT) {
+                    const float2 pr = __ldcs(reinterpret_cast<const float2*>(o + 1));
                     float first = 0.f;
-                    if (act) {
-                        const float* o = drow0 + (long long)(row + k * rstep) * ld_dy + 2 * l;
-                        if (l != L - 1 || has_pad) pr = __ldcs(reinterpret_cast<const float2*>(o + 1));
-                        else pr.x = __ldcs(o + 1);
-                        if (l == 0) first = __ldcs(o);
-                    }
+                    if (l == 0) first = __ldcs(o);
                     const float up = __shfl_up_sync(0xffffffffu, pr.y, 1);
                     gy[k][0] = (l == 0) ? first : up;
                     gy[k][1] = pr.x;
-                    continue;
+                } else {
+#pragma unroll
+                    for (int f = 0; f < F; ++f) gy[k][f] = __ldg(o + f);
                 }
             }
-            if (lstep == 0 && act) {
-                const float* o = drow0 + (long long)(row + k * rstep) * ld_dy + l * F;
-#pragma unroll
-                for (int f = 0; f < F; ++f) gy[k][f] = __ldg(o + f);
-            }
         }
-        // phase 2: table rows, reductions, dL/dx partials
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
-            const bool act = base + 32 * k + lane < total;
-            if (lstep != 0 && act) {
-                const float* o = drow0 + (long long)row * ld_dy + l * F;
-#pragma unroll
-                for (int f = 0; f < F; ++f) gy[k][f] = __ldg(o + f);
-            }
-            float d[3] = {0.f, 0.f, 0.f};
-            const int r_here = row;
-            if (act) {
+            if (pass + k < L) {
+                const int row = row0 + (pass + k) * rstep;
                 const float4 xv = xs[row];
-                bwd_element<F, MODE, FAST, WANT_DX>(lc, gtab, s_acc, xv.x, xv.y, xv.z, gy[k], d);
-            }
-            if constexpr (WANT_DX && MODE == IDRK_HASH_TRILINEAR) row_reduce_add(dxs, r_here & 31, act, L, l_ok, lane, d[0], d[1], d[2]);
-            row += rstep;
-            if (lstep != 0 && act) {
-                l += lstep;
-                if (l >= L) { l -= L; ++row; }
-                lc = load_level(s_lev, l);
-                gtab = s_grad[l];
+                float d[3] = {0.f, 0.f, 0.f};
+                bwd_element<F, MODE, true, WANT_DX>(lc, gtab, s_acc, xv.x, xv.y, xv.z, gy[k], d);
+                if constexpr (WANT_DX && MODE == IDRK_HASH_TRILINEAR) row_reduce_add(dxs, row, true, L, true, lane, d[0], d[1], d[2]);
             }
         }
     }
@@ -524,7 +517,10 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
     __syncthreads();
     const int pre = C > 0 ? 3 + 2 * C : 0;
     const bool has_pad = ld_dy > g.width;
-    const bool shift = F == 2 && L > 0 && (32 % L) == 0 && (pre & 1) && (ld_dy & 1) == 0 && (reinterpret_cast<uintptr_t>(dy) & 7u) == 0;
+    const bool l_fixed = L > 0 && (32 % L) == 0;
+    const bool shift = F == 2 && l_fixed && (pre & 1) && has_pad && (ld_dy & 1) == 0 && (reinterpret_cast<uintptr_t>(dy) & 7u) == 0;
+    const LevelC lc = load_level(s_lev, L > 0 ? lane % L : 0);
+    float* gtab = L > 0 ? s_grad[lane % L] : nullptr;
     const bool want_dx = dx != nullptr;
     float res_max = 0.f;
     for (int l = 0; l < L; ++l) res_max = fmaxf(res_max, fabsf(g.res[l]));
@@ -584,13 +580,17 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
         if (L > 0 && (MODE == IDRK_HASH_TRILINEAR || gd.any_grad)) {
             const float amax = fmaxf(fabsf(x0), fmaxf(fabsf(x1), fabsf(x2))) * res_max;
             const bool fast = __all_sync(0xffffffffu, amax < 2147483520.f);
-            if (!fast) {
-                if (want_dx) bwd_levels<F, MODE, false, true>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy, false, has_pad);
-                else         bwd_levels<F, MODE, false, false>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy, false, has_pad);
-            } else if (want_dx) {
-                bwd_levels<F, MODE, true, true>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy, shift, has_pad);
+            if (fast && rows_here == 32 && l_fixed) {
+                if (F == 2 && shift) {
+                    if (want_dx) bwd_levels_full<F, MODE, true, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
+                    else         bwd_levels_full<F, MODE, false, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
+                } else {
+                    if (want_dx) bwd_levels_full<F, MODE, true, false>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
+                    else         bwd_levels_full<F, MODE, false, false>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
+                }
             } else {
-                bwd_levels<F, MODE, true, false>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy, shift, has_pad);
+                if (want_dx) bwd_levels_generic<F, MODE, true>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy);
+                else         bwd_levels_generic<F, MODE, false>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy);
             }
         }
         if (want_dx) {

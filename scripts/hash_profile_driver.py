@@ -1,5 +1,26 @@
-import sys, os, torch
+"""ncu driver: one launch of every hash-encode kernel variant (4M points, L=16, F=2, T=2^19).
+
+    ncu --set full --clock-control none --import-source on -k regex:hash_encode -o gpurun_out/hash_all python scripts/hash_profile_driver.py
+"""
+import os
+import sys
+
+import torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from scripts.hash_microbench import run
+from idrk import kernels as K                                                   # noqa: E402
+from idrk.model.embeddings.hashGridEmbedding import MultiResHashGridMLP          # noqa: E402
+
+n = 1 << 22
 for mode in ("reference", "trilinear"):
-    print(run(1 << 22, 19, mode))
+    m = MultiResHashGridMLP(True, 3, 16, 2, 19, 16, 2048, frac_mode=mode).cuda()
+    spec, tables, B = m.spec(), tuple(t.detach() for t in m.tables()), m.freq_encoding.B
+    x = torch.rand(n, 3, device="cuda")
+    out = torch.empty(n, K.pad4(spec.width), device="cuda")
+    dy = torch.randn(n, K.pad4(spec.width), device="cuda")
+    grads = [torch.zeros_like(t) for t in tables]
+    K.hash_encode_fwd(spec, x, tables, B, out=out)
+    K.hash_encode_bwd(spec, x, tables, B, dy, grads, False)
+    K.hash_encode_bwd(spec, x, tables, B, dy, grads, True)
+    torch.cuda.synchronize()
+    print(mode, "ok", float(out[0, 40]))
