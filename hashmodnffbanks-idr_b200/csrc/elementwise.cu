@@ -21,6 +21,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void split_tf32_kernel(const float* __restrict__ x, long long rows, int cols, int ldx, float scale,
                                   float* __restrict__ hi, float* __restrict__ lo, int ldo, int pad_cols,
                                   const int* __restrict__ m_count) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     long long r_eff = rows;
     if (m_count) { const long long c = *m_count; r_eff = c < rows ? c : rows; }
     const int w = cols + pad_cols;
@@ -42,6 +44,8 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, long long rows, i
 __global__ void weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v, int N, int K, int ldv,
                                        float* __restrict__ W, float* __restrict__ W_hi, float* __restrict__ W_lo, int ldw,
                                        float* __restrict__ Wt, float* __restrict__ Wt_hi, float* __restrict__ Wt_lo, int ldwt) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -64,6 +68,8 @@ __global__ void weight_norm_fwd_kernel(const float* __restrict__ g, const float*
 
 __global__ void weight_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v, const float* __restrict__ dW,
                                        int N, int K, int ldv, int lddw, float* __restrict__ dg, float* __restrict__ dv, int lddv) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -81,6 +87,8 @@ __global__ void weight_norm_bwd_kernel(const float* __restrict__ g, const float*
 
 // out[c] += sum_r x[r, c]
 __global__ void colsum_kernel(const float* __restrict__ x, long long rows, int cols, int ldx, float* __restrict__ out) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ry = threadIdx.x >> 5;                    // 8 row lanes
     __shared__ float part[8][33];
@@ -111,6 +119,8 @@ __device__ __forceinline__ float sdf_squash(float s, float beta) {
 __global__ void sdf_head_kernel(const float* __restrict__ h, long long rows, int K, int ldh, const float* __restrict__ w,
                                 const float* __restrict__ bias, float beta, float* __restrict__ out,
                                 const int* __restrict__ m_count) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     long long r_eff = rows;
     if (m_count) { const long long c = *m_count; r_eff = c < rows ? c : rows; }
     const int lane = threadIdx.x & 31;
@@ -125,6 +135,8 @@ __global__ void sdf_head_kernel(const float* __restrict__ h, long long rows, int
 }
 
 __global__ void sdf_squash_kernel(const float* __restrict__ s, long long n, float beta, float* __restrict__ out, float* __restrict__ dout) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float v = s[i];
         const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
@@ -140,6 +152,8 @@ __global__ void act_bwd_kernel(const float* __restrict__ dH, int ld_dh, const fl
                                const float* __restrict__ S, int ld_s, const float* __restrict__ H, int ld_h,
                                long long rows, int cols, int mode, float act, float scale,
                                float* __restrict__ dZ, float* __restrict__ hi, float* __restrict__ lo, int ld_out) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const long long total = rows * (long long)ld_out;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / ld_out;
@@ -177,8 +191,8 @@ extern "C" int idrk_split_tf32(const float* x, int64_t rows, int32_t cols, int32
                                int32_t ld_out, int32_t pad_cols, const int32_t* m_count, void* stream) {
     if (!x || !hi || rows < 0 || cols < 1 || ldx < cols || pad_cols < 0 || ld_out < cols + pad_cols) return IDRK_E_ARG;
     if (rows == 0) return 0;
-    split_tf32_kernel<<<ew_blocks(rows * (long long)(cols + pad_cols), 256), 256, 0, (cudaStream_t)stream>>>(
-        x, rows, cols, ldx, scale, hi, lo, ld_out, pad_cols, m_count);
+    IDRK_CUDA_TRY(launch_k(split_tf32_kernel, dim3(ew_blocks(rows * (long long)(cols + pad_cols), 256)), dim3(256), 0, (cudaStream_t)stream, 
+        x, rows, cols, ldx, scale, hi, lo, ld_out, pad_cols, m_count));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -189,7 +203,7 @@ extern "C" int idrk_weight_norm_fwd(const float* g, const float* v, int32_t N, i
     if (!v || N < 1 || K < 1 || ldv < K || ldw < K) return IDRK_E_ARG;
     if ((W_hi == nullptr) != (W_lo == nullptr) || (Wt_hi == nullptr) != (Wt_lo == nullptr)) return IDRK_E_ARG;
     if ((Wt || Wt_hi) && ldwt < N) return IDRK_E_ARG;
-    weight_norm_fwd_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, v, N, K, ldv, W, W_hi, W_lo, ldw, Wt, Wt_hi, Wt_lo, ldwt);
+    IDRK_CUDA_TRY(launch_k(weight_norm_fwd_kernel, dim3((N + 7) / 8), dim3(256), 0, (cudaStream_t)stream, g, v, N, K, ldv, W, W_hi, W_lo, ldw, Wt, Wt_hi, Wt_lo, ldwt));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -197,7 +211,7 @@ extern "C" int idrk_weight_norm_fwd(const float* g, const float* v, int32_t N, i
 extern "C" int idrk_weight_norm_bwd(const float* g, const float* v, const float* dW, int32_t N, int32_t K, int32_t ldv,
                                     int32_t lddw, float* dg, float* dv, int32_t lddv, void* stream) {
     if (!g || !v || !dW || !dg || !dv || N < 1 || K < 1 || ldv < K || lddw < K || lddv < K) return IDRK_E_ARG;
-    weight_norm_bwd_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, v, dW, N, K, ldv, lddw, dg, dv, lddv);
+    IDRK_CUDA_TRY(launch_k(weight_norm_bwd_kernel, dim3((N + 7) / 8), dim3(256), 0, (cudaStream_t)stream, g, v, dW, N, K, ldv, lddw, dg, dv, lddv));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -209,7 +223,7 @@ extern "C" int idrk_colsum(const float* x, int64_t rows, int32_t cols, int32_t l
     if (ysplit < 1) ysplit = 1;
     if (ysplit > 128) ysplit = 128;
     dim3 grid((cols + 31) / 32, (unsigned)ysplit);
-    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, out);
+    IDRK_CUDA_TRY(launch_k(colsum_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, rows, cols, ldx, out));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -221,7 +235,7 @@ extern "C" int idrk_sdf_head(const float* h, int64_t rows, int32_t K, int32_t ld
     long long blocks = (rows + 7) / 8;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    sdf_head_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(h, rows, K, ldh, w, bias, beta, out, m_count);
+    IDRK_CUDA_TRY(launch_k(sdf_head_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, h, rows, K, ldh, w, bias, beta, out, m_count));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -229,7 +243,7 @@ extern "C" int idrk_sdf_head(const float* h, int64_t rows, int32_t K, int32_t ld
 extern "C" int idrk_sdf_squash(const float* s, int64_t n, float beta, float* out, float* dout, void* stream) {
     if (!s || !out || n < 0 || !(beta > 0.f)) return IDRK_E_ARG;
     if (n == 0) return 0;
-    sdf_squash_kernel<<<ew_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(s, n, beta, out, dout);
+    IDRK_CUDA_TRY(launch_k(sdf_squash_kernel, dim3(ew_blocks(n, 256)), dim3(256), 0, (cudaStream_t)stream, s, n, beta, out, dout));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -241,8 +255,8 @@ extern "C" int idrk_act_bwd(const float* dH, int32_t ld_dh, const float* dS, int
     if ((dZ_hi == nullptr) != (dZ_lo == nullptr)) return IDRK_E_ARG;
     if (dS && (mode == IDRK_EPI_SINE || mode == IDRK_EPI_TANH) && !H) return IDRK_E_ARG;
     if (rows == 0) return 0;
-    act_bwd_kernel<<<ew_blocks(rows * (long long)ld_out, 256), 256, 0, (cudaStream_t)stream>>>(
-        dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, dZ_hi, dZ_lo, ld_out);
+    IDRK_CUDA_TRY(launch_k(act_bwd_kernel, dim3(ew_blocks(rows * (long long)ld_out, 256)), dim3(256), 0, (cudaStream_t)stream, 
+        dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, dZ_hi, dZ_lo, ld_out));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

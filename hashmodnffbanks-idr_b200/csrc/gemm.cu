@@ -107,6 +107,9 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try(bar, parity)) {}
 }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -319,13 +322,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_V2, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                  long long M, int N, int K, EpiParams e, const int* __restrict__ m_count, int kb_per_split, int splits) {
+    pdl_trigger();
     using P = SmemPlan<BN, TERMS>;
-    long long m_eff = M;
-    if (m_count != nullptr) { const long long c = *m_count; m_eff = c < M ? c : M; }
-    const int m_tiles = (int)((m_eff + BM - 1) / BM);
     const int n_tiles = (N + BN - 1) / BN;
-    const int items = m_tiles * n_tiles * splits;
-    if ((int)blockIdx.x >= items) return;
     const int kb_total = (K + BK - 1) / BK;
 
     extern __shared__ uint8_t smem_raw[];
@@ -340,6 +339,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto acc_empty_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + ACC_STAGES + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 32) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
     if (threadIdx.x == 0) {
         for (int s = 0; s < P::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(acc_full_bar(a), 1); mbar_init(acc_empty_bar(a), EPI_WARPS); }
@@ -354,6 +354,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                 // barriers, TMEM and descriptors above overlap the producer's tail; its data is read below
+    long long m_eff = M;
+    if (m_count != nullptr) { const long long c = *m_count; m_eff = c < M ? c : M; }
+    const int m_tiles = (int)((m_eff + BM - 1) / BM);
+    const int items = m_tiles * n_tiles * splits;          // CTAs beyond the device-side row count fall through to the teardown
 
     // work item -> (m tile, n tile, k range); n fastest so concurrently running CTAs share A rows in L2
     auto decode = [&](int item, long long& m0, int& n0, int& kb0, int& kb1) {
@@ -526,14 +531,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS_V2, 1)
 gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                       long long M, int N, int K, EpiParams e, const int* __restrict__ m_count) {
+    pdl_trigger();
     using P = SmemPlan2<TERMS>;
-    long long m_eff = M;
-    if (m_count != nullptr) { const long long c = *m_count; m_eff = c < M ? c : M; }
-    const int m_tiles = (int)((m_eff + 2 * BM - 1) / (2 * BM));
     const int n_tiles = (N + BN2 - 1) / BN2;
-    const int items = m_tiles * n_tiles;
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    if (pair >= items) return;                                   // uniform for both CTAs of the cluster
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int kb_total = (K + BK - 1) / BK;
@@ -550,6 +551,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     auto acc_empty_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + ACC_STAGES + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 32) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
     if (threadIdx.x == 0) {
         for (int s = 0; s < P::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(acc_full_bar(a), 1); mbar_init(acc_empty_bar(a), 2 * EPI_WARPS); }
@@ -565,6 +567,11 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     cluster_sync_all();                                          // peer barriers initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                 // barriers, TMEM and descriptors above overlap the producer's tail; its data is read below
+    long long m_eff = M;
+    if (m_count != nullptr) { const long long c = *m_count; m_eff = c < M ? c : M; }
+    const int m_tiles = (int)((m_eff + 2 * BM - 1) / (2 * BM));
+    const int items = m_tiles * n_tiles;
 
     auto decode = [&](int item, long long& m0, int& n0) {
         n0 = (item % n_tiles) * BN2;
@@ -754,13 +761,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_V2, 1)
 gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl,
                  long long M, int N, int K, EpiParamsH e, const int* __restrict__ m_count) {
+    pdl_trigger();
     using P = SmemPlanH;
-    long long m_eff = M;
-    if (m_count != nullptr) { const long long c = *m_count; m_eff = c < M ? c : M; }
-    const int m_tiles = (int)((m_eff + BM - 1) / BM);
     const int n_tiles = (N + BNH - 1) / BNH;
-    const int items = m_tiles * n_tiles;
-    if ((int)blockIdx.x >= items) return;
     const int kb_total = (K + BKH - 1) / BKH;
 
     extern __shared__ uint8_t smem_raw[];
@@ -775,6 +778,7 @@ gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto acc_empty_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + ACC_STAGES + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 32) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBl); }
     if (threadIdx.x == 0) {
         for (int s = 0; s < P::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(acc_full_bar(a), 1); mbar_init(acc_empty_bar(a), EPI_WARPS); }
@@ -789,6 +793,11 @@ gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                 // barriers, TMEM and descriptors above overlap the producer's tail; its data is read below
+    long long m_eff = M;
+    if (m_count != nullptr) { const long long c = *m_count; m_eff = c < M ? c : M; }
+    const int m_tiles = (int)((m_eff + BM - 1) / BM);
+    const int items = m_tiles * n_tiles;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -884,6 +893,8 @@ gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 __global__ void split_f16_kernel(const float* __restrict__ x, long long rows, int cols, int ldx, float scale,
                                  __half* __restrict__ h, __half* __restrict__ l, int ldo, int pad_cols, const int* __restrict__ m_count) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     long long r_eff = rows;
     if (m_count) { const long long c = *m_count; r_eff = c < rows ? c : rows; }
     const int w = cols + pad_cols;
@@ -909,6 +920,8 @@ template <int TM, int TN>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ A, long long sa_m, long long sa_k, const float* __restrict__ B, long long sb_n,
                 long long sb_k, long long M, int N, int K, EpiParams e, const int* __restrict__ m_count, int k_per_split) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     constexpr int SBM = 16 * TM, SBN = 16 * TN, SBK = 16;
     __shared__ float sA[SBK][SBM + 1];
     __shared__ float sB[SBK][SBN + 1];
@@ -1021,7 +1034,7 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtens
     splits = (kb_total + kbps - 1) / kbps;
     const long long items = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
     const long long grid = items < sm_count() ? items : sm_count();      // persistent: one CTA per SM
-    kern<<<(unsigned)grid, GEMM_THREADS_V2, P::TOTAL, st>>>(tA, tAl, tB, tBl, M, N, K, e, m_count, kbps, splits);
+    IDRK_CUDA_TRY(launch_k(kern, dim3((unsigned)grid), dim3(GEMM_THREADS_V2), P::TOTAL, st, tA, tAl, tB, tBl, M, N, K, e, m_count, kbps, splits));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -1053,7 +1066,7 @@ static int launch_2cta(const CUtensorMap& tA, const CUtensorMap& tAl, const CUte
     const long long items = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2);
     long long pairs = sm_count() / 2;
     if (pairs > items) pairs = items;
-    kern<<<(unsigned)(2 * pairs), GEMM_THREADS_V2, P::TOTAL, st>>>(tA, tAl, tB, tBl, M, N, K, e, m_count);
+    IDRK_CUDA_TRY(launch_k(kern, dim3((unsigned)(2 * pairs)), dim3(GEMM_THREADS_V2), P::TOTAL, st, tA, tAl, tB, tBl, M, N, K, e, m_count));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -1096,7 +1109,7 @@ extern "C" int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N
         kps = (kps + 15) / 16 * 16;
         const int splits = (K + kps - 1) / kps;
         dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)splits);
-        gemm_f32_kernel<4, 4><<<grid, 256, 0, st>>>(A, sa_m, sa_k, B, sb_n, sb_k, M, N, K, e, m_count, kps);
+        IDRK_CUDA_TRY(launch_k(gemm_f32_kernel<4, 4>, dim3(grid), dim3(256), 0, st, A, sa_m, sa_k, B, sb_n, sb_k, M, N, K, e, m_count, kps));
         IDRK_LAUNCH_CHECK();
         return 0;
     }
@@ -1116,7 +1129,11 @@ extern "C" int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N
         }
         return launch_2cta<1>(tA, tA, tB, tB, M, N, K, e, m_count, st);
     }
-    const int bn = (N <= 64 || M <= 4096) ? 64 : 128;      // small row counts: more, shorter tiles
+    // Operand ingest (L2 -> shared memory), not the tensor pipe, bounds these launches: a 128 x 64 tile moves 48 KB per
+    // 32-wide k block against 384 MMA cycles, a 128 x 128 tile 64 KB against 768.  Measured (graph of back-to-back
+    // launches, 3xTF32, N = K = 512): M = 2048 -> 13.5 us (BN 64) vs 16.3 us (BN 128, 64 tiles leave SMs idle);
+    // M = 3072 -> 21.5 vs 16.6 us; M = 4096 -> 21.9 vs 16.7 us.
+    const int bn = (N <= 64 || M <= 2048) ? 64 : 128;
     CUtensorMap tA, tAl, tB, tBl;
     int rc;
     // K-major: dims (K, rows) box (32, rows_per_tile).  MN-major: dims (rows_mn, K) box (32, BK)
@@ -1165,7 +1182,7 @@ extern "C" int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, 
     }
     const long long items = ((M + BM - 1) / BM) * ((N + BNH - 1) / BNH);
     const long long grid = items < sm_count() ? items : sm_count();
-    gemm_f16s_kernel<<<(unsigned)grid, GEMM_THREADS_V2, SmemPlanH::TOTAL, (cudaStream_t)stream>>>(tA, tAl, tB, tBl, M, N, K, e, m_count);
+    IDRK_CUDA_TRY(launch_k(gemm_f16s_kernel, dim3((unsigned)grid), dim3(GEMM_THREADS_V2), SmemPlanH::TOTAL, (cudaStream_t)stream, tA, tAl, tB, tBl, M, N, K, e, m_count));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -1178,7 +1195,7 @@ extern "C" int idrk_split_f16(const float* x, int64_t rows, int32_t cols, int32_
     long long b = (total + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (b > cap) b = cap;
-    split_f16_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, scale, (__half*)h, (__half*)l, ld_out, pad_cols, m_count);
+    IDRK_CUDA_TRY(launch_k(split_f16_kernel, dim3((int)b), dim3(256), 0, (cudaStream_t)stream, x, rows, cols, ldx, scale, (__half*)h, (__half*)l, ld_out, pad_cols, m_count));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

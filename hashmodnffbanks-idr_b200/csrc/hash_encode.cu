@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
                             float* __restrict__ out, int ld_out, uint32_t* __restrict__ idx_dbg,
                             const int* __restrict__ m_count) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     extern __shared__ uint4 smem_u4[];
     if (m_count != nullptr) { const long long c = *m_count; n = c < n ? c : n; }
     const int C = g.n_fourier, L = g.n_levels;
@@ -497,6 +499,8 @@ template <int F, int MODE, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __restrict__ x, long long n, int ldx,
                             const float* __restrict__ dy, int ld_dy, float* __restrict__ dx) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     extern __shared__ uint4 smem_u4[];
     const int C = g.n_fourier, L = g.n_levels;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -659,7 +663,7 @@ static int launch_fwd(const GridDev& g, const float* x, long long n, int ldx, fl
     const size_t smem = ((size_t)2 * g.n_levels + WARPS * 32) * 16 + (size_t)3 * g.n_fourier * sizeof(float);
     auto kern = hash_encode_fwd_elem_kernel<F, MODE, WARPS>;
     const int grid = persistent_grid(kern, WARPS * 32, smem, (n + WARPS * 32 - 1) / (WARPS * 32));
-    kern<<<grid, WARPS * 32, smem, st>>>(g, x, n, ldx, out, ld_out, idx_dbg, m_count);
+    IDRK_CUDA_TRY(launch_k(kern, dim3(grid), dim3(WARPS * 32), smem, st, g, x, n, ldx, out, ld_out, idx_dbg, m_count));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -673,7 +677,7 @@ static int launch_bwd(const GridDev& g, const GradDev& gd, const float* x, long 
     auto kern = hash_encode_bwd_elem_kernel<F, MODE, WARPS>;
     IDRK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = persistent_grid(kern, WARPS * 32, smem, (n + WARPS * 32 - 1) / (WARPS * 32));
-    kern<<<grid, WARPS * 32, smem, st>>>(g, gd, x, n, ldx, dy, ld_dy, dx);
+    IDRK_CUDA_TRY(launch_k(kern, dim3(grid), dim3(WARPS * 32), smem, st, g, gd, x, n, ldx, dy, ld_dy, dx));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

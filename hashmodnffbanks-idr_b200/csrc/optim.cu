@@ -9,6 +9,8 @@
 namespace idrk {
 
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     float acc = 0.f;
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -35,6 +37,8 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
 __global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                  long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
                                  float max_norm, const float* __restrict__ sumsq, float grad_scale) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     float coef = grad_scale;
     if (max_norm > 0.f) {
         const float total = sqrtf(*sumsq) * grad_scale;
@@ -64,7 +68,7 @@ extern "C" int idrk_sumsq(const float* g, int64_t n, float* out, void* stream) {
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    sumsq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(g, n, out);
+    IDRK_CUDA_TRY(launch_k(sumsq_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, g, n, out));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -78,8 +82,8 @@ extern "C" int idrk_clip_adam(float* p, const float* g, float* m, float* v, int6
     long long blocks = (n + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    clip_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), max_norm,
-                                                                   sumsq, grad_scale);
+    IDRK_CUDA_TRY(launch_k(clip_adam_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), max_norm,
+                                                                   sumsq, grad_scale));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

@@ -9,6 +9,8 @@ struct Bands { float f[32]; int n; };
 
 __global__ void posenc_fwd_kernel(const float* __restrict__ x, long long n, int d, int ldx, Bands b, int include_input,
                                   float* __restrict__ out, int ld_out, int width) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const long long total = n * (long long)ld_out;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long p = i / ld_out;
@@ -31,6 +33,8 @@ __global__ void posenc_fwd_kernel(const float* __restrict__ x, long long n, int 
 
 __global__ void posenc_bwd_kernel(const float* __restrict__ x, long long n, int d, int ldx, Bands b, int include_input,
                                   const float* __restrict__ dy, int ld_dy, float* __restrict__ dx, int ld_dx) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const long long total = n * (long long)d;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long p = i / d;
@@ -67,7 +71,7 @@ extern "C" int idrk_posenc_fwd(const float* x, int64_t n, int32_t d, int32_t ldx
     long long blocks = (total + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    posenc_fwd_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(x, n, d, ldx, b, include_input, out, ld_out, width);
+    IDRK_CUDA_TRY(launch_k(posenc_fwd_kernel, dim3((int)blocks), dim3(threads), 0, (cudaStream_t)stream, x, n, d, ldx, b, include_input, out, ld_out, width));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -85,7 +89,7 @@ extern "C" int idrk_posenc_bwd(const float* x, int64_t n, int32_t d, int32_t ldx
     long long blocks = (total + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    posenc_bwd_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(x, n, d, ldx, b, include_input, dy, ld_dy, dx, ld_dx);
+    IDRK_CUDA_TRY(launch_k(posenc_bwd_kernel, dim3((int)blocks), dim3(threads), 0, (cudaStream_t)stream, x, n, d, ldx, b, include_input, dy, ld_dy, dx, ld_dx));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

@@ -51,6 +51,8 @@ __device__ __forceinline__ int warp_append(int* counter, int want) {
 
 __global__ void rt_init_kernel(RayState S, const float* __restrict__ t_sph, const unsigned char* __restrict__ hit,
                                float* __restrict__ pts, int* __restrict__ counter) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < S.n;
     const bool h = in && hit[i];
@@ -77,6 +79,8 @@ __device__ __forceinline__ void gather_vals(const RayState& S, int i, const floa
 
 // loop top (ray_tracing.py:131-142): current sdf, threshold, unfinished masks, count of unfinished rays
 __global__ void rt_top_kernel(RayState S, const float* __restrict__ vals, int gather_mode, float thr, int* __restrict__ n_unf) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool any = false;
     if (i < S.n) {
@@ -95,6 +99,8 @@ __global__ void rt_top_kernel(RayState S, const float* __restrict__ vals, int ga
 
 // make a step (:150-162) and list the unfinished end points for evaluation
 __global__ void rt_step_kernel(RayState S, const int* __restrict__ gate, float* __restrict__ pts, int* __restrict__ counter) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     if (*gate == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < S.n;
@@ -119,6 +125,8 @@ __global__ void rt_step_kernel(RayState S, const int* __restrict__ gate, float* 
 // one back-off iteration of the line search (:167-183)
 __global__ void rt_linesearch_kernel(RayState S, const int* __restrict__ gate, const float* __restrict__ vals, int gather_mode,
                                      float factor, float* __restrict__ pts, int* __restrict__ counter) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     if (*gate == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < S.n;
@@ -140,6 +148,8 @@ __global__ void rt_linesearch_kernel(RayState S, const int* __restrict__ gate, c
 
 // end of an iteration (:185-186)
 __global__ void rt_end_kernel(RayState S, const int* __restrict__ gate, const float* __restrict__ vals, int gather_mode) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     if (*gate == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S.n) return;
@@ -152,6 +162,8 @@ __global__ void rt_end_kernel(RayState S, const int* __restrict__ gate, const fl
 // after sphere tracing (:39-42): network mask and the list of rays handed to the sampler
 __global__ void rt_select_sampler_kernel(RayState S, unsigned char* __restrict__ net_mask, int* __restrict__ ray_of_slot,
                                          int* __restrict__ counter) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < S.n;
     const bool sel = in && S.unf_s[i];
@@ -171,12 +183,16 @@ __device__ __forceinline__ int chunk_slots(int slot0, int n_slots, const int* n_
 }
 
 __global__ void rt_chunk_counts_kernel(const int* __restrict__ n_dev, int per_chunk, int mult, int n_chunks, int* __restrict__ out) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n_chunks) out[c] = chunk_slots(c * per_chunk, per_chunk, n_dev) * mult;
 }
 
 __global__ void rt_sampler_points_kernel(RayState S, const int* __restrict__ ray_of_slot, int slot0, int n_slots, int n_steps,
                                          const float* __restrict__ lin, float* __restrict__ pts, const int* __restrict__ n_dev) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     n_slots = chunk_slots(slot0, n_slots, n_dev);
     const long long total = (long long)n_slots * n_steps;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
@@ -197,6 +213,8 @@ __global__ void rt_sampler_resolve_kernel(RayState S, const int* __restrict__ ra
                                           unsigned char* __restrict__ net_mask, float* __restrict__ z_lo, float* __restrict__ z_hi,
                                           float* __restrict__ s_lo, float* __restrict__ s_hi, int* __restrict__ sec_slots,
                                           int* __restrict__ sec_counter, const int* __restrict__ n_dev) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     n_slots = chunk_slots(0, n_slots, n_dev);
@@ -253,6 +271,8 @@ __global__ void rt_secant_kernel(RayState S, const int* __restrict__ ray_of_slot
                                  int mode, const float* __restrict__ vals, float* __restrict__ z_lo, float* __restrict__ z_hi,
                                  float* __restrict__ s_lo, float* __restrict__ s_hi, float* __restrict__ pts,
                                  const int* __restrict__ n_dev) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     n_sec = chunk_slots(0, n_sec, n_dev);
     if (k >= n_sec) return;
@@ -276,6 +296,8 @@ __global__ void rt_secant_kernel(RayState S, const int* __restrict__ ray_of_slot
 __global__ void rt_select_minsdf_kernel(RayState S, const unsigned char* __restrict__ net_mask, const unsigned char* __restrict__ object_mask,
                                         const unsigned char* __restrict__ hit, const unsigned char* __restrict__ sampler_mask,
                                         int* __restrict__ ray_of_slot, int* __restrict__ counter) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < S.n;
     bool sel = false;
@@ -303,6 +325,8 @@ __global__ void rt_select_minsdf_kernel(RayState S, const unsigned char* __restr
 // steps = u[j] * (max_dis - min_dis) + min_dis  (:277-286)
 __global__ void rt_minsdf_points_kernel(RayState S, const int* __restrict__ ray_of_slot, int slot0, int n_slots, int n_steps,
                                         const float* __restrict__ u, float* __restrict__ pts, const int* __restrict__ n_dev) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     n_slots = chunk_slots(slot0, n_slots, n_dev);
     const long long total = (long long)n_slots * n_steps;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
@@ -316,6 +340,8 @@ __global__ void rt_minsdf_points_kernel(RayState S, const int* __restrict__ ray_
 
 __global__ void rt_minsdf_resolve_kernel(RayState S, const int* __restrict__ ray_of_slot, int n_slots, int n_steps,
                                          const float* __restrict__ u, const float* __restrict__ vals, const int* __restrict__ n_dev) {
+    pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     n_slots = chunk_slots(0, n_slots, n_dev);
@@ -365,7 +391,7 @@ extern "C" int idrk_rt_init(const idrk_ray_state_t* h_state, const float* t_sph,
                             void* stream) {
     RT_PRELUDE();
     if (!t_sph || !hit || !pts || !counter) return IDRK_E_ARG;
-    rt_init_kernel<<<blocks, threads, 0, st>>>(S, t_sph, hit, pts, counter);
+    IDRK_CUDA_TRY(launch_k(rt_init_kernel, dim3(blocks), dim3(threads), 0, st, S, t_sph, hit, pts, counter));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -374,7 +400,7 @@ extern "C" int idrk_rt_top(const idrk_ray_state_t* h_state, const float* vals, i
                            int32_t* n_unfinished, void* stream) {
     RT_PRELUDE();
     if (!n_unfinished || (gather_mode && !vals)) return IDRK_E_ARG;
-    rt_top_kernel<<<blocks, threads, 0, st>>>(S, vals, gather_mode, sdf_threshold, n_unfinished);
+    IDRK_CUDA_TRY(launch_k(rt_top_kernel, dim3(blocks), dim3(threads), 0, st, S, vals, gather_mode, sdf_threshold, n_unfinished));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -382,7 +408,7 @@ extern "C" int idrk_rt_top(const idrk_ray_state_t* h_state, const float* vals, i
 extern "C" int idrk_rt_step(const idrk_ray_state_t* h_state, const int32_t* gate, float* pts, int32_t* counter, void* stream) {
     RT_PRELUDE();
     if (!gate || !pts || !counter) return IDRK_E_ARG;
-    rt_step_kernel<<<blocks, threads, 0, st>>>(S, gate, pts, counter);
+    IDRK_CUDA_TRY(launch_k(rt_step_kernel, dim3(blocks), dim3(threads), 0, st, S, gate, pts, counter));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -391,7 +417,7 @@ extern "C" int idrk_rt_linesearch(const idrk_ray_state_t* h_state, const int32_t
                                   float factor, float* pts, int32_t* counter, void* stream) {
     RT_PRELUDE();
     if (!gate || !pts || !counter || (gather_mode && !vals)) return IDRK_E_ARG;
-    rt_linesearch_kernel<<<blocks, threads, 0, st>>>(S, gate, vals, gather_mode, factor, pts, counter);
+    IDRK_CUDA_TRY(launch_k(rt_linesearch_kernel, dim3(blocks), dim3(threads), 0, st, S, gate, vals, gather_mode, factor, pts, counter));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -399,7 +425,7 @@ extern "C" int idrk_rt_linesearch(const idrk_ray_state_t* h_state, const int32_t
 extern "C" int idrk_rt_end(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, int32_t gather_mode, void* stream) {
     RT_PRELUDE();
     if (!gate || (gather_mode && !vals)) return IDRK_E_ARG;
-    rt_end_kernel<<<blocks, threads, 0, st>>>(S, gate, vals, gather_mode);
+    IDRK_CUDA_TRY(launch_k(rt_end_kernel, dim3(blocks), dim3(threads), 0, st, S, gate, vals, gather_mode));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -408,7 +434,7 @@ extern "C" int idrk_rt_select_sampler(const idrk_ray_state_t* h_state, uint8_t* 
                                       void* stream) {
     RT_PRELUDE();
     if (!net_mask || !ray_of_slot || !counter) return IDRK_E_ARG;
-    rt_select_sampler_kernel<<<blocks, threads, 0, st>>>(S, net_mask, ray_of_slot, counter);
+    IDRK_CUDA_TRY(launch_k(rt_select_sampler_kernel, dim3(blocks), dim3(threads), 0, st, S, net_mask, ray_of_slot, counter));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -422,7 +448,7 @@ extern "C" int idrk_rt_sampler_points(const idrk_ray_state_t* h_state, const int
     long long b = ((long long)n_slots * n_steps + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
     if (b > cap) b = cap;
-    rt_sampler_points_kernel<<<(int)b, threads, 0, st>>>(S, ray_of_slot, slot0, n_slots, n_steps, lin, pts, n_dev);
+    IDRK_CUDA_TRY(launch_k(rt_sampler_points_kernel, dim3((int)b), dim3(threads), 0, st, S, ray_of_slot, slot0, n_slots, n_steps, lin, pts, n_dev));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -436,8 +462,8 @@ extern "C" int idrk_rt_sampler_resolve(const idrk_ray_state_t* h_state, const in
     if (!ray_of_slot || !lin || !vals || !object_mask || !net_mask || !z_lo || !z_hi || !s_lo || !s_hi || !sec_slots || !sec_counter)
         return IDRK_E_ARG;
     if (n_slots <= 0) return 0;
-    rt_sampler_resolve_kernel<<<(n_slots + 7) / 8, 256, 0, st>>>(S, ray_of_slot, n_slots, n_steps, lin, vals, object_mask, training,
-                                                                net_mask, z_lo, z_hi, s_lo, s_hi, sec_slots, sec_counter, n_dev);
+    IDRK_CUDA_TRY(launch_k(rt_sampler_resolve_kernel, dim3((n_slots + 7) / 8), dim3(256), 0, st, S, ray_of_slot, n_slots, n_steps, lin, vals, object_mask, training,
+                                                                net_mask, z_lo, z_hi, s_lo, s_hi, sec_slots, sec_counter, n_dev));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -449,8 +475,8 @@ extern "C" int idrk_rt_secant(const idrk_ray_state_t* h_state, const int32_t* ra
     (void)blocks;
     if (!ray_of_slot || !sec_slots || !z_lo || !z_hi || !s_lo || !s_hi || ((mode == 1 || mode == 2) && !vals) || (mode < 2 && !pts)) return IDRK_E_ARG;
     if (n_sec <= 0) return 0;
-    rt_secant_kernel<<<(n_sec + threads - 1) / threads, threads, 0, st>>>(S, ray_of_slot, sec_slots, n_sec, mode, vals, z_lo, z_hi,
-                                                                       s_lo, s_hi, pts, n_dev);
+    IDRK_CUDA_TRY(launch_k(rt_secant_kernel, dim3((n_sec + threads - 1) / threads), dim3(threads), 0, st, S, ray_of_slot, sec_slots, n_sec, mode, vals, z_lo, z_hi,
+                                                                       s_lo, s_hi, pts, n_dev));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -460,7 +486,7 @@ extern "C" int idrk_rt_select_minsdf(const idrk_ray_state_t* h_state, const uint
                                      void* stream) {
     RT_PRELUDE();
     if (!net_mask || !object_mask || !hit || !sampler_mask || !ray_of_slot || !counter) return IDRK_E_ARG;
-    rt_select_minsdf_kernel<<<blocks, threads, 0, st>>>(S, net_mask, object_mask, hit, sampler_mask, ray_of_slot, counter);
+    IDRK_CUDA_TRY(launch_k(rt_select_minsdf_kernel, dim3(blocks), dim3(threads), 0, st, S, net_mask, object_mask, hit, sampler_mask, ray_of_slot, counter));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -474,7 +500,7 @@ extern "C" int idrk_rt_minsdf_points(const idrk_ray_state_t* h_state, const int3
     long long b = ((long long)n_slots * n_steps + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
     if (b > cap) b = cap;
-    rt_minsdf_points_kernel<<<(int)b, threads, 0, st>>>(S, ray_of_slot, slot0, n_slots, n_steps, u, pts, n_dev);
+    IDRK_CUDA_TRY(launch_k(rt_minsdf_points_kernel, dim3((int)b), dim3(threads), 0, st, S, ray_of_slot, slot0, n_slots, n_steps, u, pts, n_dev));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -485,7 +511,7 @@ extern "C" int idrk_rt_minsdf_resolve(const idrk_ray_state_t* h_state, const int
     (void)blocks;
     if (!ray_of_slot || !u || !vals) return IDRK_E_ARG;
     if (n_slots <= 0) return 0;
-    rt_minsdf_resolve_kernel<<<(n_slots + 7) / 8, 256, 0, st>>>(S, ray_of_slot, n_slots, n_steps, u, vals, n_dev);
+    IDRK_CUDA_TRY(launch_k(rt_minsdf_resolve_kernel, dim3((n_slots + 7) / 8), dim3(256), 0, st, S, ray_of_slot, n_slots, n_steps, u, vals, n_dev));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -493,7 +519,7 @@ extern "C" int idrk_rt_minsdf_resolve(const idrk_ray_state_t* h_state, const int
 extern "C" int idrk_rt_chunk_counts(const int32_t* n_dev, int32_t per_chunk, int32_t mult, int32_t n_chunks, int32_t* out, void* stream) {
     if (!n_dev || !out || per_chunk < 1 || mult < 1 || n_chunks < 0) return IDRK_E_ARG;
     if (n_chunks == 0) return 0;
-    rt_chunk_counts_kernel<<<(n_chunks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_dev, per_chunk, mult, n_chunks, out);
+    IDRK_CUDA_TRY(launch_k(rt_chunk_counts_kernel, dim3((n_chunks + 127) / 128), dim3(128), 0, (cudaStream_t)stream, n_dev, per_chunk, mult, n_chunks, out));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
