@@ -140,6 +140,47 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr) : "memory");
 }
 
+// ---- warp-converged issue -------------------------------------------------------------------
+// The TMA-producer and MMA-issuer warps run their loops with all 32 lanes converged and predicate the single-thread
+// instructions on an elected lane.  Issuing from inside an `if (lane == 0)` region instead makes ptxas wrap every
+// uniform-datapath instruction (UTMALDG / UTCHMMA / UTCBAR) in an ELECT + BRA.U.ANY waterfall; ncu showed the
+// issuing thread 100 % busy with that bookkeeping while the tensor pipe idled (36 % active at M = 32700).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint32_t bar, uint32_t bytes, uint32_t leader) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+                 :: "r"(bar), "r"(bytes), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_p(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        :: "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tc_commit_p(uint32_t bar, uint32_t leader) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" :: "r"(bar), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                             uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                              uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+
 // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor), SWIZZLE_128B
 // layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B - the only swizzled layout
 // the hardware offers for MN-major 32-bit operands (cutlass sm100_common.inl sm100_smem_selector):
@@ -695,15 +736,18 @@ struct EpiParamsH {
     const float* bias;
     int ldc, ldh;
     int mode; float act; float scale;
+    int vec16;                      // C_h / C_l rows 16-byte aligned: quad-transposed 16-byte stores
 };
 
-struct SmemPlanH {
+template <int BN_, int STAGES_>
+struct SmemPlanHT {
     static constexpr int A_BYTES = BM * BKH * 2;
-    static constexpr int B_BYTES = BNH * BKH * 2;
+    static constexpr int B_BYTES = BN_ * BKH * 2;
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
-    static constexpr int STAGES = 3;
+    static constexpr int STAGES = STAGES_;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
 };
+
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -713,26 +757,87 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// softplus_beta(z) * scale in base 2:  (ln2 / beta) * log2(1 + 2^(z * beta * log2 e)),  linear above beta*z = 20
+// (torch's threshold).  Two MUFU ops and ~7 FP32 instructions per element; abs error <= 3e-9 at beta = 100.
+struct SoftplusC { float k_in, k_out, scale; };      // beta * log2(e),  ln(2) / beta * scale,  scale
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 template <int MODE>
-__device__ __forceinline__ void epi_frag_h(const EpiParamsH& e, const uint32_t* r0, const uint32_t* r1, int lane, long long row0,
-                                           long long m_eff, int col0, int N) {
+__device__ __forceinline__ float epi_act_h(float z, const SoftplusC& c) {
+    if constexpr (MODE == IDRK_EPI_SOFTPLUS) {
+        const float t = z * c.k_in;
+        const float soft = lg2_approx(1.f + ex2_approx(fminf(t, 30.f))) * c.k_out;
+        return t > 28.853900817779268f ? z * c.scale : soft;          // 20 * log2(e)
+    } else {
+        return z * c.scale;
+    }
+}
+
+// 4 x 4 transpose of 32-bit values across the 4 lanes of a quad (lane t, register i) -> (lane i, register t):
+// two butterfly steps, 4 shuffles.  Turns "lane t holds column pairs 8 i + 2 t" into "lane t holds the 8 consecutive
+// columns 8 t .. 8 t + 7", i.e. one 16-byte store per lane and full 32-byte sectors per row.
+__device__ __forceinline__ void quad_transpose(uint32_t (&p)[4], int t) {
+    const bool o1 = t & 1, o2 = t & 2;
+    uint32_t r;
+    r = __shfl_xor_sync(0xffffffffu, o1 ? p[0] : p[1], 1); if (o1) p[0] = r; else p[1] = r;
+    r = __shfl_xor_sync(0xffffffffu, o1 ? p[2] : p[3], 1); if (o1) p[2] = r; else p[3] = r;
+    r = __shfl_xor_sync(0xffffffffu, o2 ? p[0] : p[2], 2); if (o2) p[0] = r; else p[2] = r;
+    r = __shfl_xor_sync(0xffffffffu, o2 ? p[1] : p[3], 2); if (o2) p[1] = r; else p[3] = r;
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// One 16-row x 32-column accumulator fragment pair (D0, D1) of a warp -> activation -> fp32 and / or fp16-pair stores.
+// bias2[i] = bias of columns col0 + 8 i + 2 t + {0, 1} (prefetched by the caller before the accumulator wait).
+// FULL: all 32 columns are inside N (no per-column bounds checks); with e.vec16 the fp16 pair goes out as 16-byte
+// stores after a quad transpose (4 B stores write quarter sectors: 4 x the L1 -> L2 requests, which is what bounded
+// the epilogue - 36 of 60 us at M = 32700 in the ablation).
+template <int MODE, bool FULL>
+__device__ __forceinline__ void epi_frag_h(const EpiParamsH& e, const SoftplusC& c, const uint32_t* r0, const uint32_t* r1,
+                                           const float2 (&bias2)[4], int lane, long long row0, long long m_eff, int col0, int N) {
     constexpr int NB = 4;
     const int t = lane & 3, g = lane >> 2;
     const long long ra = row0 + g, rb = ra + 8;
     const bool va = ra < m_eff, vb = rb < m_eff;
-    const float inv_act = MODE == IDRK_EPI_SOFTPLUS ? 1.f / e.act : 0.f;
+    if (FULL && e.vec16 && e.C == nullptr) {
+        uint32_t ha[4], la[4], hb[4], lb[4];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float z = fmaf(__uint_as_float(r1[4 * i + k]), 1.f / F16S_SCALE, __uint_as_float(r0[4 * i + k])) + ((k & 1) ? bias2[i].y : bias2[i].x);
+                v[k] = epi_act_h<MODE>(z, c);
+            }
+            const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            ha[i] = h2_bits(h0); hb[i] = h2_bits(h1);
+            la[i] = h2_bits(__floats2half2_rn((v[0] - f0.x) * F16S_SCALE, (v[1] - f0.y) * F16S_SCALE));
+            lb[i] = h2_bits(__floats2half2_rn((v[2] - f1.x) * F16S_SCALE, (v[3] - f1.y) * F16S_SCALE));
+        }
+        quad_transpose(ha, t); quad_transpose(la, t); quad_transpose(hb, t); quad_transpose(lb, t);
+        const int col = col0 + 8 * t;
+        if (va) {
+            const long long o = ra * e.ldh + col;
+            *reinterpret_cast<uint4*>(e.C_h + o) = make_uint4(ha[0], ha[1], ha[2], ha[3]);
+            *reinterpret_cast<uint4*>(e.C_l + o) = make_uint4(la[0], la[1], la[2], la[3]);
+        }
+        if (vb) {
+            const long long o = rb * e.ldh + col;
+            *reinterpret_cast<uint4*>(e.C_h + o) = make_uint4(hb[0], hb[1], hb[2], hb[3]);
+            *reinterpret_cast<uint4*>(e.C_l + o) = make_uint4(lb[0], lb[1], lb[2], lb[3]);
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         const int col = col0 + 8 * i + 2 * t;
-        if (col >= N) continue;
-        const bool both = col + 1 < N;
-        float b0 = 0.f, b1 = 0.f;
-        if (e.bias != nullptr) { b0 = __ldg(e.bias + col); b1 = both ? __ldg(e.bias + col + 1) : 0.f; }
-        float v[4], sd;
+        if (!FULL && col >= N) continue;
+        const bool both = FULL || col + 1 < N;
+        float v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float z = fmaf(__uint_as_float(r1[4 * i + k]), 1.f / F16S_SCALE, __uint_as_float(r0[4 * i + k])) + ((k & 1) ? b1 : b0);
-            v[k] = epi_fast<MODE>(z, e.act, inv_act, e.scale, sd);
+            const float z = fmaf(__uint_as_float(r1[4 * i + k]), 1.f / F16S_SCALE, __uint_as_float(r0[4 * i + k])) + ((k & 1) ? bias2[i].y : bias2[i].x);
+            v[k] = epi_act_h<MODE>(z, c);
         }
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
@@ -744,47 +849,65 @@ __device__ __forceinline__ void epi_frag_h(const EpiParamsH& e, const uint32_t* 
                 else e.C[row * e.ldc + col] = x0;
             }
             if (e.C_h) {
-                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                const __half l0 = __float2half_rn((x0 - __half2float(h0)) * F16S_SCALE);
-                const __half l1 = __float2half_rn((x1 - __half2float(h1)) * F16S_SCALE);
+                const __half2 h = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn((x0 - hf.x) * F16S_SCALE, (x1 - hf.y) * F16S_SCALE);
                 const long long o = row * e.ldh + col;
                 if (both) {
-                    *reinterpret_cast<__half2*>(e.C_h + o) = __halves2half2(h0, h1);
-                    *reinterpret_cast<__half2*>(e.C_l + o) = __halves2half2(l0, l1);
-                } else { e.C_h[o] = h0; e.C_l[o] = l0; }
+                    *reinterpret_cast<__half2*>(e.C_h + o) = h;
+                    *reinterpret_cast<__half2*>(e.C_l + o) = l;
+                } else { e.C_h[o] = __low2half(h); e.C_l[o] = __low2half(l); }
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS_V2, 1)
+// bias of this lane's 4 column pairs of the warp's 32-column group (zero outside N / without a bias vector)
+__device__ __forceinline__ void load_bias2(const float* __restrict__ bias, int col0, int lane, int N, float2 (&b)[4]) {
+    const int t = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int col = col0 + 8 * i + 2 * t;
+        b[i] = make_float2(0.f, 0.f);
+        if (bias != nullptr && col < N) { b[i].x = __ldg(bias + col); if (col + 1 < N) b[i].y = __ldg(bias + col + 1); }
+    }
+}
+
+// Template parameters: BN_ output columns per tile, STAGES_ operand stages, ACCS TMEM accumulator stages, EPIW epilogue
+// warps (4 lane quarters x BN_/32 column groups), MINB resident CTAs per SM.
+//   <128, 3, 2, 16, 1> is the shipped configuration: persistent, 192 KB of operand stages, epilogue(i) overlaps
+//   mainloop(i+1).  Measured alternative for one-wave launches (M = 4096): <64, 2, 1, 8, 2>, two CTAs per SM so that one
+//   CTA's epilogue and the next launch's prologue overlap the other's mainloop - 11.0 us vs 9.7 us, slower (more
+//   shared-memory traffic per MMA cycle at BN = 64), not instantiated.
+template <int BN_, int STAGES_, int ACCS, int EPIW, int MINB>
+__global__ void __launch_bounds__(64 + 32 * EPIW, MINB)
 gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl,
                  long long M, int N, int K, EpiParamsH e, const int* __restrict__ m_count) {
     pdl_trigger();
-    using P = SmemPlanH;
-    const int n_tiles = (N + BNH - 1) / BNH;
+    using P = SmemPlanHT<BN_, STAGES_>;
+    const int n_tiles = (N + BN_ - 1) / BN_;
     const int kb_total = (K + BKH - 1) / BKH;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::STAGES * P::STAGE_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P::STAGES + 2 * ACC_STAGES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P::STAGES + 2 * ACCS);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (P::STAGES + s); };
     auto acc_full_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + a); };
-    auto acc_empty_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + ACC_STAGES + a); };
+    auto acc_empty_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + ACCS + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 32) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBl); }
     if (threadIdx.x == 0) {
         for (int s = 0; s < P::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(acc_full_bar(a), 1); mbar_init(acc_empty_bar(a), EPI_WARPS); }
+        for (int a = 0; a < ACCS; ++a) { mbar_init(acc_full_bar(a), 1); mbar_init(acc_empty_bar(a), EPIW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    constexpr uint32_t TMEM_COLS = ACC_STAGES * 2 * BNH;         // two accumulators (D0, D1) per stage = 512 columns
+    constexpr uint32_t TMEM_COLS = ACCS * 2 * BN_;         // two accumulators (D0, D1) per stage
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -800,87 +923,100 @@ gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int items = m_tiles * n_tiles;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one();
             int it = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int n0 = (item % n_tiles) * BNH;
+                const int n0 = (item % n_tiles) * BN_;
                 const int m0 = (item / n_tiles) * BM;
                 for (int kb = 0; kb < kb_total; ++kb, ++it) {
                     const int s = it % P::STAGES;
                     const uint32_t ph = (it / P::STAGES) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx(full_bar(s), P::STAGE_BYTES);
+                    mbar_expect_tx_p(full_bar(s), P::STAGE_BYTES, leader);
                     const uint32_t st = smem_base + s * P::STAGE_BYTES;
                     const int k0 = kb * BKH;
-                    tma_load_2d(st, &tmA, full_bar(s), k0, m0);
-                    tma_load_2d(st + P::A_BYTES, &tmB, full_bar(s), k0, n0);
-                    tma_load_2d(st + P::A_BYTES + P::B_BYTES, &tmAl, full_bar(s), k0, m0);
-                    tma_load_2d(st + 2 * P::A_BYTES + P::B_BYTES, &tmBl, full_bar(s), k0, n0);
+                    tma_load_2d_p(st, &tmA, full_bar(s), k0, m0, leader);
+                    tma_load_2d_p(st + 2 * P::A_BYTES, &tmB, full_bar(s), k0, n0, leader);
+                    tma_load_2d_p(st + P::A_BYTES, &tmAl, full_bar(s), k0, m0, leader);
+                    tma_load_2d_p(st + 2 * P::A_BYTES + P::B_BYTES, &tmBl, full_bar(s), k0, n0, leader);
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one();
             // kind::f16: A, B fp16 (format 0), f32 accumulate, K-major, M = 128, N = 128, K = 16 per instruction
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BNH >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN_) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int it = 0, ti = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
-                const int a = ti & 1;
-                mbar_wait(acc_empty_bar(a), ((ti >> 1) & 1) ^ 1u);
+                const int a = ti % ACCS;
+                mbar_wait(acc_empty_bar(a), ((ti / ACCS) & 1) ^ 1u);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + (uint32_t)(a * 2 * BNH);
-                const uint32_t d1 = d0 + BNH;
+                const uint32_t d0 = tmem_base + (uint32_t)(a * 2 * BN_);
+                const uint32_t d1 = d0 + BN_;
                 for (int kb = 0; kb < kb_total; ++kb, ++it) {
                     const int s = it % P::STAGES;
                     const uint32_t ph = (it / P::STAGES) & 1;
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t st = smem_base + s * P::STAGE_BYTES;
+                    // stage = [A_h | A_l | B_h | B_l]: B_h and B_l are adjacent, so [B_h ; B_l] is one 256-row K-major operand
+                    // and [D0 | D1] one 256-column accumulator - Ah.Bh and Ah.Bl issue as ONE N = 256 instruction that reads
+                    // A_h from shared memory once (shared-memory bandwidth, MMA operand reads + TMA fills, bounds this kernel)
                     const uint64_t a_h = umma_desc(st, 16, 1024, 2);
-                    const uint64_t b_h = umma_desc(st + P::A_BYTES, 16, 1024, 2);
-                    const uint64_t a_l = umma_desc(st + P::A_BYTES + P::B_BYTES, 16, 1024, 2);
-                    const uint64_t b_l = umma_desc(st + 2 * P::A_BYTES + P::B_BYTES, 16, 1024, 2);
+                    const uint64_t a_l = umma_desc(st + P::A_BYTES, 16, 1024, 2);
+                    const uint64_t b_h = umma_desc(st + 2 * P::A_BYTES, 16, 1024, 2);
 #pragma unroll
                     for (int k = 0; k < BKH / 16; ++k) {
                         const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                        tc_mma_f16(d0, a_h + 2 * k, b_h + 2 * k, idesc, acc);
-                        tc_mma_f16(d1, a_h + 2 * k, b_l + 2 * k, idesc, acc);
-                        tc_mma_f16(d1, a_l + 2 * k, b_h + 2 * k, idesc, 1u);
+                        tc_mma_f16_p(d0, a_h + 2 * k, b_h + 2 * k, idesc2, acc, leader);     // [D0 | D1] (+)= Ah . [Bh ; Bl]^T
+                        tc_mma_f16_p(d1, a_l + 2 * k, b_h + 2 * k, idesc, 1u, leader);       //  D1      +=  Al . Bh^T
                     }
-                    tc_commit(empty_bar(s));
+                    tc_commit_p(empty_bar(s), leader);
                 }
-                tc_commit(acc_full_bar(a));
+                tc_commit_p(acc_full_bar(a), leader);
             }
         }
     } else {
         const int q = warp & 3;
         const int grp = (warp - 2) >> 2;                        // 32-column group of this warp
+        const SoftplusC spc = {e.act * 1.4426950408889634f, e.mode == IDRK_EPI_SOFTPLUS ? 0.6931471805599453f / e.act * e.scale : 0.f, e.scale};
         int ti = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
-            const int n0 = (item % n_tiles) * BNH;
+            const int n0 = (item % n_tiles) * BN_;
             const long long m0 = (long long)(item / n_tiles) * BM;
-            const int a = ti & 1;
-            mbar_wait(acc_full_bar(a), (ti >> 1) & 1);
+            const int a = ti % ACCS;
+            const int col0 = n0 + grp * 32;
+            float2 bias2[4];
+            load_bias2(e.bias, col0, lane, N, bias2);            // in flight while the accumulator is still being produced
+            mbar_wait(acc_full_bar(a), (ti / ACCS) & 1);
             tc_fence_after();
-            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 2 * BNH + grp * 32);
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 2 * BN_ + grp * 32);
             uint32_t a0[16], a1[16], b0[16], b1[16];            // D0 / D1 fragments of rows +0..15 and +16..31
             tc_ld_16x256b_x4(t0, a0);
-            tc_ld_16x256b_x4(t0 + BNH, a1);
+            tc_ld_16x256b_x4(t0 + BN_, a1);
             tc_ld_16x256b_x4(t0 + (16u << 16), b0);
-            tc_ld_16x256b_x4(t0 + (16u << 16) + BNH, b1);
+            tc_ld_16x256b_x4(t0 + (16u << 16) + BN_, b1);
             tc_wait_ld();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty_bar(a));
             const long long row_base = m0 + q * 32;
-            const int col0 = n0 + grp * 32;
             if (col0 >= N || row_base >= m_eff) continue;
+            const bool full = col0 + 32 <= N;
             if (e.mode == IDRK_EPI_SOFTPLUS) {
-                epi_frag_h<IDRK_EPI_SOFTPLUS>(e, a0, a1, lane, row_base, m_eff, col0, N);
-                epi_frag_h<IDRK_EPI_SOFTPLUS>(e, b0, b1, lane, row_base + 16, m_eff, col0, N);
+                if (full) {
+                    epi_frag_h<IDRK_EPI_SOFTPLUS, true>(e, spc, a0, a1, bias2, lane, row_base, m_eff, col0, N);
+                    epi_frag_h<IDRK_EPI_SOFTPLUS, true>(e, spc, b0, b1, bias2, lane, row_base + 16, m_eff, col0, N);
+                } else {
+                    epi_frag_h<IDRK_EPI_SOFTPLUS, false>(e, spc, a0, a1, bias2, lane, row_base, m_eff, col0, N);
+                    epi_frag_h<IDRK_EPI_SOFTPLUS, false>(e, spc, b0, b1, bias2, lane, row_base + 16, m_eff, col0, N);
+                }
             } else {
-                epi_frag_h<IDRK_EPI_NONE>(e, a0, a1, lane, row_base, m_eff, col0, N);
-                epi_frag_h<IDRK_EPI_NONE>(e, b0, b1, lane, row_base + 16, m_eff, col0, N);
+                epi_frag_h<IDRK_EPI_NONE, false>(e, spc, a0, a1, bias2, lane, row_base, m_eff, col0, N);
+                epi_frag_h<IDRK_EPI_NONE, false>(e, spc, b0, b1, bias2, lane, row_base + 16, m_eff, col0, N);
             }
         }
     }
@@ -1166,6 +1302,7 @@ extern "C" int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, 
     e.C = h_epi->C; e.C_h = (__half*)h_epi->C_h; e.C_l = (__half*)h_epi->C_l; e.bias = h_epi->bias;
     e.ldc = h_epi->ldc; e.ldh = h_epi->ldh; e.mode = h_epi->mode; e.act = h_epi->act_param; e.scale = h_epi->scale;
     if (!e.C && !e.C_h) return IDRK_E_ARG;
+    e.vec16 = e.C_h && e.C_l && (e.ldh % 8) == 0 && aligned16(e.C_h) && aligned16(e.C_l);
     if ((e.C_h == nullptr) != (e.C_l == nullptr)) return IDRK_E_ARG;
     if (e.mode != IDRK_EPI_NONE && e.mode != IDRK_EPI_SOFTPLUS) return IDRK_E_UNSUP;
     if ((e.C && (e.ldc < N || (e.ldc & 1))) || (e.C_h && (e.ldh < N || (e.ldh & 1)))) return IDRK_E_ARG;
@@ -1173,16 +1310,19 @@ extern "C" int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, 
     int rc;
     if ((rc = make_tmap_h(&tA, A_h, (uint64_t)K, (uint64_t)M, lda, BM))) return rc;
     if ((rc = make_tmap_h(&tAl, A_l, (uint64_t)K, (uint64_t)M, lda, BM))) return rc;
+    const long long m_tiles = (M + BM - 1) / BM;
+    auto kern = gemm_f16s_kernel<BNH, 3, 2, 16, 1>;
+    using P = SmemPlanHT<BNH, 3>;
     if ((rc = make_tmap_h(&tB, B_h, (uint64_t)K, (uint64_t)N, ldb, BNH))) return rc;
     if ((rc = make_tmap_h(&tBl, B_l, (uint64_t)K, (uint64_t)N, ldb, BNH))) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        IDRK_CUDA_TRY(cudaFuncSetAttribute(gemm_f16s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlanH::TOTAL));
+        IDRK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL));
         attr_done = true;
     }
-    const long long items = ((M + BM - 1) / BM) * ((N + BNH - 1) / BNH);
+    const long long items = m_tiles * ((N + BNH - 1) / BNH);
     const long long grid = items < sm_count() ? items : sm_count();
-    IDRK_CUDA_TRY(launch_k(gemm_f16s_kernel, dim3((unsigned)grid), dim3(GEMM_THREADS_V2), SmemPlanH::TOTAL, (cudaStream_t)stream, tA, tAl, tB, tBl, M, N, K, e, m_count));
+    IDRK_CUDA_TRY(launch_k(kern, dim3((unsigned)grid), dim3(GEMM_THREADS_V2), P::TOTAL, (cudaStream_t)stream, tA, tAl, tB, tBl, M, N, K, e, m_count));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

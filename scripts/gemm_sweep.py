@@ -38,10 +38,29 @@ def case(layout, M, N, Kc, split_k=1, mode=K.EPI_NONE):
     print("%s M=%d N=%d K=%d split=%d: %.1f us  (%.1f TF/s alg)" % ({K.GEMM_NT: "NT", K.GEMM_NN: "NN", K.GEMM_TN: "TN"}[layout], M, N, Kc, split_k, us, 2.0 * M * N * Kc / us / 1e6), flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     for M in (2048, 3072, 4096):
         case(K.GEMM_NT, M, 512, 512, mode=K.EPI_SOFTPLUS)
         case(K.GEMM_NN, M, 512, 512)
     for Kc in (2048, 3072):
         for sk in (1, 2, 4, 8):
             case(K.GEMM_TN, 512, 512, Kc, split_k=sk)
+
+
+def case_h(M, N, Kc):
+    A = torch.randn(M, Kc, device="cuda") * 0.05
+    W = torch.randn(N, Kc, device="cuda") * 0.05
+    b = torch.randn(N, device="cuda") * 0.01
+    Ah, Al = K.split_f16(A); Wh, Wl = K.split_f16(W)
+    Ch, Cl = K.empty_half(M, N, "cuda"), K.empty_half(M, N, "cuda")
+    def fn():
+        K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, C_h=Ch, C_l=Cl, bias=b, mode=K.EPI_SOFTPLUS, act=100.0)
+    us = timed(fn)
+    print("f16s M=%d N=%d K=%d: %.1f us  (%.1f TF/s alg)" % (M, N, Kc, us, 2.0 * M * N * Kc / us / 1e6), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "f16s":
+    for M in (2048, 4096, 8192, 32700, 131072):
+        case_h(M, 512, 512)
+    case_h(32700, 485, 512)
+    case_h(32700, 512, 485)
