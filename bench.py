@@ -330,6 +330,8 @@ def run_ours(args):
         "roofline": {"kernel": "gemm_f16s_kernel (tcgen05 kind::f16 fp16-pair MLP contraction tiles; launches with >= 8192 rows)",
                      "bound": "tensor", "achieved": round(achieved, 2), "peak": round(f16_peak, 1), "unit": "TFLOP/s",
                      "frac": round(achieved / f16_peak, 4), "traffic": TRAFFIC.get("gemm_f16s_dram_bytes_per_launch"),
+                     "traffic_note": "DRAM bytes of one full M=32700 launch (ncu --set full, profiles/r01_gemm_f16s_ncu_full_summary.txt); "
+                                     "algorithmic: 68 MB read + 67 MB written, the written fp16 pair is re-read by the next layer from L2",
                      "peak_source": "%s: sustained dense bf16/fp16 (cuBLAS)" % src,
                      "note": "achieved = algorithmic 2*M*N*K FLOPs of those launches / their summed CUDA-event time; the "
                              "fp16-pair format issues 3 MMAs per algorithmic MAC, so 1/3 of the peak is the ceiling of this "
