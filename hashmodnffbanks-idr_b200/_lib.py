@@ -169,7 +169,7 @@ def _declare(L):
     L.idrk_gemm.argtypes = [i32, i32, i64, i32, i32, vp, vp, i32, vp, vp, i32, c.POINTER(Epilogue), vp, i32, vp]
     L.idrk_split_tf32.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp]
     L.idrk_weight_norm_fwd.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp]
-    L.idrk_weight_norm_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]
+    L.idrk_weight_norm_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp]
     L.idrk_colsum.argtypes = [vp, i64, i32, i32, vp, vp]
     L.idrk_sdf_head.argtypes = [vp, i64, i32, i32, vp, vp, f32, vp, vp, vp]
     L.idrk_sdf_squash.argtypes = [vp, i64, f32, vp, vp, vp]

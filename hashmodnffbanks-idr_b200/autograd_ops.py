@@ -25,6 +25,7 @@ class _HashEncode(torch.autograd.Function):
         out = K.hash_encode_fwd(spec, x, tables, B)
         ctx.spec = spec
         ctx.has_B = B is not None
+        ctx.table_refs = tables
         ctx.save_for_backward(x, *( [B] if B is not None else [] ), *tables)
         return out[:, :spec.width]
 
@@ -42,12 +43,16 @@ class _HashEncode(torch.autograd.Function):
         grads: List[Optional[torch.Tensor]] = [None] * len(tables)
         gt = None
         if need_tab:
-            flat = torch.zeros(sum(r * spec.n_feat for r in spec.rows), device=dy.device, dtype=torch.float32)
-            gt, off = [], 0
-            for r in spec.rows:
-                gt.append(flat[off:off + r * spec.n_feat].view(r, spec.n_feat))
-                off += r * spec.n_feat
-            grads = list(gt)
+            direct = [K.direct_grad_target(t) for t in ctx.table_refs] if getattr(ctx, "table_refs", None) else [None]
+            if all(d is not None for d in direct) and all(ctx.needs_input_grad[3:]):
+                gt = direct                               # the scatter accumulates straight into the tables' .grad
+            else:
+                flat = K.ZERO_POOL.take(sum(r * spec.n_feat for r in spec.rows), dy.device)
+                gt, off = [], 0
+                for r in spec.rows:
+                    gt.append(flat[off:off + r * spec.n_feat].view(r, spec.n_feat))
+                    off += r * spec.n_feat
+                grads = list(gt)
         dx = None
         if second_order:
             # differentiable form of d/dx: only the Fourier prefix depends on x in reference mode

@@ -67,7 +67,8 @@ __global__ void weight_norm_fwd_kernel(const float* __restrict__ g, const float*
 }
 
 __global__ void weight_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v, const float* __restrict__ dW,
-                                       int N, int K, int ldv, int lddw, float* __restrict__ dg, float* __restrict__ dv, int lddv) {
+                                       int N, int K, int ldv, int lddw, float* __restrict__ dg, float* __restrict__ dv, int lddv,
+                                       int accumulate) {
     pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
     pdl_trigger();
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -80,9 +81,12 @@ __global__ void weight_norm_bwd_kernel(const float* __restrict__ g, const float*
     ss = warp_sum(ss); dot = warp_sum(dot);
     const float nrm = sqrtf(ss);
     const float gn = g[n];
-    if (lane == 0) dg[n] = dot / nrm;
+    if (lane == 0) dg[n] = (accumulate ? dg[n] : 0.f) + dot / nrm;
     const float a = gn / nrm, b = gn * dot / (nrm * ss);
-    for (int k = lane; k < K; k += 32) dv[(long long)n * lddv + k] = a * dr[k] - b * vr[k];
+    for (int k = lane; k < K; k += 32) {
+        float* o = dv + (long long)n * lddv + k;
+        *o = (accumulate ? *o : 0.f) + a * dr[k] - b * vr[k];
+    }
 }
 
 // out[c] += sum_r x[r, c]
@@ -209,9 +213,9 @@ extern "C" int idrk_weight_norm_fwd(const float* g, const float* v, int32_t N, i
 }
 
 extern "C" int idrk_weight_norm_bwd(const float* g, const float* v, const float* dW, int32_t N, int32_t K, int32_t ldv,
-                                    int32_t lddw, float* dg, float* dv, int32_t lddv, void* stream) {
+                                    int32_t lddw, float* dg, float* dv, int32_t lddv, int32_t accumulate, void* stream) {
     if (!g || !v || !dW || !dg || !dv || N < 1 || K < 1 || ldv < K || lddw < K || lddv < K) return IDRK_E_ARG;
-    IDRK_CUDA_TRY(launch_k(weight_norm_bwd_kernel, dim3((N + 7) / 8), dim3(256), 0, (cudaStream_t)stream, g, v, dW, N, K, ldv, lddw, dg, dv, lddv));
+    IDRK_CUDA_TRY(launch_k(weight_norm_bwd_kernel, dim3((N + 7) / 8), dim3(256), 0, (cudaStream_t)stream, g, v, dW, N, K, ldv, lddw, dg, dv, lddv, accumulate));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

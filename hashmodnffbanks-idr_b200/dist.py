@@ -99,11 +99,19 @@ class DataParallelTrainer:
 
     # -- differentiable part ---------------------------------------------------------------------
     def _shade_and_backward(self, traced, eik, rgb):
-        out = self.model.shade(traced, eik)
-        losses = self.loss_fn(out, {"rgb": rgb})
-        self.bucket.zero_grad()
-        losses["loss"].backward()
-        self.bucket.gather_stray_grads()
+        K.ZERO_POOL.begin(self.bucket.flat.device)       # one fill for every zero-initialised scratch of the step
+        try:
+            out = self.model.shade(traced, eik)
+            losses = self.loss_fn(out, {"rgb": rgb})
+            self.bucket.zero_grad()
+            K.DIRECT_GRADS[0] = True                     # kernels accumulate leaf gradients straight into the bucket
+            try:
+                losses["loss"].backward()
+            finally:
+                K.DIRECT_GRADS[0] = False
+            self.bucket.gather_stray_grads()
+        finally:
+            K.ZERO_POOL.end()
         return losses
 
     def _graphed(self, traced, eik, rgb):

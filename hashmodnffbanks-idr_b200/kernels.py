@@ -260,20 +260,81 @@ def weight_norm_fwd(g: Optional[torch.Tensor], v: torch.Tensor, want_split: bool
     return out
 
 
-def weight_norm_bwd(g: torch.Tensor, v: torch.Tensor, dW: torch.Tensor):
+def weight_norm_bwd(g: torch.Tensor, v: torch.Tensor, dW: torch.Tensor, into=None):
+    """(dg, dv) of W = g v / ||v||.  `into=(dg_buf, dv_buf)` ACCUMULATES into caller-owned contiguous buffers (the
+    parameters' .grad views of the flat bucket) instead of allocating."""
     v = rows2d(v, "weight_v")
     dW = rows2d(dW, "dW")
     N, Kd = v.shape
-    dg = torch.empty((N, 1), device=v.device, dtype=torch.float32)
-    dv = torch.empty((N, Kd), device=v.device, dtype=torch.float32)
+    if into is None:
+        dg = torch.empty((N, 1), device=v.device, dtype=torch.float32)
+        dv = torch.empty((N, Kd), device=v.device, dtype=torch.float32)
+        acc = 0
+    else:
+        dg, dv = into
+        if not (dg.is_contiguous() and dv.is_contiguous() and dg.numel() == N and dv.shape == (N, Kd)):
+            raise _lib.IdrkError("weight_norm_bwd: accumulation buffers must be contiguous [N,1] / [N,K]")
+        acc = 1
     check(lib().idrk_weight_norm_bwd(ptr(g.reshape(-1).contiguous()), ptr(v), ptr(dW), N, Kd, ld_of(v), ld_of(dW),
-                                     ptr(dg), ptr(dv), Kd, stream_ptr()), "idrk_weight_norm_bwd")
+                                     ptr(dg), ptr(dv), Kd, acc, stream_ptr()), "idrk_weight_norm_bwd")
     return dg, dv
 
 
-def colsum(x: torch.Tensor) -> torch.Tensor:
+class ZeroPool:
+    """Arena of pre-zeroed fp32 scratch for one differentiable step.
+
+    Split-K outputs, column sums and hash-table gradients all accumulate with atomics into zero-initialised buffers;
+    a step needs ~150 of them, and one `torch.zeros` each is one fill kernel each.  Between `begin()` and `end()`
+    `take()` hands out slices of ONE buffer zeroed by ONE fill; outside (or when the arena is too small - it grows
+    for the next step) it falls back to `torch.zeros`.  Slices are only valid until the next `begin()`."""
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+        self.need = 0
+        self.active = False
+
+    def begin(self, device):
+        want = max(self.need, 1 << 20)
+        if self.buf is None or self.buf.device != device or self.buf.numel() < want:
+            self.buf = torch.empty(int(want * 1.25), device=device, dtype=torch.float32)
+        self.buf.zero_()
+        self.off = 0
+        self.need = 0
+        self.active = True
+
+    def end(self):
+        self.active = False
+
+    def take(self, numel: int, device) -> torch.Tensor:
+        n = (numel + 63) // 64 * 64                      # 256-byte aligned slices
+        self.need += n
+        if not self.active or self.buf is None or self.buf.device != device or self.off + n > self.buf.numel():
+            return torch.zeros(numel, device=device, dtype=torch.float32)
+        t = self.buf[self.off:self.off + numel]
+        self.off += n
+        return t
+
+
+ZERO_POOL = ZeroPool()
+
+# Trainer mode (DataParallelTrainer sets it around .backward()): leaf gradients whose producer is one of our kernels
+# are accumulated by that kernel straight into the parameter's .grad (a view of the flat bucket) and the autograd
+# Function returns None for them - same result as AccumulateGrad (.grad += g) without the temporary and the add.
+DIRECT_GRADS = [False]
+
+
+def direct_grad_target(p):
+    if DIRECT_GRADS[0] and not torch.is_grad_enabled() and p is not None and p.is_leaf and p.grad is not None \
+            and p.grad.is_contiguous():
+        return p.grad
+    return None
+
+
+def colsum(x: torch.Tensor, into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[c] (+)= sum_r x[r, c]; `into` accumulates into a caller-owned zero-initialised / gradient buffer."""
     x = rows2d(x, "x")
-    out = torch.zeros(x.shape[1], device=x.device, dtype=torch.float32)
+    out = ZERO_POOL.take(x.shape[1], x.device) if into is None else into
     if x.shape[0]:
         check(lib().idrk_colsum(ptr(x), x.shape[0], x.shape[1], ld_of(x), ptr(out), stream_ptr()), "idrk_colsum")
     return out

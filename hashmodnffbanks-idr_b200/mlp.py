@@ -72,18 +72,19 @@ def _prep(t: torch.Tensor, split=None):
 def _raw_mm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int, bias=None,
             mode=K.EPI_NONE, act=0.0, scale=1.0, want_s=False, a_split=None, b_split=None, split_out=False):
     dev = A.device
-    C = K.empty_padded(M, N, dev)
+    split_k = 1
+    if layout == K.GEMM_TN and Kc >= 1024 and M > 0:
+        tiles = ((M + 127) // 128) * ((N + 63) // 64)
+        split_k = max(1, min(Kc // 256, 148 // max(tiles, 1)))
+    if split_k > 1:                                   # split-K accumulates with atomics: zero-initialised output
+        C = K.ZERO_POOL.take(M * K.pad4(N), dev).view(M, K.pad4(N))[:, :N]
+    else:
+        C = K.empty_padded(M, N, dev)
     S = K.empty_padded(M, N, dev) if want_s else None
     if M == 0:
         return C, S
     a, a_lo = _prep(A, a_split)
     b, b_lo = _prep(B, b_split)
-    split_k = 1
-    if layout == K.GEMM_TN and Kc >= 1024:
-        tiles = ((M + 127) // 128) * ((N + 63) // 64)
-        split_k = max(1, min(Kc // 256, 148 // max(tiles, 1)))
-        if split_k > 1:
-            C.zero_()
     C_hi = C_lo = None
     if split_out and _three_pass() and split_k == 1:
         C_hi, C_lo = K.empty_padded(M, N, dev), K.empty_padded(M, N, dev)
@@ -178,13 +179,22 @@ def colsum(x):
     return _ColSum.apply(x)
 
 
+_direct_target = K.direct_grad_target
+
+
 def _layer_backward(ctx, dZ, X, W):
     """Shared backward of Z = X W^T + b: one hi/lo split of dZ feeds both contractions."""
     need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     dsp = make_split(dZ) if (need_x and need_w) else None
     dX = mm_nn(dZ, W, dsp, ctx.w_split) if need_x else None
     dW = mm_tn(dZ, X, dsp, ctx.x_split) if need_w else None
-    db = colsum(dZ) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+    db = None
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+        tgt = _direct_target(getattr(ctx, "bias_ref", None))
+        if tgt is not None and tgt.dim() == 1 and tgt.numel() == dZ.shape[1]:
+            K.colsum(dZ.detach(), into=tgt)
+        else:
+            db = colsum(dZ)
     return dX, dW, db
 
 
@@ -199,6 +209,7 @@ class _Linear(torch.autograd.Function):
             ctx.w_split = ctx.w_split or make_split(W)
         ctx.save_for_backward(X, W)
         ctx.has_bias = b is not None
+        ctx.bias_ref = b
         return _raw_mm(K.GEMM_NT, X, W, X.shape[0], W.shape[0], X.shape[1], bias=b.detach() if b is not None else None,
                        a_split=ctx.x_split, b_split=ctx.w_split)[0]
 
@@ -233,6 +244,7 @@ class _LinearAct(torch.autograd.Function):
                        bias=b.detach() if b is not None else None, mode=_ACT_MODES[mode], act=act, scale=scale,
                        want_s=True, a_split=ctx.x_split, b_split=ctx.w_split, split_out=True)
         ctx.mode, ctx.act, ctx.scale, ctx.has_bias = mode, act, scale, b is not None
+        ctx.bias_ref = b
         ctx.save_for_backward(X, W, H, S)
         ctx.set_materialize_grads(False)
         return H, S
@@ -292,6 +304,10 @@ class _WeightNorm(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, dW):
         g, v = ctx.saved_tensors
+        tg, tv = _direct_target(g), _direct_target(v)
+        if tg is not None and tv is not None and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
+            K.weight_norm_bwd(g, v, dW, into=(tg, tv))
+            return None, None
         dg, dv = K.weight_norm_bwd(g, v, dW)
         return dg, dv
 

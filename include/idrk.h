@@ -162,7 +162,7 @@ int idrk_weight_norm_fwd(const float* g, const float* v, int32_t N, int32_t K, i
                          float* W, float* W_hi, float* W_lo, int32_t ldw,
                          float* Wt, float* Wt_hi, float* Wt_lo, int32_t ldwt, void* stream);
 int idrk_weight_norm_bwd(const float* g, const float* v, const float* dW, int32_t N, int32_t K, int32_t ldv,
-                         int32_t lddw, float* dg, float* dv, int32_t lddv, void* stream);
+                         int32_t lddw, float* dg, float* dv, int32_t lddv, int32_t accumulate, void* stream);
 int idrk_colsum(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* out, void* stream);
 int idrk_sdf_head(const float* h, int64_t rows, int32_t K, int32_t ldh, const float* w, const float* bias,
                   float beta, float* out, const int32_t* m_count, void* stream);
