@@ -274,6 +274,7 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop() if rank == 0 else None
 
+    stats = dict(model.ray_tracer.last_stats)          # of the timed (graphed) steps, before the eager instrumented pass
     # instrumented pass: device time and algorithmic FLOPs of the dominant kernel (the MLP contraction)
     K.PROFILE.reset(enabled=True)
     trainer.use_cuda_graph = False          # CUDA events cannot bracket kernels inside a replayed graph
@@ -284,7 +285,6 @@ def run_ours(args):
     barrier()
     prof = K.PROFILE.summary()
     K.PROFILE.reset(enabled=False)
-    stats = dict(model.ray_tracer.last_stats)
 
     if rank != 0:
         if world > 1:

@@ -189,7 +189,7 @@ def _declare(L):
     L.idrk_rt_minsdf_resolve.argtypes = [rs, vp, i32, i32, vp, vp, vp, vp]
     L.idrk_act_bwd.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, i32, vp]
     L.idrk_gemm_f16s.argtypes = [i64, i32, i32, vp, vp, i32, vp, vp, i32, c.POINTER(EpilogueH), vp, vp]
-    L.idrk_split_f16.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp]
+    L.idrk_split_f16.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp, vp]
     L.idrk_sumsq.argtypes = [vp, i64, vp, vp]
     L.idrk_clip_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp, f32, vp]
     for fn in EXPORTS:

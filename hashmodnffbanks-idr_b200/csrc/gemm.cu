@@ -1027,25 +1027,35 @@ gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+// x -> fp16 pair (h, l); optionally a second pair (h2, l2) of scale2 * x in another buffer in the same pass (the skip
+// connection's copy of the embedding inside the layer-4 operand).
 __global__ void split_f16_kernel(const float* __restrict__ x, long long rows, int cols, int ldx, float scale,
-                                 __half* __restrict__ h, __half* __restrict__ l, int ldo, int pad_cols, const int* __restrict__ m_count) {
+                                 __half* __restrict__ h, __half* __restrict__ l, int ldo, int pad_cols,
+                                 __half* __restrict__ h2, __half* __restrict__ l2, int ldo2, int pad_cols2, float scale2,
+                                 const int* __restrict__ m_count) {
     pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
     pdl_trigger();
     long long r_eff = rows;
     if (m_count) { const long long c = *m_count; r_eff = c < rows ? c : rows; }
-    const int w = cols + pad_cols;
+    const int pmax = (h2 && pad_cols2 > pad_cols) ? pad_cols2 : pad_cols;
+    const int w = cols + pmax;
     const long long total = r_eff * (long long)w;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / w;
         const int c = (int)(i - r * w);
-        __half hv = __float2half_rn(0.f), lv = hv;
-        if (c < cols) {
-            const float v = fminf(fmaxf(x[r * ldx + c] * scale, -65504.f), 65504.f);
-            hv = __float2half_rn(v);
-            lv = __float2half_rn((v - __half2float(hv)) * F16S_SCALE);
+        const float xv = c < cols ? x[r * ldx + c] : 0.f;
+        if (c < cols + pad_cols) {
+            const float v = fminf(fmaxf(xv * scale, -65504.f), 65504.f);
+            const __half hv = __float2half_rn(v);
+            h[r * ldo + c] = hv;
+            l[r * ldo + c] = __float2half_rn((v - __half2float(hv)) * F16S_SCALE);
         }
-        h[r * ldo + c] = hv;
-        l[r * ldo + c] = lv;
+        if (h2 != nullptr && c < cols + pad_cols2) {
+            const float v = fminf(fmaxf(xv * scale2, -65504.f), 65504.f);
+            const __half hv = __float2half_rn(v);
+            h2[r * ldo2 + c] = hv;
+            l2[r * ldo2 + c] = __float2half_rn((v - __half2float(hv)) * F16S_SCALE);
+        }
     }
 }
 
@@ -1328,14 +1338,19 @@ extern "C" int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, 
 }
 
 extern "C" int idrk_split_f16(const float* x, int64_t rows, int32_t cols, int32_t ldx, float scale, void* h, void* l,
-                              int32_t ld_out, int32_t pad_cols, const int32_t* m_count, void* stream) {
+                              int32_t ld_out, int32_t pad_cols, void* h2, void* l2, int32_t ld_out2, int32_t pad_cols2,
+                              float scale2, const int32_t* m_count, void* stream) {
     if (!x || !h || !l || rows < 0 || cols < 1 || ldx < cols || pad_cols < 0 || ld_out < cols + pad_cols) return IDRK_E_ARG;
+    if ((h2 == nullptr) != (l2 == nullptr)) return IDRK_E_ARG;
+    if (h2 && (pad_cols2 < 0 || ld_out2 < cols + pad_cols2)) return IDRK_E_ARG;
     if (rows == 0) return 0;
-    long long total = rows * (long long)(cols + pad_cols);
+    const int pmax = (h2 && pad_cols2 > pad_cols) ? pad_cols2 : pad_cols;
+    long long total = rows * (long long)(cols + pmax);
     long long b = (total + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (b > cap) b = cap;
-    IDRK_CUDA_TRY(launch_k(split_f16_kernel, dim3((int)b), dim3(256), 0, (cudaStream_t)stream, x, rows, cols, ldx, scale, (__half*)h, (__half*)l, ld_out, pad_cols, m_count));
+    IDRK_CUDA_TRY(launch_k(split_f16_kernel, dim3((int)b), dim3(256), 0, (cudaStream_t)stream, x, rows, cols, ldx, scale,
+                           (__half*)h, (__half*)l, ld_out, pad_cols, (__half*)h2, (__half*)l2, ld_out2, pad_cols2, scale2, m_count));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

@@ -417,9 +417,11 @@ def empty_half(rows: int, cols: int, device) -> torch.Tensor:
 
 
 def split_f16_into(x: torch.Tensor, rows: int, cols: int, scale: float, h: torch.Tensor, l: torch.Tensor, ld_out: int,
-                   pad_cols: int = 0, m_count: Optional[torch.Tensor] = None):
-    check(lib().idrk_split_f16(ptr(x), rows, cols, ld_of(x), float(scale), ptr(h), ptr(l), ld_out, pad_cols, ptr(m_count),
-                               stream_ptr()), "idrk_split_f16")
+                   pad_cols: int = 0, m_count: Optional[torch.Tensor] = None, second=None):
+    """`second = (h2, l2, ld_out2, pad_cols2, scale2)`: a second fp16 pair of scale2 * x written in the same pass."""
+    h2, l2, ld2, pad2, scale2 = second if second is not None else (None, None, 0, 0, 0.0)
+    check(lib().idrk_split_f16(ptr(x), rows, cols, ld_of(x), float(scale), ptr(h), ptr(l), ld_out, pad_cols,
+                               ptr(h2), ptr(l2), ld2, pad2, float(scale2), ptr(m_count), stream_ptr()), "idrk_split_f16")
 
 
 def split_f16(x: torch.Tensor, m_count: Optional[torch.Tensor] = None):

@@ -452,7 +452,18 @@ class SdfPipeline:
         dev = emb.device
         E = fl[0].n_in
         cur_h, cur_l = self._hbuf("emb_h", rows, E, dev), self._hbuf("emb_l", rows, E, dev)
-        K.split_f16_into(emb, rows, E, 1.0, cur_h, cur_l, K.pad8(E), K.pad8(E) - E, m_count)
+        # the layer feeding the skip connection writes into a dedicated buffer whose last E columns (the embedding's
+        # 1/sqrt(2) copy) are filled here, by the same launch that splits the embedding
+        second = None
+        skip_bufs = None
+        for l, f in enumerate(fl[:-1]):
+            if (l + 1) in net.skip_in:
+                width = f.n_out + E
+                skip_bufs = (l, self._hbuf(("hs", l), rows, width, dev), self._hbuf(("ls", l), rows, width, dev))
+                ldw = K.pad8(width)
+                second = (skip_bufs[1][:, f.n_out:], skip_bufs[2][:, f.n_out:], ldw, ldw - width, SQRT2_INV)
+                break
+        K.split_f16_into(emb, rows, E, 1.0, cur_h, cur_l, K.pad8(E), K.pad8(E) - E, m_count, second=second)
         cur_dim = E
         n = self.n_lin
         for l, f in enumerate(fl):
@@ -475,10 +486,13 @@ class SdfPipeline:
                 res = out if out is not None else torch.empty(rows, device=dev, dtype=torch.float32)
                 K.sdf_head(h32, fl[n - 1].Wfull[0], fl[n - 1].bias, self.beta(), res, rows, m_count)
                 return res
-            nxt_h, nxt_l = self._hbuf(("h", l & 1), rows, width, dev), self._hbuf(("l", l & 1), rows, width, dev)
+            if feeds_skip and skip_bufs is not None and skip_bufs[0] == l:
+                nxt_h, nxt_l = skip_bufs[1], skip_bufs[2]
+            else:
+                nxt_h, nxt_l = self._hbuf(("h", l & 1), rows, width, dev), self._hbuf(("l", l & 1), rows, width, dev)
             K.gemm_f16s(cur_h, cur_l, f.W_h16, f.W_l16, rows, f.n_out, cur_dim, C_h=nxt_h, C_l=nxt_l, bias=f.bias,
                         mode=K.EPI_SOFTPLUS, act=100.0, scale=scale, m_count=m_count)
-            if feeds_skip:
+            if feeds_skip and not (skip_bufs is not None and skip_bufs[0] == l):
                 ldw = K.pad8(width)
                 K.split_f16_into(emb, rows, E, SQRT2_INV, nxt_h[:, f.n_out:], nxt_l[:, f.n_out:], ldw, ldw - width, m_count)
             cur_h, cur_l, cur_dim = nxt_h, nxt_l, width

@@ -141,8 +141,10 @@ typedef struct idrk_epilogue_f16 {
 int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, const void* A_l, int32_t lda,
                    const void* B_h, const void* B_l, int32_t ldb, const idrk_epilogue_f16_t* h_epi,
                    const int32_t* m_count, void* stream);
+/* idrk_split_f16: fp32 -> fp16 pair; (h2, l2) optional second destination receiving scale2 * x in the same pass. */
 int idrk_split_f16(const float* x, int64_t rows, int32_t cols, int32_t ldx, float scale, void* h, void* l,
-                   int32_t ld_out, int32_t pad_cols, const int32_t* m_count, void* stream);
+                   int32_t ld_out, int32_t pad_cols, void* h2, void* l2, int32_t ld_out2, int32_t pad_cols2,
+                   float scale2, const int32_t* m_count, void* stream);
 
 /* -- helpers around the MLP tiles ----------------------------------------------------------
  * idrk_split_tf32: v = scale * x; hi = tf32(v), lo = tf32(v - hi) for 3xTF32 operands (lo nullable -> plain

@@ -12,8 +12,9 @@ from idrk import kernels as K                                                   
 from idrk.model.embeddings.hashGridEmbedding import MultiResHashGridMLP          # noqa: E402
 
 n = 1 << 22
+log2T = int(sys.argv[1]) if len(sys.argv) > 1 else 19
 for mode in ("reference", "trilinear"):
-    m = MultiResHashGridMLP(True, 3, 16, 2, 19, 16, 2048, frac_mode=mode).cuda()
+    m = MultiResHashGridMLP(True, 3, 16, 2, log2T, 16, 2048, frac_mode=mode).cuda()
     spec, tables, B = m.spec(), tuple(t.detach() for t in m.tables()), m.freq_encoding.B
     x = torch.rand(n, 3, device="cuda")
     out = torch.empty(n, K.pad4(spec.width), device="cuda")

@@ -163,3 +163,22 @@ def test_gemm_fp16_pair(shape):
     k = int(cnt.item())
     assert torch.allclose(C2[:k].double(), torch.nn.functional.softplus(ref[:k], beta=100) * 0.5, atol=2e-6, rtol=2e-5)
     assert (C2[((k + 127) // 128) * 128:] == 5.0).all()
+
+
+def test_split_f16_two_destinations():
+    """One launch writes the fp16 pair of x and, into a column slot of another buffer, the pair of scale2 * x."""
+    from idrk import kernels as K
+    x = _mk((777, 27), 31) * 3.0
+    xp = K.operand(x)
+    h, l = K.empty_half(777, 27, DEV), K.empty_half(777, 27, DEV)
+    big_h = torch.full((777, 512), 7.0, device=DEV, dtype=torch.float16)
+    big_l = torch.full((777, 512), 7.0, device=DEV, dtype=torch.float16)
+    cnt = torch.tensor([700], device=DEV, dtype=torch.int32)
+    K.split_f16_into(xp, 777, 27, 1.0, h, l, K.pad8(27), K.pad8(27) - 27, cnt,
+                     second=(big_h[:, 485:], big_l[:, 485:], 512, 0, 0.5))
+    rec = h[:700, :27].double() + l[:700, :27].double() / 2048.0
+    assert ((rec - x[:700].double()).abs() / x[:700].double().abs().clamp_min(1e-6)).max().item() < 1e-6
+    rec2 = big_h[:700, 485:512].double() + big_l[:700, 485:512].double() / 2048.0
+    assert ((rec2 - 0.5 * x[:700].double()).abs() / x[:700].double().abs().clamp_min(1e-6)).max().item() < 1e-6
+    assert (big_h[:, :485] == 7.0).all() and (big_h[700:] == 7.0).all()      # nothing outside the slot / the count
+    assert (h[:700, 27:] == 0).all()                                             # pad columns zero-filled
