@@ -107,7 +107,7 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_rt_init", "idrk_rt_top", "idrk_rt_step", "idrk_rt_linesearch", "idrk_rt_end",
            "idrk_rt_select_sampler", "idrk_rt_sampler_points", "idrk_rt_sampler_resolve", "idrk_rt_secant",
            "idrk_rt_select_minsdf", "idrk_rt_minsdf_points", "idrk_rt_minsdf_resolve", "idrk_rt_chunk_counts",
-           "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd", "idrk_gemm_f16s", "idrk_split_f16", "idrk_sdf_mlp_f16s"]
+           "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd", "idrk_gemm_f16s", "idrk_split_f16"]
 
 
 class EpilogueH(ctypes.Structure):
@@ -115,20 +115,6 @@ class EpilogueH(ctypes.Structure):
     _fields_ = [("C", ctypes.c_void_p), ("C_h", ctypes.c_void_p), ("C_l", ctypes.c_void_p), ("bias", ctypes.c_void_p),
                 ("ldc", ctypes.c_int32), ("ldh", ctypes.c_int32), ("mode", ctypes.c_int32),
                 ("act_param", ctypes.c_float), ("scale", ctypes.c_float)]
-
-
-class SdfMlpLayer(ctypes.Structure):
-    """Mirror of idrk_sdf_mlp_layer_t."""
-    _fields_ = [(n, ctypes.c_void_p) for n in ("A_h", "A_l", "W_h", "W_l", "bias", "out_h", "out_l", "out_f")] + \
-               [(n, ctypes.c_int32) for n in ("lda", "ldw", "ldh", "ldf", "N", "K")] + \
-               [("scale", ctypes.c_float), ("reserved", ctypes.c_int32)]
-
-
-class SdfMlpDesc(ctypes.Structure):
-    """Mirror of idrk_sdf_mlp_t."""
-    _fields_ = [("layer", SdfMlpLayer * 10), ("head_w", ctypes.c_void_p), ("head_b", ctypes.c_void_p),
-                ("sdf_out", ctypes.c_void_p), ("beta", ctypes.c_float), ("act_param", ctypes.c_float),
-                ("n_layers", ctypes.c_int32), ("head_K", ctypes.c_int32)]
 
 
 class RayStateDesc(ctypes.Structure):
@@ -204,7 +190,6 @@ def _declare(L):
     L.idrk_act_bwd.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, i32, vp]
     L.idrk_gemm_f16s.argtypes = [i64, i32, i32, vp, vp, i32, vp, vp, i32, c.POINTER(EpilogueH), vp, vp]
     L.idrk_split_f16.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp, vp]
-    L.idrk_sdf_mlp_f16s.argtypes = [c.POINTER(SdfMlpDesc), i64, vp, vp]
     L.idrk_sumsq.argtypes = [vp, i64, vp, vp]
     L.idrk_clip_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp, f32, vp]
     for fn in EXPORTS:

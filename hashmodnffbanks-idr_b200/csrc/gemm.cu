@@ -1027,270 +1027,6 @@ gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Fused SDF MLP: every hidden layer of ImplicitNetwork + the SDF head for 128-point blocks in ONE launch
-// ------------------------------------------------------------------------------------------
-// The ray tracer evaluates the SDF ~60 times per step on a few thousand points; per layer such a launch is one
-// wave of tiles and ~45 % fixed cost (launch, barrier / TMEM set-up, drain).  Here a cluster of 4 CTAs owns a block
-// of 128 points through ALL layers: CTA n computes the 128 x 128 output slice n of each layer with the same
-// TMA -> tcgen05 -> TMEM -> epilogue pipeline as gemm_f16s_kernel, writes its slice of the fp16-pair activations
-// (L2 resident), and the four CTAs hand over to the next layer through an mbarrier that every epilogue warp of the
-// cluster arrives on (release.cluster) and the TMA producers wait on (acquire.cluster + fence.proxy.async).  The
-// last hidden layer is written in fp32 and the head  tanh(s / (2 + rho(s))),  s = <h, w> + b  is computed by the
-// same cluster (32 points per CTA) with the arithmetic of sdf_head_kernel, so results are bit-identical to the
-// layer-by-layer path.  Persistent over point blocks; `m_count` bounds the rows from device memory.
-constexpr int MLP_MAX_LAYERS = 10;
-constexpr int MLP_CLUSTER = 4;
-struct alignas(64) MlpLayerDev {
-    CUtensorMap tmA_h, tmA_l, tmW_h, tmW_l;
-    const float* bias;
-    __half* out_h; __half* out_l; float* out_f;
-    int N, K, ldh, ldf;
-    float scale; int pad_;
-};
-struct MlpParamsDev {
-    MlpLayerDev layer[MLP_MAX_LAYERS];
-    const float* head_w; const float* head_b; float* sdf_out;
-    float beta, act;
-    int n_layers, head_K;
-};
-
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    }
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ float warp_sum_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float sdf_squash_f(float s, float beta) {         // == elementwise.cu sdf_squash
-    const float sg = s > 0.f ? 1.f : (s < 0.f ? -1.f : 0.f);
-    const float rho = (1.f / beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(s) / beta));
-    return tanhf(s / (2.f + rho));
-}
-
-__global__ void __cluster_dims__(MLP_CLUSTER, 1, 1) __launch_bounds__(GEMM_THREADS_V2, 1)
-sdf_mlp_f16s_kernel(const __grid_constant__ MlpParamsDev prm, long long M, const int* __restrict__ m_count) {
-    pdl_trigger();
-    using P = SmemPlanHT<BNH, 3>;
-    constexpr int ACCS = 2, EPIW = EPI_WARPS;
-    const uint32_t cn = cluster_ctarank();                          // this CTA's 128-column slice
-    const int cluster_id = (int)blockIdx.x / MLP_CLUSTER, n_clusters = (int)gridDim.x / MLP_CLUSTER;
-    const int n_layers = prm.n_layers;
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::STAGES * P::STAGE_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P::STAGES + 2 * ACCS + 2);
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_base = smem_u32(bars);
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (P::STAGES + s); };
-    auto acc_full_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + a); };
-    auto acc_empty_bar = [&](int a) { return bar_base + 8u * (2 * P::STAGES + ACCS + a); };
-    // "this layer's outputs of all 4 CTAs are visible", one barrier per interleaved point block (slot)
-    auto ready_bar = [&](int slot) { return bar_base + 8u * (2 * P::STAGES + 2 * ACCS + slot); };
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < P::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < ACCS; ++a) { mbar_init(acc_full_bar(a), 1); mbar_init(acc_empty_bar(a), EPIW); }
-        mbar_init(ready_bar(0), MLP_CLUSTER * EPIW); mbar_init(ready_bar(1), MLP_CLUSTER * EPIW);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    constexpr uint32_t TMEM_COLS = ACCS * 2 * BNH;
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();                                          // mates' barriers initialised before any remote arrive
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();
-    long long m_eff = M;
-    if (m_count != nullptr) { const long long c = *m_count; m_eff = c < M ? c : M; }
-    const int m_blocks = (int)((m_eff + BM - 1) / BM);
-
-    if (warp == 0) {
-        // ---- TMA producer ----
-        const uint32_t leader = elect_one();
-        int it = 0, sstep[2] = {0, 0};
-        for (int pr = cluster_id; 2 * pr < m_blocks; pr += n_clusters) {
-            for (int l = 0; l < n_layers; ++l) {
-#pragma unroll
-                for (int slot = 0; slot < 2; ++slot) {
-                const int rb = 2 * pr + slot;
-                if (rb >= m_blocks) continue;
-                const int step = sstep[slot]++;
-                const MlpLayerDev& L = prm.layer[l];
-                const bool has_tile = (int)cn * BNH < L.N;       // a CTA has no slice of a narrow layer
-                const int kb_total = has_tile ? (L.K + BKH - 1) / BKH : 0;
-                // weights do not depend on the previous layer: the W halves of the first stages are requested BEFORE
-                // the hand-over wait, the activation halves after it
-                const int pre = kb_total < P::STAGES ? kb_total : P::STAGES;
-                for (int kb = 0; kb < pre; ++kb) {
-                    const int s = (it + kb) % P::STAGES;
-                    const uint32_t ph = ((it + kb) / P::STAGES) & 1;
-                    mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx_p(full_bar(s), P::STAGE_BYTES, leader);
-                    const uint32_t st = smem_base + s * P::STAGE_BYTES;
-                    tma_load_2d_p(st + 2 * P::A_BYTES, &L.tmW_h, full_bar(s), kb * BKH, (int)cn * BNH, leader);
-                    tma_load_2d_p(st + 2 * P::A_BYTES + P::B_BYTES, &L.tmW_l, full_bar(s), kb * BKH, (int)cn * BNH, leader);
-                }
-                if (step > 0) {                                  // this block's previous layer is complete in all 4 CTAs
-                    mbar_wait_cluster(ready_bar(slot), (uint32_t)((step - 1) & 1));
-                    fence_proxy_async_all();
-                }
-                for (int kb = 0; kb < kb_total; ++kb, ++it) {
-                    const int s = it % P::STAGES;
-                    const uint32_t st = smem_base + s * P::STAGE_BYTES;
-                    const int k0 = kb * BKH;
-                    if (kb >= pre) {
-                        const uint32_t ph = (it / P::STAGES) & 1;
-                        mbar_wait(empty_bar(s), ph ^ 1u);
-                        mbar_expect_tx_p(full_bar(s), P::STAGE_BYTES, leader);
-                        tma_load_2d_p(st + 2 * P::A_BYTES, &L.tmW_h, full_bar(s), k0, (int)cn * BNH, leader);
-                        tma_load_2d_p(st + 2 * P::A_BYTES + P::B_BYTES, &L.tmW_l, full_bar(s), k0, (int)cn * BNH, leader);
-                    }
-                    tma_load_2d_p(st, &L.tmA_h, full_bar(s), k0, rb * BM, leader);
-                    tma_load_2d_p(st + P::A_BYTES, &L.tmA_l, full_bar(s), k0, rb * BM, leader);
-                }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ---- MMA issuer ----
-        const uint32_t leader = elect_one();
-        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BNH >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BNH) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        int it = 0, ti = 0;
-        for (int pr = cluster_id; 2 * pr < m_blocks; pr += n_clusters) {
-            for (int l = 0; l < n_layers; ++l) {
-              for (int slot = 0; slot < 2; ++slot) {
-                if (2 * pr + slot >= m_blocks) continue;
-                const MlpLayerDev& L = prm.layer[l];
-                if ((int)cn * BNH >= L.N) continue;
-                const int kb_total = (L.K + BKH - 1) / BKH;
-                const int a = ti % ACCS;
-                mbar_wait(acc_empty_bar(a), ((ti / ACCS) & 1) ^ 1u);
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + (uint32_t)(a * 2 * BNH);
-                const uint32_t d1 = d0 + BNH;
-                for (int kb = 0; kb < kb_total; ++kb, ++it) {
-                    const int s = it % P::STAGES;
-                    const uint32_t ph = (it / P::STAGES) & 1;
-                    mbar_wait(full_bar(s), ph);
-                    tc_fence_after();
-                    const uint32_t st = smem_base + s * P::STAGE_BYTES;
-                    const uint64_t a_h = umma_desc(st, 16, 1024, 2);
-                    const uint64_t a_l = umma_desc(st + P::A_BYTES, 16, 1024, 2);
-                    const uint64_t b_h = umma_desc(st + 2 * P::A_BYTES, 16, 1024, 2);
-#pragma unroll
-                    for (int k = 0; k < BKH / 16; ++k) {
-                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                        tc_mma_f16_p(d0, a_h + 2 * k, b_h + 2 * k, idesc2, acc, leader);
-                        tc_mma_f16_p(d1, a_l + 2 * k, b_h + 2 * k, idesc, 1u, leader);
-                    }
-                    tc_commit_p(empty_bar(s), leader);
-                }
-                tc_commit_p(acc_full_bar(a), leader);
-                ++ti;
-              }
-            }
-        }
-    } else {
-        // ---- epilogue warps (+ the SDF head after the last layer) ----
-        const int q = warp & 3;
-        const int grp = (warp - 2) >> 2;
-        int ti = 0, sstep[2] = {0, 0};
-        for (int pr = cluster_id; 2 * pr < m_blocks; pr += n_clusters) {
-            for (int l = 0; l < n_layers; ++l) {
-#pragma unroll
-              for (int slot = 0; slot < 2; ++slot) {
-                const int rb = 2 * pr + slot;
-                if (rb >= m_blocks) continue;
-                const int step = sstep[slot]++;
-                const long long m0 = (long long)rb * BM;
-                const MlpLayerDev& L = prm.layer[l];
-                const int n0 = (int)cn * BNH;
-                if (n0 < L.N) {
-                    EpiParamsH e;
-                    e.C = L.out_f; e.C_h = L.out_h; e.C_l = L.out_l; e.bias = L.bias; e.ldc = L.ldf; e.ldh = L.ldh;
-                    e.mode = IDRK_EPI_SOFTPLUS; e.act = prm.act; e.scale = L.scale; e.vec16 = L.out_h != nullptr;
-                    const SoftplusC spc = {prm.act * 1.4426950408889634f, 0.6931471805599453f / prm.act * L.scale, L.scale};
-                    const int a = ti % ACCS;
-                    const int col0 = n0 + grp * 32;
-                    float2 bias2[4];
-                    load_bias2(e.bias, col0, lane, L.N, bias2);
-                    mbar_wait(acc_full_bar(a), (ti / ACCS) & 1);
-                    tc_fence_after();
-                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 2 * BNH + grp * 32);
-                    uint32_t a0[16], a1[16], b0[16], b1[16];
-                    tc_ld_16x256b_x4(t0, a0);
-                    tc_ld_16x256b_x4(t0 + BNH, a1);
-                    tc_ld_16x256b_x4(t0 + (16u << 16), b0);
-                    tc_ld_16x256b_x4(t0 + (16u << 16) + BNH, b1);
-                    tc_wait_ld();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty_bar(a));
-                    ++ti;
-                    const long long row_base = m0 + q * 32;
-                    if (col0 < L.N && row_base < m_eff) {
-                        if (col0 + 32 <= L.N) {
-                            epi_frag_h<IDRK_EPI_SOFTPLUS, true>(e, spc, a0, a1, bias2, lane, row_base, m_eff, col0, L.N);
-                            epi_frag_h<IDRK_EPI_SOFTPLUS, true>(e, spc, b0, b1, bias2, lane, row_base + 16, m_eff, col0, L.N);
-                        } else {
-                            epi_frag_h<IDRK_EPI_SOFTPLUS, false>(e, spc, a0, a1, bias2, lane, row_base, m_eff, col0, L.N);
-                            epi_frag_h<IDRK_EPI_SOFTPLUS, false>(e, spc, b0, b1, bias2, lane, row_base + 16, m_eff, col0, L.N);
-                        }
-                    }
-                }
-                // publish this warp's part of the layer output to the whole cluster: __syncwarp orders the lanes' stores
-                // before lane 0, whose release.cluster arrive is cumulative over them
-                __syncwarp();
-                if (lane == 0) {
-#pragma unroll
-                    for (uint32_t r = 0; r < MLP_CLUSTER; ++r) mbar_arrive_cluster(mapa_cluster(ready_bar(slot), r));
-                }
-                if (l == n_layers - 1) {
-                    // SDF head on this CTA's 32 points of the block: two points per warp
-                    mbar_wait_cluster(ready_bar(slot), (uint32_t)(step & 1));
-                    const float* hbase = L.out_f;
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const long long p = m0 + (long long)cn * 32 + (warp - 2) * 2 + i;
-                        if (p < m_eff) {
-                            const float* row = hbase + p * L.ldf;
-                            float acc = 0.f;
-                            for (int k = lane; k < prm.head_K; k += 32) acc = fmaf(__ldcg(row + k), __ldg(prm.head_w + k), acc);
-                            acc = warp_sum_f(acc);
-                            if (lane == 0) prm.sdf_out[p] = sdf_squash_f(acc + prm.head_b[0], prm.beta);
-                        }
-                    }
-                }
-              }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-
 // x -> fp16 pair (h, l); optionally a second pair (h2, l2) of scale2 * x in another buffer in the same pass (the skip
 // connection's copy of the embedding inside the layer-4 operand).
 __global__ void split_f16_kernel(const float* __restrict__ x, long long rows, int cols, int ldx, float scale,
@@ -1597,52 +1333,6 @@ extern "C" int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, 
     const long long items = m_tiles * ((N + BNH - 1) / BNH);
     const long long grid = items < sm_count() ? items : sm_count();
     IDRK_CUDA_TRY(launch_k(kern, dim3((unsigned)grid), dim3(GEMM_THREADS_V2), P::TOTAL, (cudaStream_t)stream, tA, tAl, tB, tBl, M, N, K, e, m_count));
-    IDRK_LAUNCH_CHECK();
-    return 0;
-}
-
-extern "C" int idrk_sdf_mlp_f16s(const idrk_sdf_mlp_t* d, int64_t rows, const int32_t* m_count, void* stream) {
-    if (!d || rows < 0 || d->n_layers < 1 || d->n_layers > MLP_MAX_LAYERS) return IDRK_E_ARG;
-    if (!d->head_w || !d->head_b || !d->sdf_out || d->head_K < 1 || !(d->beta > 0.f) || !(d->act_param > 0.f)) return IDRK_E_ARG;
-    if (rows == 0) return 0;
-    static MlpParamsDev prm;                       // 6 KB: kept off the stack; launches are serialised by the caller's stream order
-    prm.n_layers = d->n_layers; prm.act = d->act_param; prm.beta = d->beta;
-    prm.head_w = d->head_w; prm.head_b = d->head_b; prm.sdf_out = d->sdf_out; prm.head_K = d->head_K;
-    for (int l = 0; l < d->n_layers; ++l) {
-        const idrk_sdf_mlp_layer_t& s = d->layer[l];
-        MlpLayerDev& L = prm.layer[l];
-        const bool last = l == d->n_layers - 1;
-        if (!s.A_h || !s.A_l || !s.W_h || !s.W_l || s.N < 1 || s.N > MLP_CLUSTER * BNH || s.K < 1) return IDRK_E_ARG;
-        if (last ? (!s.out_f || s.ldf < s.N || s.N != d->head_K) : (!s.out_h || !s.out_l || s.ldh < s.N)) return IDRK_E_ARG;
-        if (!last && ((s.ldh % 8) || !aligned16(s.out_h) || !aligned16(s.out_l))) return IDRK_E_ALIGN;
-        if (last && ((s.ldf % 2) || (reinterpret_cast<uintptr_t>(s.out_f) & 7u))) return IDRK_E_ALIGN;
-        int rc;
-        if ((rc = make_tmap_h(&L.tmA_h, s.A_h, (uint64_t)s.K, (uint64_t)rows, s.lda, BM))) return rc;
-        if ((rc = make_tmap_h(&L.tmA_l, s.A_l, (uint64_t)s.K, (uint64_t)rows, s.lda, BM))) return rc;
-        if ((rc = make_tmap_h(&L.tmW_h, s.W_h, (uint64_t)s.K, (uint64_t)s.N, s.ldw, BNH))) return rc;
-        if ((rc = make_tmap_h(&L.tmW_l, s.W_l, (uint64_t)s.K, (uint64_t)s.N, s.ldw, BNH))) return rc;
-        L.bias = s.bias;
-        L.out_h = last ? nullptr : (__half*)s.out_h; L.out_l = last ? nullptr : (__half*)s.out_l; L.out_f = last ? s.out_f : nullptr;
-        L.N = s.N; L.K = s.K; L.ldh = s.ldh; L.ldf = s.ldf; L.scale = s.scale; L.pad_ = 0;
-    }
-    using P = SmemPlanHT<BNH, 3>;
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
-        IDRK_CUDA_TRY(cudaFuncSetAttribute(sdf_mlp_f16s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P::TOTAL));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(MLP_CLUSTER * 32); cfg.blockDim = dim3(GEMM_THREADS_V2); cfg.dynamicSmemBytes = P::TOTAL;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = MLP_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        int n = 0;
-        IDRK_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, sdf_mlp_f16s_kernel, &cfg));
-        max_clusters = n > 0 ? n : 1;
-    }
-    const long long pairs = ((rows + BM - 1) / BM + 1) / 2;          // a cluster interleaves two 128-point blocks
-    const long long clusters = pairs < max_clusters ? pairs : max_clusters;
-    IDRK_CUDA_TRY(launch_k(sdf_mlp_f16s_kernel, dim3((unsigned)(clusters * MLP_CLUSTER)), dim3(GEMM_THREADS_V2), P::TOTAL,
-                           (cudaStream_t)stream, prm, (long long)rows, m_count));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

@@ -1,7 +1,6 @@
 """Thin typed wrappers around the C ABI (include/idrk.h): tensors in, kernels launched on the
 current CUDA stream.  No arithmetic happens here and nothing falls back to PyTorch."""
 import ctypes
-import os
 import math
 from typing import List, Optional, Sequence
 
@@ -415,46 +414,6 @@ def pad8(n: int) -> int:
 
 def empty_half(rows: int, cols: int, device) -> torch.Tensor:
     return torch.empty((rows, pad8(cols)), device=device, dtype=torch.float16)[:, :cols]
-
-
-_FUSED_SDF_MLP = [os.environ.get("IDRK_FUSED_SDF_MLP", "1") != "0"]
-
-
-def fused_sdf_mlp() -> bool:
-    """True: the no-grad SDF query runs all hidden layers + head in one cluster kernel (default)."""
-    return _FUSED_SDF_MLP[0]
-
-
-def set_fused_sdf_mlp(on: bool):
-    _FUSED_SDF_MLP[0] = bool(on)
-
-
-def sdf_mlp_f16s(layers, head_w: torch.Tensor, head_b: torch.Tensor, beta: float, act: float, rows: int,
-                 sdf_out: torch.Tensor, m_count: Optional[torch.Tensor] = None):
-    """Fused no-grad SDF MLP (csrc/gemm.cu sdf_mlp_f16s_kernel).  `layers`: dicts with in_h, in_l, K, W_h, W_l, bias, N,
-    scale and either (out_h, out_l) or out_f (last hidden layer, fp32)."""
-    d = _lib.SdfMlpDesc()
-    d.n_layers, d.head_K, d.beta, d.act_param = len(layers), head_w.numel(), float(beta), float(act)
-    d.head_w, d.head_b, d.sdf_out = head_w.data_ptr(), head_b.data_ptr(), sdf_out.data_ptr()
-    for i, L in enumerate(layers):
-        e = d.layer[i]
-        e.A_h, e.A_l, e.lda = L["in_h"].data_ptr(), L["in_l"].data_ptr(), half_ld(L["in_h"])
-        e.W_h, e.W_l, e.ldw = L["W_h"].data_ptr(), L["W_l"].data_ptr(), half_ld(L["W_h"])
-        e.bias = L["bias"].data_ptr() if L.get("bias") is not None else None
-        e.N, e.K, e.scale = int(L["N"]), int(L["K"]), float(L["scale"])
-        if L.get("out_f") is not None:
-            e.out_f, e.ldf = L["out_f"].data_ptr(), op_ld(L["out_f"])
-        else:
-            e.out_h, e.out_l, e.ldh = L["out_h"].data_ptr(), L["out_l"].data_ptr(), half_ld(L["out_h"])
-    if PROFILE.enabled:
-        PROFILE.pending_tag = "[fused sdf mlp rows=%d layers=%d%s]" % (rows, len(layers), " cnt" if m_count is not None else "")
-        fl = float(sum(2.0 * L["N"] * L["K"] for L in layers))
-        if m_count is not None:
-            cnt = m_count.clone()
-            PROFILE.pending_flops = lambda cnt=cnt, rows=rows, fl=fl: fl * min(rows, int(cnt.item()))
-        else:
-            PROFILE.pending_flops = fl * rows
-    check(lib().idrk_sdf_mlp_f16s(ctypes.byref(d), rows, ptr(m_count), stream_ptr()), "idrk_sdf_mlp_f16s")
 
 
 def split_f16_into(x: torch.Tensor, rows: int, cols: int, scale: float, h: torch.Tensor, l: torch.Tensor, ld_out: int,

@@ -466,28 +466,6 @@ class SdfPipeline:
         K.split_f16_into(emb, rows, E, 1.0, cur_h, cur_l, K.pad8(E), K.pad8(E) - E, m_count, second=second)
         cur_dim = E
         n = self.n_lin
-        if want == "sdf" and K.fused_sdf_mlp() and 2 <= n <= 11 and all(f.n_out <= 512 for f in fl[:-1]) \
-                and (not net.skip_in or skip_bufs is not None):
-            # all hidden layers + head in ONE cluster kernel (same buffers the layer-by-layer path would use)
-            plan, in_h, in_l, kd = [], cur_h, cur_l, E
-            for l, f in enumerate(fl[:-1]):
-                feeds_skip = (l + 1) in net.skip_in
-                width = f.n_out + (E if feeds_skip else 0)
-                ent = {"in_h": in_h, "in_l": in_l, "K": kd, "W_h": f.W_h16, "W_l": f.W_l16, "bias": f.bias, "N": f.n_out,
-                       "scale": SQRT2_INV if feeds_skip else 1.0}
-                if l == n - 2:
-                    ent["out_f"] = self._buf("h_last", rows, width, dev)
-                else:
-                    if feeds_skip:
-                        oh, ol = skip_bufs[1], skip_bufs[2]
-                    else:
-                        oh, ol = self._hbuf(("h", l & 1), rows, width, dev), self._hbuf(("l", l & 1), rows, width, dev)
-                    ent["out_h"], ent["out_l"] = oh, ol
-                    in_h, in_l, kd = oh, ol, width
-                plan.append(ent)
-            res = out if out is not None else torch.empty(rows, device=dev, dtype=torch.float32)
-            K.sdf_mlp_f16s(plan, fl[n - 1].Wfull[0], fl[n - 1].bias, self.beta(), 100.0, rows, res, m_count)
-            return res
         for l, f in enumerate(fl):
             last = l == n - 1
             if last:

@@ -141,29 +141,6 @@ typedef struct idrk_epilogue_f16 {
 int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, const void* A_l, int32_t lda,
                    const void* B_h, const void* B_l, int32_t ldb, const idrk_epilogue_f16_t* h_epi,
                    const int32_t* m_count, void* stream);
-/* idrk_sdf_mlp_f16s: ALL hidden layers of ImplicitNetwork (Linear + Softplus(beta = act_param), skip connection laid out
- * by the caller) and the SDF head in one launch, for the ray tracer's no-grad queries
- * (implicit_differentiable_renderer.py:96-112 under ray_tracing.py:26-298).  Layer l reads the fp16 pair (A_h, A_l) and
- * writes the pair (out_h, out_l) that layer l + 1 names as its input; the last layer writes fp32 (out_f) and the head
- * sdf = tanh(s / (2 + rho(s))), s = <out_f[p, :head_K], head_w> + head_b[0] goes to sdf_out[p].  N <= 512 per layer. */
-typedef struct idrk_sdf_mlp_layer {
-    const void* A_h; const void* A_l;      /* [rows, lda] input halves                */
-    const void* W_h; const void* W_l;      /* [N, ldw] folded weight halves           */
-    const float* bias;                     /* [N]                                     */
-    void* out_h; void* out_l;              /* [rows, ldh] output halves (not last)    */
-    float* out_f;                          /* [rows, ldf] fp32 output (last layer)    */
-    int32_t lda, ldw, ldh, ldf;
-    int32_t N, K;
-    float scale;                           /* output scale (1/sqrt(2) before the skip) */
-    int32_t reserved;
-} idrk_sdf_mlp_layer_t;
-typedef struct idrk_sdf_mlp {
-    idrk_sdf_mlp_layer_t layer[10];
-    const float* head_w; const float* head_b; float* sdf_out;
-    float beta, act_param;
-    int32_t n_layers, head_K;
-} idrk_sdf_mlp_t;
-int idrk_sdf_mlp_f16s(const idrk_sdf_mlp_t* desc, int64_t rows, const int32_t* m_count, void* stream);
 /* idrk_split_f16: fp32 -> fp16 pair; (h2, l2) optional second destination receiving scale2 * x in the same pass. */
 int idrk_split_f16(const float* x, int64_t rows, int32_t cols, int32_t ldx, float scale, void* h, void* l,
                    int32_t ld_out, int32_t pad_cols, void* h2, void* l2, int32_t ld_out2, int32_t pad_cols2,
