@@ -1,0 +1,90 @@
+// Device helpers shared by the hash-grid kernels (hash_encode.cu) and the fused filter-bank encoder (nffb.cu).
+#pragma once
+#include "common.cuh"
+
+namespace idrk {
+
+struct GridDev {
+    int n_levels, n_feat, n_fourier, width;
+    float res[IDRK_MAX_LEVELS];
+    uint32_t rows[IDRK_MAX_LEVELS];
+    uint32_t pow2mask[IDRK_MAX_LEVELS];     // rows-1 when rows is a power of two, else 0
+    unsigned long long magic[IDRK_MAX_LEVELS];   // 2^64 / rows + 1 (Lemire fastmod), used when rows is not a power of two
+    const float* tables[IDRK_MAX_LEVELS];
+    const float* B;                         // [3, C]
+};
+
+
+__device__ __forceinline__ uint32_t hash3(uint32_t c0, uint32_t c1, uint32_t c2) {
+    return c0 ^ (c1 * 3u) ^ (c2 * 2654435761u);
+}
+// h mod rows.  Power-of-two tables mask; others use the exact 64-bit fastmod  (M*h mod 2^64) * rows >> 64.
+__device__ __forceinline__ uint32_t wrap(uint32_t h, uint32_t rows, uint32_t mask, unsigned long long magic) {
+    return mask ? (h & mask) : (uint32_t)__umul64hi(magic * (unsigned long long)h, (unsigned long long)rows);
+}
+// .long() of an fp32 value: truncate toward zero to int64, keep the low 32 bits.  Inside the int32 range the
+// 32-bit conversion has the same low bits (two's complement); only huge magnitudes need the 64-bit one.
+__device__ __forceinline__ uint32_t trunc_u32(float v) {
+    return fabsf(v) < 2147483520.f ? (uint32_t)__float2int_rz(v) : (uint32_t)(unsigned long long)__float2ll_rz(v);
+}
+
+// sin/cos of a moderate fp32 argument: two-constant Cody-Waite reduction by 2*pi, then the SFU approximations
+// on [-pi, pi] (abs error < 1e-6, inside the 4e-6 parity tolerance); huge arguments take the accurate libm path.
+__device__ __forceinline__ void sincos_fast(float x, float* sn, float* cs) {
+    if (fabsf(x) > 8192.f) { sincosf(x, sn, cs); return; }
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);          // 2*pi rounded to fp32
+    r = fmaf(-k, -1.7484555314695172e-07f, r);           // 2*pi - fp32(2*pi)
+    *sn = __sinf(r);
+    *cs = __cosf(r);
+}
+
+template <int F> struct Feat;
+template <> struct Feat<1> { using T = float;  };
+template <> struct Feat<2> { using T = float2; };
+template <> struct Feat<4> { using T = float4; };
+template <> struct Feat<8> { using T = float4; };   // two float4
+
+template <int F>
+__device__ __forceinline__ void gather(const float* table, uint32_t idx, float (&v)[F]) {
+    if constexpr (F == 1) {
+        v[0] = __ldg(table + idx);
+    } else if constexpr (F == 2) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(table) + idx);
+        v[0] = t.x; v[1] = t.y;
+    } else if constexpr (F == 4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(table) + idx);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        float4 a = __ldg(reinterpret_cast<const float4*>(table) + 2 * (size_t)idx);
+        float4 b = __ldg(reinterpret_cast<const float4*>(table) + 2 * (size_t)idx + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+
+
+inline int fill_grid(const idrk_hashgrid_t* h, GridDev& g) {
+    if (h == nullptr) return IDRK_E_ARG;
+    if (h->n_levels < 0 || h->n_levels > IDRK_MAX_LEVELS) return IDRK_E_ARG;
+    if (h->n_levels == 0 && h->n_fourier == 0) return IDRK_E_ARG;
+    if (h->n_feat != 1 && h->n_feat != 2 && h->n_feat != 4 && h->n_feat != 8) return IDRK_E_UNSUP;
+    if (h->n_fourier < 0 || h->n_fourier > 64) return IDRK_E_ARG;
+    if (h->n_fourier > 0 && h->fourier_B == nullptr) return IDRK_E_ARG;
+    if (h->frac_mode != IDRK_HASH_REFERENCE && h->frac_mode != IDRK_HASH_TRILINEAR) return IDRK_E_ARG;
+    g.n_levels = h->n_levels; g.n_feat = h->n_feat; g.n_fourier = h->n_fourier;
+    g.width = (h->n_fourier > 0 ? 3 + 2 * h->n_fourier : 0) + h->n_levels * h->n_feat;
+    g.B = h->fourier_B;
+    const size_t align = (h->n_feat >= 4) ? 16 : 4 * (size_t)h->n_feat;
+    for (int l = 0; l < h->n_levels; ++l) {
+        if (h->tables[l] == nullptr || h->rows[l] == 0) return IDRK_E_ARG;
+        if (reinterpret_cast<uintptr_t>(h->tables[l]) % align) return IDRK_E_ALIGN;
+        g.res[l] = h->res[l]; g.rows[l] = h->rows[l]; g.tables[l] = h->tables[l];
+        g.pow2mask[l] = ((h->rows[l] & (h->rows[l] - 1)) == 0) ? h->rows[l] - 1 : 0;
+        g.magic[l] = ~0ull / h->rows[l] + 1ull;
+        if (h->rows[l] == 1) { g.pow2mask[l] = 0; g.magic[l] = 0; }
+    }
+    for (int l = h->n_levels; l < IDRK_MAX_LEVELS; ++l) { g.res[l] = 0; g.rows[l] = 1; g.tables[l] = nullptr; g.pow2mask[l] = 0; g.magic[l] = 0; }
+    return 0;
+}
+
+}  // namespace idrk

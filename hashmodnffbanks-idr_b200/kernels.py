@@ -416,6 +416,52 @@ def empty_half(rows: int, cols: int, device) -> torch.Tensor:
     return torch.empty((rows, pad8(cols)), device=device, dtype=torch.float16)[:, :cols]
 
 
+def nffb_encode_fwd(ffb, x: torch.Tensor, out: Optional[torch.Tensor] = None, m_count: Optional[torch.Tensor] = None,
+                    rows: Optional[int] = None) -> torch.Tensor:
+    """K7: the whole FourierFilterBanks forward (no autograd) in one launch.  `ffb` is the module
+    (model/embeddings/nffb3d.py); returns the padded [n, pad4(3 + width)] buffer."""
+    x = rows2d(x, "x")
+    n = x.shape[0] if rows is None else rows
+    W = ffb.feature_Vector_size
+    ld = pad4(3 + W)
+    if out is None:
+        out = torch.empty((n, ld), device=x.device, dtype=torch.float32)
+    if n == 0:
+        return out
+    grid = ffb.grid_enc
+    d = _lib.NffbDesc()
+    d.grid = grid.spec().desc(tuple(t.detach() for t in grid.tables()), grid.freq_encoding.B)
+    bands = ffb.ff_enc[0].freq_bands
+    for i, b in enumerate(bands):
+        d.bands[i] = float(b)
+    d.n_bands, d.include_input = len(bands), 1 if ffb.include_input else 0
+    d.n_lin, d.width, d.chunk = ffb.n_nffb_layers - 1, W, 2 * ffb.max_points_per_level
+    d.style, d.n_levels_div = (1 if ffb.modulationApplied else 0), ffb.grid_levels
+    d.bound, d.w0 = float(ffb.bound), float(ffb.sin_w0)
+    keep = []
+    for j in range(ffb.n_nffb_layers - 1):
+        lin = getattr(ffb, "ff_lin%d" % j)
+        w, b = lin.weight.detach().contiguous(), lin.bias.detach().contiguous()
+        keep += [w, b]
+        d.lin_w[j], d.lin_b[j] = w.data_ptr(), b.data_ptr()
+    ow, ob = ffb.out_layer.weight.detach().contiguous(), ffb.out_layer.bias.detach().contiguous()
+    keep += [ow, ob]
+    d.out_w, d.out_b = ow.data_ptr(), ob.data_ptr()
+    if ffb.modulationApplied:
+        st = ffb.StyleAttentionBlock
+        sw, sb = st.linear_transform.weight.detach().contiguous(), st.linear_transform.bias.detach().contiguous()
+        keep += [sw, sb]
+        d.style_w, d.style_b, d.eps = sw.data_ptr(), sb.data_ptr(), float(st.eps)
+    check(lib().idrk_nffb_encode_fwd(ctypes.byref(d), ptr(x), n, ld_of(x), ptr(out), ld_of(out), ptr(m_count), stream_ptr()),
+          "idrk_nffb_encode_fwd")
+    return out
+
+
+def nffb_fused_supported(ffb) -> bool:
+    W = ffb.feature_Vector_size
+    return W <= 64 and (ffb.n_nffb_layers - 2) * 2 * ffb.max_points_per_level <= 32 and ffb.n_nffb_layers - 1 <= 16
+
+
 def split_f16_into(x: torch.Tensor, rows: int, cols: int, scale: float, h: torch.Tensor, l: torch.Tensor, ld_out: int,
                    pad_cols: int = 0, m_count: Optional[torch.Tensor] = None, second=None):
     """`second = (h2, l2, ld_out2, pad_cols2, scale2)`: a second fp16 pair of scale2 * x written in the same pass."""

@@ -74,6 +74,19 @@ class ImplicitNetwork(nn.Module):
     def _embed(self, x):
         return self.embed_fn(x) if self.embed_fn is not None else x
 
+    def _fused_filter_bank(self):
+        """The FourierFilterBanks module when the one-launch no-grad encoder (csrc/nffb.cu) covers its shape."""
+        if self.embed_fn is None or self.embed_model.embed_type not in ("FFB", "StyleModNFFB"):
+            return None
+        ffb = self.embed_model.embedder_obj
+        return ffb if K.nffb_fused_supported(ffb) else None
+
+    def _embed_nograd(self, x):
+        ffb = self._fused_filter_bank()
+        if ffb is not None:
+            return K.nffb_encode_fwd(ffb, x)[:, :ffb.embeddings_dim]
+        return self._embed(x)
+
     # -- inference paths (no autograd) -----------------------------------------------------
     @torch.no_grad()
     def sdf(self, x: torch.Tensor) -> torch.Tensor:
@@ -82,7 +95,7 @@ class ImplicitNetwork(nn.Module):
         x = x.reshape(-1, x.shape[-1])
         if x.shape[0] == 0:
             return torch.empty(0, device=x.device)
-        emb = K.operand(self._embed(x))
+        emb = K.operand(self._embed_nograd(x))
         return self._pipeline.run(emb, x.shape[0], want="sdf")
 
     def refresh_inference_weights(self, force: bool = False):
@@ -105,15 +118,19 @@ class ImplicitNetwork(nn.Module):
             grid = self.embed_model.embedder_obj
             emb = pipe._buf("emb", rows, grid.embeddings_dim, pts.device)
             K.hash_encode_fwd(grid.spec(), pts, grid.tables(), grid.freq_encoding.B, out=emb, m_count=m_count, rows=rows)
+        elif self._fused_filter_bank() is not None:
+            ffb = self.embed_model.embedder_obj
+            emb = pipe._buf("emb", rows, ffb.embeddings_dim, pts.device)
+            K.nffb_encode_fwd(ffb, pts, out=emb, m_count=m_count, rows=rows)
         else:
-            # filter-bank / positional encoders: evaluated on the whole (fixed-capacity) buffer with their module
+            # positional encoders (and filter banks wider than the fused kernel): evaluated on the whole (fixed-capacity) buffer with their module
             # kernels - rows beyond the device-side count hold stale points and are never consumed - so the call
             # sequence stays free of host syncs and can live in a CUDA graph
             emb = K.operand(self._embed(pts[:rows]))
         pipe.run(emb, rows, want="sdf", m_count=m_count, out=out)
 
     def _forward_inference(self, x):
-        emb = K.operand(self._embed(x))
+        emb = K.operand(self._embed_nograd(x))
         return self._pipeline.run(emb, x.shape[0], want="full").clone()
 
     # -- reference API -----------------------------------------------------------------------

@@ -124,6 +124,27 @@ int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N, int32_t K
               const float* A, const float* A_lo, int32_t lda, const float* B, const float* B_lo, int32_t ldb,
               const idrk_epilogue_t* h_epi, const int32_t* m_count, int32_t split_k, void* stream);
 
+/* -- K7: fused Fourier-filter-bank encoder, forward only (no-grad SDF queries of the ray tracer) ----------------
+ * FourierFilterBanks.forward of the configuration the reference's selector uses (PositionalEncodingNET + SIREN,
+ * has_out = False; nffb3d.py:122-194) with the optional StyleAttention block (styleMod.py:17-44) in ONE launch:
+ * out[p] = [u | f / n_levels_div], u = (x + bound) / (2 bound).  Weights are the module's own tensors
+ * (ff_lin{j}.weight [width, in] row-major, out_layer, StyleAttentionBlock.linear_transform).  width <= 64. */
+typedef struct idrk_nffb {
+    idrk_hashgrid_t grid;          /* grid_enc (reference frac mode), evaluated at u                  */
+    float bands[32];               /* PositionalEncoding freq_bands                                   */
+    int32_t n_bands, include_input;
+    int32_t n_lin;                 /* SIREN layers ff_lin0 .. ff_lin{n_lin-1}                          */
+    int32_t width, chunk;          /* filter-bank width; grid columns per chunk (2 * features/level)  */
+    int32_t style, n_levels_div;   /* style modulation on/off; divisor of the accumulated features    */
+    float bound, w0, eps;
+    const float* lin_w[16];
+    const float* lin_b[16];
+    const float* out_w; const float* out_b;
+    const float* style_w; const float* style_b;
+} idrk_nffb_t;
+int idrk_nffb_encode_fwd(const idrk_nffb_t* desc, const float* x, int64_t n, int32_t ldx, float* out, int32_t ld_out,
+                         const int32_t* m_count, void* stream);
+
 /* -- K4c: fp16-pair contraction for the no-grad SDF path ------------------------------------
  * Operands are pairs of IEEE halves  x ~= h + l * 2^-11  (h = fp16(x), l = fp16((x - h) * 2^11)): 4 bytes per element,
  * three kind::f16 MMAs per product (Ah.Bh | Ah.Bl + Al.Bh) into two TMEM accumulators, result = D0 + 2^-11 D1.

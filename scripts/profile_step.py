@@ -9,6 +9,17 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
+def _conf():
+    """IDRK_PROFILE_CONF=FFB | StyleModNFFB selects a filter-bank configuration instead of the bench's HashGrid one."""
+    from tests_support import make_conf
+    which = os.environ.get("IDRK_PROFILE_CONF", "")
+    if which == "FFB":
+        return make_conf("FFB", 6, 5, 16, 512, 0.45, view_type="FFB")
+    if which == "StyleModNFFB":
+        return make_conf("StyleModNFFB", 6, 22, 16, 512, 0.45, view_type="StyleModNFFB")
+    return bench.model_conf()
+
+
 def main():
     from idrk import kernels as K
     from idrk.dist import DataParallelTrainer
@@ -19,7 +30,7 @@ def main():
     prec = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
     K.set_precision(prec)
     torch.manual_seed(0)
-    model = quiet_build(IDRNetwork, bench.model_conf()).cuda().train()
+    model = quiet_build(IDRNetwork, _conf()).cuda().train()
     use_graph = len(sys.argv) > 2 and sys.argv[2] == "graph"
     tr = DataParallelTrainer(model, IDRLoss(0.1, 100.0, 50.0), lr=1e-4, use_cuda_graph=use_graph)
     inp, rgb = O.synthetic_batch(bench.N_RAYS, seed=1)

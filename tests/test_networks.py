@@ -116,3 +116,31 @@ def test_full_width_vs_oracle(prec, rel):
     g_ref = sd["implicit_network.embed_model.embedder_obj.levels.5.embedding.weight"].grad
     g_got = net.embed_model.embedder_obj.levels[5].embedding.weight.grad
     assert close(g_got, g_ref, rel=max(rel, 1e-3), abs_=1e-8)
+
+
+@pytest.mark.parametrize("tag", ["ffb", "style"])
+def test_fused_filter_bank_encoder_matches_module_and_golden(golden, tag):
+    """csrc/nffb.cu (one launch, FP32 FMAs) vs the module path (contraction / posenc kernels) vs the reference's
+    golden embedding-dependent outputs; plus the device-side row count (rows beyond it are not written)."""
+    from idrk import kernels as K
+    g = golden("networks")
+    model = build_model(tag, g)
+    net = model.implicit_network
+    ffb = net.embed_model.embedder_obj
+    assert net._fused_filter_bank() is ffb
+    x = T(g["x"]).to(DEV)
+    with torch.no_grad():
+        ref = ffb(x)
+        got = K.nffb_encode_fwd(ffb, x)
+    assert got.shape[1] == K.pad4(ffb.embeddings_dim)
+    # sin(w0 .) chains with the reference's SIREN weights amplify last-ulp differences of the two summation orders
+    assert close(got[:, :ffb.embeddings_dim], ref, rel=2e-4, abs_=2e-6)
+    assert (got[:, ffb.embeddings_dim:] == 0).all()
+    xs = torch.rand(3001, 3, generator=torch.Generator().manual_seed(3)).to(DEV) * 0.8 - 0.4
+    cnt = torch.tensor([1234], device=DEV, dtype=torch.int32)
+    out = torch.full((3001, K.pad4(ffb.embeddings_dim)), 7.0, device=DEV)
+    with torch.no_grad():
+        K.nffb_encode_fwd(ffb, xs, out=out, m_count=cnt)
+        full = ffb(xs)
+    assert close(out[:1234, :ffb.embeddings_dim], full[:1234], rel=2e-4, abs_=2e-6)
+    assert (out[1234:] == 7.0).all()
