@@ -364,6 +364,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                  long long M, int N, int K, EpiParams e, const int* __restrict__ m_count, int kb_per_split, int splits) {
     pdl_trigger();
+    if (m_count != nullptr) {            // device-side row count of zero (gated tracer queries): leave before any set-up
+        pdl_wait();
+        if (*m_count <= 0) return;
+    }
     using P = SmemPlan<BN, TERMS>;
     const int n_tiles = (N + BN - 1) / BN;
     const int kb_total = (K + BK - 1) / BK;
@@ -573,6 +577,10 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                       long long M, int N, int K, EpiParams e, const int* __restrict__ m_count) {
     pdl_trigger();
+    if (m_count != nullptr) {            // device-side row count of zero (gated tracer queries): leave before any set-up
+        pdl_wait();
+        if (*m_count <= 0) return;
+    }
     using P = SmemPlan2<TERMS>;
     const int n_tiles = (N + BN2 - 1) / BN2;
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -885,6 +893,10 @@ gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl,
                  long long M, int N, int K, EpiParamsH e, const int* __restrict__ m_count) {
     pdl_trigger();
+    if (m_count != nullptr) {            // device-side row count of zero (gated tracer queries): leave before any set-up
+        pdl_wait();
+        if (*m_count <= 0) return;
+    }
     using P = SmemPlanHT<BN_, STAGES_>;
     const int n_tiles = (N + BN_ - 1) / BN_;
     const int kb_total = (K + BKH - 1) / BKH;

@@ -180,6 +180,7 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
     pdl_trigger();
     extern __shared__ uint4 smem_u4[];
     if (m_count != nullptr) { const long long c = *m_count; n = c < n ? c : n; }
+    if (n <= 0) return;                     // gated tracer query: nothing to encode
     const int C = g.n_fourier, L = g.n_levels;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     LevelC* s_lev = reinterpret_cast<LevelC*>(smem_u4);                               // [L]

@@ -60,6 +60,7 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
     pdl_trigger();
     extern __shared__ float smem[];
     if (m_count != nullptr) { const long long c = *m_count; n = c < n ? c : n; }
+    if (n <= 0) return;                     // gated tracer query: skip the weight staging
     const int W = d.width, NL = d.n_lin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // shared layout: transposed weights [mat][k][NFFB_MAX_W] (zero padded), biases [mat][NFFB_MAX_W], per-warp vectors
