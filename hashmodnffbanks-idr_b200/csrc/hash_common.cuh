@@ -12,6 +12,7 @@ struct GridDev {
     unsigned long long magic[IDRK_MAX_LEVELS];   // 2^64 / rows + 1 (Lemire fastmod), used when rows is not a power of two
     const float* tables[IDRK_MAX_LEVELS];
     const float* B;                         // [3, C]
+    int pair_x;                             // 8-corner mode: x-neighbour corners share one 16-byte access when they can
 };
 
 
@@ -74,6 +75,7 @@ inline int fill_grid(const idrk_hashgrid_t* h, GridDev& g) {
     g.n_levels = h->n_levels; g.n_feat = h->n_feat; g.n_fourier = h->n_fourier;
     g.width = (h->n_fourier > 0 ? 3 + 2 * h->n_fourier : 0) + h->n_levels * h->n_feat;
     g.B = h->fourier_B;
+    { static const int pair = [] { const char* e = getenv("IDRK_HASH_PAIR_X"); return (e && e[0] == '0') ? 0 : 1; }(); g.pair_x = pair; }
     const size_t align = (h->n_feat >= 4) ? 16 : 4 * (size_t)h->n_feat;
     for (int l = 0; l < h->n_levels; ++l) {
         if (h->tables[l] == nullptr || h->rows[l] == 0) return IDRK_E_ARG;

@@ -73,6 +73,14 @@ template <bool FAST> __device__ __forceinline__ uint32_t trunc_sel(float v) {
     if constexpr (FAST) return (uint32_t)__float2int_rz(v); else return trunc_u32(v);
 }
 
+// x-neighbour pairing (8-corner backward, F == 2).  hash3's x term has prime 1, so for an EVEN floor coordinate c0
+// the two x-neighbours hash to h and h ^ 1, and with an even row count (h mod T) keeps them in one aligned pair of
+// rows = one 16-byte slot of the gradient table.  Such an element issues 4 reductions (RED.128) instead of 8; an odd
+// c0 keeps a separate 8-byte reduction for its x+1 corner.  The table-gradient backward is bound by L2 reduction
+// operations (one per touched sector), so this is -25 % of them on average: 0.87 -> 1.16-1.21 Gpts/s at T = 2^19,
+// 0.65 -> 0.79 at T = 2^22 (profiles/r01_hash_pair_ab.txt).  The same pairing of the forward's gathers (LDG.128)
+// was measured and did not pay: no change while the tables sit in L2, slower for T >= 2^22.
+
 // one (point, level) element of the forward
 template <int F, int MODE, bool FAST>
 __device__ __forceinline__ void fwd_element(const LevelC& lc, float x0, float x1, float x2, float (&acc)[F]) {
@@ -171,8 +179,8 @@ __device__ __forceinline__ void fwd_levels_full(const LevelC& lc, const float4* 
     }
 }
 
-template <int F, int MODE, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int F, int MODE, int WARPS, int MINB = 0>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
                             float* __restrict__ out, int ld_out, uint32_t* __restrict__ idx_dbg,
                             const int* __restrict__ m_count) {
@@ -313,9 +321,9 @@ __device__ __forceinline__ void scatter_sel(float* gtab, float* s_acc, uint32_t 
     }
 }
 
-template <int F, int MODE, bool FAST, bool WANT_DX>
+template <int F, int MODE, bool FAST, bool WANT_DX, bool PAIR = false>
 __device__ __forceinline__ void bwd_element(const LevelC& lc, float* gtab, float* s_acc, float x0, float x1, float x2,
-                                            const float (&gy)[F], float (&d)[3]) {
+                                            const float (&gy)[F], float (&d)[3], bool pair_lane = false) {
     const float s0 = __fmul_rn(x0, lc.res), s1 = __fmul_rn(x1, lc.res), s2 = __fmul_rn(x2, lc.res);
     if constexpr (MODE == IDRK_HASH_REFERENCE) {
         if (gtab == nullptr) return;
@@ -345,7 +353,20 @@ __device__ __forceinline__ void bwd_element(const LevelC& lc, float* gtab, float
                 float v[F];
 #pragma unroll
                 for (int f = 0; f < F; ++f) v[f] = wk * gy[f];
-                scatter_sel<F>(gtab, s_acc, lc.soff, idx[k], v);
+                if (PAIR && F == 2 && pair_lane) {
+                    // paired x-neighbours (see level_pairable): the x corner goes out as a 16-byte reduction on its
+                    // aligned row pair, carrying the x+1 corner in the other half when c0 is even (zeros otherwise)
+                    if ((k & 1) == 0) {
+                        const float wn = ((c0 & 1u) == 0) ? w0 * a1 * a2 : 0.f;
+                        const float nx = wn * gy[0], ny = wn * gy[1];
+                        const bool o = idx[k] & 1u;
+                        red_add_v4(gtab + (size_t)(idx[k] & ~1u) * F, o ? nx : v[0], o ? ny : v[1], o ? v[0] : nx, o ? v[1] : ny);
+                    } else if (c0 & 1u) {
+                        red_add_v2(gtab + (size_t)idx[k] * F, v[0], v[1]);
+                    }
+                } else {
+                    scatter_sel<F>(gtab, s_acc, lc.soff, idx[k], v);
+                }
             }
             if constexpr (WANT_DX) {
                 float dot = 0.f;
@@ -400,9 +421,9 @@ __device__ __forceinline__ void bwd_levels_generic(const LevelC* s_lev, float* c
 
 // Full 32-row tile with L | 32 (see fwd_levels_full).  SHIFT: dL/dy features are read as the aligned pair
 // (own f1, next level's f0); the lane's f0 arrives from the previous lane by shuffle.
-template <int F, int MODE, bool WANT_DX, bool SHIFT>
+template <int F, int MODE, bool WANT_DX, bool SHIFT, bool PAIR = false>
 __device__ __forceinline__ void bwd_levels_full(const LevelC& lc, float* gtab, float* s_acc, const float4* xs, float* dxs,
-                                                int L, int lane, const float* __restrict__ drow0, int ld_dy) {
+                                                int L, int lane, const float* __restrict__ drow0, int ld_dy, bool pair_lane = false) {
     constexpr int KB = (MODE == IDRK_HASH_REFERENCE) ? (F <= 2 ? 4 : 2) : (WANT_DX ? 1 : 2);
     const int rstep = 32 / L, row0 = lane / L, l = lane - row0 * L;
     const float* __restrict__ o0 = drow0 + row0 * ld_dy + l * F;
@@ -432,7 +453,7 @@ __device__ __forceinline__ void bwd_levels_full(const LevelC& lc, float* gtab, f
                 const int row = row0 + (pass + k) * rstep;
                 const float4 xv = xs[row];
                 float d[3] = {0.f, 0.f, 0.f};
-                bwd_element<F, MODE, true, WANT_DX>(lc, gtab, s_acc, xv.x, xv.y, xv.z, gy[k], d);
+                bwd_element<F, MODE, true, WANT_DX, PAIR>(lc, gtab, s_acc, xv.x, xv.y, xv.z, gy[k], d, pair_lane);
                 if constexpr (WANT_DX && MODE == IDRK_HASH_TRILINEAR) row_reduce_add(dxs, row, true, L, true, lane, d[0], d[1], d[2]);
             }
         }
@@ -470,6 +491,10 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
     const LevelC lc = load_level(s_lev, L > 0 ? lane % L : 0);
     float* gtab = L > 0 ? s_grad[lane % L] : nullptr;
     const bool want_dx = dx != nullptr;
+    // paired reductions need the gradient table (not the value table) on a 16-byte boundary
+    const bool pair_lane = MODE == IDRK_HASH_TRILINEAR && F == 2 && g.pair_x && L > 0 && gd.any_grad &&
+                           (lc.rows & 1u) == 0 && lc.soff == 0xffffffffu && (reinterpret_cast<uintptr_t>(gtab) & 15u) == 0;
+    const bool pair_x = __any_sync(0xffffffffu, pair_lane);
     float res_max = 0.f;
     for (int l = 0; l < L; ++l) res_max = fmaxf(res_max, fabsf(g.res[l]));
     const int jstep = C > 0 ? 32 % C : 0, jrstep = C > 0 ? 32 / C : 0;
@@ -529,9 +554,15 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
             const float amax = fmaxf(fabsf(x0), fmaxf(fabsf(x1), fabsf(x2))) * res_max;
             const bool fast = __all_sync(0xffffffffu, amax < 2147483520.f);
             if (fast && rows_here == 32 && l_fixed) {
-                if (F == 2 && shift) {
+                if (F == 2 && shift && pair_x) {
+                    if (want_dx) bwd_levels_full<F, MODE, true, F == 2, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
+                    else         bwd_levels_full<F, MODE, false, F == 2, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
+                } else if (F == 2 && shift) {
                     if (want_dx) bwd_levels_full<F, MODE, true, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
                     else         bwd_levels_full<F, MODE, false, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
+                } else if (F == 2 && pair_x) {
+                    if (want_dx) bwd_levels_full<F, MODE, true, false, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
+                    else         bwd_levels_full<F, MODE, false, false, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
                 } else {
                     if (want_dx) bwd_levels_full<F, MODE, true, false>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
                     else         bwd_levels_full<F, MODE, false, false>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
@@ -583,6 +614,10 @@ static int launch_fwd(const GridDev& g, const float* x, long long n, int ldx, fl
                       uint32_t* idx_dbg, const int* m_count, cudaStream_t st) {
     const size_t smem = ((size_t)2 * g.n_levels + WARPS * 32) * 16 + (size_t)3 * g.n_fourier * sizeof(float);
     auto kern = hash_encode_fwd_elem_kernel<F, MODE, WARPS>;
+    // 8-corner, F = 2: capping the kernel at 4 resident CTAs per SM (118 registers instead of 80) lets ptxas keep both
+    // batched elements' 16 gathers in flight: +5 % with L2-resident tables, +27 % / +12 % at T = 2^22 / 2^24 where every
+    // gather is a DRAM sector read (profiles/r01_hash_pair_ab.txt)
+    if constexpr (F == 2 && MODE == IDRK_HASH_TRILINEAR) kern = hash_encode_fwd_elem_kernel<F, MODE, WARPS, 4>;
     const int grid = persistent_grid(kern, WARPS * 32, smem, (n + WARPS * 32 - 1) / (WARPS * 32));
     IDRK_CUDA_TRY(launch_k(kern, dim3(grid), dim3(WARPS * 32), smem, st, g, x, n, ldx, out, ld_out, idx_dbg, m_count));
     IDRK_LAUNCH_CHECK();

@@ -141,6 +141,50 @@ def test_aligned_store_paths_l16(mode):
         assert bad.sum().item() <= 3
 
 
+def test_trilinear_paired_corners_mixed_levels():
+    """8-corner mode, F = 2: x-neighbour corners of an even cell coordinate are fetched / reduced as ONE 16-byte
+    access when the level's row count is even and its (gradient) table is 16-byte aligned.  Here L = 8 levels mix odd
+    row counts (15^3, 33^3) with even ones, and a second run puts every table and gradient table on an 8-byte-only
+    boundary (views into a flat buffer, as in the trainer's bucket), so paired and unpaired lanes share warps and the
+    fall-back is taken.  Forward must equal the oracle to rounding and be bit-identical between the two placements."""
+    from idrk import kernels as K
+    L, F, n = 8, 2, 4096 + 77
+    m, sd = make_grid(L, F, 16, 15, 255, mode="trilinear", seed=21)
+    rows = [lvl.embedding.weight.shape[0] for lvl in m.levels]
+    assert any(r % 2 for r in rows) and any(r % 2 == 0 for r in rows)
+    gen = torch.Generator().manual_seed(8)
+    x = torch.rand(n, 3, generator=gen) * 2 - 1
+    w = torch.randn(n, K.pad4(3 + 2 * L + L * F), generator=gen)
+    w[:, 3 + 2 * L + L * F:] = 0
+    for v in sd.values():
+        v.requires_grad_(v.dim() == 2 and v.shape[0] != 3)
+    ref = O.hashgrid_embed(x, sd, "", L, 15, 255, "trilinear")
+    (ref * w[:, :ref.shape[1]]).sum().backward()
+    spec, B = m.spec(), m.freq_encoding.B
+    xd, wd = x.to(DEV), w.to(DEV)
+    outs = []
+    for shift in (0, 2):                    # floats: 0 -> 16-byte aligned tables, 2 -> 8-byte-only
+        tabs, grads = [], []
+        for lvl in m.levels:
+            t = lvl.embedding.weight.detach()
+            flat = torch.zeros(t.numel() + 4, device=DEV)
+            gflat = torch.zeros(t.numel() + 4, device=DEV)
+            tv = flat[shift:shift + t.numel()].view_as(t)
+            tv.copy_(t)
+            tabs.append(tv)
+            grads.append(gflat[shift:shift + t.numel()].view_as(t))
+            assert tv.data_ptr() % 16 == 4 * shift
+        y = K.hash_encode_fwd(spec, xd, tuple(tabs), B)
+        K.hash_encode_bwd(spec, xd, tuple(tabs), B, wd, grads, False)
+        pre = 3 + 2 * L
+        assert torch.allclose(y[:, pre:ref.shape[1]].cpu(), ref[:, pre:].detach(), atol=2e-6, rtol=1e-5)
+        for l in range(L):
+            r = sd["levels.%d.embedding.weight" % l].grad
+            assert torch.allclose(grads[l].cpu(), r, atol=1e-5 * r.abs().max().item(), rtol=1e-4), (shift, l)
+        outs.append(y)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_unpadded_rows_and_huge_coordinates():
     """ld_out == width (odd: no vector path, no pad column) and coordinates whose scaled value leaves the int32
     range (the .long() emulation has to take the 64-bit conversion): indices stay bit-exact."""
