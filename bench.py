@@ -178,7 +178,12 @@ def hash_encode_section(torch, hbm, src):
                      "bwd_with_dx_mpts_per_s": round(r["bwd_with_dx_mpts"], 1),
                      "bwd_with_dx_frac_of_hbm_peak": round(r["bwd_with_dx_frac"], 4),
                      "algorithmic_bytes_per_point": dict(zip(("fwd", "bwd_tables", "bwd_tables_dx"), r["bytes_per_pt"]))}
-    out["points"] = 1 << 24
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out["points"] = (1 << 24) * world
+    out["n_gpus"] = world
+    if world > 1:
+        out["note"] = ("2^24 points per GPU (weak); Mpts/s are whole-job, fractions are of n_gpus x the HBM peak; every "
+                       "backward pass ends with the NCCL all-reduce of the 48.5 MB table-gradient bucket, inside the timing")
     out["table"] = "L=16, F=2, T=2^19 (48.5 MB)"
     out["peak_gbs"] = hbm
     out["peak_source"] = src
@@ -253,13 +258,15 @@ def run_ours(args):
     # The hash-encode microbench (its own workload, own buffers) runs before the training loop: measured on this
     # pool, 4.5 GB buffers cudaMalloc'ed late in the process (after the step's graphs and pools exist) make the same
     # kernels 15-35 % slower than buffers allocated early - a physical-placement effect outside the kernels' control.
+    # At N > 1 every rank runs it on its own 2^24 points and the backward includes the table-gradient all-reduce.
     hash_line = None
-    if rank == 0:
-        try:
-            hash_line = hash_encode_section(torch, *[peaks()[i] for i in (0, 3)])
-        except Exception as exc:      # the microbench must never take the headline down
-            hash_line = {"error": repr(exc)}
-        torch.cuda.empty_cache()
+    try:
+        hash_line = hash_encode_section(torch, *[peaks()[i] for i in (0, 3)])
+    except Exception as exc:      # the microbench must never take the headline down
+        hash_line = {"error": repr(exc)}
+        if world > 1:
+            raise                 # ... but ranks must not diverge around collectives
+    torch.cuda.empty_cache()
     barrier()
     for _ in range(max(args.warmup, 3)):
         step_resident()

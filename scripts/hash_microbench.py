@@ -17,7 +17,16 @@ def peaks():
         return 6650.0, "fallback"
 
 
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def time_cuda(fn, warm=3, iters=10, flush=None):
+    """Median device time of fn (CUDA events on the launching stream).  With torch.distributed initialised every
+    iteration starts behind a barrier and counts as the MAX over ranks."""
+    import torch.distributed as dist
+    world = _world()
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -25,12 +34,18 @@ def time_cuda(fn, warm=3, iters=10, flush=None):
     for _ in range(iters):
         if flush is not None:
             flush.zero_()
+        if world > 1:
+            dist.barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()
         e.record()
         torch.cuda.synchronize()
         ts.append(s.elapsed_time(e))
+    if world > 1:
+        t = torch.tensor(ts, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ts = t.tolist()
     ts.sort()
     return ts[len(ts) // 2]
 
@@ -43,11 +58,28 @@ def run(n, log2T, mode, L=16, F=2, flush=None):
     x = torch.rand(n, 3, device="cuda")
     out = torch.empty(n, K.pad4(spec.width), device="cuda")
     dy = torch.randn(n, K.pad4(spec.width), device="cuda")
-    grads = [torch.zeros_like(t) for t in tables]
+    # gradient tables = views of ONE flat buffer (what the trainer's bucket looks like, and what NCCL reduces)
+    flat = torch.zeros(sum(t.numel() for t in tables), device="cuda")
+    grads, o = [], 0
+    for t in tables:
+        grads.append(flat[o:o + t.numel()].view_as(t))
+        o += t.numel()
     G = 1 if mode == "reference" else 8
+    world = _world()
+    if world > 1:
+        import torch.distributed as dist
+
+        def bwd(want_dx):
+            # cfg5 at N > 1: every rank owns n points, the step ends with the table-gradient all-reduce
+            K.hash_encode_bwd(spec, x, tables, B, dy, grads, want_dx)
+            dist.all_reduce(flat)
+    else:
+        def bwd(want_dx):
+            K.hash_encode_bwd(spec, x, tables, B, dy, grads, want_dx)
     t_f = time_cuda(lambda: K.hash_encode_fwd(spec, x, tables, B, out=out), flush=flush)
-    t_b = time_cuda(lambda: K.hash_encode_bwd(spec, x, tables, B, dy, grads, False), flush=flush)      # table gradients
-    t_bx = time_cuda(lambda: K.hash_encode_bwd(spec, x, tables, B, dy, grads, True), flush=flush)     # + dL/dx
+    t_b = time_cuda(lambda: bwd(False), flush=flush)      # table gradients
+    t_bx = time_cuda(lambda: bwd(True), flush=flush)      # + dL/dx
+    n = n * world                                         # whole-job points per pass (weak scaling: n per GPU)
     # algorithmic bytes per point.  fwd: x + prefix columns + level columns written, one F-float table row read per
     # gather.  bwd (table gradients): x + the level columns of dL/dy read (the prefix columns are not needed), one
     # read-modify-write of a table row per reduction.  bwd + dL/dx additionally reads the prefix columns of dL/dy and
@@ -57,11 +89,11 @@ def run(n, log2T, mode, L=16, F=2, flush=None):
     bb = 12 + 4 * L * F + 2 * G * L * 4 * F
     bbx = bb + pre + 12 + (G * L * 4 * F if mode != "reference" else 0)
     hbm, src = peaks()
-    return {"n": n, "log2T": log2T, "mode": mode,
-            "fwd_ms": t_f, "fwd_mpts": n / t_f / 1e3, "fwd_frac": n * bf / (t_f * 1e-3) / (hbm * 1e9),
-            "bwd_ms": t_b, "bwd_mpts": n / t_b / 1e3, "bwd_frac": n * bb / (t_b * 1e-3) / (hbm * 1e9),
+    return {"n": n, "log2T": log2T, "mode": mode, "n_gpus": world, "hbm_peak_gbs_all_gpus": hbm * world,
+            "fwd_ms": t_f, "fwd_mpts": n / t_f / 1e3, "fwd_frac": n * bf / (t_f * 1e-3) / (hbm * world * 1e9),
+            "bwd_ms": t_b, "bwd_mpts": n / t_b / 1e3, "bwd_frac": n * bb / (t_b * 1e-3) / (hbm * world * 1e9),
             "bwd_with_dx_ms": t_bx, "bwd_with_dx_mpts": n / t_bx / 1e3,
-            "bwd_with_dx_frac": n * bbx / (t_bx * 1e-3) / (hbm * 1e9),
+            "bwd_with_dx_frac": n * bbx / (t_bx * 1e-3) / (hbm * world * 1e9),
             "bytes_per_pt": [bf, bb, bbx], "peak": src}
 
 
@@ -71,8 +103,18 @@ if __name__ == "__main__":
     ap.add_argument("--log2T", type=int, nargs="+", default=[14, 19, 22])
     ap.add_argument("--modes", nargs="+", default=["reference", "trilinear"])
     a = ap.parse_args()
+    rank = 0
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:          # torchrun: cfg5 at 2 / 4 / 8 GPUs, --n is per GPU
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+        rank = dist.get_rank()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for mode in a.modes:
         for lt in a.log2T:
             for n in a.n:
-                print(json.dumps(run(n, lt, mode, flush=flush)), flush=True)
+                r = run(n, lt, mode, flush=flush)
+                if rank == 0:
+                    print(json.dumps(r), flush=True)
+    if _world() > 1:
+        torch.distributed.destroy_process_group()
