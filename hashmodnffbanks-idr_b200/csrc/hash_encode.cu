@@ -492,9 +492,11 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
     float* gtab = L > 0 ? s_grad[lane % L] : nullptr;
     const bool want_dx = dx != nullptr;
     // paired reductions need the gradient table (not the value table) on a 16-byte boundary
-    const bool pair_lane = MODE == IDRK_HASH_TRILINEAR && F == 2 && g.pair_x && L > 0 && gd.any_grad &&
-                           (lc.rows & 1u) == 0 && lc.soff == 0xffffffffu && (reinterpret_cast<uintptr_t>(gtab) & 15u) == 0;
-    const bool pair_x = __any_sync(0xffffffffu, pair_lane);
+    constexpr bool PAIRK = MODE == IDRK_HASH_TRILINEAR && F == 2;      // compile-time: other kernels carry no pairing code
+    bool pair_lane = false;                                            // per lane = per level on the full-tile path
+    if constexpr (PAIRK)
+        pair_lane = g.pair_x && L > 0 && gd.any_grad && (lc.rows & 1u) == 0 && lc.soff == 0xffffffffu &&
+                    (reinterpret_cast<uintptr_t>(gtab) & 15u) == 0;
     float res_max = 0.f;
     for (int l = 0; l < L; ++l) res_max = fmaxf(res_max, fabsf(g.res[l]));
     const int jstep = C > 0 ? 32 % C : 0, jrstep = C > 0 ? 32 / C : 0;
@@ -554,18 +556,12 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
             const float amax = fmaxf(fabsf(x0), fmaxf(fabsf(x1), fabsf(x2))) * res_max;
             const bool fast = __all_sync(0xffffffffu, amax < 2147483520.f);
             if (fast && rows_here == 32 && l_fixed) {
-                if (F == 2 && shift && pair_x) {
-                    if (want_dx) bwd_levels_full<F, MODE, true, F == 2, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
-                    else         bwd_levels_full<F, MODE, false, F == 2, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
-                } else if (F == 2 && shift) {
-                    if (want_dx) bwd_levels_full<F, MODE, true, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
-                    else         bwd_levels_full<F, MODE, false, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
-                } else if (F == 2 && pair_x) {
-                    if (want_dx) bwd_levels_full<F, MODE, true, false, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
-                    else         bwd_levels_full<F, MODE, false, false, F == 2>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
+                if (F == 2 && shift) {
+                    if (want_dx) bwd_levels_full<F, MODE, true, F == 2, PAIRK>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
+                    else         bwd_levels_full<F, MODE, false, F == 2, PAIRK>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
                 } else {
-                    if (want_dx) bwd_levels_full<F, MODE, true, false>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
-                    else         bwd_levels_full<F, MODE, false, false>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy);
+                    if (want_dx) bwd_levels_full<F, MODE, true, false, PAIRK>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
+                    else         bwd_levels_full<F, MODE, false, false, PAIRK>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
                 }
             } else {
                 if (want_dx) bwd_levels_generic<F, MODE, true>(s_lev, s_grad, s_acc, xs, dxs, L, lane, rows_here, drow0 + pre, ld_dy);

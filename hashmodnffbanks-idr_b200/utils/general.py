@@ -33,3 +33,20 @@ def merge_output(res, total_pixels, batch_size):
             merged[key] = torch.cat([r[key].reshape(batch_size, -1, r[key].shape[-1]) for r in res], 1) \
                 .reshape(batch_size * total_pixels, -1)
     return merged
+
+
+def render_image(model, model_input, total_pixels, n_pixels=10000, keys=("rgb_values",)):
+    """Full-image rendering as the reference's evaluation loop does it (evaluation/eval.py:150-160): the image's
+    pixels go through `model` (eval mode) in splits of `n_pixels` rays and the per-split outputs are merged back
+    to [batch * total_pixels, C].  Every split runs the device-driven tracer and the eval branch of
+    IDRNetwork.forward; nothing but the merged result leaves the device."""
+    was_training = model.training
+    model.eval()
+    try:
+        res = []
+        for part in split_input(model_input, total_pixels, n_pixels):
+            out = model(part)
+            res.append({k: out[k].detach() for k in keys})
+    finally:
+        model.train(was_training)
+    return merge_output(res, total_pixels, model_input['uv'].shape[0])
