@@ -124,7 +124,8 @@ class EpilogueH(ctypes.Structure):
     """Mirror of idrk_epilogue_f16_t."""
     _fields_ = [("C", ctypes.c_void_p), ("C_h", ctypes.c_void_p), ("C_l", ctypes.c_void_p), ("bias", ctypes.c_void_p),
                 ("ldc", ctypes.c_int32), ("ldh", ctypes.c_int32), ("mode", ctypes.c_int32),
-                ("act_param", ctypes.c_float), ("scale", ctypes.c_float)]
+                ("act_param", ctypes.c_float), ("scale", ctypes.c_float),
+                ("dot_w", ctypes.c_void_p), ("dot_out", ctypes.c_void_p), ("ld_dot", ctypes.c_int32)]
 
 
 class RayStateDesc(ctypes.Structure):

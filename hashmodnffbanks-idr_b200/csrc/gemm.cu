@@ -745,6 +745,7 @@ struct EpiParamsH {
     int ldc, ldh;
     int mode; float act; float scale;
     int vec16;                      // C_h / C_l rows 16-byte aligned: quad-transposed 16-byte stores
+    const float* dot_w; float* dot_out; int ld_dot;     // fused row-dot (SDF head), see idrk_epilogue_f16_t
 };
 
 template <int BN_, int STAGES_>
@@ -806,6 +807,32 @@ __device__ __forceinline__ void epi_frag_h(const EpiParamsH& e, const SoftplusC&
     const int t = lane & 3, g = lane >> 2;
     const long long ra = row0 + g, rb = ra + 8;
     const bool va = ra < m_eff, vb = rb < m_eff;
+    if (e.dot_w != nullptr) {
+        // fused row-dot: this lane holds 8 columns of rows ra and rb; products are summed per lane in column order,
+        // then over the quad's 4 lanes - a fixed order, so the result does not depend on scheduling
+        float pa = 0.f, pb = 0.f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int col = col0 + 8 * i + 2 * t;
+            float w0 = 0.f, w1 = 0.f;
+            if (FULL || col < N) w0 = __ldg(e.dot_w + col);
+            if (FULL || col + 1 < N) w1 = __ldg(e.dot_w + col + 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float z = fmaf(__uint_as_float(r1[4 * i + k]), 1.f / F16S_SCALE, __uint_as_float(r0[4 * i + k])) + ((k & 1) ? bias2[i].y : bias2[i].x);
+                const float v = epi_act_h<MODE>(z, c);
+                if (k < 2) pa = fmaf(v, (k & 1) ? w1 : w0, pa); else pb = fmaf(v, (k & 1) ? w1 : w0, pb);
+            }
+        }
+        pa += __shfl_xor_sync(0xffffffffu, pa, 1); pb += __shfl_xor_sync(0xffffffffu, pb, 1);
+        pa += __shfl_xor_sync(0xffffffffu, pa, 2); pb += __shfl_xor_sync(0xffffffffu, pb, 2);
+        if (t == 0) {
+            const int j = col0 >> 5;
+            if (va) e.dot_out[ra * e.ld_dot + j] = pa;
+            if (vb) e.dot_out[rb * e.ld_dot + j] = pb;
+        }
+        return;
+    }
     if (FULL && e.vec16 && e.C == nullptr) {
         uint32_t ha[4], la[4], hb[4], lb[4];
 #pragma unroll
@@ -1323,7 +1350,10 @@ extern "C" int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, 
     EpiParamsH e;
     e.C = h_epi->C; e.C_h = (__half*)h_epi->C_h; e.C_l = (__half*)h_epi->C_l; e.bias = h_epi->bias;
     e.ldc = h_epi->ldc; e.ldh = h_epi->ldh; e.mode = h_epi->mode; e.act = h_epi->act_param; e.scale = h_epi->scale;
-    if (!e.C && !e.C_h) return IDRK_E_ARG;
+    e.dot_w = h_epi->dot_w; e.dot_out = h_epi->dot_out; e.ld_dot = h_epi->ld_dot;
+    if (e.dot_w) {
+        if (e.C || e.C_h || h_epi->C_l || !e.dot_out || e.ld_dot < (N + 31) / 32) return IDRK_E_ARG;
+    } else if (!e.C && !e.C_h) return IDRK_E_ARG;
     e.vec16 = e.C_h && e.C_l && (e.ldh % 8) == 0 && aligned16(e.C_h) && aligned16(e.C_l);
     if ((e.C_h == nullptr) != (e.C_l == nullptr)) return IDRK_E_ARG;
     if (e.mode != IDRK_EPI_NONE && e.mode != IDRK_EPI_SOFTPLUS) return IDRK_E_UNSUP;

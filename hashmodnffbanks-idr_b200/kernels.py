@@ -484,8 +484,15 @@ def half_ld(t: torch.Tensor) -> int:
 
 
 def gemm_f16s(A_h, A_l, B_h, B_l, M: int, N: int, Kc: int, *, C=None, C_h=None, C_l=None, bias=None, mode=EPI_NONE,
-              act=0.0, scale=1.0, m_count=None):
+              act=0.0, scale=1.0, m_count=None, dot_w=None, dot_out=None):
+    """fp16-pair contraction.  With `dot_w` [N] the activated tile is not stored: `dot_out` [M, >= ceil(N/32)] receives one
+    fp32 partial of sum_c act(z[r, c]) * dot_w[c] per 32-column group (the fused SDF head)."""
     e = EpilogueH()
+    if dot_w is not None:
+        if dot_out is None or dot_out.dtype != torch.float32 or dot_out.stride(-1) != 1 or dot_out.shape[0] < M \
+                or dot_w.dtype != torch.float32 or dot_w.numel() < N or not dot_w.is_contiguous():
+            raise _lib.IdrkError("gemm_f16s: bad dot_w / dot_out")
+        e.dot_w, e.dot_out, e.ld_dot = dot_w.data_ptr(), dot_out.data_ptr(), dot_out.stride(0)
     e.C = C.data_ptr() if C is not None else None
     e.C_h = C_h.data_ptr() if C_h is not None else None
     e.C_l = C_l.data_ptr() if C_l is not None else None

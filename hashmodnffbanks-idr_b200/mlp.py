@@ -479,12 +479,20 @@ class SdfPipeline:
             width = f.n_out + (E if feeds_skip else 0)
             head_next = (l == n - 2) and want == "sdf"
             scale = SQRT2_INV if feeds_skip else 1.0
-            if head_next:                                         # last hidden layer: fp32 activations for the SDF head
-                h32 = self._buf("h_last", rows, width, dev)
-                K.gemm_f16s(cur_h, cur_l, f.W_h16, f.W_l16, rows, f.n_out, cur_dim, C=h32, bias=f.bias,
-                            mode=K.EPI_SOFTPLUS, act=100.0, scale=scale, m_count=m_count)
+            if head_next:
+                # last hidden layer + SDF head in one launch: the epilogue multiplies the fp32 activations with row 0
+                # of the last Linear and leaves one partial per 32-column group; the 512-column activation (67 MB
+                # per 32 K-point chunk, written and read back before) never exists.  The head kernel then only
+                # sums the partials in a fixed order, adds the bias and applies the Laplace squash.
+                groups = (f.n_out + 31) // 32
+                part = self._buf("sdf_partials", rows, groups, dev)
+                ones = self._bufs.get("ones")
+                if ones is None or ones.numel() < groups or ones.device != dev:
+                    ones = self._bufs["ones"] = torch.ones(max(groups, 32), device=dev, dtype=torch.float32)
+                K.gemm_f16s(cur_h, cur_l, f.W_h16, f.W_l16, rows, f.n_out, cur_dim, bias=f.bias, mode=K.EPI_SOFTPLUS,
+                            act=100.0, scale=scale, m_count=m_count, dot_w=fl[n - 1].Wfull[0], dot_out=part)
                 res = out if out is not None else torch.empty(rows, device=dev, dtype=torch.float32)
-                K.sdf_head(h32, fl[n - 1].Wfull[0], fl[n - 1].bias, self.beta(), res, rows, m_count)
+                K.sdf_head(part, ones[:groups], fl[n - 1].bias, self.beta(), res, rows, m_count)
                 return res
             if feeds_skip and skip_bufs is not None and skip_bufs[0] == l:
                 nxt_h, nxt_l = skip_bufs[1], skip_bufs[2]

@@ -158,6 +158,15 @@ typedef struct idrk_epilogue_f16 {
     int32_t ldc, ldh;
     int32_t mode;        /* IDRK_EPI_NONE or IDRK_EPI_SOFTPLUS             */
     float act_param, scale;
+    /* Fused row-dot of the activated tile (the SDF head: ImplicitNetwork's last Linear, row 0,
+     * implicit_differentiable_renderer.py:96-112 with only column 0 consumed, ray_tracing.py SDF queries).
+     * With dot_w != NULL the [M, N] activation is NOT stored (C, C_h, C_l must be NULL); instead
+     *   dot_out[r * ld_dot + j] = sum over columns c in [32 j, 32 j + 32) of act(z[r, c]) * dot_w[c],
+     * one fp32 partial per 32-column group (ld_dot >= ceil(N / 32)), summed in a fixed order: deterministic.
+     * idrk_sdf_head over the partials (K = ceil(N / 32), w = ones) finishes: + bias, Laplace squash. */
+    const float* dot_w;  /* [N] (nullable)                                 */
+    float* dot_out;      /* [M, ld_dot]                                    */
+    int32_t ld_dot;
 } idrk_epilogue_f16_t;
 int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, const void* A_l, int32_t lda,
                    const void* B_h, const void* B_l, int32_t ldb, const idrk_epilogue_f16_t* h_epi,

@@ -165,6 +165,56 @@ def test_gemm_fp16_pair(shape):
     assert (C2[((k + 127) // 128) * 128:] == 5.0).all()
 
 
+@pytest.mark.parametrize("shape", [(4096, 512, 512), (33000, 512, 512), (300, 445, 67), (129, 96, 64)])
+def test_gemm_fp16_pair_fused_row_dot(shape):
+    """Fused SDF head: softplus tile times a weight row, one fp32 partial per 32-column group, nothing else stored.
+    Partials vs fp64 (abs 2e-5 of sum|act||w| per group), the finished head (sum of partials + bias, Laplace squash)
+    vs the two-launch path (activation stored, idrk_sdf_head over K columns), bit-identical run to run, rows beyond
+    the device count untouched."""
+    from idrk import kernels as K
+    M, N, Kc = shape
+    A, W, b = _mk((M, Kc), 41) * 0.3, _mk((N, Kc), 42) * 0.1, _mk((N,), 43) * 0.01
+    w = _mk((N,), 44)
+    b0 = _mk((1,), 45)
+    Ah, Al = K.split_f16(A)
+    Wh, Wl = K.split_f16(W)
+    G = (N + 31) // 32
+    cnt_v = min(M, 3001)
+    cnt = torch.tensor([cnt_v], device=DEV, dtype=torch.int32)
+    part = torch.full((M, K.pad4(G)), 9.0, device=DEV)
+    K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, bias=b, mode=K.EPI_SOFTPLUS, act=100.0, scale=0.70710678, m_count=cnt,
+                dot_w=w, dot_out=part)
+    act = torch.nn.functional.softplus(A.double() @ W.double().t() + b.double(), beta=100) * 0.70710678
+    prod = act * w.double()
+    padc = G * 32 - N
+    prod_p = torch.nn.functional.pad(prod, (0, padc))
+    ref = prod_p.reshape(M, G, 32).sum(-1)
+    mag = prod_p.abs().reshape(M, G, 32).sum(-1) + 1e-30
+    got = part[:cnt_v, :G].double()
+    assert ((got - ref[:cnt_v]).abs() / mag[:cnt_v]).max().item() < 2e-5
+    assert (part[((cnt_v + 127) // 128) * 128:] == 9.0).all()
+    part2 = torch.full_like(part, 9.0)
+    K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, bias=b, mode=K.EPI_SOFTPLUS, act=100.0, scale=0.70710678, m_count=cnt,
+                dot_w=w, dot_out=part2)
+    assert torch.equal(part[:cnt_v, :G], part2[:cnt_v, :G])
+    # finished head vs the unfused pair of launches
+    out_f = torch.zeros(M, device=DEV)
+    K.sdf_head(part, torch.ones(G, device=DEV), b0, 0.9001, out_f, M, cnt)
+    H = K.empty_padded(M, N, DEV)
+    K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, C=H, bias=b, mode=K.EPI_SOFTPLUS, act=100.0, scale=0.70710678, m_count=cnt)
+    out_u = torch.zeros(M, device=DEV)
+    K.sdf_head(H, w, b0, 0.9001, out_u, M, cnt)
+    assert (out_f[:cnt_v] - out_u[:cnt_v]).abs().max().item() <= 2e-6 * max(1.0, mag.sum(-1).max().item())
+    # argument errors: the activation cannot be stored at the same time; partial rows too short
+    from idrk._lib import IdrkError
+    with pytest.raises(IdrkError):
+        K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, C=H, bias=b, mode=K.EPI_SOFTPLUS, act=100.0, dot_w=w, dot_out=part)
+    if G > 1:
+        with pytest.raises(IdrkError):
+            K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, bias=b, mode=K.EPI_SOFTPLUS, act=100.0, dot_w=w,
+                        dot_out=torch.zeros(M, G - 1, device=DEV))
+
+
 def test_split_f16_two_destinations():
     """One launch writes the fp16 pair of x and, into a column slot of another buffer, the pair of scale2 * x."""
     from idrk import kernels as K
