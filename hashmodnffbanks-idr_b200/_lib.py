@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libidrk.so")
 MAX_LEVELS = 32
 HASH_REFERENCE = 0
 HASH_TRILINEAR = 1
+HASH_NGP = 2          # tiny-cuda-nn grid semantics (include/idrk.h)
 
 
 class IdrkError(RuntimeError):

@@ -60,7 +60,7 @@ class _HashEncode(torch.autograd.Function):
                 xp = torch.matmul(TWO_PI * x[:, :3], B)
                 dxp = dy[:, 3:3 + C] * torch.cos(xp) - dy[:, 3 + C:3 + 2 * C] * torch.sin(xp)
                 dx = dy[:, :3] + TWO_PI * torch.matmul(dxp, B.t())
-            if spec.frac_mode == K._lib.HASH_TRILINEAR:
+            if spec.frac_mode != K._lib.HASH_REFERENCE:
                 with torch.no_grad():
                     zero_pre = dy.detach().clone()
                     if C > 0:
@@ -71,7 +71,7 @@ class _HashEncode(torch.autograd.Function):
                 with torch.no_grad():
                     K.hash_encode_bwd(spec, x.detach(), tables, B, dy.detach(), gt, False) if spec.n_levels else None
         elif need_dx or need_tab:
-            kernel_dx = need_dx and (C > 0 or spec.frac_mode == K._lib.HASH_TRILINEAR)
+            kernel_dx = need_dx and (C > 0 or spec.frac_mode != K._lib.HASH_REFERENCE)
             if kernel_dx or (need_tab and spec.n_levels > 0):
                 with torch.no_grad():
                     dx = K.hash_encode_bwd(spec, x.detach(), tables, B, dy.detach(), gt, kernel_dx)

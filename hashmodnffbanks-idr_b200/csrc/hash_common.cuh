@@ -1,5 +1,6 @@
 // Device helpers shared by the hash-grid kernels (hash_encode.cu) and the fused filter-bank encoder (nffb.cu).
 #pragma once
+#include <math.h>
 #include "common.cuh"
 
 namespace idrk {
@@ -12,6 +13,8 @@ struct GridDev {
     unsigned long long magic[IDRK_MAX_LEVELS];   // 2^64 / rows + 1 (Lemire fastmod), used when rows is not a power of two
     const float* tables[IDRK_MAX_LEVELS];
     const float* B;                         // [3, C]
+    uint32_t ngp_res[IDRK_MAX_LEVELS];      // IDRK_HASH_NGP: grid resolution R_l = ceil(scale_l) + 1
+    uint32_t ngp_dense[IDRK_MAX_LEVELS];    // IDRK_HASH_NGP: 1 = dense indexing (R^3 <= rows), 0 = hashed
     int pair_x;                             // 8-corner mode: x-neighbour corners share one 16-byte access when they can
 };
 
@@ -71,7 +74,8 @@ inline int fill_grid(const idrk_hashgrid_t* h, GridDev& g) {
     if (h->n_feat != 1 && h->n_feat != 2 && h->n_feat != 4 && h->n_feat != 8) return IDRK_E_UNSUP;
     if (h->n_fourier < 0 || h->n_fourier > 64) return IDRK_E_ARG;
     if (h->n_fourier > 0 && h->fourier_B == nullptr) return IDRK_E_ARG;
-    if (h->frac_mode != IDRK_HASH_REFERENCE && h->frac_mode != IDRK_HASH_TRILINEAR) return IDRK_E_ARG;
+    if (h->frac_mode != IDRK_HASH_REFERENCE && h->frac_mode != IDRK_HASH_TRILINEAR && h->frac_mode != IDRK_HASH_NGP) return IDRK_E_ARG;
+    if (h->frac_mode == IDRK_HASH_NGP && h->n_feat != 2) return IDRK_E_UNSUP;
     g.n_levels = h->n_levels; g.n_feat = h->n_feat; g.n_fourier = h->n_fourier;
     g.width = (h->n_fourier > 0 ? 3 + 2 * h->n_fourier : 0) + h->n_levels * h->n_feat;
     g.B = h->fourier_B;
@@ -84,8 +88,15 @@ inline int fill_grid(const idrk_hashgrid_t* h, GridDev& g) {
         g.pow2mask[l] = ((h->rows[l] & (h->rows[l] - 1)) == 0) ? h->rows[l] - 1 : 0;
         g.magic[l] = ~0ull / h->rows[l] + 1ull;
         if (h->rows[l] == 1) { g.pow2mask[l] = 0; g.magic[l] = 0; }
+        g.ngp_res[l] = 0; g.ngp_dense[l] = 0;
+        if (h->frac_mode == IDRK_HASH_NGP) {
+            if (!(h->res[l] > 0.f) || h->res[l] > 1.0e6f) return IDRK_E_ARG;
+            const unsigned long long R = (unsigned long long)ceilf(h->res[l]) + 1ull;
+            g.ngp_res[l] = (uint32_t)R;
+            g.ngp_dense[l] = (R * R * R <= (unsigned long long)h->rows[l]) ? 1u : 0u;
+        }
     }
-    for (int l = h->n_levels; l < IDRK_MAX_LEVELS; ++l) { g.res[l] = 0; g.rows[l] = 1; g.tables[l] = nullptr; g.pow2mask[l] = 0; g.magic[l] = 0; }
+    for (int l = h->n_levels; l < IDRK_MAX_LEVELS; ++l) { g.res[l] = 0; g.rows[l] = 1; g.tables[l] = nullptr; g.pow2mask[l] = 0; g.magic[l] = 0; g.ngp_res[l] = 0; g.ngp_dense[l] = 0; }
     return 0;
 }
 

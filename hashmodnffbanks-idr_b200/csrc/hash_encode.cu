@@ -56,18 +56,57 @@ __device__ __forceinline__ void scatter_add(float* table, uint32_t idx, const fl
 // ~0.7 KB of shared memory per warp, occupancy limited by registers only.  When L (or C) divides 32 a lane's
 // level (frequency) never changes, so its constants - resolution, rows, fastmod magic, table pointer, B column -
 // live in registers for the whole kernel.
-struct LevelC {                      // 32 bytes, read as two 16-byte shared loads
+struct LevelC {                      // 48 bytes, read as 16-byte shared loads (the third only in IDRK_HASH_NGP kernels)
     float res; uint32_t rows, mask, soff;
     unsigned long long magic; const float* tab;
+    uint32_t ngp_res, ngp_dense, pad0, pad1;
 };
 
+template <bool NGP = false>
 __device__ __forceinline__ LevelC load_level(const LevelC* s_lev, int l) {
-    const uint4 a = reinterpret_cast<const uint4*>(s_lev)[2 * l], b = reinterpret_cast<const uint4*>(s_lev)[2 * l + 1];
+    const uint4 a = reinterpret_cast<const uint4*>(s_lev)[3 * l], b = reinterpret_cast<const uint4*>(s_lev)[3 * l + 1];
     LevelC c;
     c.res = __uint_as_float(a.x); c.rows = a.y; c.mask = a.z; c.soff = a.w;
     c.magic = ((unsigned long long)b.y << 32) | b.x;
     c.tab = reinterpret_cast<const float*>(((unsigned long long)b.w << 32) | b.z);
+    c.ngp_res = 0; c.ngp_dense = 0; c.pad0 = 0; c.pad1 = 0;
+    if constexpr (NGP) { const uint4 d = reinterpret_cast<const uint4*>(s_lev)[3 * l + 2]; c.ngp_res = d.x; c.ngp_dense = d.y; }
     return c;
+}
+
+// The 8 corner rows and the 3 interpolation weights of one (point, level) element in the 8-corner modes.
+//   IDRK_HASH_TRILINEAR: the reference's hash (primes 1, 3, 2654435761) on floor(x * res).
+//   IDRK_HASH_NGP: tiny-cuda-nn's grid (pos = fma(x, scale, 0.5); dense stride index while the level fits its table,
+//   else the coherent prime hash 1, 2654435761, 805459861); corner bit 0 = x, bit 1 = y, bit 2 = z in both.
+template <int MODE, bool FAST>
+__device__ __forceinline__ void corner_rows(const LevelC& lc, float x0, float x1, float x2, uint32_t (&idx)[8],
+                                            float& w0, float& w1, float& w2, uint32_t& c0_out) {
+    float s0, s1, s2;
+    if constexpr (MODE == IDRK_HASH_NGP) { s0 = fmaf(x0, lc.res, 0.5f); s1 = fmaf(x1, lc.res, 0.5f); s2 = fmaf(x2, lc.res, 0.5f); }
+    else { s0 = __fmul_rn(x0, lc.res); s1 = __fmul_rn(x1, lc.res); s2 = __fmul_rn(x2, lc.res); }
+    const float f0 = floorf(s0), f1 = floorf(s1), f2 = floorf(s2);
+    w0 = s0 - f0; w1 = s1 - f1; w2 = s2 - f2;
+    uint32_t c0, c1, c2;
+    if constexpr (FAST) { c0 = (uint32_t)__float2int_rz(f0); c1 = (uint32_t)__float2int_rz(f1); c2 = (uint32_t)__float2int_rz(f2); }
+    else { c0 = trunc_u32(f0); c1 = trunc_u32(f1); c2 = trunc_u32(f2); }
+    c0_out = c0;
+    if constexpr (MODE == IDRK_HASH_NGP) {
+        const bool dense = lc.ngp_dense != 0;
+        const uint32_t R = lc.ngp_res, py = dense ? R : 2654435761u, pz = dense ? R * R : 805459861u;
+        const uint32_t hx0 = c0, hx1 = c0 + 1u, hy0 = c1 * py, hy1 = hy0 + py, hz0 = c2 * pz, hz1 = hz0 + pz;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t a = (k & 1) ? hx1 : hx0, b = (k & 2) ? hy1 : hy0, c = (k & 4) ? hz1 : hz0;
+            idx[k] = wrap(dense ? a + b + c : a ^ b ^ c, lc.rows, lc.mask, lc.magic);
+        }
+    } else {
+        // hash3 is an xor of three per-dimension terms: form the 2 x 3 terms once, xor per corner
+        const uint32_t hx0 = c0, hx1 = c0 + 1u, hy0 = c1 * 3u, hy1 = hy0 + 3u;
+        const uint32_t hz0 = c2 * 2654435761u, hz1 = hz0 + 2654435761u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            idx[k] = wrap(((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0), lc.rows, lc.mask, lc.magic);
+    }
 }
 template <bool FAST> __device__ __forceinline__ uint32_t trunc_sel(float v) {
     if constexpr (FAST) return (uint32_t)__float2int_rz(v); else return trunc_u32(v);
@@ -89,16 +128,12 @@ __device__ __forceinline__ void fwd_element(const LevelC& lc, float x0, float x1
         const uint32_t h = hash3(trunc_sel<FAST>(s0), trunc_sel<FAST>(s1), trunc_sel<FAST>(s2));
         gather<F>(lc.tab, wrap(h, lc.rows, lc.mask, lc.magic), acc);
     } else {
-        const float f0 = floorf(s0), f1 = floorf(s1), f2 = floorf(s2);
-        const float w0 = s0 - f0, w1 = s1 - f1, w2 = s2 - f2;
-        const uint32_t c0 = trunc_sel<FAST>(f0), c1 = trunc_sel<FAST>(f1), c2 = trunc_sel<FAST>(f2);
-        // hash3 is an xor of three per-dimension terms: form the 2 x 3 terms once, xor per corner
-        const uint32_t hx0 = c0, hx1 = c0 + 1u, hy0 = c1 * 3u, hy1 = hy0 + 3u;
-        const uint32_t hz0 = c2 * 2654435761u, hz1 = hz0 + 2654435761u;
+        float w0, w1, w2;
+        uint32_t idx[8], c0;
+        corner_rows<MODE, FAST>(lc, x0, x1, x2, idx, w0, w1, w2, c0);
         float v[8][F];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            gather<F>(lc.tab, wrap(((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0), lc.rows, lc.mask, lc.magic), v[k]);
+        for (int k = 0; k < 8; ++k) gather<F>(lc.tab, idx[k], v[k]);
 #pragma unroll
         for (int f = 0; f < F; ++f) acc[f] = 0.f;
 #pragma unroll
@@ -132,7 +167,7 @@ __device__ __forceinline__ void fwd_levels_generic(const LevelC* s_lev, const fl
     const int total = rows_here * L;
     for (int e = lane; e < total; e += 32) {
         const int row = e / L, l = e - row * L;
-        const LevelC lc = load_level(s_lev, l);
+        const LevelC lc = load_level<MODE == IDRK_HASH_NGP>(s_lev, l);
         const float4 xv = xs[row];
         float acc[F];
         fwd_element<F, MODE, false>(lc, xv.x, xv.y, xv.z, acc);
@@ -192,10 +227,11 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
     const int C = g.n_fourier, L = g.n_levels;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     LevelC* s_lev = reinterpret_cast<LevelC*>(smem_u4);                               // [L]
-    float4* xs = reinterpret_cast<float4*>(smem_u4 + 2 * L) + warp * 32;              // [32] per warp
-    float* s_B = reinterpret_cast<float*>(smem_u4 + 2 * L + WARPS * 32);              // [3][C]
+    float4* xs = reinterpret_cast<float4*>(smem_u4 + 3 * L) + warp * 32;              // [32] per warp
+    float* s_B = reinterpret_cast<float*>(smem_u4 + 3 * L + WARPS * 32);              // [3][C]
     for (int i = threadIdx.x; i < L; i += WARPS * 32) {
         LevelC c; c.res = g.res[i]; c.rows = g.rows[i]; c.mask = g.pow2mask[i]; c.soff = 0; c.magic = g.magic[i]; c.tab = g.tables[i];
+        c.ngp_res = g.ngp_res[i]; c.ngp_dense = g.ngp_dense[i]; c.pad0 = 0; c.pad1 = 0;
         s_lev[i] = c;
     }
     for (int i = threadIdx.x; i < 3 * C; i += WARPS * 32) s_B[i] = g.B[i];
@@ -210,7 +246,7 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
     const bool c_fixed = C >= 2 && (32 % C) == 0 && al8;    // lane <-> frequency is fixed, aligned pair stores
     float res_max = 0.f;
     for (int l = 0; l < L; ++l) res_max = fmaxf(res_max, fabsf(g.res[l]));
-    LevelC lc = load_level(s_lev, L > 0 ? lane % L : 0);
+    LevelC lc = load_level<MODE == IDRK_HASH_NGP>(s_lev, L > 0 ? lane % L : 0);
     // Fourier prefix, c_fixed: column 3 + j is even for odd j, so odd lanes store the aligned pairs (s_j, s_j+1) and
     // (c_j, c_j+1) - the partner value comes from the next lane - lane j = 0 stores (x2, s_0) and one even lane
     // (x0, x1): every sector of the prefix is written in full 8-byte words.
@@ -294,6 +330,13 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
                 const float r = g.res[l];
                 const float s0 = __fmul_rn(xv.x, r), s1 = __fmul_rn(xv.y, r), s2 = __fmul_rn(xv.z, r);
                 uint32_t c0, c1, c2;
+                if constexpr (MODE == IDRK_HASH_NGP) {
+                    const LevelC lcd = load_level<true>(s_lev, l);
+                    uint32_t id8[8], cc; float q0, q1, q2;
+                    corner_rows<MODE, false>(lcd, xv.x, xv.y, xv.z, id8, q0, q1, q2, cc);
+                    for (int k = 0; k < 8; ++k) idx_dbg[((p0 + row) * L + l) * 8 + k] = id8[k];
+                    continue;
+                }
                 if constexpr (MODE == IDRK_HASH_REFERENCE) { c0 = trunc_u32(s0); c1 = trunc_u32(s1); c2 = trunc_u32(s2); }
                 else { c0 = trunc_u32(floorf(s0)); c1 = trunc_u32(floorf(s1)); c2 = trunc_u32(floorf(s2)); }
                 for (int k = 0; k < 8; ++k)
@@ -330,15 +373,9 @@ __device__ __forceinline__ void bwd_element(const LevelC& lc, float* gtab, float
         const uint32_t h = hash3(trunc_sel<FAST>(s0), trunc_sel<FAST>(s1), trunc_sel<FAST>(s2));
         scatter_sel<F>(gtab, s_acc, lc.soff, wrap(h, lc.rows, lc.mask, lc.magic), gy);
     } else {
-        const float f0 = floorf(s0), f1 = floorf(s1), f2 = floorf(s2);
-        const float w0 = s0 - f0, w1 = s1 - f1, w2 = s2 - f2;
-        const uint32_t c0 = trunc_sel<FAST>(f0), c1 = trunc_sel<FAST>(f1), c2 = trunc_sel<FAST>(f2);
-        const uint32_t hx0 = c0, hx1 = c0 + 1u, hy0 = c1 * 3u, hy1 = hy0 + 3u;
-        const uint32_t hz0 = c2 * 2654435761u, hz1 = hz0 + 2654435761u;
-        uint32_t idx[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            idx[k] = wrap(((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0), lc.rows, lc.mask, lc.magic);
+        float w0, w1, w2;
+        uint32_t idx[8], c0;
+        corner_rows<MODE, FAST>(lc, x0, x1, x2, idx, w0, w1, w2, c0);
         float t[8][F];
         if constexpr (WANT_DX) {
 #pragma unroll
@@ -405,7 +442,7 @@ __device__ __forceinline__ void bwd_levels_generic(const LevelC* s_lev, float* c
     const int total = rows_here * L;
     for (int e = lane; e < total; e += 32) {
         const int row = e / L, l = e - row * L;
-        const LevelC lc = load_level(s_lev, l);
+        const LevelC lc = load_level<MODE == IDRK_HASH_NGP>(s_lev, l);
         const float* o = drow0 + row * ld_dy + l * F;
         float gy[F];
 #pragma unroll
@@ -413,7 +450,7 @@ __device__ __forceinline__ void bwd_levels_generic(const LevelC* s_lev, float* c
         float d[3] = {0.f, 0.f, 0.f};
         const float4 xv = xs[row];
         bwd_element<F, MODE, false, WANT_DX>(lc, s_grad[l], s_acc, xv.x, xv.y, xv.z, gy, d);
-        if constexpr (WANT_DX && MODE == IDRK_HASH_TRILINEAR) {
+        if constexpr (WANT_DX && MODE != IDRK_HASH_REFERENCE) {
             atomicAdd(dxs + 4 * row, d[0]); atomicAdd(dxs + 4 * row + 1, d[1]); atomicAdd(dxs + 4 * row + 2, d[2]);
         }
     }
@@ -454,7 +491,7 @@ __device__ __forceinline__ void bwd_levels_full(const LevelC& lc, float* gtab, f
                 const float4 xv = xs[row];
                 float d[3] = {0.f, 0.f, 0.f};
                 bwd_element<F, MODE, true, WANT_DX, PAIR>(lc, gtab, s_acc, xv.x, xv.y, xv.z, gy[k], d, pair_lane);
-                if constexpr (WANT_DX && MODE == IDRK_HASH_TRILINEAR) row_reduce_add(dxs, row, true, L, true, lane, d[0], d[1], d[2]);
+                if constexpr (WANT_DX && MODE != IDRK_HASH_REFERENCE) row_reduce_add(dxs, row, true, L, true, lane, d[0], d[1], d[2]);
             }
         }
     }
@@ -470,14 +507,15 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
     const int C = g.n_fourier, L = g.n_levels;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     LevelC* s_lev = reinterpret_cast<LevelC*>(smem_u4);                               // [L]
-    float4* xs = reinterpret_cast<float4*>(smem_u4 + 2 * L) + warp * 32;              // [32] per warp
-    float* dxs = reinterpret_cast<float*>(smem_u4 + 2 * L + WARPS * 32) + warp * 128; // [32][4] per warp
-    float** s_grad = reinterpret_cast<float**>(smem_u4 + 2 * L + 2 * WARPS * 32);     // [L] (padded to even)
+    float4* xs = reinterpret_cast<float4*>(smem_u4 + 3 * L) + warp * 32;              // [32] per warp
+    float* dxs = reinterpret_cast<float*>(smem_u4 + 3 * L + WARPS * 32) + warp * 128; // [32][4] per warp
+    float** s_grad = reinterpret_cast<float**>(smem_u4 + 3 * L + 2 * WARPS * 32);     // [L] (padded to even)
     float* s_B = reinterpret_cast<float*>(s_grad + ((L + 1) & ~1));                   // [3][C]
     float* s_acc = s_B + ((3 * C + 3) & ~3);                                          // [small_total]
     for (int i = threadIdx.x; i < L; i += WARPS * 32) {
         LevelC c; c.res = g.res[i]; c.rows = g.rows[i]; c.mask = g.pow2mask[i];
         c.soff = gd.small_off[i] >= 0 ? (uint32_t)gd.small_off[i] : 0xffffffffu; c.magic = g.magic[i]; c.tab = g.tables[i];
+        c.ngp_res = g.ngp_res[i]; c.ngp_dense = g.ngp_dense[i]; c.pad0 = 0; c.pad1 = 0;
         s_lev[i] = c;
         s_grad[i] = gd.grad[i];
     }
@@ -488,7 +526,7 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
     const bool has_pad = ld_dy > g.width;
     const bool l_fixed = L > 0 && (32 % L) == 0;
     const bool shift = F == 2 && l_fixed && (pre & 1) && has_pad && (ld_dy & 1) == 0 && (reinterpret_cast<uintptr_t>(dy) & 7u) == 0;
-    const LevelC lc = load_level(s_lev, L > 0 ? lane % L : 0);
+    const LevelC lc = load_level<MODE == IDRK_HASH_NGP>(s_lev, L > 0 ? lane % L : 0);
     float* gtab = L > 0 ? s_grad[lane % L] : nullptr;
     const bool want_dx = dx != nullptr;
     // paired reductions need the gradient table (not the value table) on a 16-byte boundary
@@ -552,7 +590,7 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
             if (jstep != 0) { const int j0 = lane % C; b0 = s_B[j0]; b1 = s_B[C + j0]; b2 = s_B[2 * C + j0]; }
         }
         __syncwarp();
-        if (L > 0 && (MODE == IDRK_HASH_TRILINEAR || gd.any_grad)) {
+        if (L > 0 && (MODE != IDRK_HASH_REFERENCE || gd.any_grad)) {
             const float amax = fmaxf(fabsf(x0), fmaxf(fabsf(x1), fabsf(x2))) * res_max;
             const bool fast = __all_sync(0xffffffffu, amax < 2147483520.f);
             if (fast && rows_here == 32 && l_fixed) {
@@ -608,12 +646,12 @@ static int persistent_grid(K kernel, int threads, size_t smem, long long n_tiles
 template <int F, int MODE, int WARPS>
 static int launch_fwd(const GridDev& g, const float* x, long long n, int ldx, float* out, int ld_out,
                       uint32_t* idx_dbg, const int* m_count, cudaStream_t st) {
-    const size_t smem = ((size_t)2 * g.n_levels + WARPS * 32) * 16 + (size_t)3 * g.n_fourier * sizeof(float);
+    const size_t smem = ((size_t)3 * g.n_levels + WARPS * 32) * 16 + (size_t)3 * g.n_fourier * sizeof(float);
     auto kern = hash_encode_fwd_elem_kernel<F, MODE, WARPS>;
     // 8-corner, F = 2: capping the kernel at 4 resident CTAs per SM (118 registers instead of 80) lets ptxas keep both
     // batched elements' 16 gathers in flight: +5 % with L2-resident tables, +27 % / +12 % at T = 2^22 / 2^24 where every
     // gather is a DRAM sector read (profiles/r01_hash_pair_ab.txt)
-    if constexpr (F == 2 && MODE == IDRK_HASH_TRILINEAR) kern = hash_encode_fwd_elem_kernel<F, MODE, WARPS, 4>;
+    if constexpr (F == 2 && MODE != IDRK_HASH_REFERENCE) kern = hash_encode_fwd_elem_kernel<F, MODE, WARPS, 4>;
     const int grid = persistent_grid(kern, WARPS * 32, smem, (n + WARPS * 32 - 1) / (WARPS * 32));
     IDRK_CUDA_TRY(launch_k(kern, dim3(grid), dim3(WARPS * 32), smem, st, g, x, n, ldx, out, ld_out, idx_dbg, m_count));
     IDRK_LAUNCH_CHECK();
@@ -624,7 +662,7 @@ template <int F, int MODE, int WARPS>
 static int launch_bwd(const GridDev& g, const GradDev& gd, const float* x, long long n, int ldx, const float* dy,
                       int ld_dy, float* dx, cudaStream_t st) {
     const int L = g.n_levels, C = g.n_fourier;
-    const size_t smem = ((size_t)2 * L + 2 * WARPS * 32) * 16 + (size_t)((L + 1) & ~1) * 8 +
+    const size_t smem = ((size_t)3 * L + 2 * WARPS * 32) * 16 + (size_t)((L + 1) & ~1) * 8 +
                         (size_t)((3 * C + 3) & ~3) * 4 + (size_t)gd.small_total * 4;
     auto kern = hash_encode_bwd_elem_kernel<F, MODE, WARPS>;
     IDRK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -644,6 +682,7 @@ static int launch_bwd(const GridDev& g, const GradDev& gd, const float* x, long 
         case 4 * 2 + 1: return CALL(4, IDRK_HASH_TRILINEAR);                                   \
         case 8 * 2 + 0: return CALL(8, IDRK_HASH_REFERENCE);                                   \
         case 8 * 2 + 1: return CALL(8, IDRK_HASH_TRILINEAR);                                   \
+        case 2 * 2 + 2: return CALL(2, IDRK_HASH_NGP);                                         \
         default: return IDRK_E_UNSUP;                                                          \
     }
 

@@ -43,10 +43,11 @@ class HashGridSpec:
     """Host-side description of one multi-resolution grid (levels + optional Fourier prefix)."""
 
     def __init__(self, res: Sequence[int], rows: Sequence[int], n_feat: int, frac_mode: int, n_fourier: int):
-        self.res = [int(r) for r in res]
+        self.frac_mode = int(frac_mode)
+        # reference / 8-corner modes: integer resolutions; HASH_NGP: the (float) per-level scale base * s^l - 1
+        self.res = [float(r) if self.frac_mode == _lib.HASH_NGP else int(r) for r in res]
         self.rows = [int(r) for r in rows]
         self.n_feat = int(n_feat)
-        self.frac_mode = int(frac_mode)
         self.n_fourier = int(n_fourier)
 
     @property

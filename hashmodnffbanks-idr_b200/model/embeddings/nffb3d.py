@@ -25,6 +25,15 @@ from .style_Attention.styleMod import StyleAttention
 
 
 class FourierFilterBanks(nn.Module):
+    WIDTH_MULT = 2          # trunk width = 2 x the positional encoding's width (nffb3d.py:67-69)
+
+    def _make_grid(self, cfg):
+        return MultiResHashGridMLP(self.include_input, self.num_inputs, self.n_levels, self.max_points_per_level,
+                                   cfg['log2_hashmap_size'], cfg['base_resolution'], cfg['desired_resolution'])
+
+    def _chunk_width(self):
+        return 2 * self.max_points_per_level          # the reference's chunking of the grid columns (nffb3d.py:137-139)
+
     def __init__(self, GridEncoderNetConfig, freq_enc_type, has_out, bound, layers_type, style_modulation=False):
         super().__init__()
         cfg = GridEncoderNetConfig
@@ -41,14 +50,12 @@ class FourierFilterBanks(nn.Module):
         self.grid_levels = self.n_levels
         if 2 + self.max_points_per_level != 2 * self.max_points_per_level:
             raise ValueError("the reference's chunking (nffb3d.py:137-139) requires max_points_per_entry == 2")
-        self.grid_enc = MultiResHashGridMLP(self.include_input, self.num_inputs, self.n_levels,
-                                            self.max_points_per_level, cfg['log2_hashmap_size'],
-                                            cfg['base_resolution'], cfg['desired_resolution'])
+        self.grid_enc = self._make_grid(cfg)
         enc = [PositionalEncoding(include_input=self.include_input, input_dims=self.max_points_per_level,
                                   max_freq_log2=self.n_levels - 1, num_freqs=self.n_levels, log_sampling=True,
                                   periodic_fns=[torch.sin, torch.cos]) for _ in range(self.grid_levels)]
         self.ff_enc = nn.Sequential(*enc)
-        width = 2 * enc[-1].embeddings_dim
+        width = self.WIDTH_MULT * enc[-1].embeddings_dim
         self.nffb_lin_dims = [self.num_inputs] + [width] * (self.grid_levels - 1)
         self.n_nffb_layers = len(self.nffb_lin_dims)
         assert self.n_nffb_layers >= 3, "The NFFB should have at least 3 levels"
@@ -76,7 +83,7 @@ class FourierFilterBanks(nn.Module):
                 sine_init(lin, self.sin_w0)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
-        L, F2 = self.grid_levels, 2 * self.max_points_per_level
+        L, F2 = self.grid_levels, self._chunk_width()
         z = input / self.bound
         u = (input + self.bound) / (2 * self.bound)
         grid = self.grid_enc(u)[..., input.shape[-1]:]

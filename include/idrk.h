@@ -33,6 +33,14 @@ extern "C" {
 #define IDRK_HASH_REFERENCE 0  /* reference semantics: xf == 0, floor-corner row, trunc toward zero
                                   (model/embeddings/hashGridEmbedding.py:84-102)                */
 #define IDRK_HASH_TRILINEAR 1  /* floor/frac with 8 weighted corners (documented extension)     */
+#define IDRK_HASH_NGP       2  /* instant-ngp / tiny-cuda-nn grid semantics, what tcnn.Encoding("Grid", "Hash", "Linear")
+                                  computes for the reference's HashGridTcnn / FFBTcnn selector entries
+                                  (model/embeddings/tcnn_src/hashGridEncoderTcnn.py:63-80; tiny-cuda-nn itself is an unpinned,
+                                  un-vendored dependency, so this follows its published algorithm): inputs in [0, 1],
+                                  pos = fma(x, scale_l, 0.5) with scale_l = res[l] = base * per_level_scale^l - 1,
+                                  grid resolution R_l = ceil(scale_l) + 1, 8 corners weighted by pos - floor(pos);
+                                  table row = x + y R + z R^2 when R^3 <= rows[l] (dense level), else
+                                  (x * 1) ^ (y * 2654435761) ^ (z * 805459861); both taken mod rows[l].  F = 2 only. */
 
 /* Host-side description of one MultiResHashGridMLP (model/embeddings/hashGridEmbedding.py:105-155).
  * Output row layout: [x(3) | sin(C) | cos(C) | level_0(F) ... level_{L-1}(F)], C = n_fourier.

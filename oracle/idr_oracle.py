@@ -97,6 +97,98 @@ def hash_level(x: Tensor, table: Tensor, res: int, mode: str = "reference") -> T
     return feats
 
 
+# --------------------------------------------------------------------------------------
+# tiny-cuda-nn grid semantics (HashGridTcnn / FFBTcnn)      tcnn_src/hashGridEncoderTcnn.py:63-80
+# --------------------------------------------------------------------------------------
+# PARITY UNPINNED for this block: the arithmetic lives in tiny-cuda-nn (NVlabs), which the reference installs from
+# git HEAD (README.md:58-60; absent from requirements.txt / environment.yml) and which is not present under
+# /root/reference nor importable here; the reference holds no test or vector at that boundary.  What follows restates
+# tiny-cuda-nn's published Grid encoding (include/tiny-cuda-nn/encodings/grid.h: grid_scale, grid_resolution,
+# pos_fract, grid_index, coherent prime hash; GridEncodingTemplated ctor for the per-level parameter counts) for
+# otype "Grid", type "Hash", interpolation "Linear", as configured at tcnn_src/hashGridEncoderTcnn.py:63-80.
+NGP_PRIME_Y = 2654435761
+NGP_PRIME_Z = 805459861
+
+
+def ngp_level_layout(n_levels: int, log2_T: int, base_res: int, per_level_scale: float):
+    """(scale_l, R_l, rows_l, row offsets) per level: scale = exp2f(l * log2f(s)) * base - 1, R = ceil(scale) + 1,
+    rows = min(next_multiple(R^3, 8), 2^log2_T)."""
+    log2s = np.float32(math.log2(per_level_scale))
+    scales, res, rows, offs = [], [], [], [0]
+    for l in range(n_levels):
+        sc = np.float32(np.exp2(np.float32(l) * log2s) * np.float32(base_res) - np.float32(1.0))
+        R = int(np.ceil(sc)) + 1
+        n = min(R ** 3, (2 ** 32 - 1) // 2)
+        n = min(((n + 7) // 8) * 8, 1 << log2_T)
+        scales.append(float(sc)); res.append(R); rows.append(n); offs.append(offs[-1] + n)
+    return scales, res, rows, offs
+
+
+def ngp_corner_rows(x: Tensor, scale: float, R: int, rows: int) -> Tuple[np.ndarray, Tensor]:
+    """(rows [P, 8] int64, frac [P, 3]) of one level: pos = fma(x, scale, 0.5); vertex = floor(pos) (+1 per set corner
+    bit, bit d of k <-> dimension d); dense stride index while R^3 <= rows, else the coherent prime hash; mod rows."""
+    x32 = x.detach().to(torch.float32).numpy()
+    pos = (x32.astype(np.float64) * np.float64(np.float32(scale)) + 0.5).astype(np.float32)     # fma: one rounding
+    fl = np.floor(pos)
+    frac = torch.from_numpy(pos - fl)
+    g = fl.astype(np.int64)
+    dense = R ** 3 <= rows
+    out = np.empty((x32.shape[0], 8), dtype=np.int64)
+    M = np.uint64(0xFFFFFFFF)
+    for k in range(8):
+        c = [(g[:, d] + ((k >> d) & 1)).astype(np.uint64) & M for d in range(3)]
+        if dense:
+            idx = (c[0] + ((c[1] * np.uint64(R)) & M) + ((c[2] * np.uint64(R * R)) & M)) & M
+        else:
+            idx = c[0] ^ ((c[1] * np.uint64(NGP_PRIME_Y)) & M) ^ ((c[2] * np.uint64(NGP_PRIME_Z)) & M)
+        out[:, k] = (idx % np.uint64(rows)).astype(np.int64)
+    return out, frac
+
+
+def ngp_grid_encode(x: Tensor, params: Tensor, n_levels: int, n_feat: int, log2_T: int, base_res: int,
+                    per_level_scale: float = 2.0) -> Tensor:
+    """tcnn.Encoding("Grid", "Hash", "Linear")(x) for x in [0, 1]^3 -> [P, L * F]; differentiable in `params` (the flat
+    parameter vector, level-major, rows of F) - the gradient w.r.t. x follows from the trilinear weights
+    (d/dx = scale * sum_k dw_k/dfrac * row_k) and is returned by ngp_grid_dx."""
+    scales, res, rows, offs = ngp_level_layout(n_levels, log2_T, base_res, per_level_scale)
+    feats = []
+    for l in range(n_levels):
+        table = params[offs[l] * n_feat: offs[l + 1] * n_feat].view(rows[l], n_feat)
+        idx, fr = ngp_corner_rows(x, scales[l], res[l], rows[l])
+        idx = torch.from_numpy(idx)
+        acc = torch.zeros(x.shape[0], n_feat, dtype=torch.float32)
+        for k in range(8):
+            w = torch.ones(x.shape[0], dtype=torch.float32)
+            for d in range(3):
+                w = w * (fr[:, d] if (k >> d) & 1 else (1.0 - fr[:, d]))
+            acc = acc + w[:, None] * table[idx[:, k]]
+        feats.append(acc)
+    return torch.cat(feats, dim=-1)
+
+
+def ngp_grid_dx(x: Tensor, params: Tensor, dy: Tensor, n_levels: int, n_feat: int, log2_T: int, base_res: int,
+                per_level_scale: float = 2.0) -> Tensor:
+    """dL/dx [P, 3] of ngp_grid_encode for upstream dy [P, L * F] (piecewise: valid inside a cell)."""
+    scales, res, rows, offs = ngp_level_layout(n_levels, log2_T, base_res, per_level_scale)
+    dx = torch.zeros(x.shape[0], 3, dtype=torch.float64)
+    for l in range(n_levels):
+        table = params.detach()[offs[l] * n_feat: offs[l + 1] * n_feat].view(rows[l], n_feat).double()
+        idx, fr = ngp_corner_rows(x, scales[l], res[l], rows[l])
+        idx, fr = torch.from_numpy(idx), fr.double()
+        g = dy[:, l * n_feat:(l + 1) * n_feat].double()
+        for k in range(8):
+            dot = (table[idx[:, k]] * g).sum(-1)
+            for d in range(3):
+                w = torch.ones(x.shape[0], dtype=torch.float64)
+                for e in range(3):
+                    if e == d:
+                        w = w * (1.0 if (k >> e) & 1 else -1.0)
+                    else:
+                        w = w * (fr[:, e] if (k >> e) & 1 else (1.0 - fr[:, e]))
+                dx[:, d] += w * dot * float(np.float32(scales[l]))
+    return dx.float()
+
+
 def fourier_feature(x: Tensor, B: Tensor, include_input: bool = True) -> Tensor:
     """[x | sin(2*pi*x@B) | cos(2*pi*x@B)].  frequency_enc.py:63-67"""
     proj = torch.matmul(2 * np.pi * x, B)
