@@ -97,6 +97,48 @@ class DataParallelTrainer:
         self._static_out = None
         self._graph_key = None
 
+    # -- optimiser state in torch.optim.Adam's format ---------------------------------------------
+    def optimizer_state_dict(self) -> Dict:
+        """State of the fused clip + Adam in the layout of `torch.optim.Adam(model.parameters()).state_dict()` - what the
+        reference writes to OptimizerParameters/*.pth (training/idr_train.py:185-190) - so a run can move between the
+        reference's optimiser and this trainer in either direction."""
+        b = self.bucket
+        state = {}
+        if self.t > 0:
+            for i, (p, o) in enumerate(zip(b.params, b.offsets)):
+                state[i] = {"step": torch.tensor(float(self.t)),
+                            "exp_avg": self.m[o:o + p.numel()].view_as(p).clone(),
+                            "exp_avg_sq": self.v[o:o + p.numel()].view_as(p).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(b.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: Dict) -> None:
+        b = self.bucket
+        groups = sd["param_groups"]
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(b.params):
+            raise ValueError("optimizer state has %d parameters, the model %d" % (len(order), len(b.params)))
+        self.lr = float(groups[0]["lr"])
+        self.betas = tuple(float(x) for x in groups[0]["betas"])
+        self.eps = float(groups[0]["eps"])
+        self.m.zero_()
+        self.v.zero_()
+        steps = set()
+        for i, (p, o) in zip(order, zip(b.params, b.offsets)):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError("optimizer state %d has shape %s, parameter %s" % (i, tuple(st["exp_avg"].shape), tuple(p.shape)))
+            self.m[o:o + p.numel()].view_as(p).copy_(st["exp_avg"])
+            self.v[o:o + p.numel()].view_as(p).copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ (%s): the fused optimiser keeps one" % sorted(steps))
+        self.t = steps.pop() if steps else 0
+
     # -- differentiable part ---------------------------------------------------------------------
     def _shade_and_backward(self, traced, eik, rgb):
         K.ZERO_POOL.begin(self.bucket.flat.device)       # one fill for every zero-initialised scratch of the step

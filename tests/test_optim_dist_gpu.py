@@ -61,3 +61,57 @@ def test_trainer_step_reduces_loss_and_matches_manual_step(use_graph):
     for _ in range(5):
         last = float(tr.step(inp, gt))
     assert last < first
+
+
+def test_trainer_checkpoint_roundtrip_and_handover_to_torch_adam(tmp_path):
+    """Reference-layout checkpoint (utils/checkpoints.py) written by the trainer after 2 steps: (a) a fresh trainer
+    restored from it takes a bit-identical 3rd step; (b) the reference's own optimiser, torch.optim.Adam, loads the
+    same optimiser file and takes the same 3rd step (fp32 rounding of the fused kernel: abs 5e-6)."""
+    from idrk.dist import DataParallelTrainer
+    from idrk.model.implicit_differentiable_renderer import IDRNetwork
+    from idrk.model.loss import IDRLoss
+    from idrk.utils import checkpoints as ck
+    from oracle import idr_oracle as O
+    from tests_support import make_conf, quiet_build
+    torch.manual_seed(0)
+    conf = make_conf("HashGrid", 6, 5, 64, 512, 1.0, width=128, feature=32)
+    inp, rgb = O.synthetic_batch(256, seed=1)
+    inp = {k: v.to(DEV) for k, v in inp.items()}
+    gt = {"rgb": rgb.to(DEV)}
+    eik = torch.rand(128, 3, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    u = torch.rand(100, generator=torch.Generator().manual_seed(2))
+    loss_fn = IDRLoss(0.1, 100.0, 50.0)
+
+    def build():
+        m = quiet_build(IDRNetwork, conf).to(DEV).train()
+        m.injected_eikonal_points, m.ray_tracer.injected_min_sdf_steps = eik, u
+        return m
+
+    model = build()
+    tr = DataParallelTrainer(model, loss_fn, lr=1e-3, max_norm=1.0)
+    for _ in range(2):
+        tr.step(inp, gt)
+    root = str(tmp_path / "checkpoints")
+    ck.save_checkpoints(root, 2, model, optimizer=tr)
+
+    m2 = build()
+    tr2 = DataParallelTrainer(m2, loss_fn, lr=123.0, max_norm=1.0)
+    assert ck.load_checkpoints(root, m2, optimizer=tr2) == 2
+    assert tr2.t == 2 and tr2.lr == 1e-3 and torch.equal(tr2.m, tr.m) and torch.equal(tr2.v, tr.v)
+
+    m3 = build()
+    opt = torch.optim.Adam(m3.parameters(), lr=55.0)
+    saved = torch.load(root + "/ModelParameters/latest.pth")
+    m3.load_state_dict(saved["model_state_dict"])
+    opt.load_state_dict(torch.load(root + "/OptimizerParameters/latest.pth")["optimizer_state_dict"])
+
+    tr.step(inp, gt)
+    tr2.step(inp, gt)
+    lo = loss_fn(m3(inp), gt)
+    opt.zero_grad()
+    lo["loss"].backward()
+    torch.nn.utils.clip_grad_norm_(m3.parameters(), 1.0)
+    opt.step()
+    for (n1, a), (_, b), (_, c) in zip(model.named_parameters(), m2.named_parameters(), m3.named_parameters()):
+        assert torch.equal(a, b), n1
+        assert torch.allclose(a, c, atol=5e-6, rtol=1e-4), n1
