@@ -108,7 +108,8 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_rt_init", "idrk_rt_top", "idrk_rt_step", "idrk_rt_linesearch", "idrk_rt_end",
            "idrk_rt_select_sampler", "idrk_rt_sampler_points", "idrk_rt_sampler_resolve", "idrk_rt_secant",
            "idrk_rt_select_minsdf", "idrk_rt_minsdf_points", "idrk_rt_minsdf_resolve", "idrk_rt_chunk_counts",
-           "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd", "idrk_gemm_f16s", "idrk_split_f16", "idrk_nffb_encode_fwd"]
+           "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd", "idrk_gemm_f16s", "idrk_split_f16", "idrk_nffb_encode_fwd",
+           "idrk_hash_encode_f16pair"]
 
 
 class NffbDesc(ctypes.Structure):
@@ -203,6 +204,7 @@ def _declare(L):
     L.idrk_gemm_f16s.argtypes = [i64, i32, i32, vp, vp, i32, vp, vp, i32, c.POINTER(EpilogueH), vp, vp]
     L.idrk_split_f16.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp, vp]
     L.idrk_nffb_encode_fwd.argtypes = [c.POINTER(NffbDesc), vp, i64, i32, vp, i32, vp, vp]
+    L.idrk_hash_encode_f16pair.argtypes = [c.POINTER(HashGridDesc), vp, i64, i32, vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp]
     L.idrk_sumsq.argtypes = [vp, i64, vp, vp]
     L.idrk_clip_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp, f32, vp]
     for fn in EXPORTS:

@@ -20,6 +20,7 @@
 //   * backward: table gradients go out as vector reductions (red.global.add.v2/v4.f32).  Levels whose whole table
 //     fits a shared-memory budget are first accumulated per CTA in shared memory and flushed once (kills the
 //     contention on tiny tables such as the reference configs' T = 32); dL/dx partials are shuffle-reduced per row.
+#include <cuda_fp16.h>
 #include "hash_common.cuh"
 
 namespace idrk {
@@ -627,6 +628,75 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
 }
 
 
+// ------------------------------------------------------------------------------------------
+// encode -> fp16 pair (tracer queries)
+// ------------------------------------------------------------------------------------------
+// The ray tracer's SDF queries feed the fp16-pair contraction (gemm.cu): instead of writing the fp32 embedding and
+// splitting it in a second launch, one thread per (point, output column) forms the column with exactly the arithmetic
+// of the element kernels above (same helpers, same operation order -> bit-identical values) and stores it as the pair
+// h = fp16(v), l = fp16((v - h) * 2^11) - optionally a second scaled copy (the skip connection's 1/sqrt(2) embedding
+// columns inside the layer-4 operand).  Row counts here are <= 32 K and the row is 27-67 columns, so the redundant
+// re-evaluation of a level by its F column threads is cheaper than a second launch on the query's critical path.
+template <int F, int MODE>
+__global__ void hash_encode_pair_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
+                                        const int* __restrict__ m_count, __half* __restrict__ h, __half* __restrict__ l,
+                                        int ldo, int pad_cols, __half* __restrict__ h2, __half* __restrict__ l2, int ldo2,
+                                        int pad_cols2, float scale2) {
+    pdl_wait();
+    pdl_trigger();
+    if (m_count != nullptr) { const long long c = *m_count; n = c < n ? c : n; }
+    if (n <= 0) return;
+    const int C = g.n_fourier, L = g.n_levels;
+    const int pre = C > 0 ? 3 + 2 * C : 0;
+    const int width = pre + L * F;
+    const int pmax = (h2 != nullptr && pad_cols2 > pad_cols) ? pad_cols2 : pad_cols;
+    const int wt = width + pmax;
+    const long long total = n * (long long)wt;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / wt;
+        const int c = (int)(i - r * wt);
+        float v = 0.f;
+        if (c < width) {
+            const float x0 = x[r * ldx], x1 = x[r * ldx + 1], x2 = x[r * ldx + 2];
+            if (c < pre) {
+                if (c < 3) {
+                    v = c == 0 ? x0 : (c == 1 ? x1 : x2);
+                } else {
+                    const int j = c - 3 < C ? c - 3 : c - 3 - C;
+                    float xp = __fmul_rn(__fmul_rn(x0, 6.283185307179586f), g.B[j]);
+                    xp = __fmaf_rn(__fmul_rn(x1, 6.283185307179586f), g.B[C + j], xp);
+                    xp = __fmaf_rn(__fmul_rn(x2, 6.283185307179586f), g.B[2 * C + j], xp);
+                    float sn, cs;
+                    sincos_fast(xp, &sn, &cs);
+                    v = c - 3 < C ? sn : cs;
+                }
+            } else {
+                const int lev = (c - pre) / F, f = (c - pre) - lev * F;
+                LevelC lc;
+                lc.res = g.res[lev]; lc.rows = g.rows[lev]; lc.mask = g.pow2mask[lev]; lc.soff = 0; lc.magic = g.magic[lev];
+                lc.tab = g.tables[lev]; lc.ngp_res = g.ngp_res[lev]; lc.ngp_dense = g.ngp_dense[lev]; lc.pad0 = 0; lc.pad1 = 0;
+                float acc[F];
+                fwd_element<F, MODE, false>(lc, x0, x1, x2, acc);
+                v = acc[0];
+#pragma unroll
+                for (int k = 1; k < F; ++k) if (f == k) v = acc[k];
+            }
+        }
+        if (c < width + pad_cols) {
+            const float u = fminf(fmaxf(v, -65504.f), 65504.f);
+            const __half hv = __float2half_rn(u);
+            h[r * ldo + c] = hv;
+            l[r * ldo + c] = __float2half_rn((u - __half2float(hv)) * 2048.f);
+        }
+        if (h2 != nullptr && c < width + pad_cols2) {
+            const float u = fminf(fmaxf(v * scale2, -65504.f), 65504.f);
+            const __half hv = __float2half_rn(u);
+            h2[r * ldo2 + c] = hv;
+            l2[r * ldo2 + c] = __float2half_rn((u - __half2float(hv)) * 2048.f);
+        }
+    }
+}
+
 // Persistent grid = resident CTAs per SM x SM count.  Also pins the L1 / shared-memory split to what the kernel
 // needs: the random table reads live off L1 + L2, and with the default preference the driver keeps the large
 // shared-memory carve-out left behind by a preceding GEMM launch (measured: -35 % on the 8-corner forward).
@@ -714,6 +784,40 @@ extern "C" int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* 
 #define CALL(F, M) launch_fwd<F, M, 4>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
     IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
+}
+
+template <int F, int MODE>
+static int launch_pair(const GridDev& g, const float* x, long long n, int ldx, const int* m_count, __half* h, __half* l,
+                       int ldo, int pad_cols, __half* h2, __half* l2, int ldo2, int pad_cols2, float scale2, cudaStream_t st) {
+    const int pmax = (h2 && pad_cols2 > pad_cols) ? pad_cols2 : pad_cols;
+    const long long total = n * (long long)(g.width + pmax);
+    long long b = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (b > cap) b = cap;
+    IDRK_CUDA_TRY(launch_k(hash_encode_pair_kernel<F, MODE>, dim3((int)b), dim3(256), 0, st, g, x, n, ldx, m_count, h, l, ldo,
+                           pad_cols, h2, l2, ldo2, pad_cols2, scale2));
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_hash_encode_f16pair(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
+                                        const int32_t* m_count, void* h, void* l, int32_t ld_out, int32_t pad_cols,
+                                        void* h2, void* l2, int32_t ld_out2, int32_t pad_cols2, float scale2, void* stream) {
+    GridDev g;
+    int rc = fill_grid(h_grid, g);
+    if (rc) return rc;
+    if (n < 0 || ldx < 3 || x == nullptr || h == nullptr || l == nullptr || pad_cols < 0 || ld_out < g.width + pad_cols) return IDRK_E_ARG;
+    if ((h2 == nullptr) != (l2 == nullptr)) return IDRK_E_ARG;
+    if (h2 && (pad_cols2 < 0 || ld_out2 < g.width + pad_cols2)) return IDRK_E_ARG;
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mode = h_grid->frac_mode;
+    if (g.n_feat != 2) return IDRK_E_UNSUP;
+#define PAIR(M) launch_pair<2, M>(g, x, n, ldx, m_count, (__half*)h, (__half*)l, ld_out, pad_cols, (__half*)h2, (__half*)l2, ld_out2, pad_cols2, scale2, st)
+    if (mode == IDRK_HASH_REFERENCE) return PAIR(IDRK_HASH_REFERENCE);
+    if (mode == IDRK_HASH_TRILINEAR) return PAIR(IDRK_HASH_TRILINEAR);
+    return PAIR(IDRK_HASH_NGP);
+#undef PAIR
 }
 
 extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,

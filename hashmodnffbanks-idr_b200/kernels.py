@@ -94,6 +94,20 @@ def hash_encode_fwd(spec: HashGridSpec, x: torch.Tensor, tables, B, out: Optiona
     return (out, idx) if want_idx else out
 
 
+def hash_encode_f16pair(spec: HashGridSpec, x: torch.Tensor, tables, B, rows: int, h: torch.Tensor, l: torch.Tensor,
+                        ld_out: int, pad_cols: int = 0, m_count: Optional[torch.Tensor] = None, second=None):
+    """K1p: the embedding of the first min(rows, *m_count) points written directly as the fp16 pair the SDF pipeline's
+    contraction consumes (and, with `second = (h2, l2, ld_out2, pad_cols2, scale2)`, a scaled second copy)."""
+    x = rows2d(x, "x")
+    if rows == 0:
+        return
+    h2, l2, ld2, pad2, scale2 = second if second is not None else (None, None, 0, 0, 0.0)
+    d = spec.desc(tables, B)
+    check(lib().idrk_hash_encode_f16pair(ctypes.byref(d), ptr(x), rows, ld_of(x), ptr(m_count), ptr(h), ptr(l), ld_out,
+                                         pad_cols, ptr(h2), ptr(l2), ld2, pad2, float(scale2), stream_ptr()),
+          "idrk_hash_encode_f16pair")
+
+
 def hash_encode_bwd(spec: HashGridSpec, x: torch.Tensor, tables, B, dy: torch.Tensor,
                     grad_tables: Optional[List[torch.Tensor]], want_dx: bool):
     """K2.  Accumulates into grad_tables (list of [T_l, F], may be None) and returns dx [n,3] or None."""

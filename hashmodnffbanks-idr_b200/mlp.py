@@ -445,11 +445,11 @@ class SdfPipeline:
             self._bufs[key] = b
         return b
 
-    def _run_f16(self, emb, rows, want, m_count, out, fl):
+    def _run_f16(self, emb, rows, want, m_count, out, fl, encode=None):
         """Same pipeline with fp16-pair operands (csrc/gemm.cu gemm_f16s_kernel): half the operand bytes and half the
         tensor-pipe time of the 3xTF32 pair at the same accuracy class; used only here (no autograd)."""
         net = self.net
-        dev = emb.device
+        dev = emb.device if emb is not None else fl[0].Wfull.device
         E = fl[0].n_in
         cur_h, cur_l = self._hbuf("emb_h", rows, E, dev), self._hbuf("emb_l", rows, E, dev)
         # the layer feeding the skip connection writes into a dedicated buffer whose last E columns (the embedding's
@@ -463,7 +463,11 @@ class SdfPipeline:
                 ldw = K.pad8(width)
                 second = (skip_bufs[1][:, f.n_out:], skip_bufs[2][:, f.n_out:], ldw, ldw - width, SQRT2_INV)
                 break
-        K.split_f16_into(emb, rows, E, 1.0, cur_h, cur_l, K.pad8(E), K.pad8(E) - E, m_count, second=second)
+        if encode is not None:
+            # the encoder writes the operand pair itself (one launch instead of encode + split)
+            encode(cur_h, cur_l, K.pad8(E), K.pad8(E) - E, second)
+        else:
+            K.split_f16_into(emb, rows, E, 1.0, cur_h, cur_l, K.pad8(E), K.pad8(E) - E, m_count, second=second)
         cur_dim = E
         n = self.n_lin
         for l, f in enumerate(fl):
@@ -508,15 +512,18 @@ class SdfPipeline:
 
     # -- execution -----------------------------------------------------------------------
     @torch.no_grad()
-    def run(self, emb: torch.Tensor, rows: int, want: str = "sdf", m_count: Optional[torch.Tensor] = None,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """emb: fp32 embedding buffer [>=rows, ld] (padded operand), width = net input width."""
+    def run(self, emb: Optional[torch.Tensor], rows: int, want: str = "sdf", m_count: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None, encode=None) -> torch.Tensor:
+        """emb: fp32 embedding buffer [>=rows, ld] (padded operand), width = net input width.  `encode(h, l, ld, pad,
+        second)` (fp16-pair mode only): a callable that writes the embedding's operand pair itself; emb may be None."""
         net = self.net
         fl = self.folded()
         if K.inference_fp16x2():
             if fl[0].W_h16 is None:
                 fl = self.folded(force=True)
-            return self._run_f16(emb, rows, want, m_count, out, fl)
+            return self._run_f16(emb, rows, want, m_count, out, fl, encode)
+        if emb is None:
+            raise IdrkError("SdfPipeline.run: an fp32 embedding is required outside the fp16-pair mode")
         split = K.get_precision() == K.PREC_3XTF32
         dev = emb.device
         E = fl[0].n_in

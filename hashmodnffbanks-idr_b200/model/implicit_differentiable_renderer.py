@@ -116,6 +116,13 @@ class ImplicitNetwork(nn.Module):
             K.split_into(pts, rows, 3, 1.0, emb, None, 4, 1, m_count)
         elif self.embed_model.embed_type == "HashGrid":
             grid = self.embed_model.embedder_obj
+            if K.inference_fp16x2() and grid.n_features == 2:
+                # one launch: hash encode straight into the fp16-pair operand (+ the skip connection's scaled copy)
+                def encode(h, l, ld, pad, second):
+                    K.hash_encode_f16pair(grid.spec(), pts, grid.tables(), grid.freq_encoding.B, rows, h, l, ld, pad,
+                                          m_count, second)
+                pipe.run(None, rows, want="sdf", m_count=m_count, out=out, encode=encode)
+                return
             emb = pipe._buf("emb", rows, grid.embeddings_dim, pts.device)
             K.hash_encode_fwd(grid.spec(), pts, grid.tables(), grid.freq_encoding.B, out=emb, m_count=m_count, rows=rows)
         elif self._fused_filter_bank() is not None:

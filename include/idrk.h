@@ -70,6 +70,15 @@ int idrk_device_sm_count(int* out_sms);        /* SM count of the current device
 int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
                          float* out, int32_t ld_out, uint32_t* idx_debug, const int32_t* m_count, void* stream);
 
+/* -- K1p: hash-grid encode straight into the fp16-pair operand of idrk_gemm_f16s ----------------
+ * Same values as idrk_hash_encode_fwd (bit-identical fp32 columns) stored as h = fp16(v), l = fp16((v - h) * 2^11)
+ * into (h, l) [n, ld_out] halves, columns width .. width + pad_cols - 1 zero-filled; optionally scale2 * v into a
+ * second pair (h2, l2) [n, ld_out2] (the skip connection's copy of the embedding).  Replaces
+ * MultiResHashGridMLP.forward inside the ray tracer's SDF queries (ray_tracing.py: sdf(points)), F = 2. */
+int idrk_hash_encode_f16pair(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
+                             const int32_t* m_count, void* h, void* l, int32_t ld_out, int32_t pad_cols,
+                             void* h2, void* l2, int32_t ld_out2, int32_t pad_cols2, float scale2, void* stream);
+
 /* -- K2: hash-grid encode backward ------------------------------------------------------
  * Replaces autograd through the same functions: embedding_dense_backward scatter-add into
  * every level's table gradient and d/dx of the Fourier prefix.  dy [n, ld_dy] is dL/d(out).

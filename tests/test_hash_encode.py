@@ -185,6 +185,42 @@ def test_trilinear_paired_corners_mixed_levels():
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("mode", ["reference", "trilinear", "ngp"])
+def test_encode_to_fp16_pair_equals_encode_then_split(mode):
+    """K1p (one launch: encode -> fp16 pair, + the scaled second copy) == K1 followed by split_f16, bit for bit, for
+    the first *m_count rows; rows beyond the count and columns outside the slot untouched; pad columns zero."""
+    from idrk import kernels as K
+    n, cnt_v = 3000, 2777
+    gen = torch.Generator().manual_seed(4)
+    if mode == "ngp":
+        from idrk.model.embeddings.tcnn_src.hashGridEncoderTcnn import NgpGrid
+        m = NgpGrid(6, 2, 12, 16, 2.0)
+        with torch.no_grad():
+            m.params.copy_(torch.randn(m.params.shape, generator=gen))
+        m = m.to(DEV)
+        spec, tables, B = m.spec(), m.tables(), None
+        x = torch.rand(n, 3, generator=gen).to(DEV)
+    else:
+        m, _ = make_grid(6, 2, 5, 64, 512, mode=mode, seed=9)
+        spec, tables, B = m.spec(), m.tables(), m.freq_encoding.B
+        x = (torch.rand(n, 3, generator=gen) * 2 - 1).to(DEV)
+    E = spec.width
+    cnt = torch.tensor([cnt_v], device=DEV, dtype=torch.int32)
+    emb = K.hash_encode_fwd(spec, x, tables, B)
+    ld, big = K.pad8(E), 512
+    h0, l0 = torch.full((n, ld), 7.0, device=DEV, dtype=torch.float16), torch.full((n, ld), 7.0, device=DEV, dtype=torch.float16)
+    bh0, bl0 = torch.full((n, big), 7.0, device=DEV, dtype=torch.float16), torch.full((n, big), 7.0, device=DEV, dtype=torch.float16)
+    h1, l1, bh1, bl1 = h0.clone(), l0.clone(), bh0.clone(), bl0.clone()
+    off = big - K.pad8(E)
+    K.split_f16_into(emb, n, E, 1.0, h0, l0, ld, ld - E, cnt, second=(bh0[:, off:], bl0[:, off:], big, K.pad8(E) - E, 0.70710678))
+    K.hash_encode_f16pair(spec, x, tables, B, n, h1, l1, ld, ld - E, cnt, second=(bh1[:, off:], bl1[:, off:], big, K.pad8(E) - E, 0.70710678))
+    for a, b in ((h0, h1), (l0, l1), (bh0, bh1), (bl0, bl1)):
+        assert torch.equal(a, b)
+    assert (h1[cnt_v:] == 7.0).all() and (bh1[:, :off] == 7.0).all() and (h1[:cnt_v, E:] == 0).all()
+    rec = h1[:cnt_v, :E].double() + l1[:cnt_v, :E].double() / 2048.0
+    assert (rec - emb[:cnt_v, :E].double()).abs().max().item() <= 1e-6 * max(1.0, emb.abs().max().item())
+
+
 def test_unpadded_rows_and_huge_coordinates():
     """ld_out == width (odd: no vector path, no pad column) and coordinates whose scaled value leaves the int32
     range (the .long() emulation has to take the 64-bit conversion): indices stay bit-exact."""

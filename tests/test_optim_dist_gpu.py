@@ -65,7 +65,7 @@ def test_trainer_step_reduces_loss_and_matches_manual_step(use_graph):
 
 def test_trainer_checkpoint_roundtrip_and_handover_to_torch_adam(tmp_path):
     """Reference-layout checkpoint (utils/checkpoints.py) written by the trainer after 2 steps: (a) a fresh trainer
-    restored from it takes a bit-identical 3rd step; (b) the reference's own optimiser, torch.optim.Adam, loads the
+    restored from it takes the same 3rd step (abs 2e-6); (b) the reference's own optimiser, torch.optim.Adam, loads the
     same optimiser file and takes the same 3rd step (fp32 rounding of the fused kernel: abs 5e-6)."""
     from idrk.dist import DataParallelTrainer
     from idrk.model.implicit_differentiable_renderer import IDRNetwork
@@ -113,5 +113,5 @@ def test_trainer_checkpoint_roundtrip_and_handover_to_torch_adam(tmp_path):
     torch.nn.utils.clip_grad_norm_(m3.parameters(), 1.0)
     opt.step()
     for (n1, a), (_, b), (_, c) in zip(model.named_parameters(), m2.named_parameters(), m3.named_parameters()):
-        assert torch.equal(a, b), n1
+        assert torch.allclose(a, b, atol=2e-6, rtol=1e-5), n1       # not bit-equal: fp32 atomics (split-K, table flush) reorder sums
         assert torch.allclose(a, c, atol=5e-6, rtol=1e-4), n1
