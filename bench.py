@@ -210,8 +210,7 @@ def run_ours(args):
     from idrk.model.implicit_differentiable_renderer import IDRNetwork
     from idrk.model.loss import IDRLoss
     from idrk.dist import DataParallelTrainer
-    from oracle import idr_oracle as O          # synthetic-input recipe + cpu_baseline leg only
-    from tests_support import quiet_build
+    from tests_support import quiet_build, synthetic_batch      # the oracle is imported by the cpu_baseline leg only
 
     K.set_precision(args.precision)
     torch.manual_seed(0)
@@ -221,7 +220,7 @@ def run_ours(args):
                                   use_cuda_graph=not args.no_graph)
 
     # per-rank synthetic batch (weak scaling: every GPU traces its own 2048 rays)
-    inp_cpu, rgb_cpu = O.synthetic_batch(N_RAYS, seed=1 + 10 * rank)
+    inp_cpu, rgb_cpu = synthetic_batch(N_RAYS, seed=1 + 10 * rank)
     pinned = {k: v.pin_memory() for k, v in inp_cpu.items()}
     rgb_pin = rgb_cpu.pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in pinned.values()) + rgb_pin.numel() * 4

@@ -5,7 +5,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tests_support import make_conf, quiet_build
-from oracle import idr_oracle as O
+from tests_support import synthetic_batch
 
 
 def run(tag, conf, n_rays, steps=3, graph=True):
@@ -15,7 +15,7 @@ def run(tag, conf, n_rays, steps=3, graph=True):
     torch.manual_seed(0)
     model = quiet_build(IDRNetwork, conf).cuda().train()
     tr = DataParallelTrainer(model, IDRLoss(0.1, 100.0, 50.0), lr=1e-4, use_cuda_graph=graph)
-    inp, rgb = O.synthetic_batch(n_rays, seed=1)
+    inp, rgb = synthetic_batch(n_rays, seed=1)
     inp = {k: v.cuda() for k, v in inp.items()}
     gt = {"rgb": rgb.cuda()}
     for _ in range(3):

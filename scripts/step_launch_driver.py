@@ -20,13 +20,13 @@ def main():
     from idrk.dist import DataParallelTrainer
     from idrk.model.implicit_differentiable_renderer import IDRNetwork
     from idrk.model.loss import IDRLoss
-    from oracle import idr_oracle as O          # synthetic-input recipe only
+    from tests_support import synthetic_batch
     from tests_support import quiet_build
     K.set_precision("3xtf32")
     torch.manual_seed(0)
     model = quiet_build(IDRNetwork, bench.model_conf()).cuda().train()
     tr = DataParallelTrainer(model, IDRLoss(0.1, 100.0, 50.0), lr=1e-4, use_cuda_graph=True)
-    inp, rgb = O.synthetic_batch(bench.N_RAYS, seed=1)
+    inp, rgb = synthetic_batch(bench.N_RAYS, seed=1)
     inp = {k: v.cuda() for k, v in inp.items()}
     gt = {"rgb": rgb.cuda()}
     for _ in range(4):

@@ -51,3 +51,32 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_oracle_is_imported_only_by_the_checker_side():
+    """Outside tests/, only __graft_entry__/tests_support (smoke) and bench.py's cpu_baseline / reference-arm functions
+    may import the oracle; scripts/ (profiling drivers) take their synthetic inputs from tests_support instead."""
+    import ast
+    for dp, _, files in os.walk(os.path.join(ROOT, "scripts")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    allowed = {"oracle_cfg", "cpu_step_fn", "run_reference"}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef):
+            for sub in ast.walk(node):
+                if isinstance(sub, ast.ImportFrom) and (sub.module or "").split(".")[0] == "oracle":
+                    assert node.name in allowed, node.name
+    for node in tree.body:                                   # no module-level import either
+        assert not (isinstance(node, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(node))
+
+
+def test_synthetic_batch_recipe_is_shared():
+    import torch
+    from oracle import idr_oracle as O
+    from tests_support import synthetic_batch
+    a, ra = synthetic_batch(300, seed=4)
+    b, rb = O.synthetic_batch(300, seed=4)
+    assert torch.equal(ra, rb) and all(torch.equal(a[k], b[k]) for k in a)

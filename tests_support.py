@@ -10,6 +10,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def synthetic_batch(n_rays: int, seed: int = 1):
+    """SURVEY.md section 8(d) synthetic camera and batch: pose = I, t = (0, 0, -3), f = 500, c = 128, uv in [0, 256),
+    random object mask and target colours - an INPUT recipe (no reference arithmetic), shared by bench.py, scripts/
+    and the oracle-side tests so that every arm sees the same rays."""
+    pose = torch.eye(4).unsqueeze(0)
+    pose[0, 2, 3] = -3.0
+    K = torch.eye(4).unsqueeze(0)
+    K[0, 0, 0] = K[0, 1, 1] = 500.0
+    K[0, 0, 2] = K[0, 1, 2] = 128.0
+    uv = torch.rand(1, n_rays, 2, generator=torch.Generator().manual_seed(seed)) * 256
+    mask = torch.rand(1, n_rays, generator=torch.Generator().manual_seed(seed + 1)) > 0.5
+    rgb = torch.rand(1, n_rays, 3, generator=torch.Generator().manual_seed(seed + 2)) * 2 - 1
+    return {"uv": uv, "pose": pose, "intrinsics": K, "object_mask": mask}, rgb
+
+
 def load_sd_into(module: torch.nn.Module, sd: dict, prefix: str = "", strict: bool = True):
     """Copies a reference-keyed state dict (optionally under `prefix`) into a product module."""
     sub = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
