@@ -12,4 +12,6 @@ from scripts.gemm_micro import run_h          # noqa: E402
 
 run_h(32700, 512, 512, reps=2)
 run_h(4096, 512, 512, reps=2)
+run_h(32700, 512, 512, reps=2, dot=True)        # last hidden layer with the fused SDF-head row-dot
+run_h(32700, 512, 512, reps=2, fp32_out=True)   # what that layer did before (fp32 activation stored, head reads it back)
 torch.cuda.synchronize()

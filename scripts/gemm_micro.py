@@ -35,7 +35,7 @@ if __name__ == "__main__":
     run(2048, 512, 512, prec="tf32", split_out=False)
 
 
-def run_h(M, N, Kc, reps=4, mode=K.EPI_SOFTPLUS, fp32_out=False):
+def run_h(M, N, Kc, reps=4, mode=K.EPI_SOFTPLUS, fp32_out=False, dot=False):
     A = torch.randn(M, Kc, device="cuda") * 0.05
     W = torch.randn(N, Kc, device="cuda") * 0.05
     b = torch.randn(N, device="cuda") * 0.01
@@ -47,12 +47,14 @@ def run_h(M, N, Kc, reps=4, mode=K.EPI_SOFTPLUS, fp32_out=False):
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        if fp32_out:
+        if dot:         # fused SDF head: row-dot partials instead of the activation
+            K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, bias=b, mode=mode, act=100.0, dot_w=b, dot_out=C)
+        elif fp32_out:
             K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, C=C, bias=b, mode=mode, act=100.0)
         else:
             K.gemm_f16s(Ah, Al, Wh, Wl, M, N, Kc, C_h=Ch, C_l=Cl, bias=b, mode=mode, act=100.0)
         e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e) * 1e3)
-    print("f16s M=%d N=%d K=%d fp32_out=%s: %s us  (%.1f TF/s alg)" % (M, N, Kc, fp32_out, ["%.1f" % t for t in ts], 2.0 * M * N * Kc / min(ts) / 1e6))
+    print("f16s M=%d N=%d K=%d fp32_out=%s dot=%s: %s us  (%.1f TF/s alg)" % (M, N, Kc, fp32_out, dot, ["%.1f" % t for t in ts], 2.0 * M * N * Kc / min(ts) / 1e6))
 
 
 if __name__ == "__main__":
