@@ -179,6 +179,58 @@ __global__ void act_bwd_kernel(const float* __restrict__ dH, int ld_dh, const fl
     }
 }
 
+// float4 form of act_bwd_kernel: every leading dimension a multiple of 4 and every pointer 16-byte aligned (the padded
+// operand layout), one thread per 4 columns.  Same arithmetic per element.
+__global__ void act_bwd_vec4_kernel(const float* __restrict__ dH, int ld_dh, const float* __restrict__ dS, int ld_ds,
+                                    const float* __restrict__ S, int ld_s, const float* __restrict__ H, int ld_h,
+                                    long long rows, int cols, int mode, float act, float scale,
+                                    float* __restrict__ dZ, float* __restrict__ hi, float* __restrict__ lo, int ld_out) {
+    pdl_wait();
+    pdl_trigger();
+    const int q = ld_out >> 2;
+    const long long total = rows * (long long)q;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / q;
+        const int c = (int)(i - r * q) << 2;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < cols) {
+            const float4 s4 = *reinterpret_cast<const float4*>(S + r * ld_s + c);
+            const float s[4] = {s4.x, s4.y, s4.z, s4.w};
+            if (dH) {
+                const float4 d4 = *reinterpret_cast<const float4*>(dH + r * ld_dh + c);
+                v[0] = d4.x * s[0] * scale; v[1] = d4.y * s[1] * scale; v[2] = d4.z * s[2] * scale; v[3] = d4.w * s[3] * scale;
+            }
+            if (dS) {
+                const float4 g4 = *reinterpret_cast<const float4*>(dS + r * ld_ds + c);
+                const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+                float h[4] = {0.f, 0.f, 0.f, 0.f};
+                if (mode == IDRK_EPI_SINE || mode == IDRK_EPI_TANH) {
+                    const float4 h4 = *reinterpret_cast<const float4*>(H + r * ld_h + c);
+                    h[0] = h4.x; h[1] = h4.y; h[2] = h4.z; h[3] = h4.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float s2 = 0.f;
+                    if (mode == IDRK_EPI_SOFTPLUS) s2 = act * s[k] * (1.f - s[k]);
+                    else if (mode == IDRK_EPI_SINE) s2 = -(act * act) * h[k] / scale;
+                    else if (mode == IDRK_EPI_TANH) s2 = -2.f * h[k] * s[k] / scale;
+                    v[k] = fmaf(g[k], s2, v[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (c + k >= cols) v[k] = 0.f;       // pad columns of the last group
+        }
+        *reinterpret_cast<float4*>(dZ + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        if (hi) {
+            float a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { a[k] = tf32_round(v[k]); b[k] = tf32_round(v[k] - a[k]); }
+            *reinterpret_cast<float4*>(hi + i * 4) = make_float4(a[0], a[1], a[2], a[3]);
+            *reinterpret_cast<float4*>(lo + i * 4) = make_float4(b[0], b[1], b[2], b[3]);
+        }
+    }
+}
+
 static inline int ew_blocks(long long total, int threads) {
     long long b = (total + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
@@ -259,6 +311,18 @@ extern "C" int idrk_act_bwd(const float* dH, int32_t ld_dh, const float* dS, int
     if ((dZ_hi == nullptr) != (dZ_lo == nullptr)) return IDRK_E_ARG;
     if (dS && (mode == IDRK_EPI_SINE || mode == IDRK_EPI_TANH) && !H) return IDRK_E_ARG;
     if (rows == 0) return 0;
+    const bool need_h = dS && (mode == IDRK_EPI_SINE || mode == IDRK_EPI_TANH);
+    const bool vec4 = (ld_out & 3) == 0 && (ld_s & 3) == 0 && aligned16(S) && aligned16(dZ) &&
+                      (!dH || ((ld_dh & 3) == 0 && aligned16(dH))) && (!dS || ((ld_ds & 3) == 0 && aligned16(dS))) &&
+                      (!need_h || ((ld_h & 3) == 0 && aligned16(H))) && (!dZ_hi || (aligned16(dZ_hi) && aligned16(dZ_lo))) &&
+                      ld_s >= ((cols + 3) & ~3) && (!dH || ld_dh >= ((cols + 3) & ~3)) && (!dS || ld_ds >= ((cols + 3) & ~3)) &&
+                      (!need_h || ld_h >= ((cols + 3) & ~3));
+    if (vec4) {
+        IDRK_CUDA_TRY(launch_k(act_bwd_vec4_kernel, dim3(ew_blocks(rows * (long long)(ld_out >> 2), 256)), dim3(256), 0, (cudaStream_t)stream,
+            dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, dZ_hi, dZ_lo, ld_out));
+        IDRK_LAUNCH_CHECK();
+        return 0;
+    }
     IDRK_CUDA_TRY(launch_k(act_bwd_kernel, dim3(ew_blocks(rows * (long long)ld_out, 256)), dim3(256), 0, (cudaStream_t)stream, 
         dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, dZ_hi, dZ_lo, ld_out));
     IDRK_LAUNCH_CHECK();

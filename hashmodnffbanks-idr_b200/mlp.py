@@ -226,6 +226,34 @@ def linear(X, W, b=None):
 _ACT_MODES = {"softplus": K.EPI_SOFTPLUS, "relu": K.EPI_RELU, "sine": K.EPI_SINE, "tanh": K.EPI_TANH}
 
 
+class _MulAct(torch.autograd.Function):
+    """dZ = scale * dH * S on the RECORDED backward pass (ImplicitNetwork.gradient, create_graph=True): one kernel forms the
+    product and its 3xTF32 operand pair (a torch mul + a split launch before), and stays differentiable in dH and S -
+    the loss on the gradient (eikonal term, normals) back-propagates through it with the same kernel."""
+
+    @staticmethod
+    def forward(ctx, dH, S, scale):
+        ctx.scale = scale
+        ctx.save_for_backward(dH, S)
+        dZ, hi, lo = K.act_bwd(dH.detach(), None, S.detach(), None, K.EPI_RELU, 0.0, scale, _three_pass())
+        if hi is not None:
+            tag_split(dZ, hi, lo)
+        return dZ
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        dH, S = ctx.saved_tensors
+        g_dH = g_S = None
+        if ctx.needs_input_grad[0]:
+            g_dH, hi, lo = K.act_bwd(g, None, S, None, K.EPI_RELU, 0.0, ctx.scale, _three_pass())
+            if hi is not None:
+                tag_split(g_dH, hi, lo)
+        if ctx.needs_input_grad[1]:
+            g_S = K.act_bwd(g, None, dH, None, K.EPI_RELU, 0.0, ctx.scale, False)[0]
+        return g_dH, g_S, None
+
+
 class _LinearAct(torch.autograd.Function):
     """(H, S) = act(X W^T + b) and its derivative, both from one kernel epilogue.
 
@@ -265,7 +293,10 @@ class _LinearAct(torch.autograd.Function):
             return (*_layer_backward(ctx, dZ, X, W), None, None, None)
         dZ = None
         if dH is not None:
-            dZ = dH * S if ctx.scale == 1.0 else dH * (S * ctx.scale)
+            if dS is None and dH.dim() == 2 and dH.dtype == torch.float32:
+                dZ = _MulAct.apply(dH, S, ctx.scale)
+            else:
+                dZ = dH * S if ctx.scale == 1.0 else dH * (S * ctx.scale)
         if dS is not None:
             if ctx.mode == "softplus":
                 s2 = (ctx.act * S) * (1.0 - S)
