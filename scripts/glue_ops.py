@@ -27,27 +27,21 @@ def main():
         tr.step(inp, gt)
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
         tr.step(inp, gt)
         torch.cuda.synchronize()
-    avg = prof.key_averages(group_by_stack_n=12)
-    rows = []
-    for ev in avg:
-        if not ev.key.startswith("aten::") or ev.device_time_total <= 0:
-            continue
-        site = "?"
-        for fr in ev.stack:
-            if "hashmodnffbanks-idr_b200" in fr:
-                site = fr.split("hashmodnffbanks-idr_b200/")[-1][:90]
-                break
-        rows.append((ev.count, ev.key, site, ev.device_time_total))
     agg = collections.defaultdict(lambda: [0, 0.0])
-    for c, k, sname, t in rows:
-        agg[(k, sname)][0] += c
-        agg[(k, sname)][1] += t
-    print("aten ops with device time, by first frame inside the package (count, device us):")
-    for (k, sname), (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:70]:
-        print("%4d %8.1f  %-26s %s" % (c, t, k, sname))
+    for ev in prof.key_averages(group_by_input_shape=True):
+        if not ev.key.startswith("aten::") or ev.self_device_time_total <= 0:
+            continue
+        shapes = str([tuple(x) for x in ev.input_shapes if x])[:70]
+        agg[(ev.key, shapes)][0] += ev.count
+        agg[(ev.key, shapes)][1] += ev.self_device_time_total
+    tot = sum(v[1] for v in agg.values())
+    print("aten ops with their own device time in one eager step: %.0f us in %d launches-ish" % (tot, sum(v[0] for v in agg.values())))
+    print("count   self_us  op  input shapes")
+    for (k, shapes), (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+        print("%4d %8.1f  %-28s %s" % (c, t, k, shapes))
 
 
 if __name__ == "__main__":
