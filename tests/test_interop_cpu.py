@@ -1,7 +1,6 @@
 """Checkpoint interop and the pixel sampler - host logic, CPU only.
-The trainer itself needs CUDA; its optimiser-state conversion is exercised on a stand-in with the same fields."""
+The trainer's step needs CUDA; constructing it and converting its optimiser state does not."""
 import os
-import types
 
 import numpy as np
 import torch
@@ -11,23 +10,10 @@ from idrk.utils import checkpoints as ck
 from idrk.utils.sampling import DevicePixelSampler, uv_lattice
 
 
-class _Bucket:
-    def __init__(self, params):
-        self.params = params
-        self.offsets = [0]
-        for p in params:
-            self.offsets.append(self.offsets[-1] + (p.numel() + 3) // 4 * 4)
-
-
 def _fake_trainer(model):
-    t = types.SimpleNamespace()
-    t.bucket = _Bucket([p for p in model.parameters() if p.requires_grad])
-    n = t.bucket.offsets[-1]
-    t.m, t.v = torch.zeros(n), torch.zeros(n)
-    t.lr, t.betas, t.eps, t.t = 1e-4, (0.9, 0.999), 1e-8, 0
-    t.optimizer_state_dict = types.MethodType(DataParallelTrainer.optimizer_state_dict, t)
-    t.load_optimizer_state_dict = types.MethodType(DataParallelTrainer.load_optimizer_state_dict, t)
-    return t
+    """The real trainer object (its constructor only re-homes the parameters into the flat bucket and allocates the
+    Adam moments - no kernel is launched), on CPU tensors."""
+    return DataParallelTrainer(model, loss_fn=None, lr=1e-4, max_norm=1.0)
 
 
 def _model():
