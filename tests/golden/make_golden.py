@@ -282,7 +282,36 @@ def gen_idr(R):
     save("idr_step", **out)
 
 
+def gen_idr_eval(R):
+    """IDRNetwork.forward in EVAL mode (implicit_differentiable_renderer.py:299-302; ray_tracing.py:66-69,233 eval
+    branches) on the models of idr_step.npz (their state dicts are read back from that fixture, not stored twice)."""
+    g = np.load(os.path.join(HERE, "idr_step.npz"))
+    uv, pose, K, mask = (torch.from_numpy(g[k]) for k in ("uv", "pose", "K", "mask"))
+    out = {}
+    for tag, (et, L, log2T, base, des, bound) in {
+            "hash": ("HashGrid", 6, 5, 64, 512, 1.0),
+            "style": ("StyleModNFFB", 6, 5, 16, 512, 0.45)}.items():
+        conf = small_conf(R, et, L, log2T, base, des, bound)
+        with shim.quiet():
+            model = R.idr.IDRNetwork(conf)
+        sd = {k[len("sd_%s/" % tag):]: torch.from_numpy(np.array(g[k])) for k in g.files if k.startswith("sd_%s/" % tag)}
+        model.load_state_dict(sd)
+        model.eval()
+        with shim.quiet():
+            o = model({"uv": uv, "pose": pose, "intrinsics": K, "object_mask": mask})
+        for k in ("points", "rgb_values", "sdf_output", "network_object_mask"):
+            out["%s_%s" % (k, tag)] = o[k].detach().numpy()
+        assert o["grad_theta"] is None
+    save("idr_eval", **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "idr_eval":          # add this fixture without rewriting the others
+        if not shim.available():
+            raise SystemExit("reference tree not found")
+        torch.set_num_threads(8)
+        gen_idr_eval(shim.load())
+        return
     if not shim.available():
         raise SystemExit("reference tree not found; golden vectors can only be generated in the build container")
     torch.set_num_threads(8)
@@ -292,6 +321,7 @@ def main():
     gen_networks(R)
     gen_raytracing(R)
     gen_idr(R)
+    gen_idr_eval(R)
 
 
 if __name__ == "__main__":

@@ -185,3 +185,25 @@ def test_idr_step(golden, tag):
             assert ref.abs().max() == 0, k
             continue
         assert torch.allclose(gq, ref, atol=5e-4 * max(ref.abs().max().item(), 1e-8), rtol=1e-2), k
+
+
+@pytest.mark.parametrize("tag", list(IDR_CFGS))
+def test_idr_eval_forward(golden, tag):
+    """Eval-mode forward (implicit_differentiable_renderer.py:299-302; tracer eval branches ray_tracing.py:66-69,233) of
+    the oracle vs the real reference on the idr_step models: hit masks bit-exact, points 1e-5, sdf 1e-5, rgb 1e-4."""
+    g, e = golden("idr_step"), golden("idr_eval")
+    et, L, log2T, base, des, bound = IDR_CFGS[tag]
+    cfg = O.IDRCfg(O.EmbedCfg(et, L, log2T, 2, base, des, bound),
+                   ray_tracer=dict(object_bounding_sphere=1.0, sdf_threshold=5.0e-5, line_search_step=0.5,
+                                   line_step_iters=3, sphere_tracing_iters=10, n_steps=100, n_secant_steps=8))
+    sd = sd_from(g, "sd_%s/" % tag)
+    inp = {"uv": T(g["uv"]), "pose": T(g["pose"]), "intrinsics": T(g["K"]), "object_mask": T(g["mask"])}
+    out = O.idr_forward(inp, sd, cfg, False)
+    assert out["grad_theta"] is None
+    assert torch.equal(out["network_object_mask"], T(e["network_object_mask_" + tag]))
+    assert torch.allclose(out["points"], T(e["points_" + tag]), atol=1e-5)
+    assert torch.allclose(out["sdf_output"].detach(), T(e["sdf_output_" + tag]), atol=1e-5)
+    assert torch.allclose(out["rgb_values"].detach(), T(e["rgb_values_" + tag]), atol=1e-4)
+    # eval mode differs from training mode on this batch (the sampler does not consult the ground-truth mask)
+    assert not torch.equal(T(e["network_object_mask_" + tag]), T(g["network_object_mask_" + tag])) or \
+        not torch.allclose(T(e["rgb_values_" + tag]), T(g["rgb_values_" + tag]))
