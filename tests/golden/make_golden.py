@@ -305,12 +305,69 @@ def gen_idr_eval(R):
     save("idr_eval", **out)
 
 
+def _import_ref_utils():
+    """utils.plots / utils.general of the reference with its absent plotting / mesh dependencies stubbed (only the
+    grid and split helpers are called)."""
+    import types
+    for name in ("plotly", "plotly.graph_objs", "plotly.offline", "trimesh", "torchvision", "PIL", "PIL.Image"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    sys.modules["plotly"].graph_objs = sys.modules["plotly.graph_objs"]
+    sys.modules["plotly"].offline = sys.modules["plotly.offline"]
+    sk = sys.modules["skimage"]
+    sk.measure = types.ModuleType("skimage.measure")
+    sys.modules["skimage.measure"] = sk.measure
+    if not hasattr(sys.modules["PIL"], "Image"):
+        sys.modules["PIL"].Image = sys.modules["PIL.Image"]
+    import utils.general as rg
+    import utils.plots as rp
+    return rp, rg
+
+
+def gen_eval_helpers(R):
+    """Grids of utils/plots.py:226-271 and the split / merge helpers of utils/general.py:23-50, from the reference."""
+    rp, rg = _import_ref_utils()
+    out = {}
+    gu = rp.get_grid_uniform(5)
+    out["uniform5_points"] = gu["grid_points"].numpy()
+    for short in range(3):
+        ext = [1.0, 1.3, 1.7]
+        ext[short] = 0.5
+        pts = (torch.rand(200, 3, generator=torch.Generator().manual_seed(short)) - 0.5) * torch.tensor(ext)
+        gg = rp.get_grid(pts, 6)
+        out["cloud_%d" % short] = pts.numpy()
+        out["grid_%d_points" % short] = gg["grid_points"].numpy()
+        out["grid_%d_meta" % short] = np.array([gg["shortest_axis_index"], gg["shortest_axis_length"]], dtype=np.float64)
+        for d in range(3):
+            out["grid_%d_axis%d" % (short, d)] = np.asarray(gg["xyz"][d], dtype=np.float64)
+    B, N = 2, 23000                                        # the reference splits in chunks of 10 000 pixels
+    gen = torch.Generator().manual_seed(4)
+    inp = {"uv": torch.rand(B, N, 2, generator=gen), "object_mask": torch.rand(B, N, generator=gen) > 0.5,
+           "pose": torch.eye(4).repeat(B, 1, 1), "intrinsics": torch.eye(4).repeat(B, 1, 1)}
+    parts = rg.split_input(inp, N)
+    out["split_sizes"] = np.array([p["uv"].shape[1] for p in parts])
+    res = [{"rgb_values": torch.cat([p["uv"], p["uv"][..., :1]], -1).reshape(-1, 3) * (i + 1),
+            "flag": p["object_mask"].reshape(-1).float()} for i, p in enumerate(parts)]
+    merged = rg.merge_output(res, N, B)
+    # inputs are regenerated from the seed by the test; of the merged [B * N, .] outputs keep rows around the split
+    # boundaries of both batch entries and the column sums (small fixture)
+    idx = np.array([b * N + i for b in range(B) for i in (0, 1, 9999, 10000, 10001, 19999, 20000, 22999)])
+    out["merged_idx"] = idx
+    out["merged_rgb_rows"], out["merged_flag_rows"] = merged["rgb_values"].numpy()[idx], merged["flag"].numpy()[idx]
+    out["merged_rgb_sum"] = merged["rgb_values"].double().sum(0).numpy()
+    out["merged_flag_sum"] = np.array([merged["flag"].double().sum().item()])
+    save("eval_helpers", **out)
+
+
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] == "idr_eval":          # add this fixture without rewriting the others
+    if len(sys.argv) > 1 and sys.argv[1] in ("idr_eval", "eval_helpers"):   # add one fixture without rewriting the others
         if not shim.available():
             raise SystemExit("reference tree not found")
         torch.set_num_threads(8)
-        gen_idr_eval(shim.load())
+        {"idr_eval": gen_idr_eval, "eval_helpers": gen_eval_helpers}[sys.argv[1]](shim.load())
         return
     if not shim.available():
         raise SystemExit("reference tree not found; golden vectors can only be generated in the build container")
@@ -322,6 +379,7 @@ def main():
     gen_raytracing(R)
     gen_idr(R)
     gen_idr_eval(R)
+    gen_eval_helpers(R)
 
 
 if __name__ == "__main__":

@@ -169,3 +169,41 @@ def test_sdf_volume_vs_oracle(golden, tag):
     i, j, k = 3, 11, 17
     p = torch.tensor([[x[i], x[j], x[k]]], dtype=torch.float32, device=DEV)
     assert abs(float(model.implicit_network.sdf(p)[0]) - float(vol[i, j, k])) <= 2e-6
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU: the helpers against outputs of the REAL reference functions (tests/golden/eval_helpers.npz)
+# ----------------------------------------------------------------------------------------------
+def test_grids_equal_reference_functions(golden):
+    """utils/plots.py get_grid_uniform / get_grid of the reference (generated by tests/golden/make_golden.py) ==
+    idrk.utils.plots, bit for bit: point order, axes, shortest axis and its length."""
+    from idrk.utils import plots
+    g = golden("eval_helpers")
+    assert np.array_equal(plots.get_grid_uniform(5, device=None)["grid_points"].numpy(), g["uniform5_points"])
+    for short in range(3):
+        o = plots.get_grid(T(g["cloud_%d" % short]), 6, device=None)
+        assert np.array_equal(o["grid_points"].numpy(), g["grid_%d_points" % short])
+        assert o["shortest_axis_index"] == int(g["grid_%d_meta" % short][0]) == short
+        assert float(o["shortest_axis_length"]) == float(g["grid_%d_meta" % short][1])
+        for d in range(3):
+            assert np.array_equal(np.asarray(o["xyz"][d], dtype=np.float64), g["grid_%d_axis%d" % (short, d)])
+
+
+def test_split_merge_equal_reference_functions(golden):
+    """utils/general.py split_input (10 000-pixel chunks) / merge_output of the reference == ours on the same input."""
+    from idrk.utils.general import merge_output, split_input
+    g = golden("eval_helpers")
+    B, N = 2, 23000
+    gen = torch.Generator().manual_seed(4)
+    inp = {"uv": torch.rand(B, N, 2, generator=gen), "object_mask": torch.rand(B, N, generator=gen) > 0.5,
+           "pose": torch.eye(4).repeat(B, 1, 1), "intrinsics": torch.eye(4).repeat(B, 1, 1)}
+    parts = split_input(inp, N)                      # default n_pixels = 10000 like the reference
+    assert [p["uv"].shape[1] for p in parts] == list(g["split_sizes"]) == [10000, 10000, 3000]
+    res = [{"rgb_values": torch.cat([p["uv"], p["uv"][..., :1]], -1).reshape(-1, 3) * (i + 1),
+            "flag": p["object_mask"].reshape(-1).float()} for i, p in enumerate(parts)]
+    m = merge_output(res, N, B)
+    idx = torch.from_numpy(g["merged_idx"])
+    assert np.array_equal(m["rgb_values"][idx].numpy(), g["merged_rgb_rows"])
+    assert np.array_equal(m["flag"][idx].numpy(), g["merged_flag_rows"])
+    assert np.allclose(m["rgb_values"].double().sum(0).numpy(), g["merged_rgb_sum"], rtol=0, atol=1e-9)
+    assert float(m["flag"].double().sum()) == float(g["merged_flag_sum"][0])
