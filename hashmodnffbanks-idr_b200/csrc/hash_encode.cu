@@ -392,7 +392,7 @@ __device__ __forceinline__ void bwd_element(const LevelC& lc, float* gtab, float
 #pragma unroll
                 for (int f = 0; f < F; ++f) v[f] = wk * gy[f];
                 if (PAIR && F == 2 && pair_lane) {
-                    // paired x-neighbours (see level_pairable): the x corner goes out as a 16-byte reduction on its
+                    // paired x-neighbours (see the note above fwd_element): the x corner goes out as a 16-byte reduction on its
                     // aligned row pair, carrying the x+1 corner in the other half when c0 is even (zeros otherwise)
                     if ((k & 1) == 0) {
                         const float wn = ((c0 & 1u) == 0) ? w0 * a1 * a2 : 0.f;
