@@ -760,7 +760,7 @@ static int launch_bwd(const GridDev& g, const GradDev& gd, const float* x, long 
 
 using namespace idrk;
 
-extern "C" int idrk_version(void) { return 1; }
+extern "C" int idrk_version(void) { return 2; }   // 2: idrk_epilogue_f16_t gained dot_w / dot_out / ld_dot, IDRK_HASH_NGP, idrk_hash_encode_f16pair
 
 extern "C" int idrk_device_sm_count(int* out_sms) {
     if (!out_sms) return IDRK_E_ARG;
