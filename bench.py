@@ -129,23 +129,43 @@ def cpu_step_fn(n_rays, seed=0):
     return step
 
 
+def one_thread_figure(n_rays=256):
+    """The reference's own thread setting (training/idr_train.py:21: torch.set_num_threads(1)): one step on a bounded
+    sample, timed single-threaded."""
+    import torch
+    prev = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        step = cpu_step_fn(n_rays)
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+    finally:
+        torch.set_num_threads(prev)
+    return {"value": n_rays / dt, "unit": "rays/s", "cores": 1,
+            "sample": "1 full train step on %d of the %d rays, torch.set_num_threads(1) as idr_train.py:21" % (n_rays, N_RAYS)}
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle port, all host threads) on the SAME config as our arm:
+    every step is one full train step on all N_RAYS rays (about 1 s on the GPU boxes' hosts).  Only if the host is so
+    slow that warmup + steps would exceed ~4 minutes is the ray count halved - and the line then says same_config false."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    probe = cpu_step_fn(256)
-    t = time.perf_counter()
-    probe()
-    t_probe = time.perf_counter() - t
-    budget = 150.0
     n = N_RAYS
-    total = args.steps + args.warmup
-    while n > 128 and t_probe * (n / 256.0) * total > budget:
-        n //= 2
     step = cpu_step_fn(n)
+    t = time.perf_counter()
+    step()                                       # untimed first step (allocator / thread-pool warm-up)
+    t_first = time.perf_counter() - t
+    total = args.steps + args.warmup
+    while n > 256 and t_first * (n / float(N_RAYS)) * total > 240.0:
+        n //= 2
+    if n != N_RAYS:
+        step = cpu_step_fn(n)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -158,8 +178,9 @@ def run_reference(args):
         "impl": "reference", "metric": "idr_train_rays_per_s", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_step": n},
-        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "rays_per_step": n, "same_config": n == N_RAYS},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample,
+                         "one_thread": one_thread_figure()},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -167,28 +188,148 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def hash_encode_section(torch, hbm, src):
-    """Hash-encode microbench (BASELINE cfg5 slice): 2^24 points, L=16, F=2, T=2^19, both frac modes."""
+    """Hash-encode microbench (BASELINE cfg5 slice): 2^24 points, L=16, F=2, T in {2^19, 2^22}, both frac modes."""
     from scripts.hash_microbench import run
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     out = {}
-    for mode in ("trilinear", "reference"):
-        r = run(1 << 24, 19, mode, flush=flush)
-        out[mode] = {"fwd_mpts_per_s": round(r["fwd_mpts"], 1), "bwd_mpts_per_s": round(r["bwd_mpts"], 1),
-                     "fwd_frac_of_hbm_peak": round(r["fwd_frac"], 4), "bwd_frac_of_hbm_peak": round(r["bwd_frac"], 4),
-                     "bwd_with_dx_mpts_per_s": round(r["bwd_with_dx_mpts"], 1),
-                     "bwd_with_dx_frac_of_hbm_peak": round(r["bwd_with_dx_frac"], 4),
-                     "algorithmic_bytes_per_point": dict(zip(("fwd", "bwd_tables", "bwd_tables_dx"), r["bytes_per_pt"]))}
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    for log2T in (19, 22):
+        for mode in ("trilinear", "reference"):
+            r = run(1 << 24, log2T, mode, flush=flush)
+            d = {"fwd_mpts_per_s": round(r["fwd_mpts"], 1), "bwd_mpts_per_s": round(r["bwd_mpts"], 1),
+                 "fwd_frac_of_hbm_peak": round(r["fwd_frac"], 4), "bwd_frac_of_hbm_peak": round(r["bwd_frac"], 4),
+                 "bwd_with_dx_mpts_per_s": round(r["bwd_with_dx_mpts"], 1),
+                 "bwd_with_dx_frac_of_hbm_peak": round(r["bwd_with_dx_frac"], 4),
+                 "algorithmic_bytes_per_point": dict(zip(("fwd", "bwd_tables", "bwd_tables_dx"), r["bytes_per_pt"]))}
+            for k in ("bwd_presorted_mpts", "bwd_presorted_frac", "bwd_sort_included_mpts", "bwd_sort_included_frac",
+                      "fwd_presorted_mpts", "fwd_presorted_frac", "sort_ms"):
+                if k in r:
+                    d[k] = round(r[k], 4)
+            if log2T == 19:
+                out[mode] = d                      # the round-1 keys keep their meaning (T = 2^19)
+            else:
+                out["%s_T2^%d" % (mode, log2T)] = d
     out["points"] = (1 << 24) * world
     out["n_gpus"] = world
     if world > 1:
         out["note"] = ("2^24 points per GPU (weak); Mpts/s are whole-job, fractions are of n_gpus x the HBM peak; every "
-                       "backward pass ends with the NCCL all-reduce of the 48.5 MB table-gradient bucket, inside the timing")
-    out["table"] = "L=16, F=2, T=2^19 (48.5 MB)"
+                       "backward pass ends with the NCCL all-reduce of the table-gradient bucket, inside the timing")
+    out["table"] = "L=16, F=2, T=2^19 (48.5 MB) and T=2^22 (314 MB)"
     out["peak_gbs"] = hbm
     out["peak_source"] = src
     del flush
     return out
+
+
+def _event_ms(torch, fn, reps):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(reps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps
+
+
+def extra_config(torch, dist, tag, desc, conf, global_rays, world, rank, dev, steps=5, warm=3):
+    """One more BASELINE configuration, STRONG scaling: `global_rays` rays per step sharded equally over the ranks,
+    whole training step, barrier + device events, max over ranks.  Also times the all-reduce of the flat gradient bucket
+    alone."""
+    from idrk.dist import DataParallelTrainer, shard_rays
+    from idrk.model.implicit_differentiable_renderer import IDRNetwork
+    from idrk.model.loss import IDRLoss
+    from tests_support import quiet_build, synthetic_batch
+    torch.manual_seed(0)
+    model = quiet_build(IDRNetwork, conf).to(dev).train()
+    trainer = DataParallelTrainer(model, IDRLoss(0.1, 100.0, 50.0), lr=1e-4, max_norm=1.0, world_size=world,
+                                  use_cuda_graph=True, sample_seed=1234)
+    inp_cpu, rgb_cpu = synthetic_batch(global_rays, seed=1)
+    inp_cpu, gt_cpu = shard_rays(inp_cpu, {"rgb": rgb_cpu}, rank, world)
+    inp = {k: v.to(dev) for k, v in inp_cpu.items()}
+    gt = {"rgb": gt_cpu["rgb"].to(dev)}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warm):
+        loss = trainer.step(inp, gt)
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        loss = trainer.step(inp, gt)
+    e.record()
+    barrier()
+    ms = torch.tensor([s.elapsed_time(e) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    ar_ms = None
+    if world > 1:
+        scratch = torch.zeros_like(trainer.bucket.grad)
+        dist.all_reduce(scratch)
+        ar = torch.tensor([_event_ms(torch, lambda: dist.all_reduce(scratch), 5)], device=dev)
+        dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+        ar_ms = round(ar.item(), 3)
+        del scratch
+    chk = trainer.parameters_checksum()
+    same = True
+    if world > 1:
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        same = all(torch.equal(allc[0], c) for c in allc)
+    out = {"workload": desc, "global_rays_per_step": global_rays, "rays_per_gpu": global_rays // world, "scaling": "strong",
+           "ms_per_step": round(ms, 3), "rays_per_s": round(global_rays / (ms * 1e-3), 1), "steps": steps, "warmup": warm,
+           "loss": round(float(loss), 5), "params_M": round(trainer.bucket.flat.numel() / 1e6, 2),
+           "grad_bucket_MB": round(trainer.bucket.grad.numel() * 4 / 1e6, 1), "allreduce_ms": ar_ms,
+           "replicas_identical": bool(same), "tracer": dict(model.ray_tracer.last_stats),
+           "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    del trainer, model, inp, gt
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def dp_equals_single_check(torch, dist, model, trainer, world, rank, dev):
+    """One-off data-parallel correctness check on the real trainer (N > 1): the all-reduced, 1/world-scaled gradient
+    bucket of N ranks on their own shards must equal rank 0's gradient on the CONCATENATED batch (IDRLoss normalises by
+    the local ray count, reference loss.py:19,48, and the eikonal term is a mean, so equal shards average exactly).
+    Host draws are injected so both runs see the same eikonal points / min-SDF steps.  Returns max |dp - single| / max |single|."""
+    from tests_support import synthetic_batch
+    gen = torch.Generator().manual_seed(99)
+    u = torch.rand(100, generator=gen)
+    eiks = [torch.rand(N_RAYS // 2, 3, generator=torch.Generator().manual_seed(500 + r)) * 2 - 1 for r in range(world)]
+    batches = [synthetic_batch(N_RAYS, seed=1 + 10 * r) for r in range(world)]
+    b = trainer.bucket
+
+    def grads_of(inp_cpu, rgb_cpu, eik):
+        model.injected_eikonal_points, model.ray_tracer.injected_min_sdf_steps = eik, u
+        inp = {k: v.to(dev) for k, v in inp_cpu.items()}
+        traced = model.trace(inp)
+        trainer._shade_and_backward(traced, eik.to(dev), rgb_cpu.to(dev))
+        return b.grad.clone()
+    try:
+        g_dp = grads_of(batches[rank][0], batches[rank][1], eiks[rank])
+        dist.all_reduce(g_dp)
+        g_dp.mul_(1.0 / world)
+        rel = torch.zeros(1, device=dev)
+        if rank == 0:
+            inp0 = dict(batches[0][0])
+            inp0["uv"] = torch.cat([bb[0]["uv"] for bb in batches], 1)
+            inp0["object_mask"] = torch.cat([bb[0]["object_mask"] for bb in batches], 1)
+            rgb0 = torch.cat([bb[1] for bb in batches], 1)
+            # the single-process eikonal set is [all eikonal draws | all points]; the mean over it equals the mean of the
+            # per-rank means because every rank contributes the same number of rows
+            g_1 = grads_of(inp0, rgb0, torch.cat(eiks, 0))
+            rel[0] = (g_dp - g_1).abs().max() / g_1.abs().max().clamp_min(1e-30)
+        dist.broadcast(rel, src=0)
+    finally:
+        model.injected_eikonal_points = model.ray_tracer.injected_min_sdf_steps = None
+        b.zero_grad()
+    return float(rel.item())
 
 
 def run_ours(args):
@@ -216,8 +357,9 @@ def run_ours(args):
     torch.manual_seed(0)
     model = quiet_build(IDRNetwork, model_conf()).to(dev).train()
     loss_fn = IDRLoss(eikonal_weight=0.1, mask_weight=100.0, alpha=50.0)
+    # per-rank generator for the host draws (eikonal points, min-SDF steps): shards see independent samples
     trainer = DataParallelTrainer(model, loss_fn, lr=1e-4, max_norm=1.0, world_size=world,
-                                  use_cuda_graph=not args.no_graph)
+                                  use_cuda_graph=not args.no_graph, sample_seed=1234)
 
     # per-rank synthetic batch (weak scaling: every GPU traces its own 2048 rays)
     inp_cpu, rgb_cpu = synthetic_batch(N_RAYS, seed=1 + 10 * rank)
@@ -267,6 +409,9 @@ def run_ours(args):
             raise                 # ... but ranks must not diverge around collectives
     torch.cuda.empty_cache()
     barrier()
+    dp_rel = None
+    if world > 1:
+        dp_rel = dp_equals_single_check(torch, dist, model, trainer, world, rank, dev)
     for _ in range(max(args.warmup, 3)):
         step_resident()
     clocks = ClockSampler(local)
@@ -281,6 +426,13 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
 
     stats = dict(model.ray_tracer.last_stats)          # of the timed (graphed) steps, before the eager instrumented pass
+    # replica consistency after the timed steps: float64 checksums of the flat parameter bucket must be bit-identical
+    chk = trainer.parameters_checksum()
+    replicas_identical = True
+    if world > 1:
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        replicas_identical = all(torch.equal(allc[0], c) for c in allc)
     # instrumented pass: device time and algorithmic FLOPs of the dominant kernel (the MLP contraction)
     K.PROFILE.reset(enabled=True)
     trainer.use_cuda_graph = False          # CUDA events cannot bracket kernels inside a replayed graph
@@ -291,6 +443,28 @@ def run_ours(args):
     barrier()
     prof = K.PROFILE.summary()
     K.PROFILE.reset(enabled=False)
+
+    # the other BASELINE configurations (every rank takes part: strong scaling over the ranks)
+    extra = {}
+    if args.configs != "none":
+        trainer = model = inp_dev = gt_dev = None      # release the headline config's graphs, pools and buckets
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        from tests_support import make_conf
+        todo = [("cfg3", "BASELINE configs[2]: NFFB (FFB L=6 T=2^5 base 16 -> 512 bound 0.45, FFB view embedder) + 8x512 SDF / "
+                         "4x512 rendering MLPs, 65536 rays/step with sphere tracing + secant refinement",
+                 make_conf("FFB", 6, 5, 16, 512, 0.45, view_type="FFB"), 65536),
+                ("cfg4", "BASELINE configs[3]: StyleModNFFB, 2^22-row tables per level (10.8 M rows, 86 MB), 65536 global "
+                         "rays/step sharded over the GPUs, NCCL all-reduce of the flat gradient bucket",
+                 make_conf("StyleModNFFB", 6, 22, 16, 512, 0.45, view_type="StyleModNFFB"), 65536)]
+        for tag, desc, conf, rays in todo:
+            try:
+                extra[tag] = extra_config(torch, dist, tag, desc, conf, rays, world, rank, dev)
+            except Exception as exc:
+                if world > 1:
+                    raise
+                extra[tag] = {"error": repr(exc)}
 
     if rank != 0:
         if world > 1:
@@ -310,13 +484,16 @@ def run_ours(args):
     value = world * N_RAYS * args.steps / (ms * 1e-3)
     e2e_value = world * N_RAYS * args.steps / (ms_e2e * 1e-3)
 
-    cpu_fn = cpu_step_fn(512)
+    cpu_fn = cpu_step_fn(N_RAYS)                       # same config as the GPU arm: all 2048 rays
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cpu_fn()
     t0 = time.perf_counter()
-    cpu_fn()
-    cpu_dt = time.perf_counter() - t0
+    cpu_reps = 0
+    while cpu_reps < 3 and (cpu_reps == 0 or time.perf_counter() - t0 < 12.0):
+        cpu_fn()
+        cpu_reps += 1
+    cpu_dt = (time.perf_counter() - t0) / cpu_reps
 
     line = {
         "metric": "idr_train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -351,10 +528,17 @@ def run_ours(args):
                      "measured_in": "an instrumented eager pass (2 steps) after the timed region: CUDA graphs off so that "
                                     "events can bracket each launch"},
         "kernel_time_ms_per_step": {k: round(v["ms"] / 2, 3) for k, v in sorted(prof.items())},
-        "cpu_baseline": {"value": 512 / cpu_dt, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": "1 full train step on 512 of the 2048 rays, oracle port of the reference's "
-                                   "PyTorch path, %d threads" % cores},
+        "cpu_baseline": {"value": N_RAYS / cpu_dt, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": "%d full train steps on all %d rays of the bench config (after one untimed step), oracle "
+                                   "port of the reference's PyTorch path, %d threads" % (cpu_reps, N_RAYS, cores),
+                         "one_thread": one_thread_figure()},
+        "replicas_identical": replicas_identical,
+        "dp_equals_single": None if dp_rel is None else {"max_rel_err": dp_rel, "ok": bool(dp_rel <= 1e-5),
+                                                         "what": "all-reduced 1/N-scaled gradient bucket of N ranks on their "
+                                                                 "shards vs rank 0 on the concatenated %d rays; tolerance "
+                                                                 "1e-5 of max-abs" % (N_RAYS * world)},
     }
+    line["configs"] = extra
     line["hash_encode"] = hash_line
     print(json.dumps(line))
     if world > 1:
@@ -369,6 +553,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="run the differentiable part eagerly (no CUDA graph)")
+    ap.add_argument("--configs", default="all", choices=["all", "none"],
+                    help="also run BASELINE cfg3 / cfg4 (65536 global rays, strong scaling) after the headline config")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -73,6 +73,41 @@ def allreduce_mean_(flat_grad: torch.Tensor, world: int, group=None) -> float:
     return 1.0 / world
 
 
+class MultiStepLR:
+    """The reference's learning-rate schedule (training/idr_train.py:131-134: torch.optim.lr_scheduler.MultiStepLR on
+    the Adam optimiser, stepped once per epoch at :312) for the fused optimiser: multiplies `trainer.lr` by `gamma` at
+    every milestone.  `state_dict()` carries torch's keys so SchedulerParameters/*.pth files move both ways."""
+
+    def __init__(self, trainer, milestones, gamma: float = 0.1, last_epoch: int = -1):
+        self.trainer, self.gamma = trainer, float(gamma)
+        self.milestones = sorted(int(m) for m in milestones)
+        self.base_lrs = [trainer.lr]
+        self.last_epoch = last_epoch
+        self.step()
+
+    def _lr_at(self, epoch: int) -> float:
+        return self.base_lrs[0] * self.gamma ** sum(1 for m in self.milestones if m <= epoch)
+
+    def step(self) -> None:
+        self.last_epoch += 1
+        self.trainer.lr = self._lr_at(self.last_epoch)
+
+    def get_last_lr(self):
+        return [self.trainer.lr]
+
+    def state_dict(self) -> Dict:
+        from collections import Counter
+        return {"milestones": Counter(self.milestones), "gamma": self.gamma, "base_lrs": list(self.base_lrs),
+                "last_epoch": self.last_epoch, "_step_count": self.last_epoch + 1, "_last_lr": [self.trainer.lr]}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        self.milestones = sorted(int(m) for m, c in dict(sd["milestones"]).items() for _ in range(int(c)))
+        self.gamma = float(sd["gamma"])
+        self.base_lrs = [float(x) for x in sd["base_lrs"]]
+        self.last_epoch = int(sd["last_epoch"])
+        self.trainer.lr = self._lr_at(self.last_epoch)
+
+
 class DataParallelTrainer:
     """model + loss + clip + Adam, replicated per rank, gradients all-reduced once per step.
 
@@ -81,10 +116,26 @@ class DataParallelTrainer:
     into a CUDA graph and replayed every step (the launch-bound part of the step: ~600 small kernels)."""
 
     def __init__(self, model: torch.nn.Module, loss_fn, lr: float = 1e-4, max_norm: float = 1.0, world_size: int = 1,
-                 betas=(0.9, 0.999), eps: float = 1e-8, use_cuda_graph: bool = False):
+                 betas=(0.9, 0.999), eps: float = 1e-8, use_cuda_graph: bool = False, rank: Optional[int] = None,
+                 sample_seed: Optional[int] = None, broadcast_parameters: bool = True):
         self.model, self.loss_fn = model, loss_fn
-        self.lr, self.max_norm, self.world, self.betas, self.eps = lr, max_norm, world_size, betas, eps
+        # `lr` is read at every step() (the optimiser kernel takes it by value, outside any CUDA graph): assign
+        # `trainer.lr` - or drive it with `MultiStepLR(trainer, ...)` below - like the reference's scheduler.step()
+        # (training/idr_train.py:131-134,312).  `param_groups` mirrors torch.optim's attribute for code that
+        # rescales `group["lr"]` in place.
+        self.param_groups = [{"lr": float(lr)}]
+        self.max_norm, self.world, self.betas, self.eps = max_norm, world_size, betas, eps
+        self.rank = (dist.get_rank() if (world_size > 1 and dist.is_initialized()) else 0) if rank is None else rank
         self.bucket = FlatBucket(list(model.parameters()))
+        if world_size > 1 and broadcast_parameters and dist.is_initialized():
+            # replicas must start identical; do not rely on identical seeding / checkpoint loads
+            dist.broadcast(self.bucket.flat, src=0)
+        # Host-side draws of the step (eikonal points :279, min-SDF steps ray_tracing.py:277).  With `sample_seed`
+        # every rank owns a generator seeded `sample_seed + rank`, so data-parallel shards see INDEPENDENT eikonal
+        # samples; with None the global host generator is used exactly like the reference (world 1 parity runs).
+        self.sample_generator = None
+        if sample_seed is not None or world_size > 1:
+            self.sample_generator = torch.Generator().manual_seed((0 if sample_seed is None else sample_seed) + 7919 * self.rank)
         self.m = torch.zeros_like(self.bucket.flat)
         self.v = torch.zeros_like(self.bucket.flat)
         self.sumsq = torch.zeros(1, device=self.bucket.flat.device, dtype=torch.float32)
@@ -92,10 +143,26 @@ class DataParallelTrainer:
         self.use_cuda_graph = use_cuda_graph
         if hasattr(model, "ray_tracer"):
             model.ray_tracer.use_cuda_graph = use_cuda_graph
+            if self.sample_generator is not None:
+                model.sample_generator = model.ray_tracer.sample_generator = self.sample_generator
         self._graph = None
         self._static = None
         self._static_out = None
         self._graph_key = None
+        self._retired_graphs = []
+
+    @property
+    def lr(self) -> float:
+        return float(self.param_groups[0]["lr"])
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        self.param_groups[0]["lr"] = float(value)
+
+    def parameters_checksum(self) -> torch.Tensor:
+        """float64 [sum, sum of squares] of the flat parameter bucket (replica-consistency checks)."""
+        f = self.bucket.flat.double()
+        return torch.stack([f.sum(), (f * f).sum()])
 
     # -- optimiser state in torch.optim.Adam's format ---------------------------------------------
     def optimizer_state_dict(self) -> Dict:
@@ -157,8 +224,16 @@ class DataParallelTrainer:
         return losses
 
     def _graphed(self, traced, eik, rgb):
-        key = tuple((k, tuple(v.shape)) for k, v in sorted(traced.items())) + (tuple(eik.shape), tuple(rgb.shape))
+        # Everything the captured launch sequence bakes in as a host scalar is part of the key: the loss weights and
+        # alpha (the reference doubles alpha at every alpha_milestone, training/idr_train.py:227-228), the mode of the
+        # model and the generation of the shared scratch buffers whose addresses the graph holds.
+        lf = self.loss_fn
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(traced.items())) + (tuple(eik.shape), tuple(rgb.shape)) + (
+            float(getattr(lf, "alpha", 0.0)), float(getattr(lf, "eikonal_weight", 0.0)), float(getattr(lf, "mask_weight", 0.0)),
+            bool(self.model.training), K.get_precision(), K.SCRATCH_GENERATION[0])
         if self._graph is None or key != self._graph_key:
+            if self._graph is not None:
+                self._retired_graphs.append((self._graph, self._static))      # keep its pool alive; never replayed again
             self._static = ({k: v.detach().clone() for k, v in traced.items()}, eik.clone(), rgb.clone())
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -172,7 +247,8 @@ class DataParallelTrainer:
                 losses = self._shade_and_backward(*self._static)
                 self._static_out = {k: v.detach() for k, v in losses.items()}
             self._graph_launches = K._lib.LAUNCHES[0] - l0
-            self._graph_key = key
+            self._graph_key = key[:-1] + (K.SCRATCH_GENERATION[0],)     # the warm-up passes may have grown the arena
+            K.note_graph_captured()
         st_traced, st_eik, st_rgb = self._static
         for k, v in traced.items():
             st_traced[k].copy_(v)

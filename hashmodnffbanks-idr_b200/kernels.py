@@ -295,6 +295,31 @@ def weight_norm_bwd(g: torch.Tensor, v: torch.Tensor, dW: torch.Tensor, into=Non
     return dg, dv
 
 
+# ---------------------------------------------------------------------------------------------
+# scratch buffers whose addresses CUDA graphs hold
+# ---------------------------------------------------------------------------------------------
+# The ray tracer's and the trainer's CUDA graphs are captured against eagerly allocated, shared scratch (SdfPipeline
+# buffers, the zero arena) and keep raw pointers.  A buffer that has to grow after a capture is therefore never
+# freed: the old tensor is parked in `_RETIRED` (the graphs that point at it stay valid) and `SCRATCH_GENERATION`
+# moves, which is part of every graph key - holders drop their graph and recapture against the new buffers.
+SCRATCH_GENERATION = [0]
+GRAPHS_CAPTURED = [0]
+_RETIRED: list = []
+
+
+def note_graph_captured():
+    GRAPHS_CAPTURED[0] += 1
+
+
+def retire_scratch(t):
+    """Called instead of dropping a scratch tensor that is being replaced by a larger one."""
+    if t is None:
+        return
+    if GRAPHS_CAPTURED[0] > 0:
+        _RETIRED.append(t)
+        SCRATCH_GENERATION[0] += 1
+
+
 class ZeroPool:
     """Arena of pre-zeroed fp32 scratch for one differentiable step.
 
@@ -312,6 +337,9 @@ class ZeroPool:
     def begin(self, device):
         want = max(self.need, 1 << 20)
         if self.buf is None or self.buf.device != device or self.buf.numel() < want:
+            if torch.cuda.is_current_stream_capturing():
+                raise _lib.IdrkError("ZeroPool would have to grow inside a CUDA-graph capture (warm the step up eagerly first)")
+            retire_scratch(self.buf)
             self.buf = torch.empty(int(want * 1.25), device=device, dtype=torch.float32)
         self.buf.zero_()
         self.off = 0

@@ -464,6 +464,7 @@ class SdfPipeline:
         key = (name, cols)
         b = self._bufs.get(key)
         if b is None or b.shape[0] < rows or b.device != device:
+            K.retire_scratch(b)              # CUDA graphs may hold its address: parked, never freed (kernels.py)
             b = torch.empty((max(rows, 1), K.pad4(cols)), device=device, dtype=torch.float32)
             self._bufs[key] = b
         return b
@@ -472,6 +473,7 @@ class SdfPipeline:
         key = ("h16", name, cols)
         b = self._bufs.get(key)
         if b is None or b.shape[0] < rows or b.device != device:
+            K.retire_scratch(b)
             b = torch.empty((max(rows, 1), K.pad8(cols)), device=device, dtype=torch.float16)
             self._bufs[key] = b
         return b

@@ -255,6 +255,7 @@ class IDRNetwork(nn.Module):
         self.object_bounding_sphere = conf.get_float('ray_tracer.object_bounding_sphere')
         # host-side RNG draws (eikonal points, min-SDF steps) may be injected for exact parity runs
         self.injected_eikonal_points = None
+        self.sample_generator = None            # optional torch.Generator for the host draws (per-rank in data-parallel runs)
 
     def forward(self, input):
         return self.shade(self.trace(input))
@@ -310,7 +311,7 @@ class IDRNetwork(nn.Module):
         if self.injected_eikonal_points is not None:
             return self.injected_eikonal_points.to(device)
         r = self.object_bounding_sphere      # drawn on the host generator, like the reference (:279)
-        return torch.empty(n_rays // 2, 3).uniform_(-r, r).to(device)
+        return torch.empty(n_rays // 2, 3).uniform_(-r, r, generator=self.sample_generator).to(device)
 
     def render_training(self, points, dists, ray_dirs, cam_rep, surface_mask, eik):
         """Training branch of the reference forward (:264-308) on FIXED shapes, without its duplicate evaluations.

@@ -99,6 +99,7 @@ class _TraceState:
             setattr(st, name, getattr(self, name).data_ptr())
         self.desc = st
         self.graphs = {}
+        self.retired = []
         self.warm = set()
         self._tail = None
 
@@ -146,6 +147,7 @@ class RayTracing(nn.Module):
         self._stats = {}
         self._pending_counts = None
         self.injected_min_sdf_steps = None      # parity runs: the U(0,1) vector of reference :277
+        self.sample_generator = None            # optional torch.Generator for that draw (per-rank in data-parallel runs)
         self.use_cuda_graph = False             # replay the sphere-tracing launch sequence from a CUDA graph
         self._states = {}
 
@@ -281,9 +283,13 @@ class RayTracing(nn.Module):
                     if min_sdf_steps is None:
                         min_sdf_steps = self.injected_min_sdf_steps
                     if min_sdf_steps is None:       # drawn on the host generator like the reference (:277)
-                        min_sdf_steps = torch.empty(int(self.n_steps)).uniform_(0.0, 1.0)
+                        min_sdf_steps = torch.empty(int(self.n_steps)).uniform_(0.0, 1.0, generator=self.sample_generator)
                     t["u"].copy_(min_sdf_steps.to(dev, non_blocking=True).float())
                 key = bool(self.training)
+                # a graph is only valid for the scratch buffers it was captured against (kernels.SCRATCH_GENERATION)
+                if key in T.graphs and T.graphs[key][3] != K.SCRATCH_GENERATION[0]:
+                    T.retired.append(T.graphs.pop(key))
+                    T.warm.discard(key)
                 if not self.use_cuda_graph:
                     self._trace_device(T, ev)
                 elif key not in T.warm:              # first call: eager (allocations, lazy attribute setup)
@@ -298,8 +304,9 @@ class RayTracing(nn.Module):
                         with torch.cuda.graph(graph):
                             ev.owner.refresh_inference_weights(force=True)   # weight folding is part of the graph
                             self._trace_device(T, ev)
-                        T.graphs[key] = (graph, K._lib.LAUNCHES[0] - l0, ev.calls)
-                    graph, n_launches, n_calls = T.graphs[key]
+                        K.note_graph_captured()
+                        T.graphs[key] = (graph, K._lib.LAUNCHES[0] - l0, ev.calls, K.SCRATCH_GENERATION[0])
+                    graph, n_launches, n_calls, _ = T.graphs[key]
                     graph.replay()
                     K._lib.LAUNCHES[0] += n_launches            # kernels launched by the replayed graph
                     ev.calls = n_calls
@@ -366,7 +373,7 @@ class RayTracing(nn.Module):
                 if min_sdf_steps is None:
                     min_sdf_steps = self.injected_min_sdf_steps
                 if min_sdf_steps is None:       # drawn on the host generator like the reference (:277)
-                    u = torch.empty(ns).uniform_(0.0, 1.0).to(dev)
+                    u = torch.empty(ns).uniform_(0.0, 1.0, generator=self.sample_generator).to(dev)
                 else:
                     u = min_sdf_steps.to(dev).float().contiguous()
                 big_vals = torch.empty(n_min * ns, device=dev, dtype=torch.float32)

@@ -431,6 +431,11 @@ class RayTracerOracle:
         self.n_secant = n_secant_steps
         self.training = True
         self.stats: Dict[str, int] = {}
+        # Test bookkeeping (does not touch the results): for every ray the smallest distance by which any SDF value
+        # that drove one of its discrete decisions (<= threshold :134-142, < 0 :164-165 / :212-218, t0 < t1 :185-186)
+        # missed the decision boundary.  A ray whose hit/miss mask differs between two evaluators of the same SDF is
+        # only legitimate when this margin is inside the evaluators' SDF tolerance.
+        self.margin: Optional[Tensor] = None
 
     @torch.no_grad()
     def __call__(self, sdf: Callable[[Tensor], Tensor], cam_loc: Tensor, object_mask: Tensor,
@@ -443,6 +448,7 @@ class RayTracerOracle:
             self.stats["sdf_points"] += int(pts.shape[0])
             return sdf(pts)
 
+        self.margin = torch.full((B * N,), float("inf"))
         t_sph, hit = sphere_intersection(cam_loc, ray_directions, self.r)
         pts, unf_start, t0, t1, min_dis, max_dis = self._sphere_trace(B, N, f, cam_loc, ray_directions, hit, t_sph)
         net_mask = t0 < t1                                                   # :39
@@ -495,6 +501,8 @@ class RayTracerOracle:
         nxt_s[unf_s] = f(ps[unf_s])
         nxt_e = torch.zeros_like(t1)
         nxt_e[unf_e] = f(pe[unf_e])
+        self._note(unf_s, nxt_s)
+        self._note(unf_e, nxt_e)
         it = 0
         while True:
             cur_s = torch.zeros_like(t0)
@@ -516,6 +524,8 @@ class RayTracerOracle:
             nxt_s[unf_s] = f(ps[unf_s])
             nxt_e = torch.zeros_like(t1)
             nxt_e[unf_e] = f(pe[unf_e])
+            self._note(unf_s, nxt_s)
+            self._note(unf_e, nxt_e)
             bad_s, bad_e = nxt_s < 0, nxt_e < 0
             k = 0
             while (bad_s.sum() > 0 or bad_e.sum() > 0) and k < self.ls_iters:
@@ -526,11 +536,22 @@ class RayTracerOracle:
                 pe[bad_e] = (cam_loc.unsqueeze(1) + t1.reshape(B, N, 1) * dirs).reshape(-1, 3)[bad_e]
                 nxt_s[bad_s] = f(ps[bad_s])
                 nxt_e[bad_e] = f(pe[bad_e])
+                self._note(bad_s, nxt_s)
+                self._note(bad_e, nxt_e)
                 bad_s, bad_e = nxt_s < 0, nxt_e < 0
                 k += 1
+            live = unf_s | unf_e
+            self.margin[live] = torch.minimum(self.margin[live], (t1 - t0).abs()[live])
             unf_s = unf_s & (t0 < t1)
             unf_e = unf_e & (t0 < t1)
         return ps, unf_s, t0, t1, min_dis, max_dis
+
+    def _note(self, sel: Tensor, vals: Tensor) -> None:
+        """margin bookkeeping for SDF values that are compared with the threshold and with 0."""
+        if self.margin is None or int(sel.sum()) == 0:
+            return
+        v = vals[sel]
+        self.margin[sel] = torch.minimum(self.margin[sel], torch.minimum((v - self.thr).abs(), v.abs()))
 
     def _sampler(self, f, cam_loc, object_mask, dirs, mm, samp_mask):        # :189-249
         B, N, _ = dirs.shape
@@ -547,6 +568,13 @@ class RayTracerOracle:
         key = torch.sign(vals) * torch.arange(self.n_steps, 0, -1).float().reshape(1, -1)
         first = torch.argmin(key, -1)
         ar = torch.arange(P.shape[0])
+        if self.margin is not None:
+            # samples whose sign decides `first` / `net_surf`: all up to the first negative one, or all 100
+            neg_found = vals[ar, first] < 0
+            upto = torch.where(neg_found, first, torch.full_like(first, self.n_steps - 1))
+            decisive = torch.arange(self.n_steps).reshape(1, -1) <= upto.reshape(-1, 1)
+            mg = torch.where(decisive, vals.abs(), torch.full_like(vals, float("inf"))).min(-1).values
+            self.margin[ridx] = torch.minimum(self.margin[ridx], mg)
         out_pts[ridx] = P[ar, first]
         out_d[ridx] = z[ar, first]
         true_surf = object_mask[samp_mask]

@@ -50,14 +50,20 @@ def time_cuda(fn, warm=3, iters=10, flush=None):
     return ts[len(ts) // 2]
 
 
+CHUNK = 1 << 26      # points per launch: N = 256 M is processed in place, 3 GB of input, output rows recycled per chunk
+
+
 def run(n, log2T, mode, L=16, F=2, flush=None):
     from idrk import kernels as K
     from idrk.model.embeddings.hashGridEmbedding import MultiResHashGridMLP
     m = MultiResHashGridMLP(True, 3, L, F, log2T, 16, 2048, frac_mode=mode).cuda()
     spec, tables, B = m.spec(), tuple(t.detach() for t in m.tables()), m.freq_encoding.B
-    x = torch.rand(n, 3, device="cuda")
-    out = torch.empty(n, K.pad4(spec.width), device="cuda")
-    dy = torch.randn(n, K.pad4(spec.width), device="cuda")
+    x_all = torch.rand(n, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    nc = min(n, CHUNK)
+    xs = list(x_all.split(nc))
+    x = xs[0]
+    out = torch.empty(nc, K.pad4(spec.width), device="cuda")
+    dy = torch.randn(nc, K.pad4(spec.width), device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
     # gradient tables = views of ONE flat buffer (what the trainer's bucket looks like, and what NCCL reduces)
     flat = torch.zeros(sum(t.numel() for t in tables), device="cuda")
     grads, o = [], 0
@@ -71,12 +77,18 @@ def run(n, log2T, mode, L=16, F=2, flush=None):
 
         def bwd(want_dx):
             # cfg5 at N > 1: every rank owns n points, the step ends with the table-gradient all-reduce
-            K.hash_encode_bwd(spec, x, tables, B, dy, grads, want_dx)
+            for xc in xs:
+                K.hash_encode_bwd(spec, xc, tables, B, dy[:xc.shape[0]], grads, want_dx)
             dist.all_reduce(flat)
     else:
         def bwd(want_dx):
-            K.hash_encode_bwd(spec, x, tables, B, dy, grads, want_dx)
-    t_f = time_cuda(lambda: K.hash_encode_fwd(spec, x, tables, B, out=out), flush=flush)
+            for xc in xs:
+                K.hash_encode_bwd(spec, xc, tables, B, dy[:xc.shape[0]], grads, want_dx)
+
+    def fwd():
+        for xc in xs:
+            K.hash_encode_fwd(spec, xc, tables, B, out=out[:xc.shape[0]])
+    t_f = time_cuda(fwd, flush=flush)
     t_b = time_cuda(lambda: bwd(False), flush=flush)      # table gradients
     t_bx = time_cuda(lambda: bwd(True), flush=flush)      # + dL/dx
     n = n * world                                         # whole-job points per pass (weak scaling: n per GPU)

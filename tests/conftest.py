@@ -48,3 +48,16 @@ def golden():
             cache[name] = load_golden(name)
         return cache[name]
     return get
+
+
+def assert_flips_borderline(mask, mask_ref, margin, tol, what=""):
+    """Hit/miss masks may differ from the oracle's only on rays whose decisive SDF values came within `tol` of a decision
+    boundary in the oracle's own trace (RayTracerOracle.margin): count AND cause.  Returns the number of flips."""
+    mask, mask_ref = mask.reshape(-1).cpu(), mask_ref.reshape(-1).cpu()
+    flipped = mask != mask_ref
+    n = int(flipped.sum())
+    if n:
+        worst = float(margin[flipped].max())
+        assert worst <= tol, "%s: %d flipped rays, one of them %.3g away from every decision boundary (tol %.3g)" % (
+            what, n, worst, tol)
+    return n

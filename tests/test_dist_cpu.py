@@ -79,3 +79,29 @@ def test_shard_rays_rejects_uneven():
     except ValueError:
         return
     raise AssertionError("uneven shards must be rejected")
+
+
+def test_multistep_lr_shim_matches_torch_scheduler():
+    """idrk.dist.MultiStepLR drives `trainer.lr` exactly like torch's MultiStepLR drives Adam's lr in the reference loop
+    (training/idr_train.py:131-134,312), and its state dict loads into torch's scheduler and back."""
+    from types import SimpleNamespace
+    from idrk.dist import MultiStepLR
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=1e-4)
+    ref = torch.optim.lr_scheduler.MultiStepLR(opt, [3, 5, 5, 9], gamma=0.5)
+    tr = SimpleNamespace(lr=1e-4)
+    mine = MultiStepLR(tr, [3, 5, 5, 9], gamma=0.5)
+    for epoch in range(12):
+        assert abs(tr.lr - opt.param_groups[0]["lr"]) <= 1e-12 * 1e-4, epoch
+        opt.step()
+        ref.step()
+        mine.step()
+    sd = mine.state_dict()
+    opt2 = torch.optim.Adam([p], lr=1e-4)
+    ref2 = torch.optim.lr_scheduler.MultiStepLR(opt2, [1], gamma=0.1)
+    ref2.load_state_dict(sd)
+    assert ref2.last_epoch == mine.last_epoch and ref2.gamma == 0.5 and dict(ref2.milestones) == {3: 1, 5: 2, 9: 1}
+    tr3 = SimpleNamespace(lr=1e-4)
+    mine3 = MultiStepLR(tr3, [1], gamma=0.1)
+    mine3.load_state_dict(ref.state_dict())
+    assert mine3.last_epoch == ref.last_epoch and abs(tr3.lr - opt.param_groups[0]["lr"]) <= 1e-16

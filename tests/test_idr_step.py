@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import sd_from
+from conftest import assert_flips_borderline, sd_from
 from tests_support import load_sd_into, make_conf, quiet_build
 
 pytestmark = pytest.mark.gpu
@@ -40,6 +40,21 @@ def test_idr_step_golden(golden, tag):
     m = out["network_object_mask"].cpu()
     flips = (m != m_ref).sum().item()
     assert flips <= max(1, m.numel() // 100), flips
+    if flips:
+        # count AND cause: the oracle (== the reference fixture on these inputs, tests/test_oracle_golden.py) records how
+        # close every ray came to deciding differently; the fp16-pair SDF agrees with fp32 to 1e-5, so only rays within
+        # 2e-5 (NFFB: sin(30 x) chains, 1e-4) of a decision boundary may flip
+        from oracle import idr_oracle as O
+        from tests_support import RAY_TRACER_CONF
+        cfg = O.EmbedCfg(et, L, log2T, 2, base, des, bound)
+        sd_o = sd_from(g, "sd_%s/" % tag)
+        orc = O.RayTracerOracle(**RAY_TRACER_CONF)
+        dirs_o, cam_o = O.camera_rays(T(g["uv"]), T(g["pose"]), T(g["K"]))
+        with torch.no_grad():
+            _, m_orc, _ = orc(lambda q: O.implicit_forward(q, sd_o, cfg)[:, 0], cam_o, T(g["mask"]).reshape(-1), dirs_o,
+                              T(g["min_sdf_steps_" + tag]))
+        assert torch.equal(m_orc, m_ref.reshape(-1))
+        assert_flips_borderline(m, m_ref, orc.margin, 1e-4 if tag == "style" else 2e-5, tag)
     agree = m == m_ref
     dp = (out["points"].cpu() - T(g["points_" + tag])).abs().max(1).values
     assert (dp[agree] > 2e-4).sum().item() <= max(2, m.numel() // 20)     # argmin ties of the 100-sample sweeps

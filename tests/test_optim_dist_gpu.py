@@ -115,3 +115,71 @@ def test_trainer_checkpoint_roundtrip_and_handover_to_torch_adam(tmp_path):
     for (n1, a), (_, b), (_, c) in zip(model.named_parameters(), m2.named_parameters(), m3.named_parameters()):
         assert torch.allclose(a, b, atol=2e-6, rtol=1e-5), n1       # not bit-equal: fp32 atomics (split-K, table flush) reorder sums
         assert torch.allclose(a, c, atol=5e-6, rtol=1e-4), n1
+
+
+def _small_trainer(use_graph, lr=1e-3, alpha=50.0, rays=256):
+    from idrk.dist import DataParallelTrainer
+    from idrk.model.implicit_differentiable_renderer import IDRNetwork
+    from idrk.model.loss import IDRLoss
+    from oracle import idr_oracle as O
+    from tests_support import make_conf, quiet_build
+    torch.manual_seed(0)
+    conf = make_conf("HashGrid", 6, 5, 64, 512, 1.0, width=128, feature=32)
+    model = quiet_build(IDRNetwork, conf).to(DEV).train()
+    inp, rgb = O.synthetic_batch(rays, seed=1)
+    inp = {k: v.to(DEV) for k, v in inp.items()}
+    gt = {"rgb": rgb.to(DEV)}
+    model.injected_eikonal_points = torch.rand(rays // 2, 3, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    model.ray_tracer.injected_min_sdf_steps = torch.rand(100, generator=torch.Generator().manual_seed(2))
+    loss_fn = IDRLoss(0.1, 100.0, alpha)
+    return DataParallelTrainer(model, loss_fn, lr=lr, max_norm=1.0, world_size=1, use_cuda_graph=use_graph), inp, gt
+
+
+def test_graphed_trainer_follows_alpha_and_lr_changes():
+    """The reference loop doubles IDRLoss.alpha at every alpha milestone and decays the lr with MultiStepLR
+    (training/idr_train.py:227-228, 131-134): a trainer whose shade + loss + backward is replayed from a CUDA graph must
+    pick both up.  Graphed and eager trainers take the same 6 steps with alpha / lr changed after step 3
+    (losses rel 1e-5, parameters abs 5e-6 - fp32 atomics reorder sums between runs)."""
+    from idrk.dist import MultiStepLR
+    a, inp, gt = _small_trainer(True)
+    b, _, _ = _small_trainer(False)
+    sa, sb = MultiStepLR(a, [1], gamma=0.5), MultiStepLR(b, [1], gamma=0.5)
+    losses = []
+    for step in range(6):
+        if step == 3:
+            a.loss_fn.alpha *= 2.0
+            b.loss_fn.alpha *= 2.0
+            sa.step()
+            sb.step()
+            assert a.lr == 0.5e-3 and b.lr == 0.5e-3
+        la, lb = float(a.step(inp, gt)), float(b.step(inp, gt))
+        losses.append((la, lb))
+        assert abs(la - lb) <= 1e-5 * max(1.0, abs(lb)), (step, la, lb)
+        ma, mb = float(a.last_losses["mask_loss"]), float(b.last_losses["mask_loss"])
+        assert abs(ma - mb) <= 1e-5 * max(1e-3, abs(mb)), (step, ma, mb)
+    for (n1, p), (_, q) in zip(a.model.named_parameters(), b.model.named_parameters()):
+        assert torch.allclose(p, q, atol=5e-6, rtol=1e-4), n1
+
+
+def test_graphs_survive_growth_of_shared_scratch():
+    """SdfPipeline scratch and the zero arena are shared by the tracer's and the trainer's CUDA graphs; a larger SDF
+    query after capture (utils.plots.sdf_sweep uses 2^18-row chunks) must neither free memory a graph still points at nor
+    leave a stale graph in use: the graphed trainer keeps matching an eager twin step for step."""
+    from idrk import kernels as K
+    from idrk.utils import plots
+    a, inp, gt = _small_trainer(True)
+    b, _, _ = _small_trainer(False)
+    for _ in range(3):                                  # capture both graphs
+        la, lb = float(a.step(inp, gt)), float(b.step(inp, gt))
+    gen0 = K.SCRATCH_GENERATION[0]
+    pts = torch.rand(200000, 3, device=DEV) * 2 - 1     # far more rows than any tracer query of a 256-ray batch
+    with torch.no_grad():
+        big = a.model.implicit_network.sdf(pts)
+        junk = [torch.randn(1 << 22, device=DEV) for _ in range(8)]      # recycle whatever the allocator got back
+    assert K.SCRATCH_GENERATION[0] > gen0
+    for step in range(3):
+        la, lb = float(a.step(inp, gt)), float(b.step(inp, gt))
+        assert abs(la - lb) <= 1e-5 * max(1.0, abs(lb)), (step, la, lb)
+    with torch.no_grad():
+        assert torch.allclose(a.model.implicit_network.sdf(pts[:1000]), b.model.implicit_network.sdf(pts[:1000]), atol=1e-5)
+    del junk, big
