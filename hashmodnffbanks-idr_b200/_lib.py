@@ -109,7 +109,8 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_rt_select_sampler", "idrk_rt_sampler_points", "idrk_rt_sampler_resolve", "idrk_rt_secant",
            "idrk_rt_select_minsdf", "idrk_rt_minsdf_points", "idrk_rt_minsdf_resolve", "idrk_rt_chunk_counts",
            "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd", "idrk_gemm_f16s", "idrk_split_f16", "idrk_nffb_encode_fwd",
-           "idrk_hash_encode_f16pair"]
+           "idrk_hash_encode_f16pair", "idrk_camera_rays", "idrk_idr_loss", "idrk_scale3",
+           "idrk_fourier_dx_fwd", "idrk_fourier_dx_bwd"]
 
 
 class NffbDesc(ctypes.Structure):
@@ -175,7 +176,7 @@ def _declare(L):
     L.idrk_version.restype = c.c_int
     L.idrk_device_sm_count.argtypes = [c.POINTER(c.c_int)]
     L.idrk_hash_encode_fwd.argtypes = [c.POINTER(HashGridDesc), vp, i64, i32, vp, i32, vp, vp, vp]
-    L.idrk_hash_encode_bwd.argtypes = [c.POINTER(HashGridDesc), vp, i64, i32, vp, i32, c.POINTER(vp), vp, vp]
+    L.idrk_hash_encode_bwd.argtypes = [c.POINTER(HashGridDesc), vp, i64, i32, vp, i32, c.POINTER(vp), vp, i32, vp]
     fp = c.POINTER(c.c_float)
     L.idrk_posenc_fwd.argtypes = [vp, i64, i32, i32, fp, i32, i32, vp, i32, vp]
     L.idrk_posenc_bwd.argtypes = [vp, i64, i32, i32, fp, i32, i32, vp, i32, vp, i32, vp]
@@ -205,6 +206,11 @@ def _declare(L):
     L.idrk_split_f16.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp, vp]
     L.idrk_nffb_encode_fwd.argtypes = [c.POINTER(NffbDesc), vp, i64, i32, vp, i32, vp, vp]
     L.idrk_hash_encode_f16pair.argtypes = [c.POINTER(HashGridDesc), vp, i64, i32, vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp]
+    L.idrk_camera_rays.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp]
+    L.idrk_idr_loss.argtypes = [vp, i32, vp, vp, vp, vp, i32, i64, vp, i32, i64, f32, f32, f32, vp, vp, vp, vp, vp]
+    L.idrk_fourier_dx_fwd.argtypes = [vp, i32, vp, i32, vp, i32, i64, vp, vp]
+    L.idrk_fourier_dx_bwd.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i64, vp, i32, i32, vp, vp]
+    L.idrk_scale3.argtypes = [vp, vp, vp, i64, vp, vp, i64, vp, vp, i64, vp]
     L.idrk_sumsq.argtypes = [vp, i64, vp, vp]
     L.idrk_clip_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp, f32, vp]
     for fn in EXPORTS:

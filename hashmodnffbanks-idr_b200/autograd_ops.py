@@ -19,6 +19,28 @@ TWO_PI = 2.0 * math.pi
 # ---------------------------------------------------------------------------------------------
 # hash grid (+ Fourier prefix)
 # ---------------------------------------------------------------------------------------------
+class _FourierDx(torch.autograd.Function):
+    """d/dx of the Fourier prefix as ONE kernel that stays differentiable in dy and x (one more kernel): the recorded
+    backward pass of ImplicitNetwork.gradient needs it, and ~40 tensor ops (two K = 3 matmuls among them) did it before."""
+
+    @staticmethod
+    def forward(ctx, x, dy, B, width):
+        ctx.width = width
+        ctx.save_for_backward(x, dy, B)
+        return K.fourier_dx_fwd(x.detach(), dy.detach(), B)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, dy, B = ctx.saved_tensors
+        g_dy, g_x = K.fourier_dx_bwd(g, x, dy, B, ctx.width, ctx.needs_input_grad[0])
+        if g_x is not None and x.shape[1] != 3:
+            pad = torch.zeros_like(x)
+            pad[:, :3] = g_x
+            g_x = pad
+        return g_x, (g_dy if ctx.needs_input_grad[1] else None), None, None
+
+
 class _HashEncode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, B, spec, *tables):
@@ -57,9 +79,12 @@ class _HashEncode(torch.autograd.Function):
         if second_order:
             # differentiable form of d/dx: only the Fourier prefix depends on x in reference mode
             if C > 0:
-                xp = torch.matmul(TWO_PI * x[:, :3], B)
-                dxp = dy[:, 3:3 + C] * torch.cos(xp) - dy[:, 3 + C:3 + 2 * C] * torch.sin(xp)
-                dx = dy[:, :3] + TWO_PI * torch.matmul(dxp, B.t())
+                if dy.dtype == torch.float32 and dy.dim() == 2 and dy.shape[1] == spec.width:
+                    dx = _FourierDx.apply(x, dy, B, spec.width)
+                else:
+                    xp = torch.matmul(TWO_PI * x[:, :3], B)
+                    dxp = dy[:, 3:3 + C] * torch.cos(xp) - dy[:, 3 + C:3 + 2 * C] * torch.sin(xp)
+                    dx = dy[:, :3] + TWO_PI * torch.matmul(dxp, B.t())
             if spec.frac_mode != K._lib.HASH_REFERENCE:
                 with torch.no_grad():
                     zero_pre = dy.detach().clone()

@@ -16,6 +16,7 @@ struct GridDev {
     uint32_t ngp_res[IDRK_MAX_LEVELS];      // IDRK_HASH_NGP: grid resolution R_l = ceil(scale_l) + 1
     uint32_t ngp_dense[IDRK_MAX_LEVELS];    // IDRK_HASH_NGP: 1 = dense indexing (R^3 <= rows), 0 = hashed
     int pair_x;                             // 8-corner mode: x-neighbour corners share one 16-byte access when they can
+    int agg_runs;                           // 8-corner backward: in-lane aggregation of runs of points in the same cell
 };
 
 
@@ -80,6 +81,7 @@ inline int fill_grid(const idrk_hashgrid_t* h, GridDev& g) {
     g.width = (h->n_fourier > 0 ? 3 + 2 * h->n_fourier : 0) + h->n_levels * h->n_feat;
     g.B = h->fourier_B;
     { static const int pair = [] { const char* e = getenv("IDRK_HASH_PAIR_X"); return (e && e[0] == '0') ? 0 : 1; }(); g.pair_x = pair; }
+    { static const int agg = [] { const char* e = getenv("IDRK_HASH_AGG"); return (e && e[0] == '0') ? 0 : 1; }(); g.agg_runs = agg; }
     const size_t align = (h->n_feat >= 4) ? 16 : 4 * (size_t)h->n_feat;
     for (int l = 0; l < h->n_levels; ++l) {
         if (h->tables[l] == nullptr || h->rows[l] == 0) return IDRK_E_ARG;

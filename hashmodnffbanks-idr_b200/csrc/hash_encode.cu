@@ -80,17 +80,19 @@ __device__ __forceinline__ LevelC load_level(const LevelC* s_lev, int l) {
 //   IDRK_HASH_NGP: tiny-cuda-nn's grid (pos = fma(x, scale, 0.5); dense stride index while the level fits its table,
 //   else the coherent prime hash 1, 2654435761, 805459861); corner bit 0 = x, bit 1 = y, bit 2 = z in both.
 template <int MODE, bool FAST>
-__device__ __forceinline__ void corner_rows(const LevelC& lc, float x0, float x1, float x2, uint32_t (&idx)[8],
-                                            float& w0, float& w1, float& w2, uint32_t& c0_out) {
+__device__ __forceinline__ void cell_of(const LevelC& lc, float x0, float x1, float x2, uint32_t& c0, uint32_t& c1, uint32_t& c2,
+                                        float& w0, float& w1, float& w2) {
     float s0, s1, s2;
     if constexpr (MODE == IDRK_HASH_NGP) { s0 = fmaf(x0, lc.res, 0.5f); s1 = fmaf(x1, lc.res, 0.5f); s2 = fmaf(x2, lc.res, 0.5f); }
     else { s0 = __fmul_rn(x0, lc.res); s1 = __fmul_rn(x1, lc.res); s2 = __fmul_rn(x2, lc.res); }
     const float f0 = floorf(s0), f1 = floorf(s1), f2 = floorf(s2);
     w0 = s0 - f0; w1 = s1 - f1; w2 = s2 - f2;
-    uint32_t c0, c1, c2;
     if constexpr (FAST) { c0 = (uint32_t)__float2int_rz(f0); c1 = (uint32_t)__float2int_rz(f1); c2 = (uint32_t)__float2int_rz(f2); }
     else { c0 = trunc_u32(f0); c1 = trunc_u32(f1); c2 = trunc_u32(f2); }
-    c0_out = c0;
+}
+
+template <int MODE>
+__device__ __forceinline__ void rows_of_cell(const LevelC& lc, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t (&idx)[8]) {
     if constexpr (MODE == IDRK_HASH_NGP) {
         const bool dense = lc.ngp_dense != 0;
         const uint32_t R = lc.ngp_res, py = dense ? R : 2654435761u, pz = dense ? R * R : 805459861u;
@@ -108,6 +110,15 @@ __device__ __forceinline__ void corner_rows(const LevelC& lc, float x0, float x1
         for (int k = 0; k < 8; ++k)
             idx[k] = wrap(((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0), lc.rows, lc.mask, lc.magic);
     }
+}
+
+template <int MODE, bool FAST>
+__device__ __forceinline__ void corner_rows(const LevelC& lc, float x0, float x1, float x2, uint32_t (&idx)[8],
+                                            float& w0, float& w1, float& w2, uint32_t& c0_out) {
+    uint32_t c0, c1, c2;
+    cell_of<MODE, FAST>(lc, x0, x1, x2, c0, c1, c2, w0, w1, w2);
+    c0_out = c0;
+    rows_of_cell<MODE>(lc, c0, c1, c2, idx);
 }
 template <bool FAST> __device__ __forceinline__ uint32_t trunc_sel(float v) {
     if constexpr (FAST) return (uint32_t)__float2int_rz(v); else return trunc_u32(v);
@@ -419,6 +430,66 @@ __device__ __forceinline__ void bwd_element(const LevelC& lc, float* gtab, float
     }
 }
 
+// In-lane run aggregation (8-corner modes, table gradients only).  On the full-tile path a lane owns ONE level and walks the
+// points of its warp's tile range in order, so when consecutive points fall into the same cell of that level (spatially
+// ordered input: samples along a ray, Morton-sorted points; always true for the coarse levels of dense batches) their
+// 8 corner contributions are summed in registers and leave as ONE set of reductions when the cell changes.  The table-
+// gradient backward is bound by the number of L2 reduction operations (193 G/s device-wide whatever their width,
+// scripts/probes/atomics_probe.cu), so every merged element saves its 4-8 of them; an element that starts a new cell costs
+// what it cost before (one compare + the same reductions, issued one element later).
+template <int F>
+struct CellAcc {
+    uint32_t c0, c1, c2;
+    int valid;
+    float acc[8][F];
+};
+
+template <int F, int MODE, bool PAIR>
+__device__ __forceinline__ void flush_cell(const LevelC& lc, float* gtab, float* s_acc, const CellAcc<F>& st, bool pair_lane) {
+    uint32_t idx[8];
+    rows_of_cell<MODE>(lc, st.c0, st.c1, st.c2, idx);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (PAIR && F == 2 && pair_lane) {
+            if ((k & 1) == 0) {                       // same pairing rule as bwd_element
+                const bool even = (st.c0 & 1u) == 0;
+                const float nx = even ? st.acc[k + 1][0] : 0.f, ny = even ? st.acc[k + 1][F - 1] : 0.f;
+                const bool o = idx[k] & 1u;
+                red_add_v4(gtab + (size_t)(idx[k] & ~1u) * F, o ? nx : st.acc[k][0], o ? ny : st.acc[k][F - 1],
+                           o ? st.acc[k][0] : nx, o ? st.acc[k][F - 1] : ny);
+            } else if (st.c0 & 1u) {
+                red_add_v2(gtab + (size_t)idx[k] * F, st.acc[k][0], st.acc[k][F - 1]);
+            }
+        } else {
+            scatter_sel<F>(gtab, s_acc, lc.soff, idx[k], st.acc[k]);
+        }
+    }
+}
+
+// one (point, level) element of the aggregated table-gradient backward
+template <int F, int MODE, bool PAIR>
+__device__ __forceinline__ void bwd_element_agg(const LevelC& lc, float* gtab, float* s_acc, float x0, float x1, float x2,
+                                                const float (&gy)[F], CellAcc<F>& st, bool pair_lane) {
+    uint32_t c0, c1, c2;
+    float w0, w1, w2;
+    cell_of<MODE, true>(lc, x0, x1, x2, c0, c1, c2, w0, w1, w2);
+    const bool same = st.valid && c0 == st.c0 && c1 == st.c1 && c2 == st.c2;
+    if (!same) {
+        if (st.valid) flush_cell<F, MODE, PAIR>(lc, gtab, s_acc, st, pair_lane);
+        st.c0 = c0; st.c1 = c1; st.c2 = c2; st.valid = 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int f = 0; f < F; ++f) st.acc[k][f] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float wk = ((k & 1) ? w0 : 1.f - w0) * ((k & 2) ? w1 : 1.f - w1) * ((k & 4) ? w2 : 1.f - w2);
+#pragma unroll
+        for (int f = 0; f < F; ++f) st.acc[k][f] = fmaf(wk, gy[f], st.acc[k][f]);
+    }
+}
+
 // adds (v0, v1, v2) of every lane into dxs[row]: xor-shuffle over the aligned group of `grp` lanes that share the row
 // (grp = L or C when it divides 32), else shared-memory atomics.
 __device__ __forceinline__ void row_reduce_add(float* dxs, int row, bool active, int grp, bool grp_ok, int lane,
@@ -498,7 +569,45 @@ __device__ __forceinline__ void bwd_levels_full(const LevelC& lc, float* gtab, f
     }
 }
 
-template <int F, int MODE, int WARPS>
+// Full 32-row tile, aggregated table-gradient form (no dL/dx): same walk as bwd_levels_full, the lane's open cell lives
+// in `st` across passes AND tiles.
+template <int F, int MODE, bool SHIFT, bool PAIR>
+__device__ __forceinline__ void bwd_levels_full_agg(const LevelC& lc, float* gtab, float* s_acc, const float4* xs, int L, int lane,
+                                                    const float* __restrict__ drow0, int ld_dy, bool pair_lane, CellAcc<F>& st) {
+    constexpr int KB = 2;
+    const int rstep = 32 / L, row0 = lane / L, l = lane - row0 * L;
+    const float* __restrict__ o0 = drow0 + row0 * ld_dy + l * F;
+    const int step = rstep * ld_dy;
+    for (int pass = 0; pass < L; pass += KB) {
+        float gy[KB][F];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            if (pass + k < L) {
+                const float* o = o0 + (pass + k) * step;
+                if constexpr (SHIFT) {
+                    const float2 pr = __ldcs(reinterpret_cast<const float2*>(o + 1));
+                    float first = 0.f;
+                    if (l == 0) first = __ldcs(o);
+                    const float up = __shfl_up_sync(0xffffffffu, pr.y, 1);
+                    gy[k][0] = (l == 0) ? first : up;
+                    gy[k][1] = pr.x;
+                } else {
+#pragma unroll
+                    for (int f = 0; f < F; ++f) gy[k][f] = __ldg(o + f);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            if (pass + k < L) {
+                const float4 xv = xs[row0 + (pass + k) * rstep];
+                bwd_element_agg<F, MODE, PAIR>(lc, gtab, s_acc, xv.x, xv.y, xv.z, gy[k], st, pair_lane);
+            }
+        }
+    }
+}
+
+template <int F, int MODE, int WARPS, bool AGG = false>
 __global__ void __launch_bounds__(WARPS * 32)
 hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __restrict__ x, long long n, int ldx,
                             const float* __restrict__ dy, int ld_dy, float* __restrict__ dx) {
@@ -543,8 +652,21 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
     if (C > 0) { const int j = lane % C; b0 = s_B[j]; b1 = s_B[C + j]; b2 = s_B[2 * C + j]; }
 
     const long long n_wtiles = (n + 31) / 32;
-    const long long wstride = (long long)gridDim.x * WARPS;
-    for (long long wt = (long long)blockIdx.x * WARPS + warp; wt < n_wtiles; wt += wstride) {
+    long long wstride = (long long)gridDim.x * WARPS;
+    long long wt_begin = (long long)blockIdx.x * WARPS + warp, wt_end = n_wtiles;
+    // run aggregation (8-corner modes, table gradients without dL/dx): a warp walks a CONTIGUOUS range of tiles so that
+    // a lane sees the points in input order; the strided assignment stays for everything else
+    constexpr bool AGGK = AGG && MODE != IDRK_HASH_REFERENCE && F == 2;      // its own instantiation: 124 vs 80 registers
+    const bool agg = AGGK && !want_dx && gd.any_grad && l_fixed;
+    CellAcc<AGGK ? F : 1> st;
+    st.valid = 0; st.c0 = st.c1 = st.c2 = 0;
+    if (agg) {
+        const long long per = (n_wtiles + wstride - 1) / wstride;
+        wt_begin = wt_begin * per;
+        wt_end = min(n_wtiles, wt_begin + per);
+        wstride = 1;
+    }
+    for (long long wt = wt_begin; wt < wt_end; wt += wstride) {
         const long long p0 = wt * 32, p = p0 + lane;
         const int rows_here = (int)min(32LL, n - p0);
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;
@@ -594,7 +716,18 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
         if (L > 0 && (MODE != IDRK_HASH_REFERENCE || gd.any_grad)) {
             const float amax = fmaxf(fabsf(x0), fmaxf(fabsf(x1), fabsf(x2))) * res_max;
             const bool fast = __all_sync(0xffffffffu, amax < 2147483520.f);
-            if (fast && rows_here == 32 && l_fixed) {
+            if constexpr (AGGK) {
+                if (agg && !(fast && rows_here == 32) && st.valid) {           // leaving the full-tile path: close the open cell
+                    flush_cell<F, MODE, PAIRK>(lc, gtab, s_acc, st, pair_lane);
+                    st.valid = 0;
+                }
+            }
+            if (AGGK && agg && fast && rows_here == 32) {
+                if constexpr (AGGK) {
+                    if (shift) bwd_levels_full_agg<F, MODE, true, PAIRK>(lc, gtab, s_acc, xs, L, lane, drow0 + pre, ld_dy, pair_lane, st);
+                    else       bwd_levels_full_agg<F, MODE, false, PAIRK>(lc, gtab, s_acc, xs, L, lane, drow0 + pre, ld_dy, pair_lane, st);
+                }
+            } else if (fast && rows_here == 32 && l_fixed) {
                 if (F == 2 && shift) {
                     if (want_dx) bwd_levels_full<F, MODE, true, F == 2, PAIRK>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
                     else         bwd_levels_full<F, MODE, false, F == 2, PAIRK>(lc, gtab, s_acc, xs, dxs, L, lane, drow0 + pre, ld_dy, pair_lane);
@@ -611,6 +744,9 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
             __syncwarp();
             if (lane < rows_here) { dx[p * 3 + 0] = dxs[4 * lane]; dx[p * 3 + 1] = dxs[4 * lane + 1]; dx[p * 3 + 2] = dxs[4 * lane + 2]; }
         }
+    }
+    if constexpr (AGGK) {
+        if (agg && st.valid) flush_cell<F, MODE, PAIRK>(lc, gtab, s_acc, st, pair_lane);
     }
     // flush the CTA-local accumulators of the small tables
     if (gd.small_total > 0) {
@@ -730,11 +866,15 @@ static int launch_fwd(const GridDev& g, const float* x, long long n, int ldx, fl
 
 template <int F, int MODE, int WARPS>
 static int launch_bwd(const GridDev& g, const GradDev& gd, const float* x, long long n, int ldx, const float* dy,
-                      int ld_dy, float* dx, cudaStream_t st) {
+                      int ld_dy, float* dx, bool ordered, cudaStream_t st) {
     const int L = g.n_levels, C = g.n_fourier;
     const size_t smem = ((size_t)3 * L + 2 * WARPS * 32) * 16 + (size_t)((L + 1) & ~1) * 8 +
                         (size_t)((3 * C + 3) & ~3) * 4 + (size_t)gd.small_total * 4;
     auto kern = hash_encode_bwd_elem_kernel<F, MODE, WARPS>;
+    // spatially ordered input (caller's hint): the run-aggregating instantiation, see CellAcc
+    if constexpr (MODE != IDRK_HASH_REFERENCE && F == 2) {
+        if (ordered && g.agg_runs && dx == nullptr && gd.any_grad) kern = hash_encode_bwd_elem_kernel<F, MODE, WARPS, true>;
+    }
     IDRK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = persistent_grid(kern, WARPS * 32, smem, (n + WARPS * 32 - 1) / (WARPS * 32));
     IDRK_CUDA_TRY(launch_k(kern, dim3(grid), dim3(WARPS * 32), smem, st, g, gd, x, n, ldx, dy, ld_dy, dx));
@@ -760,7 +900,7 @@ static int launch_bwd(const GridDev& g, const GradDev& gd, const float* x, long 
 
 using namespace idrk;
 
-extern "C" int idrk_version(void) { return 2; }   // 2: idrk_epilogue_f16_t gained dot_w / dot_out / ld_dot, IDRK_HASH_NGP, idrk_hash_encode_f16pair
+extern "C" int idrk_version(void) { return 3; }   // 3: idrk_camera_rays / idrk_idr_loss / idrk_scale3 (render_glue.cu); 2: idrk_epilogue_f16_t gained dot_w / dot_out / ld_dot, IDRK_HASH_NGP, idrk_hash_encode_f16pair
 
 extern "C" int idrk_device_sm_count(int* out_sms) {
     if (!out_sms) return IDRK_E_ARG;
@@ -822,7 +962,7 @@ extern "C" int idrk_hash_encode_f16pair(const idrk_hashgrid_t* h_grid, const flo
 
 extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
                                     const float* dy, int32_t ld_dy, float* const* h_grad_tables, float* dx,
-                                    void* stream) {
+                                    int32_t flags, void* stream) {
     GridDev g;
     int rc = fill_grid(h_grid, g);
     if (rc) return rc;
@@ -844,7 +984,8 @@ extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* 
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = h_grid->frac_mode;
-#define CALL(F, M) launch_bwd<F, M, 4>(g, gd, x, n, ldx, dy, ld_dy, dx, st)
+    const bool ordered = (flags & IDRK_HASH_BWD_ORDERED) != 0;
+#define CALL(F, M) launch_bwd<F, M, 4>(g, gd, x, n, ldx, dy, ld_dy, dx, ordered, st)
     IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
 }

@@ -108,9 +108,13 @@ def hash_encode_f16pair(spec: HashGridSpec, x: torch.Tensor, tables, B, rows: in
           "idrk_hash_encode_f16pair")
 
 
+HASH_BWD_ORDERED = 1
+
+
 def hash_encode_bwd(spec: HashGridSpec, x: torch.Tensor, tables, B, dy: torch.Tensor,
-                    grad_tables: Optional[List[torch.Tensor]], want_dx: bool):
-    """K2.  Accumulates into grad_tables (list of [T_l, F], may be None) and returns dx [n,3] or None."""
+                    grad_tables: Optional[List[torch.Tensor]], want_dx: bool, ordered: bool = False):
+    """K2.  Accumulates into grad_tables (list of [T_l, F], may be None) and returns dx [n,3] or None.  `ordered`: the
+    points are spatially ordered (ray samples, utils.sorting.morton_order) - runs sharing a cell are merged in registers."""
     x = rows2d(x, "x")
     dy = rows2d(dy, "dy")
     n = x.shape[0]
@@ -124,7 +128,7 @@ def hash_encode_bwd(spec: HashGridSpec, x: torch.Tensor, tables, B, dy: torch.Te
     else:
         garg = ctypes.cast(None, ctypes.POINTER(ctypes.c_void_p))
     check(lib().idrk_hash_encode_bwd(ctypes.byref(d), ptr(x), n, ld_of(x), ptr(dy), ld_of(dy),
-                                     garg, ptr(dx), stream_ptr()), "idrk_hash_encode_bwd")
+                                     garg, ptr(dx), HASH_BWD_ORDERED if ordered else 0, stream_ptr()), "idrk_hash_encode_bwd")
     return dx
 
 
@@ -396,6 +400,85 @@ def sdf_squash(s: torch.Tensor, beta: float, want_grad: bool):
     if s.numel():
         check(lib().idrk_sdf_squash(ptr(s), s.numel(), float(beta), ptr(out), ptr(d), stream_ptr()), "idrk_sdf_squash")
     return out, d
+
+
+# ---------------------------------------------------------------------------------------------
+# O(rays) ends of the step: camera rays + sphere intersection, IDR loss (csrc/render_glue.cu)
+# ---------------------------------------------------------------------------------------------
+def camera_rays(uv: torch.Tensor, pose: torch.Tensor, intrinsics: torch.Tensor, radius: Optional[float] = None):
+    """uv [B,N,2], pose [B,4,4], intrinsics [B,4,4] -> (ray_dirs [B,N,3], cam_loc [B,3]) and, with `radius`, also
+    (t_sph [B,N,2], hit [B,N] bool) of the bounding sphere - one launch, no boolean indexing (no host sync)."""
+    for t, name in ((uv, "uv"), (pose, "pose"), (intrinsics, "intrinsics")):
+        _f32c(t, name)
+    B, N = uv.shape[0], uv.shape[1]
+    if tuple(pose.shape) != (B, 4, 4) or tuple(intrinsics.shape) != (B, 4, 4) or uv.shape[2] != 2:
+        raise _lib.IdrkError("camera_rays: uv [B,N,2], pose [B,4,4], intrinsics [B,4,4] expected")
+    uv, pose, intrinsics = uv.contiguous(), pose.contiguous(), intrinsics.contiguous()
+    dev = uv.device
+    dirs = torch.empty((B, N, 3), device=dev, dtype=torch.float32)
+    cam = torch.empty((B, 3), device=dev, dtype=torch.float32)
+    t_sph = hit = None
+    if radius is not None:
+        t_sph = torch.empty((B, N, 2), device=dev, dtype=torch.float32)
+        hit = torch.empty((B, N), device=dev, dtype=torch.bool)
+    check(lib().idrk_camera_rays(ptr(uv), ptr(pose), ptr(intrinsics), B, N, float(radius if radius is not None else 1.0),
+                                 ptr(dirs), ptr(cam), ptr(t_sph), ptr(hit), stream_ptr()), "idrk_camera_rays")
+    return (dirs, cam) if radius is None else (dirs, cam, t_sph, hit)
+
+
+def idr_loss(rgb_values, rgb_gt, net_mask, obj_mask, sdf_output, grad_theta, eikonal_weight, mask_weight, alpha,
+             want_grads: bool):
+    """One launch: out[4] = (loss, rgb_loss, eikonal_loss, mask_loss) and (want_grads) d loss / d (rgb_values, sdf_output,
+    grad_theta)."""
+    rgb_values = rows2d(rgb_values, "rgb_values")
+    sdf_output = rows2d(sdf_output.reshape(-1, 1), "sdf_output")
+    n = rgb_values.shape[0]
+    rgb_gt = _f32c(rgb_gt, "rgb_gt").reshape(-1, 3).contiguous()
+    nm, om = net_mask.reshape(-1).contiguous(), obj_mask.reshape(-1).contiguous()
+    if nm.dtype != torch.bool or om.dtype != torch.bool or nm.numel() != n or om.numel() != n or rgb_gt.shape[0] != n:
+        raise _lib.IdrkError("idr_loss: masks must be bool [N] and rgb_gt [N,3]")
+    m = 0
+    if grad_theta is not None and grad_theta.shape[0] > 0:
+        grad_theta = rows2d(grad_theta, "grad_theta")
+        m = grad_theta.shape[0]
+    dev = rgb_values.device
+    out = torch.empty(4, device=dev, dtype=torch.float32)
+    d_rgb = torch.empty((n, 3), device=dev, dtype=torch.float32) if want_grads else None
+    d_sdf = torch.empty((n, 1), device=dev, dtype=torch.float32) if want_grads else None
+    d_g = torch.empty((m, 3), device=dev, dtype=torch.float32) if (want_grads and m) else None
+    check(lib().idrk_idr_loss(ptr(rgb_values), ld_of(rgb_values), ptr(rgb_gt), ptr(nm), ptr(om), ptr(sdf_output),
+                              ld_of(sdf_output), n, ptr(grad_theta) if m else None, ld_of(grad_theta) if m else 0, m,
+                              float(eikonal_weight), float(mask_weight), float(alpha), ptr(out), ptr(d_rgb), ptr(d_sdf),
+                              ptr(d_g), stream_ptr()), "idrk_idr_loss")
+    return out, d_rgb, d_sdf, d_g
+
+
+def fourier_dx_fwd(x: torch.Tensor, dy: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    x, dy = rows2d(x, "x"), rows2d(dy, "dy")
+    dx = torch.empty((x.shape[0], 3), device=x.device, dtype=torch.float32)
+    check(lib().idrk_fourier_dx_fwd(ptr(x), ld_of(x), ptr(dy), ld_of(dy), ptr(B), B.shape[1], x.shape[0], ptr(dx), stream_ptr()),
+          "idrk_fourier_dx_fwd")
+    return dx
+
+
+def fourier_dx_bwd(g: torch.Tensor, x: torch.Tensor, dy: torch.Tensor, B: torch.Tensor, width: int, want_gx: bool):
+    g, x, dy = rows2d(g, "g"), rows2d(x, "x"), rows2d(dy, "dy")
+    n = x.shape[0]
+    g_dy = torch.empty((n, pad4(width)), device=x.device, dtype=torch.float32)
+    g_x = torch.empty((n, 3), device=x.device, dtype=torch.float32) if want_gx else None
+    check(lib().idrk_fourier_dx_bwd(ptr(g), ld_of(g), ptr(x), ld_of(x), ptr(dy), ld_of(dy), ptr(B), B.shape[1], n, ptr(g_dy),
+                                    pad4(width), width, ptr(g_x), stream_ptr()), "idrk_fourier_dx_bwd")
+    return g_dy[:, :width], g_x
+
+
+def scale3(scale: torch.Tensor, a, b, c):
+    """(scale * a, scale * b, scale * c) in one launch; scale is a 0-dim / 1-element device tensor, c may be None."""
+    scale = _f32c(scale.reshape(1), "scale")
+    ya, yb = torch.empty_like(a), torch.empty_like(b)
+    yc = torch.empty_like(c) if c is not None else None
+    check(lib().idrk_scale3(ptr(scale), ptr(a), ptr(ya), a.numel(), ptr(b), ptr(yb), b.numel(), ptr(c), ptr(yc),
+                            c.numel() if c is not None else 0, stream_ptr()), "idrk_scale3")
+    return ya, yb, yc
 
 
 # ---------------------------------------------------------------------------------------------

@@ -225,6 +225,10 @@ def linear(X, W, b=None):
 
 _ACT_MODES = {"softplus": K.EPI_SOFTPLUS, "relu": K.EPI_RELU, "sine": K.EPI_SINE, "tanh": K.EPI_TANH}
 
+# Parity-test tap: when set to a list, every ReLU layer appends its derivative mask S = 1[z > 0] (the activation pattern).
+# ReLU gradients are discontinuous in z, so a checker has to compare them under the SAME pattern (tests/test_full_shapes.py).
+ACT_PATTERN_TAP = [None]
+
 
 class _MulAct(torch.autograd.Function):
     """dZ = scale * dH * S on the RECORDED backward pass (ImplicitNetwork.gradient, create_graph=True): one kernel forms the
@@ -273,6 +277,8 @@ class _LinearAct(torch.autograd.Function):
                        want_s=True, a_split=ctx.x_split, b_split=ctx.w_split, split_out=True)
         ctx.mode, ctx.act, ctx.scale, ctx.has_bias = mode, act, scale, b is not None
         ctx.bias_ref = b
+        if ACT_PATTERN_TAP[0] is not None and mode == "relu":
+            ACT_PATTERN_TAP[0].append(S.detach().clone())
         ctx.save_for_backward(X, W, H, S)
         ctx.set_materialize_grads(False)
         return H, S

@@ -265,12 +265,19 @@ class IDRNetwork(nn.Module):
         part needs: ray_dirs [B,N,3], cam_loc [B,3], dists [B*N], network_object_mask, object_mask."""
         intrinsics, uv, pose = input["intrinsics"], input["uv"], input["pose"]
         object_mask = input["object_mask"].reshape(-1)
-        ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics)
+        sphere = None
+        if rend_util._kernel_path(uv, pose, intrinsics):
+            # rays and their bounding-sphere intersections from one launch (no boolean indexing, no host sync)
+            ray_dirs, cam_loc, t_sph, hit = rend_util.camera_rays_and_sphere(uv, pose, intrinsics, self.object_bounding_sphere)
+            sphere = (t_sph, hit)
+        else:
+            ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics)
         self.implicit_network.eval()
         with torch.no_grad():
             self.ray_tracer.train(self.training)
             _, network_object_mask, dists = self.ray_tracer(sdf=self.implicit_network.sdf, cam_loc=cam_loc,
-                                                            object_mask=object_mask, ray_directions=ray_dirs)
+                                                            object_mask=object_mask, ray_directions=ray_dirs,
+                                                            sphere_intersections=sphere)
         self.implicit_network.train()
         return {"ray_dirs": ray_dirs, "cam_loc": cam_loc, "dists": dists, "network_object_mask": network_object_mask,
                 "object_mask": object_mask}

@@ -23,8 +23,33 @@ def lift(x, y, z, intrinsics):
     return torch.stack((x_lift, y_lift, z, torch.ones_like(z)), dim=-1)
 
 
+def _pose44(pose):
+    if pose.shape[1] != 7:
+        return pose
+    p = torch.eye(4, device=pose.device, dtype=pose.dtype).repeat(pose.shape[0], 1, 1)
+    p[:, :3, :3] = quat_to_rot(pose[:, :4])
+    p[:, :3, 3] = pose[:, 4:]
+    return p
+
+
+def _kernel_path(uv, pose, intrinsics):
+    """The one-launch kernel (csrc/render_glue.cu) serves fixed cameras on the device; trainable poses (--train_cameras
+    needs d ray / d pose) and anything else keep the differentiable tensor-op formulation below."""
+    return (uv.is_cuda and uv.dtype == torch.float32 and pose.dtype == torch.float32 and intrinsics.dtype == torch.float32
+            and not (torch.is_grad_enabled() and (pose.requires_grad or uv.requires_grad or intrinsics.requires_grad)))
+
+
+def camera_rays_and_sphere(uv, pose, intrinsics, r=1.0):
+    """get_camera_params + get_sphere_intersection in one launch: (ray_dirs, cam_loc, t_sph [B,N,2], hit [B,N])."""
+    from .. import kernels as K
+    return K.camera_rays(uv, _pose44(pose), intrinsics.to(uv.device), radius=r)
+
+
 def get_camera_params(uv, pose, intrinsics):
     """uv [B,N,2], pose [B,4,4] (or [B,7] quaternion + location) -> ray_dirs [B,N,3], cam_loc [B,3]."""
+    if _kernel_path(uv, pose, intrinsics):
+        from .. import kernels as K
+        return K.camera_rays(uv, _pose44(pose), intrinsics.to(uv.device))
     if pose.shape[1] == 7:
         cam_loc = pose[:, 4:]
         p = torch.eye(4, device=pose.device, dtype=pose.dtype).repeat(pose.shape[0], 1, 1)

@@ -57,7 +57,7 @@ typedef struct idrk_hashgrid {
 } idrk_hashgrid_t;
 
 /* -- version / capability ------------------------------------------------------------- */
-int idrk_version(void);                        /* ABI version, currently 2 (1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
+int idrk_version(void);                        /* ABI version, currently 3 (2 -> 3: idrk_hash_encode_bwd gained `flags`; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
 int idrk_device_sm_count(int* out_sms);        /* SM count of the current device */
 
 /* -- K1: hash-grid encode forward -------------------------------------------------------
@@ -83,10 +83,14 @@ int idrk_hash_encode_f16pair(const idrk_hashgrid_t* h_grid, const float* x, int6
  * Replaces autograd through the same functions: embedding_dense_backward scatter-add into
  * every level's table gradient and d/dx of the Fourier prefix.  dy [n, ld_dy] is dL/d(out).
  * h_grad_tables: HOST array of L device pointers, each [T_l, F] (NULL = skip table gradients); ACCUMULATED
- * (caller zero-fills).  dx (nullable) [n, 3] is overwritten. */
+ * (caller zero-fills).  dx (nullable) [n, 3] is overwritten.
+ * flags: IDRK_HASH_BWD_ORDERED = the caller's hint that consecutive points are spatially close (samples along rays,
+ * Z-ordered batches): the 8-corner table-gradient pass then merges runs of points that share a cell of a level in
+ * registers before issuing reductions (same result up to fp32 summation order; harmless but slower on unordered input). */
+#define IDRK_HASH_BWD_ORDERED 1
 int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
                          const float* dy, int32_t ld_dy, float* const* h_grad_tables,
-                         float* dx, void* stream);
+                         float* dx, int32_t flags, void* stream);
 
 /* -- positional encoding ----------------------------------------------------------------
  * Replaces PositionalEncoding.embed (frequency_enc.py:19-51) and get_embedder (:156-168).
@@ -283,6 +287,38 @@ int idrk_rt_minsdf_resolve(const idrk_ray_state_t* h_state, const int32_t* ray_o
 int idrk_sumsq(const float* g, int64_t n, float* out, void* stream);
 int idrk_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int32_t step, float max_norm, const float* sumsq, float grad_scale, void* stream);
+
+/* -- K8: O(rays) ends of the step (csrc/render_glue.cu) --------------------------------------
+ * idrk_camera_rays replaces get_camera_params + lift (utils/rend_util.py:48-75, :87-100: pixel -> world ray through a
+ * 4x4 camera-to-world pose and a 4x4 intrinsics matrix with skew, normalised) and, when t_sph / hit are given,
+ * get_sphere_intersection (utils/rend_util.py:141-162: under = (d.c)^2 - (|c|^2 - r^2), hit = under > 0,
+ * t = -+sqrt(under) - d.c clamped at 0, zeros for rays that miss) - one launch, no boolean-mask indexing.
+ *   uv [B, N, 2], pose [B, 4, 4], intrinsics [B, 4, 4] -> ray_dirs [B, N, 3], cam_loc [B, 3], t_sph [B, N, 2], hit [B, N] (bytes).
+ * idrk_idr_loss replaces IDRLoss.forward (model/loss.py:5-71) and its backward with respect to the three network
+ * outputs: out_losses[4] = {loss, rgb_loss, eikonal_loss, mask_loss};
+ *   rgb_loss  = sum_{net & obj} |rgb - gt| / N,  eikonal = mean_M (|g| - 1)^2,
+ *   mask_loss = (1 / alpha) * sum_{!(net & obj)} BCEwithlogits(-alpha * sdf, obj) / N,
+ *   loss = rgb_loss + eikonal_weight * eikonal + mask_weight * mask_loss;
+ * d_rgb [N, 3], d_sdf [N], d_grad_theta [M, 3] (any may be NULL) receive d loss / d input.  Masks are bytes (torch.bool
+ * storage).  One thread block, fixed reduction order: deterministic.  idrk_scale3: y = (*scale) * x for three buffers
+ * (the chain-rule factor of the incoming loss gradient). */
+int idrk_camera_rays(const float* uv, const float* pose, const float* intrinsics, int32_t n_images, int32_t n_pixels,
+                     float radius, float* ray_dirs, float* cam_loc, float* t_sph, uint8_t* hit, void* stream);
+int idrk_idr_loss(const float* rgb_values, int32_t ld_rgb, const float* rgb_gt, const uint8_t* network_object_mask,
+                  const uint8_t* object_mask, const float* sdf_output, int32_t ld_sdf, int64_t n_rays,
+                  const float* grad_theta, int32_t ld_grad, int64_t n_grad, float eikonal_weight, float mask_weight,
+                  float alpha, float* out_losses, float* d_rgb, float* d_sdf, float* d_grad_theta, void* stream);
+/* Differentiable d/dx of the FourierFeature prefix [x | sin(2 pi x B) | cos(2 pi x B)] (model/embeddings/frequency_enc.py:63-67)
+ * for the RECORDED backward pass of ImplicitNetwork.gradient (create_graph=True, implicit_differentiable_renderer.py:116-128):
+ * fwd: dx = dy_x + 2 pi sum_j (dy_sin_j cos xp_j - dy_cos_j sin xp_j) B[:, j];  bwd: given g = d L / d dx, the gradient with
+ * respect to dy (full `width` columns, zeros beyond the prefix) and, when g_x != NULL, with respect to x. */
+int idrk_fourier_dx_fwd(const float* x, int32_t ldx, const float* dy, int32_t ld_dy, const float* B, int32_t n_fourier,
+                        int64_t n, float* dx, void* stream);
+int idrk_fourier_dx_bwd(const float* g, int32_t ld_g, const float* x, int32_t ldx, const float* dy, int32_t ld_dy,
+                        const float* B, int32_t n_fourier, int64_t n, float* g_dy, int32_t ld_gdy, int32_t width,
+                        float* g_x, void* stream);
+int idrk_scale3(const float* scale, const float* a, float* ya, int64_t na, const float* b, float* yb, int64_t nb,
+                const float* c, float* yc, int64_t nc, void* stream);
 
 #ifdef __cplusplus
 }

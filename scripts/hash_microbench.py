@@ -81,9 +81,9 @@ def run(n, log2T, mode, L=16, F=2, flush=None):
                 K.hash_encode_bwd(spec, xc, tables, B, dy[:xc.shape[0]], grads, want_dx)
             dist.all_reduce(flat)
     else:
-        def bwd(want_dx):
+        def bwd(want_dx, ordered=False):
             for xc in xs:
-                K.hash_encode_bwd(spec, xc, tables, B, dy[:xc.shape[0]], grads, want_dx)
+                K.hash_encode_bwd(spec, xc, tables, B, dy[:xc.shape[0]], grads, want_dx, ordered=ordered)
 
     def fwd():
         for xc in xs:
@@ -91,6 +91,27 @@ def run(n, log2T, mode, L=16, F=2, flush=None):
     t_f = time_cuda(fwd, flush=flush)
     t_b = time_cuda(lambda: bwd(False), flush=flush)      # table gradients
     t_bx = time_cuda(lambda: bwd(True), flush=flush)      # + dL/dx
+    extra = {}
+    if mode != "reference" and world == 1 and len(xs) == 1:
+        # spatially ordered input (what ray-marched samples look like): the backward merges runs of points that share a
+        # cell in registers.  Reported three ways: points already ordered (sort not timed), and with the Z-order sort of
+        # unordered points (keys + torch.sort + the x / dL/dy row gathers) inside the timing.
+        from idrk.utils.sorting import morton_order
+        perm = morton_order(x, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0))
+        x_sorted = x[perm].contiguous()
+        xs_saved, xs[0] = xs[0], x_sorted
+        t_bs = time_cuda(lambda: bwd(False, ordered=True), flush=flush)
+        t_fs = time_cuda(fwd, flush=flush)
+        xs[0] = xs_saved
+        dy_sorted = torch.empty_like(dy)
+
+        def sort_all():
+            pm = morton_order(x, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0))
+            torch.index_select(x, 0, pm, out=x_sorted)
+            torch.index_select(dy, 0, pm, out=dy_sorted)
+        t_sort = time_cuda(sort_all, flush=flush)
+        del dy_sorted, x_sorted, perm
+        extra = {"bwd_presorted_ms": t_bs, "fwd_presorted_ms": t_fs, "sort_ms": t_sort}
     n = n * world                                         # whole-job points per pass (weak scaling: n per GPU)
     # algorithmic bytes per point.  fwd: x + prefix columns + level columns written, one F-float table row read per
     # gather.  bwd (table gradients): x + the level columns of dL/dy read (the prefix columns are not needed), one
@@ -101,7 +122,13 @@ def run(n, log2T, mode, L=16, F=2, flush=None):
     bb = 12 + 4 * L * F + 2 * G * L * 4 * F
     bbx = bb + pre + 12 + (G * L * 4 * F if mode != "reference" else 0)
     hbm, src = peaks()
-    return {"n": n, "log2T": log2T, "mode": mode, "n_gpus": world, "hbm_peak_gbs_all_gpus": hbm * world,
+    if extra:
+        t_bs, t_fs, t_sort = extra["bwd_presorted_ms"], extra["fwd_presorted_ms"], extra["sort_ms"]
+        extra.update({"bwd_presorted_mpts": n / t_bs / 1e3, "bwd_presorted_frac": n * bb / (t_bs * 1e-3) / (hbm * 1e9),
+                      "fwd_presorted_mpts": n / t_fs / 1e3, "fwd_presorted_frac": n * bf / (t_fs * 1e-3) / (hbm * 1e9),
+                      "bwd_sort_included_mpts": n / (t_bs + t_sort) / 1e3,
+                      "bwd_sort_included_frac": n * bb / ((t_bs + t_sort) * 1e-3) / (hbm * 1e9)})
+    return {**extra, "n": n, "log2T": log2T, "mode": mode, "n_gpus": world, "hbm_peak_gbs_all_gpus": hbm * world,
             "fwd_ms": t_f, "fwd_mpts": n / t_f / 1e3, "fwd_frac": n * bf / (t_f * 1e-3) / (hbm * world * 1e9),
             "bwd_ms": t_b, "bwd_mpts": n / t_b / 1e3, "bwd_frac": n * bb / (t_b * 1e-3) / (hbm * world * 1e9),
             "bwd_with_dx_ms": t_bx, "bwd_with_dx_mpts": n / t_bx / 1e3,

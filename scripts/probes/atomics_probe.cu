@@ -80,8 +80,8 @@ int main() {
     float* out; CK(cudaMalloc(&out, 1 << 20));
     const int threads = 256;
     printf("sms %d\n", sms);
-    const size_t sizes[] = {(size_t)4 << 20, (size_t)32 << 20, (size_t)48 << 20, (size_t)96 << 20, (size_t)256 << 20, (size_t)1 << 30};
-    for (int ctas_per_sm : {4, 8}) {
+    const size_t sizes[] = {(size_t)32 << 10, (size_t)128 << 10, (size_t)512 << 10, (size_t)2 << 20, (size_t)4 << 20, (size_t)32 << 20, (size_t)48 << 20, (size_t)96 << 20, (size_t)256 << 20, (size_t)1 << 30};
+    for (int ctas_per_sm : {8}) {
         for (size_t S : sizes) {
             const int grid = sms * ctas_per_sm, iters = 256;
             const double ops = (double)grid * threads * iters * 8;
@@ -90,7 +90,7 @@ int main() {
             red_kernel<VEC, 8><<<grid, threads>>>(table, mask, 16); CK(cudaDeviceSynchronize()); \
             CK(cudaEventRecord(e0)); red_kernel<VEC, 8><<<grid, threads>>>(table, mask, iters); CK(cudaEventRecord(e1)); \
             CK(cudaDeviceSynchronize()); const float ms = time_ms(e0, e1); \
-            printf("red.v%d  table %5zu MB  ctas/sm %d : %7.1f Gops/s  (%.3f cyc/op/SM @1.9GHz)  %7.1f GB/s payload\n", VEC, S >> 20, ctas_per_sm, \
+            printf("red.v%d  table %7zu KB  ctas/sm %d : %7.1f Gops/s  (%.3f cyc/op/SM @1.9GHz)  %7.1f GB/s payload\n", VEC, S >> 10, ctas_per_sm, \
                    ops / ms / 1e6, 1.9e9 * sms / (ops / (ms * 1e-3)), ops * 4 * VEC / ms / 1e6); }
             RUN_RED(1) RUN_RED(2) RUN_RED(4)
         }

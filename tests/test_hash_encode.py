@@ -294,3 +294,49 @@ def test_posenc_and_fourier(golden):
     y = ff(x)
     ref = O.fourier_feature(T(g["x"]), ff.B.cpu())
     assert torch.allclose(y.cpu(), ref, atol=4e-6)
+
+
+@pytest.mark.parametrize("n", [31, 4096 + 17, 200000])
+def test_trilinear_backward_run_aggregation(n):
+    """8-corner table-gradient backward with in-lane run aggregation (csrc/hash_encode.cu): Z-ordered points (long runs on
+    the coarse levels), the same points in random order (no runs) and a batch of identical points (one run per lane) must
+    give the same table gradients - rel 1e-5 of max-abs, fp32 sums reorder - and match the oracle's dense gradient."""
+    from idrk import kernels as K
+    from idrk.model.embeddings.hashGridEmbedding import MultiResHashGridMLP
+    from idrk.utils.sorting import morton_order
+    L, F, log2T = 16, 2, 14
+    gen = torch.Generator().manual_seed(n)
+    m = MultiResHashGridMLP(True, 3, L, F, log2T, 16, 2048, frac_mode="trilinear").to(DEV)
+    spec, tables, B = m.spec(), tuple(t.detach() for t in m.tables()), m.freq_encoding.B
+    x = torch.rand(n, 3, generator=gen).to(DEV)
+    dy = torch.randn(n, K.pad4(spec.width), generator=gen).to(DEV)
+
+    def grads(xx, dd, ordered=True):
+        gt = [torch.zeros_like(t) for t in tables]
+        K.hash_encode_bwd(spec, xx.contiguous(), tables, B, dd.contiguous(), gt, False, ordered=ordered)
+        return gt
+    g_plain = grads(x, dy, ordered=False)                  # the plain kernel (no aggregation code)
+    g_rand = grads(x, dy)                                  # aggregating kernel on unordered input: no runs
+    for l, (a, b) in enumerate(zip(g_plain, g_rand)):
+        assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-12), l
+    perm = morton_order(x, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0))
+    g_sort = grads(x[perm], dy[perm])
+    for l, (a, b) in enumerate(zip(g_rand, g_sort)):
+        assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-12), l
+    # all points identical: every lane aggregates its whole tile range into one cell
+    x1 = x[:1].expand(n, 3).contiguous()
+    g_same = grads(x1, dy)
+    s = dy[:, 3 + 2 * L:3 + 2 * L + L * F].double().sum(0)           # per (level, feature) column sums of dL/dy
+    for l, gtab in enumerate(g_same):
+        tot = gtab.double().sum(0).cpu()                              # corner weights sum to 1: mass is conserved
+        ref = s[l * F:(l + 1) * F].cpu()
+        assert (tot - ref).abs().max().item() <= 1e-4 * max(ref.abs().max().item(), 1.0), l
+        assert (gtab != 0).any(1).sum().item() <= 8, l               # ... and lands in at most 8 rows
+    if n <= 5000:                                                     # oracle: dense autograd gradient on the CPU
+        sd = {"levels.%d.embedding.weight" % l: t.detach().cpu().clone().requires_grad_(True) for l, t in enumerate(tables)}
+        sd["freq_encoding.B"] = B.cpu()
+        y = O.hashgrid_embed(x[perm].cpu(), sd, "", L, 16, 2048, "trilinear")
+        (y * dy[perm, :spec.width].cpu()).sum().backward()
+        for l, gtab in enumerate(g_sort):
+            ref = sd["levels.%d.embedding.weight" % l].grad
+            assert (gtab.cpu() - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1e-12), l
