@@ -17,6 +17,10 @@ struct GridDev {
     uint32_t ngp_dense[IDRK_MAX_LEVELS];    // IDRK_HASH_NGP: 1 = dense indexing (R^3 <= rows), 0 = hashed
     int pair_x;                             // 8-corner mode: x-neighbour corners share one 16-byte access when they can
     int agg_runs;                           // 8-corner backward: in-lane aggregation of runs of points in the same cell
+    // level-window passes (tables larger than L2 are walked a few levels at a time, see level_groups()): a launch may
+    // cover levels [l0, l0 + n_levels) of the full grid only
+    int pre_cols;                           // columns of the row in front of this launch's first level (prefix + earlier levels)
+    int tail;                               // 1 = the launch contains the LAST level of the row (owns the pad columns)
 };
 
 
@@ -79,6 +83,8 @@ inline int fill_grid(const idrk_hashgrid_t* h, GridDev& g) {
     if (h->frac_mode == IDRK_HASH_NGP && h->n_feat != 2) return IDRK_E_UNSUP;
     g.n_levels = h->n_levels; g.n_feat = h->n_feat; g.n_fourier = h->n_fourier;
     g.width = (h->n_fourier > 0 ? 3 + 2 * h->n_fourier : 0) + h->n_levels * h->n_feat;
+    g.pre_cols = h->n_fourier > 0 ? 3 + 2 * h->n_fourier : 0;
+    g.tail = 1;
     g.B = h->fourier_B;
     { static const int pair = [] { const char* e = getenv("IDRK_HASH_PAIR_X"); return (e && e[0] == '0') ? 0 : 1; }(); g.pair_x = pair; }
     { static const int agg = [] { const char* e = getenv("IDRK_HASH_AGG"); return (e && e[0] == '0') ? 0 : 1; }(); g.agg_runs = agg; }
@@ -100,6 +106,58 @@ inline int fill_grid(const idrk_hashgrid_t* h, GridDev& g) {
     }
     for (int l = h->n_levels; l < IDRK_MAX_LEVELS; ++l) { g.res[l] = 0; g.rows[l] = 1; g.tables[l] = nullptr; g.pow2mask[l] = 0; g.magic[l] = 0; g.ngp_res[l] = 0; g.ngp_dense[l] = 0; }
     return 0;
+}
+
+// Level windows.  Tables that do not fit the 126 MB L2 turn every gather / reduction into a DRAM sector access (measured,
+// scripts/probes/atomics_probe.cu: 288 G random 8-byte gathers/s and 193 G reductions/s while the table is L2-resident,
+// 73 G/s and 33 G/s at 256 MB).  The encode is then run as several launches over consecutive level windows whose tables
+// fit a budget, so each window's tables are fetched from DRAM once and served from L2 for all points; x is re-read per
+// window (12 B) and every window writes / reads only its own columns of the row.  Windows hold a power-of-two number of
+// levels (the element-per-lane mapping wants L | 32).  Returns the number of windows; win[i] = first level of window i,
+// win[n] = L.  One window = the classic single launch.
+inline int level_groups(const GridDev& g, long long n_points, int* win) {
+    static const long long budget = [] {
+        const char* e = getenv("IDRK_HASH_GROUP_MB");
+        const long long mb = e ? atoll(e) : 80;
+        return (mb <= 0 ? (1LL << 60) : mb << 20);
+    }();
+    long long total = 0;
+    for (int l = 0; l < g.n_levels; ++l) total += (long long)g.rows[l] * g.n_feat * 4;
+    int n = 0;
+    win[0] = 0;
+    // a small batch touches a fraction of the tables anyway: extra launches and x re-reads would only cost
+    if (total <= budget || g.n_levels <= 1 || n_points < (1LL << 20)) { win[1] = g.n_levels; return 1; }
+    int l = 0;
+    while (l < g.n_levels) {
+        long long bytes = 0;
+        int cnt = 0;
+        while (l + cnt < g.n_levels && (cnt == 0 || bytes + (long long)g.rows[l + cnt] * g.n_feat * 4 <= budget)) {
+            bytes += (long long)g.rows[l + cnt] * g.n_feat * 4;
+            ++cnt;
+        }
+        int p2 = 1;
+        while (p2 * 2 <= cnt) p2 *= 2;                    // power-of-two window
+        l += p2;
+        win[++n] = l;
+    }
+    return n;
+}
+
+// GridDev of the window [l0, l1) of `g` (prefix columns only with the first window)
+inline GridDev level_window(const GridDev& g, int l0, int l1) {
+    GridDev w = g;
+    w.n_levels = l1 - l0;
+    for (int l = 0; l < IDRK_MAX_LEVELS; ++l) {
+        const int s = l0 + l;
+        const bool in = s < l1;
+        w.res[l] = in ? g.res[s] : 0.f; w.rows[l] = in ? g.rows[s] : 1; w.pow2mask[l] = in ? g.pow2mask[s] : 0;
+        w.magic[l] = in ? g.magic[s] : 0; w.tables[l] = in ? g.tables[s] : nullptr;
+        w.ngp_res[l] = in ? g.ngp_res[s] : 0; w.ngp_dense[l] = in ? g.ngp_dense[s] : 0;
+    }
+    if (l0 > 0) w.n_fourier = 0;
+    w.pre_cols = g.pre_cols + l0 * g.n_feat;
+    w.tail = (l1 == g.n_levels) ? 1 : 0;
+    return w;
 }
 
 }  // namespace idrk

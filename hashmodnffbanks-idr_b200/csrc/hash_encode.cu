@@ -195,7 +195,7 @@ __device__ __forceinline__ void fwd_levels_generic(const LevelC* s_lev, const fl
 // of the row is then written by one full request instead of two half-filled ones.
 template <int F, int MODE, bool SHIFT>
 __device__ __forceinline__ void fwd_levels_full(const LevelC& lc, const float4* xs, int L, int lane,
-                                                float* __restrict__ orow0, int ld_out, bool vec) {
+                                                float* __restrict__ orow0, int ld_out, bool vec, bool tail = true) {
     constexpr int KB = (MODE == IDRK_HASH_REFERENCE) ? (F <= 2 ? 4 : 2) : (F <= 2 ? 2 : 1);
     const int rstep = 32 / L, row0 = lane / L, l = lane - row0 * L;
     float* __restrict__ o0 = orow0 + row0 * ld_out + l * F;
@@ -216,7 +216,8 @@ __device__ __forceinline__ void fwd_levels_full(const LevelC& lc, const float4* 
                 if constexpr (SHIFT) {
                     float nx = __shfl_down_sync(0xffffffffu, acc[k][0], 1);
                     if (l == L - 1) nx = 0.f;                                  // the pad column
-                    __stcs(reinterpret_cast<float2*>(o + 1), make_float2(acc[k][1], nx));
+                    if (l == L - 1 && !tail) __stcs(o + 1, acc[k][1]);         // a later level window owns the next column
+                    else __stcs(reinterpret_cast<float2*>(o + 1), make_float2(acc[k][1], nx));
                     if (l == 0) __stcs(o, acc[k][0]);
                 } else {
                     store_feat<F>(o, acc[k], vec);
@@ -248,11 +249,12 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
     }
     for (int i = threadIdx.x; i < 3 * C; i += WARPS * 32) s_B[i] = g.B[i];
     __syncthreads();
-    const int pre = C > 0 ? 3 + 2 * C : 0;
+    const int pre = g.pre_cols;                             // prefix columns (+ the levels of earlier windows)
     const int fa = F >= 4 ? 4 : F;                          // floats a vector store must be aligned to
     const bool al8 = (ld_out & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
     const bool vec = F > 1 && (pre % fa) == 0 && (ld_out % fa) == 0 && (reinterpret_cast<uintptr_t>(out) % (4 * fa)) == 0;
-    const bool has_pad = ld_out > g.width;
+    const bool tail = g.tail != 0;
+    const bool has_pad = ld_out > g.width || !tail;         // a column follows this launch's last level
     const bool l_fixed = L > 0 && (32 % L) == 0;            // lane <-> level is fixed
     const bool shift = F == 2 && l_fixed && (pre & 1) && has_pad && al8;
     const bool c_fixed = C >= 2 && (32 % C) == 0 && al8;    // lane <-> frequency is fixed, aligned pair stores
@@ -326,13 +328,13 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
             const float amax = fmaxf(fabsf(x0), fmaxf(fabsf(x1), fabsf(x2))) * res_max;
             const bool fast = __all_sync(0xffffffffu, amax < 2147483520.f);
             if (fast && full && l_fixed) {
-                if (F == 2 && shift) { fwd_levels_full<F, MODE, F == 2>(lc, xs, L, lane, orow0 + pre, ld_out, vec); pad_done = true; }
+                if (F == 2 && shift) { fwd_levels_full<F, MODE, F == 2>(lc, xs, L, lane, orow0 + pre, ld_out, vec, tail); pad_done = true; }
                 else fwd_levels_full<F, MODE, false>(lc, xs, L, lane, orow0 + pre, ld_out, vec);
             } else {
                 fwd_levels_generic<F, MODE>(s_lev, xs, L, lane, rows_here, orow0 + pre, ld_out, vec);
             }
         }
-        if (lane < rows_here)
+        if (tail && lane < rows_here)
             for (int c = g.width + (pad_done ? 1 : 0); c < ld_out; ++c) __stcs(orow0 + lane * ld_out + c, 0.f);
 
         if (idx_dbg != nullptr) {               // debug / parity output: table row of all 8 corners
@@ -632,8 +634,8 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
     for (int i = threadIdx.x; i < 3 * C; i += WARPS * 32) s_B[i] = g.B[i];
     for (int i = threadIdx.x; i < gd.small_total; i += WARPS * 32) s_acc[i] = 0.f;
     __syncthreads();
-    const int pre = C > 0 ? 3 + 2 * C : 0;
-    const bool has_pad = ld_dy > g.width;
+    const int pre = g.pre_cols;
+    const bool has_pad = ld_dy > g.width || !g.tail;
     const bool l_fixed = L > 0 && (32 % L) == 0;
     const bool shift = F == 2 && l_fixed && (pre & 1) && has_pad && (ld_dy & 1) == 0 && (reinterpret_cast<uintptr_t>(dy) & 7u) == 0;
     const LevelC lc = load_level<MODE == IDRK_HASH_NGP>(s_lev, L > 0 ? lane % L : 0);
@@ -922,8 +924,16 @@ extern "C" int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = h_grid->frac_mode;
 #define CALL(F, M) launch_fwd<F, M, 4>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
-    IDRK_DISPATCH_F_MODE(CALL)
+    auto run = [&](const GridDev& g) -> int { IDRK_DISPATCH_F_MODE(CALL) };
 #undef CALL
+    int win[IDRK_MAX_LEVELS + 1];
+    const int nw = idx_debug != nullptr ? 1 : level_groups(g, n, win);
+    if (nw <= 1) return run(g);
+    for (int i = 0; i < nw; ++i) {                         // tables beyond L2: one launch per level window
+        rc = run(level_window(g, win[i], win[i + 1]));
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 template <int F, int MODE>
@@ -969,23 +979,36 @@ extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* 
     if (n < 0 || ldx < 3 || x == nullptr || dy == nullptr || ld_dy < g.width) return IDRK_E_ARG;
     if (h_grad_tables == nullptr && dx == nullptr) return IDRK_E_ARG;
     if (n == 0) return 0;
-    GradDev gd;
-    gd.small_total = 0;
-    gd.any_grad = h_grad_tables != nullptr ? 1 : 0;
     const int budget = 8192;                    // floats of CTA-local accumulators (32 KB)
     const size_t align = (g.n_feat >= 4) ? 16 : 4 * (size_t)g.n_feat;
-    for (int l = 0; l < IDRK_MAX_LEVELS; ++l) { gd.grad[l] = nullptr; gd.small_off[l] = -1; }
     for (int l = 0; l < g.n_levels && h_grad_tables != nullptr; ++l) {
         if (h_grad_tables[l] == nullptr) return IDRK_E_ARG;
         if (reinterpret_cast<uintptr_t>(h_grad_tables[l]) % align) return IDRK_E_ALIGN;
-        gd.grad[l] = h_grad_tables[l];
-        const long long cnt = (long long)g.rows[l] * g.n_feat;
-        if (cnt <= 2048 && gd.small_total + cnt <= budget) { gd.small_off[l] = gd.small_total; gd.small_total += (int)cnt; }
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = h_grid->frac_mode;
     const bool ordered = (flags & IDRK_HASH_BWD_ORDERED) != 0;
+    auto run = [&](const GridDev& g, int l0) -> int {
+        GradDev gd;
+        gd.small_total = 0;
+        gd.any_grad = h_grad_tables != nullptr ? 1 : 0;
+        for (int l = 0; l < IDRK_MAX_LEVELS; ++l) { gd.grad[l] = nullptr; gd.small_off[l] = -1; }
+        for (int l = 0; l < g.n_levels && h_grad_tables != nullptr; ++l) {
+            gd.grad[l] = h_grad_tables[l0 + l];
+            const long long cnt = (long long)g.rows[l] * g.n_feat;
+            if (cnt <= 2048 && gd.small_total + cnt <= budget) { gd.small_off[l] = gd.small_total; gd.small_total += (int)cnt; }
+        }
 #define CALL(F, M) launch_bwd<F, M, 4>(g, gd, x, n, ldx, dy, ld_dy, dx, ordered, st)
-    IDRK_DISPATCH_F_MODE(CALL)
+        IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
+    };
+    // level windows (tables beyond L2) for the table-gradient pass; with dL/dx the single launch stays (dx is written once)
+    int win[IDRK_MAX_LEVELS + 1];
+    const int nw = (dx != nullptr || h_grad_tables == nullptr) ? 1 : level_groups(g, n, win);
+    if (nw <= 1) return run(g, 0);
+    for (int i = 0; i < nw; ++i) {
+        rc = run(level_window(g, win[i], win[i + 1]), win[i]);
+        if (rc) return rc;
+    }
+    return 0;
 }

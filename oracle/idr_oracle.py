@@ -706,7 +706,7 @@ def idr_forward(inp: Dict[str, Tensor], sd: Dict[str, Tensor], cfg: IDRCfg, trai
         diff_pts = points[surf]
         grad_theta = None
     view = -dirs[surf]
-    rgb = torch.ones_like(points).float()
+    rgb = torch.ones_like(points)            # the reference adds .float(): points are fp32 there
     if diff_pts.shape[0] > 0:                                               # get_rbg_value :321-329
         out = net(diff_pts)
         nrm = grad(diff_pts)[:, 0, :]

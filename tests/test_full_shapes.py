@@ -126,12 +126,18 @@ def test_idr_step_full_width_given_same_trace(tag):
     # (1) the oracle's own run: values, and its rendering-network pre-activations
     o_own, lo_own, _, zs = _oracle_step(sd, cfg, inp, rgb, eik, u, tr_out, torch.float32)
     assert len(tap) == len(zs) == cfg.n_lin_rgb - 1
+    z_border = Z_BORDER
+    if nffb:
+        # how far the fp32 reference arithmetic itself is from exact on these pre-activations (sin(w0 .) chains)
+        zs64 = _oracle_step(sd, cfg, inp, rgb, eik, u, tr_out, torch.float64)[3]
+        z_border = max(Z_BORDER, 3.0 * max((a.double() - b).abs().max().item() for a, b in zip(zs, zs64)))
     relu_masks, n_toggled = [], 0
     for S, z in zip(tap, zs):
         m = (S[:, :z.shape[1]].cpu()[surf] > 0)
         differs = m != (z > 0)
         n_toggled += int(differs.sum())
-        assert (z[differs].abs() <= Z_BORDER).all(), "a ReLU unit with |z| = %.3g sits on the other side" % float(z[differs].abs().max())
+        assert (z[differs].abs() <= z_border).all(), "a ReLU unit with |z| = %.3g sits on the other side (border %.3g)" % (
+            float(z[differs].abs().max()), z_border)
         relu_masks.append(m.float())
     assert n_toggled <= max(8, int(2e-3 * n_s * 512 * len(zs))), n_toggled
 
@@ -145,7 +151,7 @@ def test_idr_step_full_width_given_same_trace(tag):
     def rel_max(a, b):
         return (a.double() - b.double()).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
-    report = ["surface rays %d, ReLU units toggled at |z| <= %.0e: %d" % (n_s, Z_BORDER, n_toggled)]
+    report = ["surface rays %d, ReLU units toggled at |z| <= %.1e: %d" % (n_s, z_border, n_toggled)]
 
     def check(name, err, tol, cond=0.0):
         tol_eff = max(tol, 3.0 * cond)
@@ -164,8 +170,8 @@ def test_idr_step_full_width_given_same_trace(tag):
         ref = float(lo_ref[k])
         ok &= check(k + " rel", abs(float(lo[k]) - ref) / max(1.0, abs(ref)), 5e-4,
                     abs(float(lo32[k]) - ref) / max(1.0, abs(ref)) if nffb else 0.0)
-        # the pattern swap changes the loss values only through units with |z| <= Z_BORDER
-        assert abs(float(lo_own[k]) - float(lo32[k])) <= 1e-5 * max(1.0, abs(float(lo32[k]))), k
+        # the pattern swap changes the loss values only through units with |z| <= z_border
+        assert abs(float(lo_own[k]) - float(lo32[k])) <= max(1e-5, z_border) * max(1.0, abs(float(lo32[k]))), k
     pd = dict(model.named_parameters())
     n_checked = 0
     for k, gq in g_ref.items():
