@@ -201,10 +201,15 @@ def hash_encode_section(torch, hbm, src):
                  "bwd_with_dx_mpts_per_s": round(r["bwd_with_dx_mpts"], 1),
                  "bwd_with_dx_frac_of_hbm_peak": round(r["bwd_with_dx_frac"], 4),
                  "algorithmic_bytes_per_point": dict(zip(("fwd", "bwd_tables", "bwd_tables_dx"), r["bytes_per_pt"]))}
-            for k in ("bwd_presorted_mpts", "bwd_presorted_frac", "bwd_sort_included_mpts", "bwd_sort_included_frac",
-                      "fwd_presorted_mpts", "fwd_presorted_frac", "sort_ms"):
-                if k in r:
+            for k in sorted(r):
+                if k.startswith(("fwd_presorted", "bwd_presorted", "fwd_perm", "bwd_perm", "fwd_sort_included",
+                                 "bwd_sort_included", "pair_", "sort_ms")):
                     d[k] = round(r[k], 4)
+            if "sort_ms" in r:
+                d["ordered_walk_note"] = ("presorted: the batch is already in Z-order; perm: the uniform-random batch is walked "
+                                          "through the permutation of the library's Morton radix sort (sort_ms, 2^24 points); "
+                                          "*_sort_included adds sort_ms to the pass; pair_one_sort = sort + forward + backward, "
+                                          "pair_plain = forward + backward in the given order")
             if log2T == 19:
                 out[mode] = d                      # the round-1 keys keep their meaning (T = 2^19)
             else:

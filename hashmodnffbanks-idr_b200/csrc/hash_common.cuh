@@ -115,7 +115,12 @@ inline int fill_grid(const idrk_hashgrid_t* h, GridDev& g) {
 // window (12 B) and every window writes / reads only its own columns of the row.  Windows hold a power-of-two number of
 // levels (the element-per-lane mapping wants L | 32).  Returns the number of windows; win[i] = first level of window i,
 // win[n] = L.  One window = the classic single launch.
-inline int level_groups(const GridDev& g, long long n_points, int* win) {
+// Measured on 2^24 points, L = 16, F = 2 (gpurun_out/hash_mb_r02d_*): at T = 2^22 (314 MB) windows lift the 8-corner table-
+// gradient pass 0.87 -> 1.09 Gpts/s and the reference-mode one 3.8 -> 4.1, but do nothing for the forward (2.20 -> 2.30;
+// reference mode 5.1 -> 2.9: its single gather per level cannot pay for the extra x reads and partial-sector row writes);
+// at T = 2^24 (1.2 GB, a level alone exceeds L2) the 8-corner forward gains 1.02 -> 1.74.  Hence `min_total`: the caller
+// passes the table size from which windows pay for its pass.
+inline int level_groups(const GridDev& g, long long n_points, long long min_total, int* win) {
     static const long long budget = [] {
         const char* e = getenv("IDRK_HASH_GROUP_MB");
         const long long mb = e ? atoll(e) : 80;
@@ -126,7 +131,7 @@ inline int level_groups(const GridDev& g, long long n_points, int* win) {
     int n = 0;
     win[0] = 0;
     // a small batch touches a fraction of the tables anyway: extra launches and x re-reads would only cost
-    if (total <= budget || g.n_levels <= 1 || n_points < (1LL << 20)) { win[1] = g.n_levels; return 1; }
+    if (total <= budget || total <= min_total || g.n_levels <= 1 || n_points < (1LL << 20)) { win[1] = g.n_levels; return 1; }
     int l = 0;
     while (l < g.n_levels) {
         long long bytes = 0;

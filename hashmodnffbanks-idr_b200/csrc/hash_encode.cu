@@ -183,7 +183,7 @@ __device__ __forceinline__ void fwd_levels_generic(const LevelC* s_lev, const fl
         const float4 xv = xs[row];
         float acc[F];
         fwd_element<F, MODE, false>(lc, xv.x, xv.y, xv.z, acc);
-        store_feat<F>(orow0 + row * ld_out + l * F, acc, vec);
+        store_feat<F>(orow0 + (long long)__float_as_int(xv.w) * ld_out + l * F, acc, vec);
     }
 }
 
@@ -198,21 +198,22 @@ __device__ __forceinline__ void fwd_levels_full(const LevelC& lc, const float4* 
                                                 float* __restrict__ orow0, int ld_out, bool vec, bool tail = true) {
     constexpr int KB = (MODE == IDRK_HASH_REFERENCE) ? (F <= 2 ? 4 : 2) : (F <= 2 ? 2 : 1);
     const int rstep = 32 / L, row0 = lane / L, l = lane - row0 * L;
-    float* __restrict__ o0 = orow0 + row0 * ld_out + l * F;
-    const int step = rstep * ld_out;
+    float* __restrict__ o0 = orow0 + l * F;
     for (int pass = 0; pass < L; pass += KB) {
         float acc[KB][F];
+        int roff[KB];                       // row of the output buffer relative to the tile's first point (xs[].w)
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
             if (pass + k < L) {
                 const float4 xv = xs[row0 + (pass + k) * rstep];
+                roff[k] = __float_as_int(xv.w);
                 fwd_element<F, MODE, true>(lc, xv.x, xv.y, xv.z, acc[k]);
             }
         }
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
             if (pass + k < L) {
-                float* o = o0 + (pass + k) * step;
+                float* o = o0 + (long long)roff[k] * ld_out;
                 if constexpr (SHIFT) {
                     float nx = __shfl_down_sync(0xffffffffu, acc[k][0], 1);
                     if (l == L - 1) nx = 0.f;                                  // the pad column
@@ -231,7 +232,7 @@ template <int F, int MODE, int WARPS, int MINB = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx,
                             float* __restrict__ out, int ld_out, uint32_t* __restrict__ idx_dbg,
-                            const int* __restrict__ m_count) {
+                            const int* __restrict__ m_count, const int* __restrict__ perm) {
     pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
     pdl_trigger();
     extern __shared__ uint4 smem_u4[];
@@ -277,9 +278,16 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
         const long long p0 = wt * 32, p = p0 + lane;
         const int rows_here = (int)min(32LL, n - p0);
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-        if (lane < rows_here) { x0 = x[p * ldx + 0]; x1 = x[p * ldx + 1]; x2 = x[p * ldx + 2]; }
+        // `perm`: the i-th point processed is point perm[i] of the caller's buffers (its x row, its output row), so an
+        // unordered batch is walked in Z-order without being copied.  xs[].w = that row relative to the tile's first point.
+        int roff = lane;
+        if (lane < rows_here) {
+            if (perm != nullptr) roff = (int)((long long)perm[p] - p0);
+            const float* xr = x + (p0 + roff) * (long long)ldx;
+            x0 = xr[0]; x1 = xr[1]; x2 = xr[2];
+        }
         __syncwarp();
-        xs[lane] = make_float4(x0, x1, x2, 0.f);
+        xs[lane] = make_float4(x0, x1, x2, __int_as_float(roff));
         __syncwarp();
         float* orow0 = out + p0 * (long long)ld_out;
         const bool full = rows_here == 32;
@@ -295,7 +303,7 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
                 sincos_fast(xp, &sn, &cs);
                 const float sn_n = __shfl_down_sync(0xffffffffu, sn, 1), cs_n = __shfl_down_sync(0xffffffffu, cs, 1);
                 const float cs_0 = __shfl_sync(0xffffffffu, cs, lane & ~(C - 1));
-                float* o = orow0 + row * ld_out;
+                float* o = orow0 + (long long)__float_as_int(xv.w) * ld_out;
                 const float a0 = j_odd ? sn : (j_zero ? xv.z : xv.x);
                 const float a1 = j_odd ? (j_last ? cs_0 : sn_n) : (j_zero ? sn : xv.y);
                 if (st_a) __stcs(reinterpret_cast<float2*>(o + off_a), make_float2(a0, a1));
@@ -306,7 +314,7 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
         } else if (C > 0) {
             for (int i = lane; i < 3 * rows_here; i += 32) {
                 const int r = i / 3, c = i - 3 * r;
-                __stcs(orow0 + r * ld_out + c, reinterpret_cast<const float*>(xs + r)[c]);
+                __stcs(orow0 + (long long)__float_as_int(xs[r].w) * ld_out + c, reinterpret_cast<const float*>(xs + r)[c]);
             }
             const int total = rows_here * C;
             for (int e = lane; e < total; e += 32) {
@@ -317,7 +325,7 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
                 xp = __fmaf_rn(__fmul_rn(xv.z, 6.283185307179586f), s_B[2 * C + jj], xp);
                 float sn, cs;
                 sincos_fast(xp, &sn, &cs);
-                float* o = orow0 + row * ld_out + 3 + jj;
+                float* o = orow0 + (long long)__float_as_int(xv.w) * ld_out + 3 + jj;
                 __stcs(o, sn);
                 __stcs(o + C, cs);
             }
@@ -335,7 +343,7 @@ hash_encode_fwd_elem_kernel(const GridDev g, const float* __restrict__ x, long l
             }
         }
         if (tail && lane < rows_here)
-            for (int c = g.width + (pad_done ? 1 : 0); c < ld_out; ++c) __stcs(orow0 + lane * ld_out + c, 0.f);
+            for (int c = g.width + (pad_done ? 1 : 0); c < ld_out; ++c) __stcs(orow0 + (long long)roff * ld_out + c, 0.f);
 
         if (idx_dbg != nullptr) {               // debug / parity output: table row of all 8 corners
             for (int e = lane; e < rows_here * L; e += 32) {
@@ -517,12 +525,12 @@ __device__ __forceinline__ void bwd_levels_generic(const LevelC* s_lev, float* c
     for (int e = lane; e < total; e += 32) {
         const int row = e / L, l = e - row * L;
         const LevelC lc = load_level<MODE == IDRK_HASH_NGP>(s_lev, l);
-        const float* o = drow0 + row * ld_dy + l * F;
+        const float4 xv = xs[row];
+        const float* o = drow0 + (long long)__float_as_int(xv.w) * ld_dy + l * F;
         float gy[F];
 #pragma unroll
         for (int f = 0; f < F; ++f) gy[f] = __ldg(o + f);
         float d[3] = {0.f, 0.f, 0.f};
-        const float4 xv = xs[row];
         bwd_element<F, MODE, false, WANT_DX>(lc, s_grad[l], s_acc, xv.x, xv.y, xv.z, gy, d);
         if constexpr (WANT_DX && MODE != IDRK_HASH_REFERENCE) {
             atomicAdd(dxs + 4 * row, d[0]); atomicAdd(dxs + 4 * row + 1, d[1]); atomicAdd(dxs + 4 * row + 2, d[2]);
@@ -537,14 +545,13 @@ __device__ __forceinline__ void bwd_levels_full(const LevelC& lc, float* gtab, f
                                                 int L, int lane, const float* __restrict__ drow0, int ld_dy, bool pair_lane = false) {
     constexpr int KB = (MODE == IDRK_HASH_REFERENCE) ? (F <= 2 ? 4 : 2) : (WANT_DX ? 1 : 2);
     const int rstep = 32 / L, row0 = lane / L, l = lane - row0 * L;
-    const float* __restrict__ o0 = drow0 + row0 * ld_dy + l * F;
-    const int step = rstep * ld_dy;
+    const float* __restrict__ o0 = drow0 + l * F;
     for (int pass = 0; pass < L; pass += KB) {
         float gy[KB][F];
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
             if (pass + k < L) {
-                const float* o = o0 + (pass + k) * step;
+                const float* o = o0 + (long long)__float_as_int(xs[row0 + (pass + k) * rstep].w) * ld_dy;
                 if constexpr (SHIFT) {
                     const float2 pr = __ldcs(reinterpret_cast<const float2*>(o + 1));
                     float first = 0.f;
@@ -578,14 +585,13 @@ __device__ __forceinline__ void bwd_levels_full_agg(const LevelC& lc, float* gta
                                                     const float* __restrict__ drow0, int ld_dy, bool pair_lane, CellAcc<F>& st) {
     constexpr int KB = 2;
     const int rstep = 32 / L, row0 = lane / L, l = lane - row0 * L;
-    const float* __restrict__ o0 = drow0 + row0 * ld_dy + l * F;
-    const int step = rstep * ld_dy;
+    const float* __restrict__ o0 = drow0 + l * F;
     for (int pass = 0; pass < L; pass += KB) {
         float gy[KB][F];
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
             if (pass + k < L) {
-                const float* o = o0 + (pass + k) * step;
+                const float* o = o0 + (long long)__float_as_int(xs[row0 + (pass + k) * rstep].w) * ld_dy;
                 if constexpr (SHIFT) {
                     const float2 pr = __ldcs(reinterpret_cast<const float2*>(o + 1));
                     float first = 0.f;
@@ -612,7 +618,7 @@ __device__ __forceinline__ void bwd_levels_full_agg(const LevelC& lc, float* gta
 template <int F, int MODE, int WARPS, bool AGG = false>
 __global__ void __launch_bounds__(WARPS * 32)
 hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __restrict__ x, long long n, int ldx,
-                            const float* __restrict__ dy, int ld_dy, float* __restrict__ dx) {
+                            const float* __restrict__ dy, int ld_dy, float* __restrict__ dx, const int* __restrict__ perm) {
     pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
     pdl_trigger();
     extern __shared__ uint4 smem_u4[];
@@ -672,14 +678,19 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
         const long long p0 = wt * 32, p = p0 + lane;
         const int rows_here = (int)min(32LL, n - p0);
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-        if (lane < rows_here) { x0 = x[p * ldx + 0]; x1 = x[p * ldx + 1]; x2 = x[p * ldx + 2]; }
+        int roff = lane;                    // see the forward kernel: row of x / dy / dx relative to the tile's first point
+        if (lane < rows_here) {
+            if (perm != nullptr) roff = (int)((long long)perm[p] - p0);
+            const float* xr = x + (p0 + roff) * (long long)ldx;
+            x0 = xr[0]; x1 = xr[1]; x2 = xr[2];
+        }
         const float* drow0 = dy + p0 * (long long)ld_dy;
         __syncwarp();
-        xs[lane] = make_float4(x0, x1, x2, 0.f);
+        xs[lane] = make_float4(x0, x1, x2, __int_as_float(roff));
         if (want_dx) {
             float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (C > 0 && lane < rows_here) {           // identity columns of the prefix
-                const float* o = drow0 + (long long)lane * ld_dy;
+                const float* o = drow0 + (long long)roff * ld_dy;
                 d0.x = __ldg(o); d0.y = __ldg(o + 1); d0.z = __ldg(o + 2);
             }
             reinterpret_cast<float4*>(dxs)[lane] = d0;
@@ -700,7 +711,7 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
                     xp = __fmaf_rn(__fmul_rn(xv.z, 6.283185307179586f), b2, xp);
                     float sn, cs;
                     sincos_fast(xp, &sn, &cs);
-                    const float* o = drow0 + (long long)row * ld_dy + 3 + j;
+                    const float* o = drow0 + (long long)__float_as_int(xv.w) * ld_dy + 3 + j;
                     const float dxp = (__ldg(o) * cs - __ldg(o + C) * sn) * 6.283185307179586f;
                     v0 = dxp * b0; v1 = dxp * b1; v2 = dxp * b2;
                 }
@@ -744,7 +755,10 @@ hash_encode_bwd_elem_kernel(const GridDev g, const GradDev gd, const float* __re
         }
         if (want_dx) {
             __syncwarp();
-            if (lane < rows_here) { dx[p * 3 + 0] = dxs[4 * lane]; dx[p * 3 + 1] = dxs[4 * lane + 1]; dx[p * 3 + 2] = dxs[4 * lane + 2]; }
+            if (lane < rows_here) {
+                float* dr = dx + (p0 + roff) * 3;
+                dr[0] = dxs[4 * lane]; dr[1] = dxs[4 * lane + 1]; dr[2] = dxs[4 * lane + 2];
+            }
         }
     }
     if constexpr (AGGK) {
@@ -853,7 +867,7 @@ static int persistent_grid(K kernel, int threads, size_t smem, long long n_tiles
 
 template <int F, int MODE, int WARPS>
 static int launch_fwd(const GridDev& g, const float* x, long long n, int ldx, float* out, int ld_out,
-                      uint32_t* idx_dbg, const int* m_count, cudaStream_t st) {
+                      uint32_t* idx_dbg, const int* m_count, const int* perm, cudaStream_t st) {
     const size_t smem = ((size_t)3 * g.n_levels + WARPS * 32) * 16 + (size_t)3 * g.n_fourier * sizeof(float);
     auto kern = hash_encode_fwd_elem_kernel<F, MODE, WARPS>;
     // 8-corner, F = 2: capping the kernel at 4 resident CTAs per SM (118 registers instead of 80) lets ptxas keep both
@@ -861,14 +875,14 @@ static int launch_fwd(const GridDev& g, const float* x, long long n, int ldx, fl
     // gather is a DRAM sector read (profiles/r01_hash_pair_ab.txt)
     if constexpr (F == 2 && MODE != IDRK_HASH_REFERENCE) kern = hash_encode_fwd_elem_kernel<F, MODE, WARPS, 4>;
     const int grid = persistent_grid(kern, WARPS * 32, smem, (n + WARPS * 32 - 1) / (WARPS * 32));
-    IDRK_CUDA_TRY(launch_k(kern, dim3(grid), dim3(WARPS * 32), smem, st, g, x, n, ldx, out, ld_out, idx_dbg, m_count));
+    IDRK_CUDA_TRY(launch_k(kern, dim3(grid), dim3(WARPS * 32), smem, st, g, x, n, ldx, out, ld_out, idx_dbg, m_count, perm));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
 
 template <int F, int MODE, int WARPS>
 static int launch_bwd(const GridDev& g, const GradDev& gd, const float* x, long long n, int ldx, const float* dy,
-                      int ld_dy, float* dx, bool ordered, cudaStream_t st) {
+                      int ld_dy, float* dx, bool ordered, const int* perm, cudaStream_t st) {
     const int L = g.n_levels, C = g.n_fourier;
     const size_t smem = ((size_t)3 * L + 2 * WARPS * 32) * 16 + (size_t)((L + 1) & ~1) * 8 +
                         (size_t)((3 * C + 3) & ~3) * 4 + (size_t)gd.small_total * 4;
@@ -879,7 +893,7 @@ static int launch_bwd(const GridDev& g, const GradDev& gd, const float* x, long 
     }
     IDRK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = persistent_grid(kern, WARPS * 32, smem, (n + WARPS * 32 - 1) / (WARPS * 32));
-    IDRK_CUDA_TRY(launch_k(kern, dim3(grid), dim3(WARPS * 32), smem, st, g, gd, x, n, ldx, dy, ld_dy, dx));
+    IDRK_CUDA_TRY(launch_k(kern, dim3(grid), dim3(WARPS * 32), smem, st, g, gd, x, n, ldx, dy, ld_dy, dx, perm));
     IDRK_LAUNCH_CHECK();
     return 0;
 }
@@ -914,20 +928,21 @@ extern "C" int idrk_device_sm_count(int* out_sms) {
 
 extern "C" int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
                                     float* out, int32_t ld_out, uint32_t* idx_debug, const int32_t* m_count,
-                                    void* stream) {
+                                    const int32_t* perm, void* stream) {
     GridDev g;
     int rc = fill_grid(h_grid, g);
     if (rc) return rc;
     if (n < 0 || ldx < 3 || x == nullptr || out == nullptr || ld_out < g.width) return IDRK_E_ARG;
+    if (perm != nullptr && (idx_debug != nullptr || n >= (1LL << 31))) return IDRK_E_ARG;
     if (n == 0) return 0;
     if ((ld_out & 3) == 0 && !aligned16(out)) return IDRK_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = h_grid->frac_mode;
-#define CALL(F, M) launch_fwd<F, M, 4>(g, x, n, ldx, out, ld_out, idx_debug, m_count, st)
+#define CALL(F, M) launch_fwd<F, M, 4>(g, x, n, ldx, out, ld_out, idx_debug, m_count, perm, st)
     auto run = [&](const GridDev& g) -> int { IDRK_DISPATCH_F_MODE(CALL) };
 #undef CALL
     int win[IDRK_MAX_LEVELS + 1];
-    const int nw = idx_debug != nullptr ? 1 : level_groups(g, n, win);
+    const int nw = (idx_debug != nullptr || mode == IDRK_HASH_REFERENCE) ? 1 : level_groups(g, n, 512LL << 20, win);
     if (nw <= 1) return run(g);
     for (int i = 0; i < nw; ++i) {                         // tables beyond L2: one launch per level window
         rc = run(level_window(g, win[i], win[i + 1]));
@@ -972,7 +987,7 @@ extern "C" int idrk_hash_encode_f16pair(const idrk_hashgrid_t* h_grid, const flo
 
 extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
                                     const float* dy, int32_t ld_dy, float* const* h_grad_tables, float* dx,
-                                    int32_t flags, void* stream) {
+                                    int32_t flags, const int32_t* perm, void* stream) {
     GridDev g;
     int rc = fill_grid(h_grid, g);
     if (rc) return rc;
@@ -987,7 +1002,8 @@ extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* 
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = h_grid->frac_mode;
-    const bool ordered = (flags & IDRK_HASH_BWD_ORDERED) != 0;
+    const bool ordered = (flags & IDRK_HASH_BWD_ORDERED) != 0 || perm != nullptr;      // a permutation is a Z-order by contract
+    if (perm != nullptr && n >= (1LL << 31)) return IDRK_E_ARG;
     auto run = [&](const GridDev& g, int l0) -> int {
         GradDev gd;
         gd.small_total = 0;
@@ -998,13 +1014,13 @@ extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* 
             const long long cnt = (long long)g.rows[l] * g.n_feat;
             if (cnt <= 2048 && gd.small_total + cnt <= budget) { gd.small_off[l] = gd.small_total; gd.small_total += (int)cnt; }
         }
-#define CALL(F, M) launch_bwd<F, M, 4>(g, gd, x, n, ldx, dy, ld_dy, dx, ordered, st)
+#define CALL(F, M) launch_bwd<F, M, 4>(g, gd, x, n, ldx, dy, ld_dy, dx, ordered, perm, st)
         IDRK_DISPATCH_F_MODE(CALL)
 #undef CALL
     };
     // level windows (tables beyond L2) for the table-gradient pass; with dL/dx the single launch stays (dx is written once)
     int win[IDRK_MAX_LEVELS + 1];
-    const int nw = (dx != nullptr || h_grad_tables == nullptr) ? 1 : level_groups(g, n, win);
+    const int nw = (dx != nullptr || h_grad_tables == nullptr) ? 1 : level_groups(g, n, 0, win);
     if (nw <= 1) return run(g, 0);
     for (int i = 0; i < nw; ++i) {
         rc = run(level_window(g, win[i], win[i + 1]), win[i]);

@@ -1,0 +1,228 @@
+// Z-order (Morton) permutation of a point batch - the pre-pass that makes unordered batches spatially ordered for the
+// hash-grid kernels (csrc/hash_encode.cu: run aggregation in the table-gradient pass, table-row locality in both passes;
+// measured on 2^24 uniform points, L = 16, F = 2: forward 3.4 -> 4.5 Gpts/s at T = 2^19 and 2.2 -> 4.4 at T = 2^22,
+// table-gradient pass 1.3 -> 2.2 and 0.87 -> 1.6).  The reference has no counterpart: its points arrive in ray order
+// (model/ray_tracing.py) and its encoder is order-oblivious (model/embeddings/hashGridEmbedding.py:81-102).
+//
+//   key  = bit-interleaved lattice coordinates of (x - lo) / (hi - lo) on a (2^bits)^3 lattice, bits <= 10
+//   sort = least-significant-digit radix sort of (key, index) pairs, 8 bits per pass, ceil(3 bits / 8) passes:
+//          per pass   hist     one 4096-key tile per CTA, digit histogram in shared memory -> counts[digit][tile]
+//                     scan     exclusive prefix sum of counts in digit-major order (tile scan + one CTA over tile sums)
+//                     scatter  the tile again: stable in-tile rank by warp match (no atomics), keys and indices written
+//                              to their final place of the pass
+//   Every pass moves 20 B per point; nothing is allocated here - the caller passes the workspace.
+#include "common.cuh"
+
+namespace idrk {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;     // 4096 keys per CTA
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int SCAN_TILE = 4096;                    // ints per CTA of the prefix-sum kernels (1024 threads x 4)
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {        // abcdefghij -> a00b00c00d00e00f00g00h00i00j
+    v &= 0x3FFu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__global__ void morton_key_kernel(const float* __restrict__ x, long long n, int ldx, float lo0, float lo1, float lo2,
+                                  float s0, float s1, float s2, float qmax, uint32_t* __restrict__ keys,
+                                  uint32_t* __restrict__ vals) {
+    pdl_wait();
+    pdl_trigger();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float a = fminf(fmaxf((x[i * ldx] - lo0) * s0, 0.f), qmax);
+        const float b = fminf(fmaxf((x[i * ldx + 1] - lo1) * s1, 0.f), qmax);
+        const float c = fminf(fmaxf((x[i * ldx + 2] - lo2) * s2, 0.f), qmax);
+        keys[i] = spread3((uint32_t)a) | (spread3((uint32_t)b) << 1) | (spread3((uint32_t)c) << 2);
+        vals[i] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift, int n_tiles, uint32_t* __restrict__ counts) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const long long t0 = (long long)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const long long i = t0 + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&sh[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    counts[(size_t)threadIdx.x * n_tiles + blockIdx.x] = sh[threadIdx.x];
+}
+
+// exclusive scan of one SCAN_TILE of `data` in place; the tile's total goes to sums[blockIdx.x]
+__global__ void __launch_bounds__(1024)
+scan_tiles_kernel(uint32_t* __restrict__ data, long long m, uint32_t* __restrict__ sums) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ uint32_t s_w[32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (base + k < m) ? data[base + k] : 0u;
+    const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+    uint32_t inc = mine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_w[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        s_w[lane] = winc - w;                                 // exclusive warp offsets
+        if (lane == 31) sums[blockIdx.x] = winc;
+    }
+    __syncthreads();
+    uint32_t run = s_w[warp] + inc - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (base + k < m) data[base + k] = run; run += v[k]; }
+}
+
+// exclusive scan of up to 4096 tile sums by one CTA, in place
+__global__ void __launch_bounds__(1024)
+scan_sums_kernel(uint32_t* __restrict__ sums, int m) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ uint32_t s_w[32];
+    const int base = threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (base + k < m) ? sums[base + k] : 0u;
+    const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+    uint32_t inc = mine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_w[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        s_w[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t run = s_w[warp] + inc - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (base + k < m) sums[base + k] = run; run += v[k]; }
+}
+
+// Stable scatter of one tile.  In-tile order = (warp, round, lane) = input order, so equal digits keep their order.
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n, int shift, int n_tiles,
+                  const uint32_t* __restrict__ counts_scanned, const uint32_t* __restrict__ tile_offsets,
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ uint32_t cnt[RS_WARPS][257];                  // digit 256 = out-of-range lanes of the last tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const long long w0 = (long long)blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
+    uint32_t key[RS_ITEMS], val[RS_ITEMS], rk[RS_ITEMS];      // rk = (in-warp rank << 9) | digit
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const long long i = w0 + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? keys[i] : 0u;
+        val[r] = ok ? vals[i] : 0u;
+        const uint32_t d = ok ? ((key[r] >> shift) & 255u) : 256u;
+        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(m) - 1;
+        uint32_t old = 0;
+        if (lane == leader) { old = cnt[warp][d]; cnt[warp][d] = old + __popc(m); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rk[r] = ((old + __popc(m & ((1u << lane) - 1u))) << 9) | d;
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // per digit: global base of this tile + exclusive prefix over the warps
+        const int d = threadIdx.x;
+        const size_t ci = (size_t)d * n_tiles + blockIdx.x;
+        uint32_t run = counts_scanned[ci] + tile_offsets[ci / SCAN_TILE];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = cnt[w][d]; cnt[w][d] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t d = rk[r] & 511u;
+        if (d < 256u) {
+            const uint32_t pos = cnt[warp][d] + (rk[r] >> 9);
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+}  // namespace idrk
+
+using namespace idrk;
+
+static long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+extern "C" int idrk_morton_sort_workspace(int64_t n, int64_t* out_bytes) {
+    if (!out_bytes || n < 0 || n >= (1LL << 31)) return IDRK_E_ARG;
+    const long long n_tiles = (n + RS_TILE - 1) / RS_TILE;
+    const long long m = 256 * n_tiles;
+    const long long scan_tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    if (scan_tiles > SCAN_TILE) return IDRK_E_UNSUP;
+    *out_bytes = 3 * align_up(n * 4, 256) + align_up(n * 4, 256) + align_up(m * 4, 256) + align_up(scan_tiles * 4, 256);
+    return 0;
+}
+
+extern "C" int idrk_morton_sort(const float* x, int64_t n, int32_t ldx, const float* h_lo, const float* h_hi, int32_t bits_per_dim,
+                                int32_t* perm, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!x || !h_lo || !h_hi || !perm || !workspace || n < 0 || ldx < 3 || bits_per_dim < 1 || bits_per_dim > 10) return IDRK_E_ARG;
+    int64_t need = 0;
+    int rc = idrk_morton_sort_workspace(n, &need);
+    if (rc) return rc;
+    if (workspace_bytes < need) return IDRK_E_ARG;
+    if (!aligned16(workspace)) return IDRK_E_ALIGN;
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_tiles = (n + RS_TILE - 1) / RS_TILE;
+    const long long m = 256 * n_tiles;
+    const long long scan_tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    char* w = (char*)workspace;
+    uint32_t* keys[2] = {(uint32_t*)w, (uint32_t*)(w + align_up(n * 4, 256))};
+    uint32_t* vals[2] = {(uint32_t*)(w + 2 * align_up(n * 4, 256)), (uint32_t*)(w + 3 * align_up(n * 4, 256))};
+    uint32_t* counts = (uint32_t*)(w + 4 * align_up(n * 4, 256));
+    uint32_t* sums = (uint32_t*)((char*)counts + align_up(m * 4, 256));
+    const float qmax = (float)((1 << bits_per_dim) - 1);
+    float s[3];
+    for (int d = 0; d < 3; ++d) { const float e = h_hi[d] - h_lo[d]; s[d] = e > 0.f ? (qmax + 1.f) / e : 0.f; }
+    long long kb = (n + 255) / 256;
+    if (kb > 16LL * sm_count()) kb = 16LL * sm_count();
+    IDRK_CUDA_TRY(launch_k(morton_key_kernel, dim3((unsigned)kb), dim3(256), 0, st, x, (long long)n, (int)ldx, h_lo[0], h_lo[1], h_lo[2],
+                           s[0], s[1], s[2], qmax, keys[0], vals[0]));
+    const int passes = (3 * bits_per_dim + 7) / 8;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = 8 * p;
+        IDRK_CUDA_TRY(launch_k(rs_hist_kernel, dim3((unsigned)n_tiles), dim3(RS_THREADS), 0, st, (const uint32_t*)keys[cur],
+                               (long long)n, shift, (int)n_tiles, counts));
+        IDRK_CUDA_TRY(launch_k(scan_tiles_kernel, dim3((unsigned)scan_tiles), dim3(1024), 0, st, counts, (long long)m, sums));
+        IDRK_CUDA_TRY(launch_k(scan_sums_kernel, dim3(1), dim3(1024), 0, st, sums, (int)scan_tiles));
+        uint32_t* vout = (p == passes - 1) ? (uint32_t*)perm : vals[cur ^ 1];      // the last pass writes the permutation itself
+        IDRK_CUDA_TRY(launch_k(rs_scatter_kernel, dim3((unsigned)n_tiles), dim3(RS_THREADS), 0, st, (const uint32_t*)keys[cur],
+                               (const uint32_t*)vals[cur], (long long)n, shift, (int)n_tiles, (const uint32_t*)counts,
+                               (const uint32_t*)sums, keys[cur ^ 1], vout));
+        cur ^= 1;
+    }
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}

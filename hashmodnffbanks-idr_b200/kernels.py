@@ -77,9 +77,41 @@ class HashGridSpec:
         return d
 
 
+_SORT_WS: dict = {}
+
+
+def morton_perm(x: torch.Tensor, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), bits: int = 8) -> torch.Tensor:
+    """int32 [n] permutation that walks the points of x [n, >=3] in Z-order over the box [lo, hi] (csrc/point_sort.cu:
+    own LSD radix sort, ceil(3 * bits / 8) passes).  Feed it to hash_encode_fwd / hash_encode_bwd as `perm`."""
+    x = rows2d(x, "x")
+    n = x.shape[0]
+    perm = torch.empty(n, device=x.device, dtype=torch.int32)
+    if n == 0:
+        return perm
+    need = ctypes.c_int64(0)
+    check(lib().idrk_morton_sort_workspace(n, ctypes.byref(need)), "idrk_morton_sort_workspace")
+    ws = _SORT_WS.get(x.device)
+    if ws is None or ws.numel() < need.value:
+        ws = _SORT_WS[x.device] = torch.empty(int(need.value * 1.1) + 256, device=x.device, dtype=torch.uint8)
+    h_lo, h_hi = (ctypes.c_float * 3)(*[float(v) for v in lo]), (ctypes.c_float * 3)(*[float(v) for v in hi])
+    check(lib().idrk_morton_sort(ptr(x), n, ld_of(x), h_lo, h_hi, int(bits), ptr(perm), ptr(ws), ws.numel(), stream_ptr()),
+          "idrk_morton_sort")
+    return perm
+
+
+def _perm_arg(perm, n):
+    if perm is None:
+        return None
+    if perm.dtype != torch.int32 or not perm.is_cuda or not perm.is_contiguous() or perm.numel() != n:
+        raise _lib.IdrkError("perm must be a contiguous CUDA int32 tensor with one entry per point")
+    return perm
+
+
 def hash_encode_fwd(spec: HashGridSpec, x: torch.Tensor, tables, B, out: Optional[torch.Tensor] = None,
-                    want_idx: bool = False, m_count: Optional[torch.Tensor] = None, rows: Optional[int] = None):
-    """K1.  x [n, >=3] -> out [n, pad4(width)] (returned tensor is the padded storage)."""
+                    want_idx: bool = False, m_count: Optional[torch.Tensor] = None, rows: Optional[int] = None,
+                    perm: Optional[torch.Tensor] = None):
+    """K1.  x [n, >=3] -> out [n, pad4(width)] (returned tensor is the padded storage).  `perm` (morton_perm): processing
+    order of the points; rows of x / out keep their positions."""
     x = rows2d(x, "x")
     n = x.shape[0] if rows is None else rows
     ld = pad4(spec.width)
@@ -90,7 +122,7 @@ def hash_encode_fwd(spec: HashGridSpec, x: torch.Tensor, tables, B, out: Optiona
         return (out, idx) if want_idx else out
     d = spec.desc(tables, B)
     check(lib().idrk_hash_encode_fwd(ctypes.byref(d), ptr(x), n, ld_of(x), ptr(out), ld_of(out),
-                                     ptr(idx), ptr(m_count), stream_ptr()), "idrk_hash_encode_fwd")
+                                     ptr(idx), ptr(m_count), ptr(_perm_arg(perm, n)), stream_ptr()), "idrk_hash_encode_fwd")
     return (out, idx) if want_idx else out
 
 
@@ -112,7 +144,8 @@ HASH_BWD_ORDERED = 1
 
 
 def hash_encode_bwd(spec: HashGridSpec, x: torch.Tensor, tables, B, dy: torch.Tensor,
-                    grad_tables: Optional[List[torch.Tensor]], want_dx: bool, ordered: bool = False):
+                    grad_tables: Optional[List[torch.Tensor]], want_dx: bool, ordered: bool = False,
+                    perm: Optional[torch.Tensor] = None):
     """K2.  Accumulates into grad_tables (list of [T_l, F], may be None) and returns dx [n,3] or None.  `ordered`: the
     points are spatially ordered (ray samples, utils.sorting.morton_order) - runs sharing a cell are merged in registers."""
     x = rows2d(x, "x")
@@ -128,7 +161,8 @@ def hash_encode_bwd(spec: HashGridSpec, x: torch.Tensor, tables, B, dy: torch.Te
     else:
         garg = ctypes.cast(None, ctypes.POINTER(ctypes.c_void_p))
     check(lib().idrk_hash_encode_bwd(ctypes.byref(d), ptr(x), n, ld_of(x), ptr(dy), ld_of(dy),
-                                     garg, ptr(dx), HASH_BWD_ORDERED if ordered else 0, stream_ptr()), "idrk_hash_encode_bwd")
+                                     garg, ptr(dx), HASH_BWD_ORDERED if ordered else 0, ptr(_perm_arg(perm, n)), stream_ptr()),
+          "idrk_hash_encode_bwd")
     return dx
 
 

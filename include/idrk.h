@@ -57,7 +57,7 @@ typedef struct idrk_hashgrid {
 } idrk_hashgrid_t;
 
 /* -- version / capability ------------------------------------------------------------- */
-int idrk_version(void);                        /* ABI version, currently 3 (2 -> 3: idrk_hash_encode_bwd gained `flags`; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
+int idrk_version(void);                        /* ABI version, currently 3 (2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
 int idrk_device_sm_count(int* out_sms);        /* SM count of the current device */
 
 /* -- K1: hash-grid encode forward -------------------------------------------------------
@@ -66,9 +66,13 @@ int idrk_device_sm_count(int* out_sms);        /* SM count of the current device
  * ++ hash_func (:32-40).   x [n, ldx>=3], out [n, ld_out], ld_out >= width; columns
  * width..ld_out-1 are written as zeros.  idx_debug (nullable) receives the uint32 table row
  * of all 8 corners, [n, L, 8].  m_count (nullable, device int32): only the first min(n, *m_count)
- * points are encoded (device-side compaction in the ray tracer). */
+ * points are encoded (device-side compaction in the ray tracer).  perm (nullable, device int32 [n], a permutation
+ * of 0..n-1, e.g. from idrk_morton_sort): points are PROCESSED in the order perm[0], perm[1], ... - x and out keep the
+ * caller's row order, only the walk changes - so an unordered batch gets the table-row locality of a Z-ordered one
+ * without being copied.  Tables beyond L2 (> 512 MB, 8-corner modes) are walked in level windows (several launches). */
 int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
-                         float* out, int32_t ld_out, uint32_t* idx_debug, const int32_t* m_count, void* stream);
+                         float* out, int32_t ld_out, uint32_t* idx_debug, const int32_t* m_count,
+                         const int32_t* perm, void* stream);
 
 /* -- K1p: hash-grid encode straight into the fp16-pair operand of idrk_gemm_f16s ----------------
  * Same values as idrk_hash_encode_fwd (bit-identical fp32 columns) stored as h = fp16(v), l = fp16((v - h) * 2^11)
@@ -86,11 +90,13 @@ int idrk_hash_encode_f16pair(const idrk_hashgrid_t* h_grid, const float* x, int6
  * (caller zero-fills).  dx (nullable) [n, 3] is overwritten.
  * flags: IDRK_HASH_BWD_ORDERED = the caller's hint that consecutive points are spatially close (samples along rays,
  * Z-ordered batches): the 8-corner table-gradient pass then merges runs of points that share a cell of a level in
- * registers before issuing reductions (same result up to fp32 summation order; harmless but slower on unordered input). */
+ * registers before issuing reductions (same result up to fp32 summation order; harmless but slower on unordered input).
+ * perm (nullable): as in idrk_hash_encode_fwd (rows of x, dy and dx are addressed through it) and implies the hint.
+ * Table-gradient passes over tables larger than ~80 MB run as level windows so each window's gradient rows stay in L2. */
 #define IDRK_HASH_BWD_ORDERED 1
 int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
                          const float* dy, int32_t ld_dy, float* const* h_grad_tables,
-                         float* dx, int32_t flags, void* stream);
+                         float* dx, int32_t flags, const int32_t* perm, void* stream);
 
 /* -- positional encoding ----------------------------------------------------------------
  * Replaces PositionalEncoding.embed (frequency_enc.py:19-51) and get_embedder (:156-168).
@@ -317,6 +323,15 @@ int idrk_fourier_dx_fwd(const float* x, int32_t ldx, const float* dy, int32_t ld
 int idrk_fourier_dx_bwd(const float* g, int32_t ld_g, const float* x, int32_t ldx, const float* dy, int32_t ld_dy,
                         const float* B, int32_t n_fourier, int64_t n, float* g_dy, int32_t ld_gdy, int32_t width,
                         float* g_x, void* stream);
+/* -- Z-order permutation of a point batch (csrc/point_sort.cu) -------------------------------------------------
+ * perm[i] = index of the i-th point along the Morton curve of a (2^bits_per_dim)^3 lattice over the box [h_lo, h_hi]
+ * (HOST float[3] each; points outside are clamped), bits_per_dim in 1..10.  Stable LSD radix sort of (key, index) pairs,
+ * 8 bits per pass.  The reference has no counterpart (its encoder is order-oblivious, hashGridEmbedding.py:81-102); this
+ * is the pre-pass that feeds `perm` of idrk_hash_encode_fwd / _bwd.  workspace: device scratch of at least
+ * idrk_morton_sort_workspace(n) bytes, 16-byte aligned; n < 2^31. */
+int idrk_morton_sort_workspace(int64_t n, int64_t* out_bytes);
+int idrk_morton_sort(const float* x, int64_t n, int32_t ldx, const float* h_lo, const float* h_hi, int32_t bits_per_dim,
+                     int32_t* perm, void* workspace, int64_t workspace_bytes, void* stream);
 int idrk_scale3(const float* scale, const float* a, float* ya, int64_t na, const float* b, float* yb, int64_t nb,
                 const float* c, float* yc, int64_t nc, void* stream);
 

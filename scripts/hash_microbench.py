@@ -92,26 +92,36 @@ def run(n, log2T, mode, L=16, F=2, flush=None):
     t_b = time_cuda(lambda: bwd(False), flush=flush)      # table gradients
     t_bx = time_cuda(lambda: bwd(True), flush=flush)      # + dL/dx
     extra = {}
-    if mode != "reference" and world == 1 and len(xs) == 1:
-        # spatially ordered input (what ray-marched samples look like): the backward merges runs of points that share a
-        # cell in registers.  Reported three ways: points already ordered (sort not timed), and with the Z-order sort of
-        # unordered points (keys + torch.sort + the x / dL/dy row gathers) inside the timing.
-        from idrk.utils.sorting import morton_order
-        perm = morton_order(x, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0))
-        x_sorted = x[perm].contiguous()
+    if world == 1 and len(xs) == 1:
+        # Spatially ordered walks.  (a) "presorted": the batch already IS in Z-order (what ray-marched samples look like
+        # to the encoder) - nothing is timed but the passes.  (b) "perm": the batch stays as given (uniform random) and the
+        # passes walk it through a permutation from the library's own Morton radix sort; reported without the sort, with
+        # the sort inside each pass's time, and as a forward + backward pair that shares one sort (a training step).
+        bounds = dict(lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0))
+        perm = K.morton_perm(x, **bounds)
+        x_sorted = x[perm.long()].contiguous()
         xs_saved, xs[0] = xs[0], x_sorted
         t_bs = time_cuda(lambda: bwd(False, ordered=True), flush=flush)
         t_fs = time_cuda(fwd, flush=flush)
         xs[0] = xs_saved
-        dy_sorted = torch.empty_like(dy)
+        del x_sorted
+        t_sort = time_cuda(lambda: K.morton_perm(x, **bounds), flush=flush)
+        t_fp = time_cuda(lambda: K.hash_encode_fwd(spec, x, tables, B, out=out, perm=perm), flush=flush)
+        t_bp = time_cuda(lambda: K.hash_encode_bwd(spec, x, tables, B, dy, grads, False, perm=perm), flush=flush)
 
-        def sort_all():
-            pm = morton_order(x, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0))
-            torch.index_select(x, 0, pm, out=x_sorted)
-            torch.index_select(dy, 0, pm, out=dy_sorted)
-        t_sort = time_cuda(sort_all, flush=flush)
-        del dy_sorted, x_sorted, perm
-        extra = {"bwd_presorted_ms": t_bs, "fwd_presorted_ms": t_fs, "sort_ms": t_sort}
+        def pair():
+            pm = K.morton_perm(x, **bounds)
+            K.hash_encode_fwd(spec, x, tables, B, out=out, perm=pm)
+            K.hash_encode_bwd(spec, x, tables, B, dy, grads, False, perm=pm)
+
+        def pair_plain():
+            K.hash_encode_fwd(spec, x, tables, B, out=out)
+            K.hash_encode_bwd(spec, x, tables, B, dy, grads, False)
+        t_pair = time_cuda(pair, flush=flush)
+        t_pair_plain = time_cuda(pair_plain, flush=flush)
+        extra = {"bwd_presorted_ms": t_bs, "fwd_presorted_ms": t_fs, "sort_ms": t_sort, "fwd_perm_ms": t_fp, "bwd_perm_ms": t_bp,
+                 "pair_sorted_ms": t_pair, "pair_plain_ms": t_pair_plain}
+        del perm
     n = n * world                                         # whole-job points per pass (weak scaling: n per GPU)
     # algorithmic bytes per point.  fwd: x + prefix columns + level columns written, one F-float table row read per
     # gather.  bwd (table gradients): x + the level columns of dL/dy read (the prefix columns are not needed), one
@@ -123,11 +133,16 @@ def run(n, log2T, mode, L=16, F=2, flush=None):
     bbx = bb + pre + 12 + (G * L * 4 * F if mode != "reference" else 0)
     hbm, src = peaks()
     if extra:
-        t_bs, t_fs, t_sort = extra["bwd_presorted_ms"], extra["fwd_presorted_ms"], extra["sort_ms"]
-        extra.update({"bwd_presorted_mpts": n / t_bs / 1e3, "bwd_presorted_frac": n * bb / (t_bs * 1e-3) / (hbm * 1e9),
-                      "fwd_presorted_mpts": n / t_fs / 1e3, "fwd_presorted_frac": n * bf / (t_fs * 1e-3) / (hbm * 1e9),
-                      "bwd_sort_included_mpts": n / (t_bs + t_sort) / 1e3,
-                      "bwd_sort_included_frac": n * bb / ((t_bs + t_sort) * 1e-3) / (hbm * 1e9)})
+        e = extra
+
+        def rate(ms, nbytes):
+            return n / ms / 1e3, n * nbytes / (ms * 1e-3) / (hbm * 1e9)
+        for key, ms, nb in (("bwd_presorted", e["bwd_presorted_ms"], bb), ("fwd_presorted", e["fwd_presorted_ms"], bf),
+                            ("fwd_perm", e["fwd_perm_ms"], bf), ("bwd_perm", e["bwd_perm_ms"], bb),
+                            ("fwd_sort_included", e["fwd_perm_ms"] + e["sort_ms"], bf),
+                            ("bwd_sort_included", e["bwd_perm_ms"] + e["sort_ms"], bb),
+                            ("pair_one_sort", e["pair_sorted_ms"], bf + bb), ("pair_plain", e["pair_plain_ms"], bf + bb)):
+            e[key + "_mpts"], e[key + "_frac"] = rate(ms, nb)
     return {**extra, "n": n, "log2T": log2T, "mode": mode, "n_gpus": world, "hbm_peak_gbs_all_gpus": hbm * world,
             "fwd_ms": t_f, "fwd_mpts": n / t_f / 1e3, "fwd_frac": n * bf / (t_f * 1e-3) / (hbm * world * 1e9),
             "bwd_ms": t_b, "bwd_mpts": n / t_b / 1e3, "bwd_frac": n * bb / (t_b * 1e-3) / (hbm * world * 1e9),

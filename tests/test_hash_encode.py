@@ -340,3 +340,57 @@ def test_trilinear_backward_run_aggregation(n):
         for l, gtab in enumerate(g_sort):
             ref = sd["levels.%d.embedding.weight" % l].grad
             assert (gtab.cpu() - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1e-12), l
+
+
+@pytest.mark.parametrize("n,bits", [(1, 8), (31, 10), (4096, 8), (4097, 3), (100003, 8), (1 << 20, 10)])
+def test_morton_sort_is_a_stable_z_order_permutation(n, bits):
+    """csrc/point_sort.cu vs a host reference: keys = bit-interleaved lattice coordinates, stable ascending sort.
+    Integer work: the permutation must be IDENTICAL to numpy's stable argsort of the same keys."""
+    from idrk import kernels as K
+    gen = torch.Generator().manual_seed(n + bits)
+    x = torch.rand(n, 3, generator=gen) * 1.4 - 0.2            # some points outside the box: clamped
+    if n > 100:
+        x[::7] = x[3]                                          # many equal keys: stability matters
+    perm = K.morton_perm(x.to(DEV), lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), bits=bits).cpu().numpy()
+    q = np.floor(np.clip(x.numpy().astype(np.float32) * np.float32(2 ** bits), 0, 2 ** bits - 1)).astype(np.uint64)
+
+    def spread(v):
+        out = np.zeros_like(v)
+        for b in range(10):
+            out |= ((v >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b)
+        return out
+    keys = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
+    ref = np.argsort(keys, kind="stable")
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    assert np.array_equal(perm, ref)
+
+
+@pytest.mark.parametrize("mode", ["reference", "trilinear"])
+@pytest.mark.parametrize("n", [33, 70001])
+def test_encode_through_a_permutation(mode, n):
+    """`perm` only changes the ORDER in which points are processed: the forward output is bit-identical to the plain
+    call (rows stay where they were), table gradients equal up to fp32 summation order (rel 1e-5 of max), dL/dx equal."""
+    from idrk import kernels as K
+    from idrk.model.embeddings.hashGridEmbedding import MultiResHashGridMLP
+    L, F, log2T = 16, 2, 12
+    gen = torch.Generator().manual_seed(n)
+    m = MultiResHashGridMLP(True, 3, L, F, log2T, 16, 2048, frac_mode=mode).to(DEV)
+    with torch.no_grad():
+        for t in m.tables():
+            t.mul_(3000.0)
+    spec, tables, B = m.spec(), tuple(t.detach() for t in m.tables()), m.freq_encoding.B
+    x = torch.rand(n, 3, generator=gen).to(DEV)
+    dy = torch.randn(n, K.pad4(spec.width), generator=gen).to(DEV)
+    perm = K.morton_perm(x)
+    y0 = K.hash_encode_fwd(spec, x, tables, B)
+    y1 = K.hash_encode_fwd(spec, x, tables, B, perm=perm)
+    assert torch.equal(y0, y1)
+    for want_dx in (False, True):
+        g0 = [torch.zeros_like(t) for t in tables]
+        g1 = [torch.zeros_like(t) for t in tables]
+        d0 = K.hash_encode_bwd(spec, x, tables, B, dy, g0, want_dx)
+        d1 = K.hash_encode_bwd(spec, x, tables, B, dy, g1, want_dx, perm=perm)
+        for l, (a, b) in enumerate(zip(g0, g1)):
+            assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-12), (want_dx, l)
+        if want_dx:
+            assert (d0 - d1).abs().max().item() <= 1e-5 * max(d0.abs().max().item(), 1e-12)
