@@ -5,7 +5,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libidrk.so")
+LIB_PATH = os.environ.get("IDRK_LIB") or os.path.join(_HERE, "csrc", "libidrk.so")      # IDRK_LIB: A/B runs of two builds
 
 MAX_LEVELS = 32
 HASH_REFERENCE = 0

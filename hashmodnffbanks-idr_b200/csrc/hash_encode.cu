@@ -201,19 +201,20 @@ __device__ __forceinline__ void fwd_levels_full(const LevelC& lc, const float4* 
     float* __restrict__ o0 = orow0 + l * F;
     for (int pass = 0; pass < L; pass += KB) {
         float acc[KB][F];
-        int roff[KB];                       // row of the output buffer relative to the tile's first point (xs[].w)
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
             if (pass + k < L) {
                 const float4 xv = xs[row0 + (pass + k) * rstep];
-                roff[k] = __float_as_int(xv.w);
                 fwd_element<F, MODE, true>(lc, xv.x, xv.y, xv.z, acc[k]);
             }
         }
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
             if (pass + k < L) {
-                float* o = o0 + (long long)roff[k] * ld_out;
+                // row of the output buffer relative to the tile's first point: re-read here (one shared-memory word) rather
+                // than carried across the gathers - registers held there cost gathers in flight (T >= 2^22 is latency-bound)
+                const int ro = __float_as_int(reinterpret_cast<const float*>(xs + row0 + (pass + k) * rstep)[3]);
+                float* o = o0 + (long long)ro * ld_out;
                 if constexpr (SHIFT) {
                     float nx = __shfl_down_sync(0xffffffffu, acc[k][0], 1);
                     if (l == L - 1) nx = 0.f;                                  // the pad column

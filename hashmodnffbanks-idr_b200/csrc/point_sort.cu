@@ -30,11 +30,52 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {        // abcdefghij -
     return v;
 }
 
-__global__ void morton_key_kernel(const float* __restrict__ x, long long n, int ldx, float lo0, float lo1, float lo2,
-                                  float s0, float s1, float s2, float qmax, uint32_t* __restrict__ keys,
-                                  uint32_t* __restrict__ vals) {
+// order-preserving float <-> uint32 map (for atomicMin / atomicMax on floats of either sign)
+__device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t b = __float_as_uint(f); return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu)); }
+
+__global__ void bbox_init_kernel(uint32_t* __restrict__ box) {
     pdl_wait();
     pdl_trigger();
+    if (threadIdx.x < 3) box[threadIdx.x] = 0xFFFFFFFFu; else if (threadIdx.x < 6) box[threadIdx.x] = 0u;
+}
+
+// bounding box of the batch, kept on the device (no host read): box[0..2] = min, box[3..5] = max in f2ord encoding
+__global__ void __launch_bounds__(256)
+bbox_kernel(const float* __restrict__ x, long long n, int ldx, uint32_t* __restrict__ box) {
+    pdl_wait();
+    pdl_trigger();
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { const float v = x[i * ldx + d]; lo[d] = fminf(lo[d], v); hi[d] = fmaxf(hi[d], v); }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (lo[d] <= hi[d]) { atomicMin(box + d, f2ord(lo[d])); atomicMax(box + 3 + d, f2ord(hi[d])); }
+        }
+    }
+}
+
+__global__ void morton_key_kernel(const float* __restrict__ x, long long n, int ldx, float lo0, float lo1, float lo2,
+                                  float s0, float s1, float s2, float qmax, const uint32_t* __restrict__ box,
+                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    pdl_wait();
+    pdl_trigger();
+    if (box != nullptr) {                                    // box measured on the device by bbox_kernel
+        lo0 = ord2f(box[0]); lo1 = ord2f(box[1]); lo2 = ord2f(box[2]);
+        const float e0 = ord2f(box[3]) - lo0, e1 = ord2f(box[4]) - lo1, e2 = ord2f(box[5]) - lo2;
+        s0 = e0 > 0.f ? (qmax + 1.f) / e0 : 0.f; s1 = e1 > 0.f ? (qmax + 1.f) / e1 : 0.f; s2 = e2 > 0.f ? (qmax + 1.f) / e2 : 0.f;
+    }
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float a = fminf(fmaxf((x[i * ldx] - lo0) * s0, 0.f), qmax);
         const float b = fminf(fmaxf((x[i * ldx + 1] - lo1) * s1, 0.f), qmax);
@@ -180,13 +221,14 @@ extern "C" int idrk_morton_sort_workspace(int64_t n, int64_t* out_bytes) {
     const long long m = 256 * n_tiles;
     const long long scan_tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
     if (scan_tiles > SCAN_TILE) return IDRK_E_UNSUP;
-    *out_bytes = 3 * align_up(n * 4, 256) + align_up(n * 4, 256) + align_up(m * 4, 256) + align_up(scan_tiles * 4, 256);
+    *out_bytes = 4 * align_up(n * 4, 256) + align_up(m * 4, 256) + align_up(scan_tiles * 4, 256) + 256;
     return 0;
 }
 
 extern "C" int idrk_morton_sort(const float* x, int64_t n, int32_t ldx, const float* h_lo, const float* h_hi, int32_t bits_per_dim,
                                 int32_t* perm, void* workspace, int64_t workspace_bytes, void* stream) {
-    if (!x || !h_lo || !h_hi || !perm || !workspace || n < 0 || ldx < 3 || bits_per_dim < 1 || bits_per_dim > 10) return IDRK_E_ARG;
+    if (!x || !perm || !workspace || n < 0 || ldx < 3 || bits_per_dim < 1 || bits_per_dim > 10) return IDRK_E_ARG;
+    if ((h_lo == nullptr) != (h_hi == nullptr)) return IDRK_E_ARG;
     int64_t need = 0;
     int rc = idrk_morton_sort_workspace(n, &need);
     if (rc) return rc;
@@ -202,13 +244,21 @@ extern "C" int idrk_morton_sort(const float* x, int64_t n, int32_t ldx, const fl
     uint32_t* vals[2] = {(uint32_t*)(w + 2 * align_up(n * 4, 256)), (uint32_t*)(w + 3 * align_up(n * 4, 256))};
     uint32_t* counts = (uint32_t*)(w + 4 * align_up(n * 4, 256));
     uint32_t* sums = (uint32_t*)((char*)counts + align_up(m * 4, 256));
+    uint32_t* box = (uint32_t*)((char*)sums + align_up(scan_tiles * 4, 256));
     const float qmax = (float)((1 << bits_per_dim) - 1);
-    float s[3];
-    for (int d = 0; d < 3; ++d) { const float e = h_hi[d] - h_lo[d]; s[d] = e > 0.f ? (qmax + 1.f) / e : 0.f; }
+    float s[3] = {0.f, 0.f, 0.f}, lo[3] = {0.f, 0.f, 0.f};
     long long kb = (n + 255) / 256;
     if (kb > 16LL * sm_count()) kb = 16LL * sm_count();
-    IDRK_CUDA_TRY(launch_k(morton_key_kernel, dim3((unsigned)kb), dim3(256), 0, st, x, (long long)n, (int)ldx, h_lo[0], h_lo[1], h_lo[2],
-                           s[0], s[1], s[2], qmax, keys[0], vals[0]));
+    if (h_lo != nullptr) {
+        for (int d = 0; d < 3; ++d) { const float e = h_hi[d] - h_lo[d]; s[d] = e > 0.f ? (qmax + 1.f) / e : 0.f; lo[d] = h_lo[d]; }
+        box = nullptr;
+    } else {                                                 // no box given: measure it on the device
+        IDRK_CUDA_TRY(launch_k(bbox_init_kernel, dim3(1), dim3(32), 0, st, box));
+        long long bb = kb > 4LL * sm_count() ? 4LL * sm_count() : kb;
+        IDRK_CUDA_TRY(launch_k(bbox_kernel, dim3((unsigned)bb), dim3(256), 0, st, x, (long long)n, (int)ldx, box));
+    }
+    IDRK_CUDA_TRY(launch_k(morton_key_kernel, dim3((unsigned)kb), dim3(256), 0, st, x, (long long)n, (int)ldx, lo[0], lo[1], lo[2],
+                           s[0], s[1], s[2], qmax, (const uint32_t*)box, keys[0], vals[0]));
     const int passes = (3 * bits_per_dim + 7) / 8;
     int cur = 0;
     for (int p = 0; p < passes; ++p) {

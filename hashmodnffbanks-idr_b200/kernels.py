@@ -80,9 +80,10 @@ class HashGridSpec:
 _SORT_WS: dict = {}
 
 
-def morton_perm(x: torch.Tensor, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), bits: int = 8) -> torch.Tensor:
-    """int32 [n] permutation that walks the points of x [n, >=3] in Z-order over the box [lo, hi] (csrc/point_sort.cu:
-    own LSD radix sort, ceil(3 * bits / 8) passes).  Feed it to hash_encode_fwd / hash_encode_bwd as `perm`."""
+def morton_perm(x: torch.Tensor, lo=None, hi=None, bits: int = 8) -> torch.Tensor:
+    """int32 [n] permutation that walks the points of x [n, >=3] in Z-order over the box [lo, hi] - by default the batch's
+    own bounding box, measured on the device (csrc/point_sort.cu: own LSD radix sort, ceil(3 * bits / 8) passes; no host
+    synchronisation).  Feed it to hash_encode_fwd / hash_encode_bwd as `perm`."""
     x = rows2d(x, "x")
     n = x.shape[0]
     perm = torch.empty(n, device=x.device, dtype=torch.int32)
@@ -93,7 +94,10 @@ def morton_perm(x: torch.Tensor, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), bits: i
     ws = _SORT_WS.get(x.device)
     if ws is None or ws.numel() < need.value:
         ws = _SORT_WS[x.device] = torch.empty(int(need.value * 1.1) + 256, device=x.device, dtype=torch.uint8)
-    h_lo, h_hi = (ctypes.c_float * 3)(*[float(v) for v in lo]), (ctypes.c_float * 3)(*[float(v) for v in hi])
+    if (lo is None) != (hi is None):
+        raise _lib.IdrkError("morton_perm: give both lo and hi, or neither")
+    h_lo = (ctypes.c_float * 3)(*[float(v) for v in lo]) if lo is not None else None
+    h_hi = (ctypes.c_float * 3)(*[float(v) for v in hi]) if hi is not None else None
     check(lib().idrk_morton_sort(ptr(x), n, ld_of(x), h_lo, h_hi, int(bits), ptr(perm), ptr(ws), ws.numel(), stream_ptr()),
           "idrk_morton_sort")
     return perm

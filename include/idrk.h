@@ -325,7 +325,8 @@ int idrk_fourier_dx_bwd(const float* g, int32_t ld_g, const float* x, int32_t ld
                         float* g_x, void* stream);
 /* -- Z-order permutation of a point batch (csrc/point_sort.cu) -------------------------------------------------
  * perm[i] = index of the i-th point along the Morton curve of a (2^bits_per_dim)^3 lattice over the box [h_lo, h_hi]
- * (HOST float[3] each; points outside are clamped), bits_per_dim in 1..10.  Stable LSD radix sort of (key, index) pairs,
+ * (HOST float[3] each; points outside are clamped; both NULL = the batch's own bounding box, measured on the device
+ * without a host read), bits_per_dim in 1..10.  Stable LSD radix sort of (key, index) pairs,
  * 8 bits per pass.  The reference has no counterpart (its encoder is order-oblivious, hashGridEmbedding.py:81-102); this
  * is the pre-pass that feeds `perm` of idrk_hash_encode_fwd / _bwd.  workspace: device scratch of at least
  * idrk_morton_sort_workspace(n) bytes, 16-byte aligned; n < 2^31. */

@@ -394,3 +394,34 @@ def test_encode_through_a_permutation(mode, n):
             assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-12), (want_dx, l)
         if want_dx:
             assert (d0 - d1).abs().max().item() <= 1e-5 * max(d0.abs().max().item(), 1e-12)
+
+
+def test_module_sorts_big_unordered_batches_transparently():
+    """MultiResHashGridMLP(frac_mode='trilinear') on >= 2^18 points walks them in Z-order (autograd_ops.AUTO_SORT): outputs
+    bit-identical to the unsorted walk, table gradients and dL/dx equal up to fp32 summation order; reference mode never sorts."""
+    from idrk import autograd_ops as ops
+    n = (1 << 18) + 77
+    gen = torch.Generator().manual_seed(1)
+    m, _ = make_grid(16, 2, 14, 16, 2048, mode="trilinear", seed=2)
+    x = torch.rand(n, 3, generator=gen).to(DEV)
+    w = torch.randn(n, m.embeddings_dim, generator=gen).to(DEV)
+
+    def run(enabled):
+        ops.AUTO_SORT["enabled"] = enabled
+        try:
+            xx = x.clone().requires_grad_(True)
+            for t in m.tables():
+                t.grad = None
+            y = m(xx)
+            (y * w).sum().backward()
+            return y.detach(), xx.grad.clone(), [t.grad.clone() for t in m.tables()]
+        finally:
+            ops.AUTO_SORT["enabled"] = True
+    y1, dx1, g1 = run(True)
+    y0, dx0, g0 = run(False)
+    assert torch.equal(y0, y1)
+    assert (dx0 - dx1).abs().max().item() <= 1e-5 * dx0.abs().max().item()
+    for l, (a, b) in enumerate(zip(g0, g1)):
+        assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-12), l
+    spec_ref = make_grid(16, 2, 14, 16, 2048, mode="reference", seed=2)[0].spec()
+    assert ops._auto_perm(spec_ref, x) is None and ops._auto_perm(m.spec(), x) is not None and ops._auto_perm(m.spec(), x[:1000]) is None
