@@ -110,7 +110,8 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_rt_select_minsdf", "idrk_rt_minsdf_points", "idrk_rt_minsdf_resolve", "idrk_rt_chunk_counts",
            "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd", "idrk_gemm_f16s", "idrk_split_f16", "idrk_nffb_encode_fwd",
            "idrk_hash_encode_f16pair", "idrk_camera_rays", "idrk_idr_loss", "idrk_scale3",
-           "idrk_fourier_dx_fwd", "idrk_fourier_dx_bwd", "idrk_morton_sort_workspace", "idrk_morton_sort"]
+           "idrk_fourier_dx_fwd", "idrk_fourier_dx_bwd", "idrk_morton_sort_workspace", "idrk_morton_sort",
+           "idrk_hash_encode_bwd_det_workspace", "idrk_hash_encode_bwd_det"]
 
 
 class NffbDesc(ctypes.Structure):
@@ -210,6 +211,8 @@ def _declare(L):
     L.idrk_idr_loss.argtypes = [vp, i32, vp, vp, vp, vp, i32, i64, vp, i32, i64, f32, f32, f32, vp, vp, vp, vp, vp]
     L.idrk_fourier_dx_fwd.argtypes = [vp, i32, vp, i32, vp, i32, i64, vp, vp]
     L.idrk_fourier_dx_bwd.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i64, vp, i32, i32, vp, vp]
+    L.idrk_hash_encode_bwd_det_workspace.argtypes = [c.POINTER(HashGridDesc), i64, c.POINTER(c.c_int64)]
+    L.idrk_hash_encode_bwd_det.argtypes = [c.POINTER(HashGridDesc), vp, i64, i32, vp, i32, c.POINTER(vp), vp, i64, vp]
     L.idrk_morton_sort_workspace.argtypes = [i64, c.POINTER(c.c_int64)]
     L.idrk_morton_sort.argtypes = [vp, i64, i32, fp, fp, i32, vp, vp, i64, vp]
     L.idrk_scale3.argtypes = [vp, vp, vp, i64, vp, vp, i64, vp, vp, i64, vp]

@@ -22,6 +22,7 @@
 //     contention on tiny tables such as the reference configs' T = 32); dL/dx partials are shuffle-reduced per row.
 #include <cuda_fp16.h>
 #include "hash_common.cuh"
+#include "sort_common.cuh"
 
 namespace idrk {
 
@@ -850,6 +851,95 @@ __global__ void hash_encode_pair_kernel(const GridDev g, const float* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// deterministic table-gradient pass
+// ------------------------------------------------------------------------------------------
+// Floating-point reductions into the tables land in scheduling order, so two runs of the passes above differ in the last
+// bits.  This pass fixes the order: every (point, level, corner) contribution gets the key (level, table row) and its
+// own index as value; a STABLE radix sort (csrc/point_sort.cu) groups the contributions of a row in ascending index
+// order; one thread then sums a row's segment front to back and is the only writer of that row.  Same arithmetic per
+// contribution (w_k * dL/dy), bit-identical results run to run and independent of the grid size.  Cost: 8 B of key /
+// value traffic per contribution and pass (1 - 4 passes: the key has ceil(log2 L) + ceil(log2 max rows) bits) and serial
+// segments on the coarse levels - meant for reproducible training steps (10^3 - 10^5 points), not for 2^24-point batches.
+struct DetGrad { float* grad[IDRK_MAX_LEVELS]; };
+
+template <int MODE>
+__device__ __forceinline__ LevelC level_consts(const GridDev& g, int lev) {
+    LevelC lc;
+    lc.res = g.res[lev]; lc.rows = g.rows[lev]; lc.mask = g.pow2mask[lev]; lc.soff = 0; lc.magic = g.magic[lev];
+    lc.tab = g.tables[lev]; lc.ngp_res = g.ngp_res[lev]; lc.ngp_dense = g.ngp_dense[lev]; lc.pad0 = 0; lc.pad1 = 0;
+    return lc;
+}
+
+template <int MODE>
+__global__ void det_keys_kernel(const GridDev g, const float* __restrict__ x, long long n, int ldx, int row_bits,
+                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    pdl_wait();
+    pdl_trigger();
+    constexpr int G = MODE == IDRK_HASH_REFERENCE ? 1 : 8;
+    const int L = g.n_levels;
+    const long long total = n * L;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long p = e / L;
+        const int l = (int)(e - p * L);
+        const LevelC lc = level_consts<MODE>(g, l);
+        const float x0 = x[p * ldx], x1 = x[p * ldx + 1], x2 = x[p * ldx + 2];
+        if constexpr (MODE == IDRK_HASH_REFERENCE) {
+            const float s0 = __fmul_rn(x0, lc.res), s1 = __fmul_rn(x1, lc.res), s2 = __fmul_rn(x2, lc.res);
+            const uint32_t row = wrap(hash3(trunc_u32(s0), trunc_u32(s1), trunc_u32(s2)), lc.rows, lc.mask, lc.magic);
+            keys[e] = ((uint32_t)l << row_bits) | row;
+            vals[e] = (uint32_t)e;
+        } else {
+            uint32_t idx[8], c0;
+            float w0, w1, w2;
+            corner_rows<MODE, false>(lc, x0, x1, x2, idx, w0, w1, w2, c0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { keys[e * G + k] = ((uint32_t)l << row_bits) | idx[k]; vals[e * G + k] = (uint32_t)(e * G + k); }
+        }
+    }
+}
+
+template <int F, int MODE>
+__global__ void det_reduce_kernel(const GridDev g, const DetGrad gd, const float* __restrict__ x, int ldx,
+                                  const float* __restrict__ dy, int ld_dy, long long m, int row_bits,
+                                  const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals) {
+    pdl_wait();
+    pdl_trigger();
+    constexpr int G = MODE == IDRK_HASH_REFERENCE ? 1 : 8;
+    const int L = g.n_levels, pre = g.pre_cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t key = keys[i];
+        if (i > 0 && keys[i - 1] == key) continue;                   // not the head of a row's segment
+        const int l = (int)(key >> row_bits);
+        const uint32_t row = key & ((1u << row_bits) - 1u);
+        const LevelC lc = level_consts<MODE>(g, l);
+        float acc[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = 0.f;
+        for (long long j = i; j < m && keys[j] == key; ++j) {        // ascending contribution index: the sort is stable
+            const uint32_t id = vals[j];
+            const long long e = id / G;
+            const int k = (int)(id - e * G);
+            const long long p = e / L;
+            const float* gy = dy + p * (long long)ld_dy + pre + l * F;
+            float wk = 1.f;
+            if constexpr (MODE != IDRK_HASH_REFERENCE) {
+                uint32_t c0, c1, c2;
+                float w0, w1, w2;
+                cell_of<MODE, false>(lc, x[p * ldx], x[p * ldx + 1], x[p * ldx + 2], c0, c1, c2, w0, w1, w2);
+                wk = ((k & 1) ? w0 : 1.f - w0) * ((k & 2) ? w1 : 1.f - w1) * ((k & 4) ? w2 : 1.f - w2);
+            }
+#pragma unroll
+            for (int f = 0; f < F; ++f) acc[f] += __fmul_rn(wk, __ldg(gy + f));
+        }
+        float* o = gd.grad[l] + (size_t)row * F;
+#pragma unroll
+        for (int f = 0; f < F; ++f) o[f] += acc[f];                  // the row's only writer
+    }
+}
+
+static int ceil_log2(unsigned long long v) { int b = 0; while ((1ull << b) < v) ++b; return b; }
+
 // Persistent grid = resident CTAs per SM x SM count.  Also pins the L1 / shared-memory split to what the kernel
 // needs: the random table reads live off L1 + L2, and with the default preference the driver keeps the large
 // shared-memory carve-out left behind by a preceding GEMM launch (measured: -35 % on the 8-corner forward).
@@ -1027,5 +1117,90 @@ extern "C" int idrk_hash_encode_bwd(const idrk_hashgrid_t* h_grid, const float* 
         rc = run(level_window(g, win[i], win[i + 1]), win[i]);
         if (rc) return rc;
     }
+    return 0;
+}
+
+// -- deterministic table gradients ---------------------------------------------------------
+static int det_layout(const GridDev& g, int mode, long long n, long long& m, int& row_bits, int& key_bits) {
+    const int G = mode == IDRK_HASH_REFERENCE ? 1 : 8;
+    unsigned long long max_rows = 1;
+    for (int l = 0; l < g.n_levels; ++l) max_rows = g.rows[l] > max_rows ? g.rows[l] : max_rows;
+    row_bits = ceil_log2(max_rows);
+    if (row_bits < 1) row_bits = 1;
+    key_bits = row_bits + ceil_log2((unsigned long long)g.n_levels);
+    m = n * g.n_levels * G;
+    if (key_bits > 32 || m >= (1LL << 31)) return IDRK_E_UNSUP;
+    return 0;
+}
+
+static long long up256(long long v) { return (v + 255) / 256 * 256; }
+
+extern "C" int idrk_hash_encode_bwd_det_workspace(const idrk_hashgrid_t* h_grid, int64_t n, int64_t* out_bytes) {
+    GridDev g;
+    int rc = fill_grid(h_grid, g);
+    if (rc) return rc;
+    if (!out_bytes || n < 0 || g.n_levels == 0) return IDRK_E_ARG;
+    long long m; int rb, kb;
+    rc = det_layout(g, h_grid->frac_mode, n, m, rb, kb);
+    if (rc) return rc;
+    const long long sc = radix_sort_scratch_bytes(m);
+    if (sc < 0) return IDRK_E_UNSUP;
+    *out_bytes = 4 * up256(m * 4) + sc;
+    return 0;
+}
+
+extern "C" int idrk_hash_encode_bwd_det(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx, const float* dy,
+                                        int32_t ld_dy, float* const* h_grad_tables, void* workspace, int64_t workspace_bytes,
+                                        void* stream) {
+    GridDev g;
+    int rc = fill_grid(h_grid, g);
+    if (rc) return rc;
+    if (n < 0 || ldx < 3 || !x || !dy || ld_dy < g.width || !h_grad_tables || !workspace || g.n_levels == 0) return IDRK_E_ARG;
+    if (n == 0) return 0;
+    long long m; int row_bits, key_bits;
+    rc = det_layout(g, h_grid->frac_mode, n, m, row_bits, key_bits);
+    if (rc) return rc;
+    int64_t need = 0;
+    rc = idrk_hash_encode_bwd_det_workspace(h_grid, n, &need);
+    if (rc) return rc;
+    if (workspace_bytes < need) return IDRK_E_ARG;
+    if (!aligned16(workspace)) return IDRK_E_ALIGN;
+    DetGrad gd;
+    for (int l = 0; l < IDRK_MAX_LEVELS; ++l) gd.grad[l] = nullptr;
+    for (int l = 0; l < g.n_levels; ++l) { if (!h_grad_tables[l]) return IDRK_E_ARG; gd.grad[l] = h_grad_tables[l]; }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = (char*)workspace;
+    uint32_t* keys[2] = {(uint32_t*)w, (uint32_t*)(w + up256(m * 4))};
+    uint32_t* vals[2] = {(uint32_t*)(w + 2 * up256(m * 4)), (uint32_t*)(w + 3 * up256(m * 4))};
+    void* scratch = w + 4 * up256(m * 4);
+    const int mode = h_grid->frac_mode;
+    long long kb = (n * g.n_levels + 255) / 256;
+    if (kb > 8LL * sm_count()) kb = 8LL * sm_count();
+    if (mode == IDRK_HASH_REFERENCE) IDRK_CUDA_TRY(launch_k(det_keys_kernel<IDRK_HASH_REFERENCE>, dim3((unsigned)kb), dim3(256), 0, st, g, x, (long long)n, (int)ldx, row_bits, keys[0], vals[0]));
+    else if (mode == IDRK_HASH_TRILINEAR) IDRK_CUDA_TRY(launch_k(det_keys_kernel<IDRK_HASH_TRILINEAR>, dim3((unsigned)kb), dim3(256), 0, st, g, x, (long long)n, (int)ldx, row_bits, keys[0], vals[0]));
+    else IDRK_CUDA_TRY(launch_k(det_keys_kernel<IDRK_HASH_NGP>, dim3((unsigned)kb), dim3(256), 0, st, g, x, (long long)n, (int)ldx, row_bits, keys[0], vals[0]));
+    int cur = 0;
+    rc = radix_sort_pairs(keys, vals, nullptr, m, key_bits, scratch, st, &cur);
+    if (rc) return rc;
+    long long rb = (m + 255) / 256;
+    if (rb > 16LL * sm_count()) rb = 16LL * sm_count();
+#define DET(F, M) launch_k(det_reduce_kernel<F, M>, dim3((unsigned)rb), dim3(256), 0, st, g, gd, x, (int)ldx, dy, (int)ld_dy, m, row_bits, \
+                           (const uint32_t*)keys[cur], (const uint32_t*)vals[cur])
+    cudaError_t e = cudaSuccess;
+    switch (g.n_feat * 4 + mode) {
+        case 1 * 4 + 0: e = DET(1, IDRK_HASH_REFERENCE); break;
+        case 2 * 4 + 0: e = DET(2, IDRK_HASH_REFERENCE); break;
+        case 4 * 4 + 0: e = DET(4, IDRK_HASH_REFERENCE); break;
+        case 8 * 4 + 0: e = DET(8, IDRK_HASH_REFERENCE); break;
+        case 1 * 4 + 1: e = DET(1, IDRK_HASH_TRILINEAR); break;
+        case 2 * 4 + 1: e = DET(2, IDRK_HASH_TRILINEAR); break;
+        case 4 * 4 + 1: e = DET(4, IDRK_HASH_TRILINEAR); break;
+        case 8 * 4 + 1: e = DET(8, IDRK_HASH_TRILINEAR); break;
+        case 2 * 4 + 2: e = DET(2, IDRK_HASH_NGP); break;
+        default: return IDRK_E_UNSUP;
+    }
+#undef DET
+    if (e != cudaSuccess) return (int)e;
+    IDRK_LAUNCH_CHECK();
     return 0;
 }

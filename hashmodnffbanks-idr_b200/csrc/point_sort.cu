@@ -11,7 +11,7 @@
 //                     scatter  the tile again: stable in-tile rank by warp match (no atomics), keys and indices written
 //                              to their final place of the pass
 //   Every pass moves 20 B per point; nothing is allocated here - the caller passes the workspace.
-#include "common.cuh"
+#include "sort_common.cuh"
 
 namespace idrk {
 
@@ -215,13 +215,51 @@ using namespace idrk;
 
 static long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
-extern "C" int idrk_morton_sort_workspace(int64_t n, int64_t* out_bytes) {
-    if (!out_bytes || n < 0 || n >= (1LL << 31)) return IDRK_E_ARG;
+namespace idrk {
+
+long long radix_sort_scratch_bytes(long long n) {
     const long long n_tiles = (n + RS_TILE - 1) / RS_TILE;
     const long long m = 256 * n_tiles;
     const long long scan_tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
-    if (scan_tiles > SCAN_TILE) return IDRK_E_UNSUP;
-    *out_bytes = 4 * align_up(n * 4, 256) + align_up(m * 4, 256) + align_up(scan_tiles * 4, 256) + 256;
+    if (scan_tiles > SCAN_TILE) return -1;
+    return align_up(m * 4, 256) + align_up(scan_tiles * 4, 256);
+}
+
+// Stable LSD radix sort of n (key, value) pairs on the low `bits` key bits.  keys[0] / vals[0] hold the input, [1] are the
+// ping-pong buffers; the sorted values land in `vals_final` when given (else in vals[*keys_in]), the sorted keys in
+// keys[*keys_in].  `scratch` >= radix_sort_scratch_bytes(n).
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t* vals_final, long long n, int bits, void* scratch,
+                     cudaStream_t st, int* keys_in) {
+    const long long n_tiles = (n + RS_TILE - 1) / RS_TILE;
+    const long long m = 256 * n_tiles;
+    const long long scan_tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t* counts = (uint32_t*)scratch;
+    uint32_t* sums = (uint32_t*)((char*)scratch + align_up(m * 4, 256));
+    const int passes = (bits + 7) / 8;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = 8 * p;
+        IDRK_CUDA_TRY(launch_k(rs_hist_kernel, dim3((unsigned)n_tiles), dim3(RS_THREADS), 0, st, (const uint32_t*)keys[cur],
+                               (long long)n, shift, (int)n_tiles, counts));
+        IDRK_CUDA_TRY(launch_k(scan_tiles_kernel, dim3((unsigned)scan_tiles), dim3(1024), 0, st, counts, (long long)m, sums));
+        IDRK_CUDA_TRY(launch_k(scan_sums_kernel, dim3(1), dim3(1024), 0, st, sums, (int)scan_tiles));
+        uint32_t* vout = (p == passes - 1 && vals_final != nullptr) ? vals_final : vals[cur ^ 1];
+        IDRK_CUDA_TRY(launch_k(rs_scatter_kernel, dim3((unsigned)n_tiles), dim3(RS_THREADS), 0, st, (const uint32_t*)keys[cur],
+                               (const uint32_t*)vals[cur], (long long)n, shift, (int)n_tiles, (const uint32_t*)counts,
+                               (const uint32_t*)sums, keys[cur ^ 1], vout));
+        cur ^= 1;
+    }
+    if (keys_in) *keys_in = cur;
+    return 0;
+}
+
+}  // namespace idrk
+
+extern "C" int idrk_morton_sort_workspace(int64_t n, int64_t* out_bytes) {
+    if (!out_bytes || n < 0 || n >= (1LL << 31)) return IDRK_E_ARG;
+    const long long sc = radix_sort_scratch_bytes(n);
+    if (sc < 0) return IDRK_E_UNSUP;
+    *out_bytes = 4 * align_up(n * 4, 256) + sc + 256;
     return 0;
 }
 
@@ -236,15 +274,11 @@ extern "C" int idrk_morton_sort(const float* x, int64_t n, int32_t ldx, const fl
     if (!aligned16(workspace)) return IDRK_E_ALIGN;
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const long long n_tiles = (n + RS_TILE - 1) / RS_TILE;
-    const long long m = 256 * n_tiles;
-    const long long scan_tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
     char* w = (char*)workspace;
     uint32_t* keys[2] = {(uint32_t*)w, (uint32_t*)(w + align_up(n * 4, 256))};
     uint32_t* vals[2] = {(uint32_t*)(w + 2 * align_up(n * 4, 256)), (uint32_t*)(w + 3 * align_up(n * 4, 256))};
-    uint32_t* counts = (uint32_t*)(w + 4 * align_up(n * 4, 256));
-    uint32_t* sums = (uint32_t*)((char*)counts + align_up(m * 4, 256));
-    uint32_t* box = (uint32_t*)((char*)sums + align_up(scan_tiles * 4, 256));
+    char* scratch = w + 4 * align_up(n * 4, 256);
+    uint32_t* box = (uint32_t*)(scratch + radix_sort_scratch_bytes(n));
     const float qmax = (float)((1 << bits_per_dim) - 1);
     float s[3] = {0.f, 0.f, 0.f}, lo[3] = {0.f, 0.f, 0.f};
     long long kb = (n + 255) / 256;
@@ -259,20 +293,8 @@ extern "C" int idrk_morton_sort(const float* x, int64_t n, int32_t ldx, const fl
     }
     IDRK_CUDA_TRY(launch_k(morton_key_kernel, dim3((unsigned)kb), dim3(256), 0, st, x, (long long)n, (int)ldx, lo[0], lo[1], lo[2],
                            s[0], s[1], s[2], qmax, (const uint32_t*)box, keys[0], vals[0]));
-    const int passes = (3 * bits_per_dim + 7) / 8;
-    int cur = 0;
-    for (int p = 0; p < passes; ++p) {
-        const int shift = 8 * p;
-        IDRK_CUDA_TRY(launch_k(rs_hist_kernel, dim3((unsigned)n_tiles), dim3(RS_THREADS), 0, st, (const uint32_t*)keys[cur],
-                               (long long)n, shift, (int)n_tiles, counts));
-        IDRK_CUDA_TRY(launch_k(scan_tiles_kernel, dim3((unsigned)scan_tiles), dim3(1024), 0, st, counts, (long long)m, sums));
-        IDRK_CUDA_TRY(launch_k(scan_sums_kernel, dim3(1), dim3(1024), 0, st, sums, (int)scan_tiles));
-        uint32_t* vout = (p == passes - 1) ? (uint32_t*)perm : vals[cur ^ 1];      // the last pass writes the permutation itself
-        IDRK_CUDA_TRY(launch_k(rs_scatter_kernel, dim3((unsigned)n_tiles), dim3(RS_THREADS), 0, st, (const uint32_t*)keys[cur],
-                               (const uint32_t*)vals[cur], (long long)n, shift, (int)n_tiles, (const uint32_t*)counts,
-                               (const uint32_t*)sums, keys[cur ^ 1], vout));
-        cur ^= 1;
-    }
+    rc = radix_sort_pairs(keys, vals, (uint32_t*)perm, n, 3 * bits_per_dim, scratch, st, nullptr);     // the last pass writes the permutation
+    if (rc) return rc;
     IDRK_LAUNCH_CHECK();
     return 0;
 }

@@ -93,6 +93,7 @@ def morton_perm(x: torch.Tensor, lo=None, hi=None, bits: int = 8) -> torch.Tenso
     check(lib().idrk_morton_sort_workspace(n, ctypes.byref(need)), "idrk_morton_sort_workspace")
     ws = _SORT_WS.get(x.device)
     if ws is None or ws.numel() < need.value:
+        retire_scratch(ws)                   # a CUDA graph may hold its address (see SCRATCH_GENERATION below)
         ws = _SORT_WS[x.device] = torch.empty(int(need.value * 1.1) + 256, device=x.device, dtype=torch.uint8)
     if (lo is None) != (hi is None):
         raise _lib.IdrkError("morton_perm: give both lo and hi, or neither")
@@ -145,11 +146,17 @@ def hash_encode_f16pair(spec: HashGridSpec, x: torch.Tensor, tables, B, rows: in
 
 
 HASH_BWD_ORDERED = 1
+# set_deterministic_table_grads(True): table gradients of every hash-grid backward are summed in a fixed order (K2d)
+DETERMINISTIC_TABLE_GRADS = [False]
+
+
+def set_deterministic_table_grads(on: bool):
+    DETERMINISTIC_TABLE_GRADS[0] = bool(on)
 
 
 def hash_encode_bwd(spec: HashGridSpec, x: torch.Tensor, tables, B, dy: torch.Tensor,
                     grad_tables: Optional[List[torch.Tensor]], want_dx: bool, ordered: bool = False,
-                    perm: Optional[torch.Tensor] = None):
+                    perm: Optional[torch.Tensor] = None, deterministic: Optional[bool] = None):
     """K2.  Accumulates into grad_tables (list of [T_l, F], may be None) and returns dx [n,3] or None.  `ordered`: the
     points are spatially ordered (ray samples, utils.sorting.morton_order) - runs sharing a cell are merged in registers."""
     x = rows2d(x, "x")
@@ -159,6 +166,20 @@ def hash_encode_bwd(spec: HashGridSpec, x: torch.Tensor, tables, B, dy: torch.Te
     if n == 0:
         return dx
     d = spec.desc(tables, B)
+    if grad_tables is not None and spec.n_levels > 0 and (deterministic or (deterministic is None and DETERMINISTIC_TABLE_GRADS[0])):
+        arr = (ctypes.c_void_p * spec.n_levels)(*[g.data_ptr() for g in grad_tables])
+        need = ctypes.c_int64(0)
+        check(lib().idrk_hash_encode_bwd_det_workspace(ctypes.byref(d), n, ctypes.byref(need)), "idrk_hash_encode_bwd_det_workspace")
+        ws = _SORT_WS.get(("det", x.device))
+        if ws is None or ws.numel() < need.value:
+            retire_scratch(ws)
+            ws = _SORT_WS[("det", x.device)] = torch.empty(int(need.value * 1.1) + 256, device=x.device, dtype=torch.uint8)
+        check(lib().idrk_hash_encode_bwd_det(ctypes.byref(d), ptr(x), n, ld_of(x), ptr(dy), ld_of(dy),
+                                             ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p)), ptr(ws), ws.numel(), stream_ptr()),
+              "idrk_hash_encode_bwd_det")
+        grad_tables = None
+        if not want_dx:
+            return None
     if grad_tables is not None:
         arr = (ctypes.c_void_p * spec.n_levels)(*[g.data_ptr() for g in grad_tables])
         garg = ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))

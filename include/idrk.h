@@ -57,7 +57,7 @@ typedef struct idrk_hashgrid {
 } idrk_hashgrid_t;
 
 /* -- version / capability ------------------------------------------------------------- */
-int idrk_version(void);                        /* ABI version, currently 3 (2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
+int idrk_version(void);                        /* ABI version, currently 3 (2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
 int idrk_device_sm_count(int* out_sms);        /* SM count of the current device */
 
 /* -- K1: hash-grid encode forward -------------------------------------------------------
@@ -73,6 +73,19 @@ int idrk_device_sm_count(int* out_sms);        /* SM count of the current device
 int idrk_hash_encode_fwd(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx,
                          float* out, int32_t ld_out, uint32_t* idx_debug, const int32_t* m_count,
                          const int32_t* perm, void* stream);
+
+/* -- K2d: deterministic table gradients ----------------------------------------------------------------------
+ * Same result as the table-gradient part of idrk_hash_encode_bwd up to fp32 summation order, but with that order FIXED:
+ * every (point, level, corner) contribution is keyed by (level, table row), a stable radix sort groups a row's
+ * contributions in ascending point order and one thread sums each row's segment - bit-identical gradients run to run
+ * (the reference's dense embedding backward is deterministic on CPU; the atomic scatter is not).  ACCUMULATES into
+ * h_grad_tables like idrk_hash_encode_bwd; dL/dx comes from idrk_hash_encode_bwd with h_grad_tables = NULL (already
+ * order-independent).  workspace: >= idrk_hash_encode_bwd_det_workspace(n) bytes of device scratch, 16-byte aligned;
+ * n * L * (8 | 1) contributions must stay below 2^31 and table rows below 2^(32 - ceil(log2 L)). */
+int idrk_hash_encode_bwd_det_workspace(const idrk_hashgrid_t* h_grid, int64_t n, int64_t* out_bytes);
+int idrk_hash_encode_bwd_det(const idrk_hashgrid_t* h_grid, const float* x, int64_t n, int32_t ldx, const float* dy,
+                             int32_t ld_dy, float* const* h_grad_tables, void* workspace, int64_t workspace_bytes,
+                             void* stream);
 
 /* -- K1p: hash-grid encode straight into the fp16-pair operand of idrk_gemm_f16s ----------------
  * Same values as idrk_hash_encode_fwd (bit-identical fp32 columns) stored as h = fp16(v), l = fp16((v - h) * 2^11)

@@ -425,3 +425,58 @@ def test_module_sorts_big_unordered_batches_transparently():
         assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1e-12), l
     spec_ref = make_grid(16, 2, 14, 16, 2048, mode="reference", seed=2)[0].spec()
     assert ops._auto_perm(spec_ref, x) is None and ops._auto_perm(m.spec(), x) is not None and ops._auto_perm(m.spec(), x[:1000]) is None
+
+
+@pytest.mark.parametrize("mode,log2T,n", [("reference", 5, 3072), ("reference", 19, 40000), ("trilinear", 5, 3072),
+                                          ("trilinear", 14, 20011)])
+def test_deterministic_table_gradients(mode, log2T, n):
+    """K2d (sorted, single-writer table gradients): bit-identical run to run - also between two different batch
+    splits is NOT claimed, only repeatability -, equal to the atomic scatter up to fp32 summation order (rel 1e-5 of max),
+    accumulating like it, and equal to the oracle's dense autograd gradient.  T = 2^5 tables: every row collects hundreds of
+    contributions (the shipped configs)."""
+    from idrk import kernels as K
+    from idrk.model.embeddings.hashGridEmbedding import MultiResHashGridMLP
+    L, F = (6, 2) if log2T == 5 else (16, 2)
+    base, des = (64, 512) if log2T == 5 else (16, 2048)
+    gen = torch.Generator().manual_seed(n)
+    m = MultiResHashGridMLP(True, 3, L, F, log2T, base, des, frac_mode=mode).to(DEV)
+    spec, tables, B = m.spec(), tuple(t.detach() for t in m.tables()), m.freq_encoding.B
+    x = (torch.rand(n, 3, generator=gen) * 2 - 1).to(DEV)
+    dy = torch.randn(n, K.pad4(spec.width), generator=gen).to(DEV)
+
+    def grads(det, init=0.0):
+        gt = [torch.full_like(t, init) for t in tables]
+        K.hash_encode_bwd(spec, x, tables, B, dy, gt, False, deterministic=det)
+        return gt
+    a, b = grads(True), grads(True)
+    for l, (p, q) in enumerate(zip(a, b)):
+        assert torch.equal(p, q), l                                   # repeatable to the bit
+    c = grads(False)
+    for l, (p, q) in enumerate(zip(a, c)):
+        assert (p - q).abs().max().item() <= 1e-5 * max(q.abs().max().item(), 1e-12), l
+    d = grads(True, init=1.5)                                         # accumulates into what is there
+    for l, (p, q) in enumerate(zip(a, d)):
+        assert (q - 1.5 - p).abs().max().item() <= 2e-6 * max(p.abs().max().item(), 1.0), l
+    if n <= 5000:
+        sd = {"levels.%d.embedding.weight" % l: t.detach().cpu().clone().requires_grad_(True) for l, t in enumerate(tables)}
+        sd["freq_encoding.B"] = B.cpu()
+        y = O.hashgrid_embed(x.cpu(), sd, "", L, base, des, mode)
+        (y * dy[:, :spec.width].cpu()).sum().backward()
+        for l, gtab in enumerate(a):
+            ref = sd["levels.%d.embedding.weight" % l].grad
+            assert (gtab.cpu() - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1e-12), l
+    # the module-level switch routes autograd through the same pass
+    K.set_deterministic_table_grads(True)
+    try:
+        outs = []
+        for _ in range(2):
+            for t in m.tables():
+                t.grad = None
+            (m(x) * dy[:, :spec.width]).sum().backward()
+            outs.append([t.grad.clone() for t in m.tables()])
+        for p, q in zip(*outs):
+            assert torch.equal(p, q)
+        for l, (p, q) in enumerate(zip(outs[0], a)):
+            assert torch.equal(p, q), l
+    finally:
+        K.set_deterministic_table_grads(False)
