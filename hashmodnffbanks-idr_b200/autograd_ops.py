@@ -43,16 +43,23 @@ class _FourierDx(torch.autograd.Function):
 
 
 # 8-corner modes on big unordered batches: walk the points in Z-order (one Morton radix sort per forward, shared with the
-# backward).  Measured on 2^24 uniform points, L = 16, F = 2, sort included: forward 0.68 -> 0.63 / backward 0.43 -> 0.65 of
-# the HBM roofline at T = 2^19, 0.34 -> 0.62 / 0.36 -> 0.52 at T = 2^22 (profiles/r02_hash_encode_sweep.txt).  The
-# reference-mode passes (one gather per level) are bound by their row traffic and lose from a permuted walk: never sorted.
-AUTO_SORT = {"enabled": os.environ.get("IDRK_HASH_AUTO_SORT", "1") != "0", "min_points": 1 << 18, "max_table_bytes": 512 << 20}
+# backward).  Measured on 2^24 uniform points, L = 16, F = 2, SORT INCLUDED (profiles/r02_hash_encode_sweep.txt, fractions
+# of the HBM roofline): forward + table-gradient pair 0.49 -> 0.69 at T = 2^19 and 0.36 -> 0.55 at T = 2^22; the forward
+# alone loses a little while the tables sit in L2 (0.67 -> 0.62) and wins once they do not (T = 2^22: 0.35 -> 0.61).  At
+# T = 2^24 (1.2 GB) nothing is gained.  The reference-mode passes (one gather per level) are bound by their row traffic and
+# lose from a permuted walk: never sorted.  Hence: sort when a backward will share the permutation, or when the tables
+# exceed L2; never beyond 512 MB of tables or below 2^18 points.
+AUTO_SORT = {"enabled": os.environ.get("IDRK_HASH_AUTO_SORT", "1") != "0", "min_points": 1 << 18,
+             "l2_table_bytes": 96 << 20, "max_table_bytes": 512 << 20}
 
 
-def _auto_perm(spec, x):
+def _auto_perm(spec, x, will_backprop=True):
     if not AUTO_SORT["enabled"] or spec.frac_mode == K._lib.HASH_REFERENCE or spec.n_levels == 0:
         return None
-    if x.shape[0] < AUTO_SORT["min_points"] or sum(spec.rows) * spec.n_feat * 4 > AUTO_SORT["max_table_bytes"]:
+    nbytes = sum(spec.rows) * spec.n_feat * 4
+    if x.shape[0] < AUTO_SORT["min_points"] or nbytes > AUTO_SORT["max_table_bytes"]:
+        return None
+    if not will_backprop and nbytes <= AUTO_SORT["l2_table_bytes"]:
         return None
     return K.morton_perm(x.detach())
 
@@ -60,7 +67,7 @@ def _auto_perm(spec, x):
 class _HashEncode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, B, spec, *tables):
-        ctx.perm = _auto_perm(spec, x)
+        ctx.perm = _auto_perm(spec, x, will_backprop=any(ctx.needs_input_grad[3:]))
         out = K.hash_encode_fwd(spec, x, tables, B, perm=ctx.perm)
         ctx.spec = spec
         ctx.has_B = B is not None

@@ -105,3 +105,31 @@ def test_multistep_lr_shim_matches_torch_scheduler():
     mine3 = MultiStepLR(tr3, [1], gamma=0.1)
     mine3.load_state_dict(ref.state_dict())
     assert mine3.last_epoch == ref.last_epoch and abs(tr3.lr - opt.param_groups[0]["lr"]) <= 1e-16
+
+
+def _trainer_worker(rank, world, init_file, ret):
+    from idrk.dist import DataParallelTrainer
+    dist.init_process_group("gloo", init_method="file://" + init_file, rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                        # replicas start DIFFERENT on purpose
+    model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+    tr = DataParallelTrainer(model, loss_fn=None, lr=1e-3, world_size=world, sample_seed=5)
+    draw = torch.empty(4).uniform_(0, 1, generator=tr.sample_generator)
+    ret[rank] = (tr.bucket.flat.clone(), draw, tr.parameters_checksum())
+    dist.destroy_process_group()
+
+
+def test_trainer_broadcasts_parameters_and_seeds_ranks_independently():
+    """DataParallelTrainer at world 2 (gloo): rank 0's parameters are broadcast at construction (replicas must not rely on
+    identical seeding), the float64 checksum used by bench.py's `replicas_identical` agrees, and every rank owns its own
+    generator for the host draws (eikonal points, min-SDF steps) so shards see independent samples."""
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mgr = mp.Manager()
+        ret = mgr.dict()
+        mp.spawn(_trainer_worker, args=(world, os.path.join(d, "init"), ret), nprocs=world, join=True)
+        (f0, d0, c0), (f1, d1, c1) = ret[0], ret[1]
+    assert torch.equal(f0, f1) and torch.equal(c0, c1)
+    torch.manual_seed(100)
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+    assert torch.equal(f0[:35], ref[0].weight.detach().reshape(-1))
+    assert not torch.equal(d0, d1)
