@@ -111,7 +111,7 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd", "idrk_gemm_f16s", "idrk_split_f16", "idrk_nffb_encode_fwd",
            "idrk_hash_encode_f16pair", "idrk_camera_rays", "idrk_idr_loss", "idrk_scale3",
            "idrk_fourier_dx_fwd", "idrk_fourier_dx_bwd", "idrk_morton_sort_workspace", "idrk_morton_sort",
-           "idrk_hash_encode_bwd_det_workspace", "idrk_hash_encode_bwd_det"]
+           "idrk_hash_encode_bwd_det_workspace", "idrk_hash_encode_bwd_det", "idrk_sdf_squash_rows"]
 
 
 class NffbDesc(ctypes.Structure):
@@ -188,6 +188,7 @@ def _declare(L):
     L.idrk_colsum.argtypes = [vp, i64, i32, i32, vp, vp]
     L.idrk_sdf_head.argtypes = [vp, i64, i32, i32, vp, vp, f32, vp, vp, vp]
     L.idrk_sdf_squash.argtypes = [vp, i64, f32, vp, vp, vp]
+    L.idrk_sdf_squash_rows.argtypes = [vp, i64, i32, i32, f32, vp, i32, vp, vp, vp]
     rs = c.POINTER(RayStateDesc)
     L.idrk_rt_init.argtypes = [rs, vp, vp, vp, vp, vp]
     L.idrk_rt_top.argtypes = [rs, vp, i32, f32, vp, vp]

@@ -151,6 +151,31 @@ __global__ void sdf_squash_kernel(const float* __restrict__ s, long long n, floa
     }
 }
 
+// out = x with column 0 replaced by tanh(s / (2 + rho(s))) (the last step of ImplicitNetwork.forward,
+// implicit_differentiable_renderer.py:108-113: rho is a constant for autograd), d = d out_0 / d s, d2 = d^2 out_0 / d s^2
+__global__ void sdf_squash_rows_kernel(const float* __restrict__ x, long long rows, int cols, int ldx, float beta,
+                                       float* __restrict__ out, int ld_out, float* __restrict__ d, float* __restrict__ d2) {
+    pdl_wait();
+    pdl_trigger();
+    const long long total = rows * (long long)ld_out;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / ld_out;
+        const int c = (int)(i - r * ld_out);
+        float v = c < cols ? x[r * ldx + c] : 0.f;
+        if (c == 0) {
+            const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+            const float rho = (1.f / beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(v) / beta));
+            const float k = 1.f / (2.f + rho);
+            const float t = tanhf(v * k);
+            const float dd = (1.f - t * t) * k;
+            if (d) d[r] = dd;
+            if (d2) d2[r] = -2.f * t * k * dd;
+            v = t;
+        }
+        out[i] = v;
+    }
+}
+
 // backward of H = scale * act(Z), S = act'(Z):  dZ = dH * S * scale + dS * act''(Z), also written as a 3xTF32 operand pair
 __global__ void act_bwd_kernel(const float* __restrict__ dH, int ld_dh, const float* __restrict__ dS, int ld_ds,
                                const float* __restrict__ S, int ld_s, const float* __restrict__ H, int ld_h,
@@ -300,6 +325,16 @@ extern "C" int idrk_sdf_squash(const float* s, int64_t n, float beta, float* out
     if (!s || !out || n < 0 || !(beta > 0.f)) return IDRK_E_ARG;
     if (n == 0) return 0;
     IDRK_CUDA_TRY(launch_k(sdf_squash_kernel, dim3(ew_blocks(n, 256)), dim3(256), 0, (cudaStream_t)stream, s, n, beta, out, dout));
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_sdf_squash_rows(const float* x, int64_t rows, int32_t cols, int32_t ldx, float beta, float* out, int32_t ld_out,
+                                    float* d, float* d2, void* stream) {
+    if (!x || !out || rows < 0 || cols < 1 || ldx < cols || ld_out < cols || !(beta > 0.f)) return IDRK_E_ARG;
+    if (rows == 0) return 0;
+    IDRK_CUDA_TRY(launch_k(sdf_squash_rows_kernel, dim3(ew_blocks(rows * (long long)ld_out, 256)), dim3(256), 0, (cudaStream_t)stream,
+                           x, (long long)rows, (int)cols, (int)ldx, beta, out, (int)ld_out, d, d2));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

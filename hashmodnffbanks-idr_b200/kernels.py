@@ -452,6 +452,19 @@ def sdf_head(h: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, beta: float, 
                               stream_ptr()), "idrk_sdf_head")
 
 
+def sdf_squash_rows(x: torch.Tensor, beta: float, want_grads: bool):
+    """out = x with column 0 squashed (padded operand), d = d out_0/ds [n,1], d2 = second derivative [n,1]."""
+    x = rows2d(x, "x")
+    n, cols = x.shape
+    out = empty_padded(n, cols, x.device)
+    d = torch.empty((n, 1), device=x.device, dtype=torch.float32) if want_grads else None
+    d2 = torch.empty((n, 1), device=x.device, dtype=torch.float32) if want_grads else None
+    if n:
+        check(lib().idrk_sdf_squash_rows(ptr(x), n, cols, ld_of(x), float(beta), ptr(out), pad4(cols), ptr(d), ptr(d2), stream_ptr()),
+              "idrk_sdf_squash_rows")
+    return out, d, d2
+
+
 def sdf_squash(s: torch.Tensor, beta: float, want_grad: bool):
     s = s.contiguous()
     out = torch.empty_like(s)

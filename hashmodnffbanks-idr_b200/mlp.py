@@ -324,6 +324,37 @@ def linear_act(X, W, b, mode: str, act: float = 0.0, scale: float = 1.0):
     return _LinearAct.apply(X, W, b, mode, float(act), float(scale))[0]
 
 
+class _SquashRows(torch.autograd.Function):
+    """out = x with column 0 -> tanh(s / (2 + rho(s))), rho a constant for autograd (the reference's last step of
+    ImplicitNetwork.forward, implicit_differentiable_renderer.py:108-113 - a dozen tensor ops there, and as many again in
+    each recorded backward).  One kernel gives out, d = d out_0 / d s and d2 = d^2 out_0 / d s^2; d is returned as a
+    differentiable OUTPUT so that the recorded backward (`gradient()`, create_graph) keeps its dependence on s:
+    d d / d s = d2.  Third order is never needed (d2 is a constant)."""
+
+    @staticmethod
+    def forward(ctx, x, beta):
+        out, d, d2 = K.sdf_squash_rows(x.detach(), beta, True)
+        ctx.cols = x.shape[1]
+        ctx.save_for_backward(d, d2)
+        ctx.set_materialize_grads(False)
+        return out, d
+
+    @staticmethod
+    def backward(ctx, g_out, g_d):
+        d, d2 = ctx.saved_tensors
+        gx = None
+        if g_out is not None:
+            gx = torch.cat([g_out[:, :1] * d, g_out[:, 1:]], 1)
+        if g_d is not None:
+            extra = torch.nn.functional.pad(g_d * d2, (0, ctx.cols - 1))
+            gx = extra if gx is None else gx + extra
+        return gx, None
+
+
+def sdf_squash_rows(x: torch.Tensor, beta: float) -> torch.Tensor:
+    return _SquashRows.apply(x, float(beta))[0]
+
+
 class _WeightNorm(torch.autograd.Function):
     """W = g * v / ||v||_row  (legacy nn.utils.weight_norm, dim=0)."""
 

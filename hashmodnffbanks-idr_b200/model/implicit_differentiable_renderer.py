@@ -158,6 +158,9 @@ class ImplicitNetwork(nn.Module):
                 x = mlp.linear_act(x, W, lin.bias, "softplus", 100.0)
             else:
                 x = mlp.linear(x, W, lin.bias)
+        if x.is_cuda and x.dtype == torch.float32:
+            # SDF squash of column 0 with the Laplace density held constant (:108-113): one kernel, differentiable twice
+            return mlp.sdf_squash_rows(x, self._pipeline.beta())
         s = x[:, 0]
         rho = self.dencity_net(s.detach())
         s = torch.tanh(s / (2 + rho))

@@ -57,7 +57,7 @@ typedef struct idrk_hashgrid {
 } idrk_hashgrid_t;
 
 /* -- version / capability ------------------------------------------------------------- */
-int idrk_version(void);                        /* ABI version, currently 3 (2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
+int idrk_version(void);                        /* ABI version, currently 3 (2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
 int idrk_device_sm_count(int* out_sms);        /* SM count of the current device */
 
 /* -- K1: hash-grid encode forward -------------------------------------------------------
@@ -239,6 +239,11 @@ int idrk_colsum(const float* x, int64_t rows, int32_t cols, int32_t ldx, float* 
 int idrk_sdf_head(const float* h, int64_t rows, int32_t K, int32_t ldh, const float* w, const float* bias,
                   float beta, float* out, const int32_t* m_count, void* stream);
 int idrk_sdf_squash(const float* s, int64_t n, float beta, float* out, float* dout, void* stream);
+/* idrk_sdf_squash_rows: out [rows, ld_out] = x [rows, ldx] with column 0 squashed (the autograd path's last step,
+ * implicit_differentiable_renderer.py:108-113), d[r] = d out_0 / d s and d2[r] = d^2 out_0 / d s^2 with rho held constant
+ * (nullable); columns cols..ld_out-1 are zero-filled. */
+int idrk_sdf_squash_rows(const float* x, int64_t rows, int32_t cols, int32_t ldx, float beta, float* out, int32_t ld_out,
+                         float* d, float* d2, void* stream);
 /* idrk_act_bwd: backward of the fused activation epilogue H = scale * act(Z), S = act'(Z) (autograd of the
  * Softplus / ReLU / Sine / Tanh layers):  dZ = dH * S * scale + dS * act''(Z)  (dH or dS may be NULL); dZ is also
  * written as a 3xTF32 operand pair when dZ_hi / dZ_lo are given.  Columns [cols, ld_out) are zero-filled. */

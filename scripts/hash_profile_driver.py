@@ -17,8 +17,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from idrk import kernels as K                                                   # noqa: E402
 from idrk.model.embeddings.hashGridEmbedding import MultiResHashGridMLP          # noqa: E402
 
-n = 1 << 22
 log2T = int(sys.argv[1]) if len(sys.argv) > 1 else 19
+n = 1 << (int(os.environ.get("IDRK_PROFILE_LOG2N", "22")))          # 2^22 points for `--set full` (replays), 2^24 for a light metric pass
 modes = sys.argv[2:] if len(sys.argv) > 2 else ["reference", "trilinear"]
 for mode in modes:
     m = MultiResHashGridMLP(True, 3, 16, 2, log2T, 16, 2048, frac_mode=mode).cuda()
