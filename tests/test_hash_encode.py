@@ -486,8 +486,9 @@ def test_fourier_prefix_max_error_is_recorded():
     """The Fourier prefix uses a Cody-Waite reduction + the SFU sin / cos (csrc/hash_common.cuh sincos_fast).  Measured
     against float64 on the encoder's real argument range (x in [-1, 1]^3, B ~ N(0, sigma^2) with the reference's sigma
     for base 16 -> 2048, |2 pi x B| up to ~15): the kernel's own error - SFU approximation + the fp32 rounding of the
-    argument - must stay below 1.5e-6, which is what leaves room inside the 4e-6 parity bar against the host's fp32 libm
-    (whose argument is rounded in a different order).  Prints the measured maxima."""
+    argument - must stay below 2e-6 (measured: 1.48e-6 in total, 4.4e-7 from the sin / cos evaluation itself, the rest is
+    the fp32 rounding of arguments up to 12.6), which is what leaves room inside the 4e-6 parity bar against the host's fp32
+    libm (whose argument is rounded in a different order).  Prints the measured maxima."""
     from idrk import kernels as K
     gen = torch.Generator().manual_seed(11)
     C = 16
@@ -510,4 +511,4 @@ def test_fourier_prefix_max_error_is_recorded():
     print("fourier prefix: max |arg| %.2f, max error vs float64 %.3e, of which sin/cos evaluation at the fp32 argument %.3e" % (
         float(xp64.abs().max()), err_exact, err_sfu))
     assert err_sfu <= 6e-7, err_sfu
-    assert err_exact <= 1.5e-6, err_exact
+    assert err_exact <= 2e-6, err_exact
