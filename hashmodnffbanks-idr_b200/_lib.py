@@ -111,7 +111,8 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_sumsq", "idrk_clip_adam", "idrk_act_bwd", "idrk_gemm_f16s", "idrk_split_f16", "idrk_nffb_encode_fwd",
            "idrk_hash_encode_f16pair", "idrk_camera_rays", "idrk_idr_loss", "idrk_scale3",
            "idrk_fourier_dx_fwd", "idrk_fourier_dx_bwd", "idrk_morton_sort_workspace", "idrk_morton_sort",
-           "idrk_hash_encode_bwd_det_workspace", "idrk_hash_encode_bwd_det", "idrk_sdf_squash_rows"]
+           "idrk_hash_encode_bwd_det_workspace", "idrk_hash_encode_bwd_det", "idrk_sdf_squash_rows", "idrk_sumsq_det",
+           "idrk_rt_linesearch_points", "idrk_rt_linesearch_resolve"]
 
 
 class NffbDesc(ctypes.Structure):
@@ -195,6 +196,8 @@ def _declare(L):
     L.idrk_rt_step.argtypes = [rs, vp, vp, vp, vp]
     L.idrk_rt_linesearch.argtypes = [rs, vp, vp, i32, f32, vp, vp, vp]
     L.idrk_rt_end.argtypes = [rs, vp, vp, i32, vp]
+    L.idrk_rt_linesearch_points.argtypes = [rs, vp, vp, fp, i32, vp, vp, vp]
+    L.idrk_rt_linesearch_resolve.argtypes = [rs, vp, vp, fp, i32, vp]
     L.idrk_rt_select_sampler.argtypes = [rs, vp, vp, vp, vp]
     L.idrk_rt_sampler_points.argtypes = [rs, vp, i32, i32, i32, vp, vp, vp, vp]
     L.idrk_rt_chunk_counts.argtypes = [vp, i32, i32, i32, vp, vp]
@@ -218,6 +221,7 @@ def _declare(L):
     L.idrk_morton_sort.argtypes = [vp, i64, i32, fp, fp, i32, vp, vp, i64, vp]
     L.idrk_scale3.argtypes = [vp, vp, vp, i64, vp, vp, i64, vp, vp, i64, vp]
     L.idrk_sumsq.argtypes = [vp, i64, vp, vp]
+    L.idrk_sumsq_det.argtypes = [vp, i64, vp, vp, i32, vp]
     L.idrk_clip_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp, f32, vp]
     for fn in EXPORTS:
         getattr(L, fn).restype = c.c_int

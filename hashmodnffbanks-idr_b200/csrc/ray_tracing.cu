@@ -146,6 +146,76 @@ __global__ void rt_linesearch_kernel(RayState S, const int* __restrict__ gate, c
     S.slot_s[i] = sa; S.slot_e[i] = sb;
 }
 
+// The whole back-off line search of one iteration as ONE evaluation (:167-183).  The reference re-evaluates a ray whose
+// new SDF is negative up to `line_step_iters` times, each time a little further back: t_k = t_{k-1} -+ f_k * cur_sdf,
+// stopping at the first non-negative value.  The candidate positions depend only on the state BEFORE the search, and an
+// SDF value does not depend on which other points share its batch, so all candidates of all offending rays are listed
+// at once (n_ls consecutive slots per ray end), evaluated together, and resolved per ray in order: the first k whose
+// value is not negative (else the last) becomes the ray's t / point / next sdf - exactly the state the sequential search
+// leaves.  One SDF query and two launches per iteration instead of n_ls of each.
+struct LsFactors { float f[8]; };
+
+__global__ void rt_linesearch_points_kernel(RayState S, const int* __restrict__ gate, const float* __restrict__ vals,
+                                            LsFactors F, int n_ls, float* __restrict__ pts, int* __restrict__ counter) {
+    pdl_wait();
+    pdl_trigger();
+    if (*gate == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < S.n;
+    bool bs = false, be = false;
+    if (in) {
+        gather_vals(S, i, vals, 1);                        // values of the step's evaluation
+        bs = S.nxt_s[i] < 0.f; be = S.nxt_e[i] < 0.f;
+    }
+    const int slot = warp_append(counter, (bs ? n_ls : 0) + (be ? n_ls : 0));
+    if (!in) return;
+    int sa = -1, sb = -1;
+    if (bs) {
+        sa = slot;
+        float t = S.t0[i];
+        const float cur = S.cur_s[i];
+        for (int k = 0; k < n_ls; ++k) { t = __fsub_rn(t, __fmul_rn(F.f[k], cur)); store3(pts, sa + k, ray_point(S, i, t)); }
+    }
+    if (be) {
+        sb = slot + (bs ? n_ls : 0);
+        float t = S.t1[i];
+        const float cur = S.cur_e[i];
+        for (int k = 0; k < n_ls; ++k) { t = __fadd_rn(t, __fmul_rn(F.f[k], cur)); store3(pts, sb + k, ray_point(S, i, t)); }
+    }
+    S.slot_s[i] = sa; S.slot_e[i] = sb;
+}
+
+__global__ void rt_linesearch_resolve_kernel(RayState S, const int* __restrict__ gate, const float* __restrict__ vals,
+                                             LsFactors F, int n_ls) {
+    pdl_wait();
+    pdl_trigger();
+    if (*gate == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n) return;
+    const int sa = S.slot_s[i], sb = S.slot_e[i];
+    if (sa >= 0) {
+        float t = S.t0[i], v = 0.f;
+        const float cur = S.cur_s[i];
+        for (int k = 0; k < n_ls; ++k) {
+            t = __fsub_rn(t, __fmul_rn(F.f[k], cur));
+            v = vals[sa + k];
+            if (!(v < 0.f)) break;                         // no longer offending: the sequential search stops here
+        }
+        S.t0[i] = t; S.nxt_s[i] = v; store3(S.ps, i, ray_point(S, i, t));
+    }
+    if (sb >= 0) {
+        float t = S.t1[i], v = 0.f;
+        const float cur = S.cur_e[i];
+        for (int k = 0; k < n_ls; ++k) {
+            t = __fadd_rn(t, __fmul_rn(F.f[k], cur));
+            v = vals[sb + k];
+            if (!(v < 0.f)) break;
+        }
+        S.t1[i] = t; S.nxt_e[i] = v; store3(S.pe, i, ray_point(S, i, t));
+    }
+    S.slot_s[i] = -1; S.slot_e[i] = -1;
+}
+
 // end of an iteration (:185-186)
 __global__ void rt_end_kernel(RayState S, const int* __restrict__ gate, const float* __restrict__ vals, int gather_mode) {
     pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
@@ -418,6 +488,28 @@ extern "C" int idrk_rt_linesearch(const idrk_ray_state_t* h_state, const int32_t
     RT_PRELUDE();
     if (!gate || !pts || !counter || (gather_mode && !vals)) return IDRK_E_ARG;
     IDRK_CUDA_TRY(launch_k(rt_linesearch_kernel, dim3(blocks), dim3(threads), 0, st, S, gate, vals, gather_mode, factor, pts, counter));
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_rt_linesearch_points(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals,
+                                         const float* h_factors, int32_t n_ls, float* pts, int32_t* counter, void* stream) {
+    RT_PRELUDE();
+    if (!gate || !vals || !h_factors || !pts || !counter || n_ls < 1 || n_ls > 8) return IDRK_E_ARG;
+    LsFactors F;
+    for (int k = 0; k < 8; ++k) F.f[k] = k < n_ls ? h_factors[k] : 0.f;
+    IDRK_CUDA_TRY(launch_k(rt_linesearch_points_kernel, dim3(blocks), dim3(threads), 0, st, S, gate, vals, F, (int)n_ls, pts, counter));
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_rt_linesearch_resolve(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals,
+                                          const float* h_factors, int32_t n_ls, void* stream) {
+    RT_PRELUDE();
+    if (!gate || !vals || !h_factors || n_ls < 1 || n_ls > 8) return IDRK_E_ARG;
+    LsFactors F;
+    for (int k = 0; k < 8; ++k) F.f[k] = k < n_ls ? h_factors[k] : 0.f;
+    IDRK_CUDA_TRY(launch_k(rt_linesearch_resolve_kernel, dim3(blocks), dim3(threads), 0, st, S, gate, vals, F, (int)n_ls));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

@@ -139,6 +139,9 @@ class DataParallelTrainer:
         self.m = torch.zeros_like(self.bucket.flat)
         self.v = torch.zeros_like(self.bucket.flat)
         self.sumsq = torch.zeros(1, device=self.bucket.flat.device, dtype=torch.float32)
+        # the squared gradient norm is summed in a FIXED order (per-CTA partials + one block): every replica derives the
+        # same clip factor from the all-reduced bucket, so parameters stay bit-identical across ranks
+        self.sumsq_partials = torch.zeros(1184, device=self.bucket.flat.device, dtype=torch.float32)
         self.t = 0
         self.use_cuda_graph = use_cuda_graph
         if hasattr(model, "ray_tracer"):
@@ -273,8 +276,7 @@ class DataParallelTrainer:
             losses = self._shade_and_backward(traced, eik, rgb)
         scale = allreduce_mean_(b.grad, self.world)
         self.t += 1
-        self.sumsq.zero_()
-        K.sumsq(b.grad, self.sumsq)
+        K.sumsq_det(b.grad, self.sumsq, self.sumsq_partials)
         K.clip_adam(b.flat, b.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t,
                     self.max_norm, self.sumsq, scale)
         mlp.weights_changed()

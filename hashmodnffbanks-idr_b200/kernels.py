@@ -560,6 +560,11 @@ def sumsq(g: torch.Tensor, out: torch.Tensor):
     check(lib().idrk_sumsq(ptr(g), g.numel(), ptr(out), stream_ptr()), "idrk_sumsq")
 
 
+def sumsq_det(g: torch.Tensor, out: torch.Tensor, partials: torch.Tensor):
+    """out[0] = sum(g^2), summed in an order fixed by (g.numel(), partials.numel()): identical on every replica."""
+    check(lib().idrk_sumsq_det(ptr(g), g.numel(), ptr(out), ptr(partials), partials.numel(), stream_ptr()), "idrk_sumsq_det")
+
+
 def clip_adam(p, g, m, v, lr, beta1, beta2, eps, step, max_norm, sumsq_buf, grad_scale):
     check(lib().idrk_clip_adam(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
                                int(step), float(max_norm), ptr(sumsq_buf), float(grad_scale), stream_ptr()), "idrk_clip_adam")

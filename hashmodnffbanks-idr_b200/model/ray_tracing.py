@@ -89,7 +89,7 @@ class _TraceState:
         self.slot_s, self.slot_e, self.ray_of_slot = ibuf[:N], ibuf[N:2 * N], ibuf[2 * N:]
         self.counters = torch.zeros(8 + (n_it + 1) * (n_ls + 3), device=dev, dtype=torch.int32)
         self.cidx = 0
-        self.cap = 2 * N
+        self.cap = 2 * N * max(1, n_ls)          # both ends of every ray x the line search's candidates per end
         self.pts = torch.empty((self.cap, 3), device=dev, dtype=torch.float32)
         self.vals = torch.empty(self.cap, device=dev, dtype=torch.float32)
         st = RayStateDesc()
@@ -163,20 +163,24 @@ class RayTracing(nn.Module):
         T.cidx = 0
         c = T.new_counter()
         check(L.idrk_rt_init(S, ptr(T.t_sph), ptr(T.hit_u8), ptr(T.pts), ptr(c), sp), "idrk_rt_init")
-        ev.on_device_count(T.pts, T.cap, c, T.vals)
+        ev.on_device_count(T.pts, 2 * T.N, c, T.vals)
         gate = T.new_counter()
         check(L.idrk_rt_top(S, ptr(T.vals), 1, float(self.sdf_threshold), ptr(gate), sp), "idrk_rt_top")
+        if n_ls > 8:
+            raise ValueError("line_step_iters > 8 is not supported")
+        factors = (ctypes.c_float * max(n_ls, 1))(*[(1 - self.line_search_step) / (2 ** k) for k in range(n_ls)])
         for it in range(n_it):
             c = T.new_counter()
             check(L.idrk_rt_step(S, ptr(gate), ptr(T.pts), ptr(c), sp), "idrk_rt_step")
-            ev.on_device_count(T.pts, T.cap, c, T.vals)
-            for k in range(n_ls):
+            ev.on_device_count(T.pts, 2 * T.N, c, T.vals)
+            if n_ls > 0:
+                # the whole back-off search in ONE evaluation: every candidate of every offending ray end (csrc/ray_tracing.cu)
                 c = T.new_counter()
-                factor = (1 - self.line_search_step) / (2 ** k)
-                check(L.idrk_rt_linesearch(S, ptr(gate), ptr(T.vals), 1 if k == 0 else 2, float(factor), ptr(T.pts),
-                                           ptr(c), sp), "idrk_rt_linesearch")
+                check(L.idrk_rt_linesearch_points(S, ptr(gate), ptr(T.vals), factors, n_ls, ptr(T.pts), ptr(c), sp),
+                      "idrk_rt_linesearch_points")
                 ev.on_device_count(T.pts, T.cap, c, T.vals)
-            check(L.idrk_rt_end(S, ptr(gate), ptr(T.vals), 1 if n_ls == 0 else 2, sp), "idrk_rt_end")
+                check(L.idrk_rt_linesearch_resolve(S, ptr(gate), ptr(T.vals), factors, n_ls, sp), "idrk_rt_linesearch_resolve")
+            check(L.idrk_rt_end(S, ptr(gate), ptr(T.vals), 1 if n_ls == 0 else 0, sp), "idrk_rt_end")
             gate = T.new_counter()
             check(L.idrk_rt_top(S, None, 0, float(self.sdf_threshold), ptr(gate), sp), "idrk_rt_top")
 

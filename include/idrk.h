@@ -57,7 +57,7 @@ typedef struct idrk_hashgrid {
 } idrk_hashgrid_t;
 
 /* -- version / capability ------------------------------------------------------------- */
-int idrk_version(void);                        /* ABI version, currently 3 (2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
+int idrk_version(void);                        /* ABI version, currently 3 (2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_sumsq_det; idrk_rt_linesearch_points / _resolve; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
 int idrk_device_sm_count(int* out_sms);        /* SM count of the current device */
 
 /* -- K1: hash-grid encode forward -------------------------------------------------------
@@ -277,6 +277,15 @@ int idrk_rt_top(const idrk_ray_state_t* h_state, const float* vals, int32_t gath
 int idrk_rt_step(const idrk_ray_state_t* h_state, const int32_t* gate, float* pts, int32_t* counter, void* stream);
 int idrk_rt_linesearch(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, int32_t gather_mode,
                        float factor, float* pts, int32_t* counter, void* stream);
+/* The back-off line search of one sphere-tracing iteration as ONE evaluation (ray_tracing.py:167-183): _points gathers
+ * the step's values, lists the n_ls candidate positions t_k = t_{k-1} -+ h_factors[k] * cur_sdf of every ray end whose new
+ * sdf is negative (n_ls consecutive slots, counted in *counter; pts needs room for 2 * n_ls * n_rays points), _resolve
+ * adopts per ray end the first candidate whose value is not negative (else the last) - the state the reference's
+ * sequential re-evaluation leaves.  h_factors: HOST float[n_ls] = (1 - line_search_step) / 2^k; n_ls <= 8. */
+int idrk_rt_linesearch_points(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, const float* h_factors,
+                              int32_t n_ls, float* pts, int32_t* counter, void* stream);
+int idrk_rt_linesearch_resolve(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, const float* h_factors,
+                               int32_t n_ls, void* stream);
 int idrk_rt_end(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, int32_t gather_mode, void* stream);
 int idrk_rt_select_sampler(const idrk_ray_state_t* h_state, uint8_t* net_mask, int32_t* ray_of_slot, int32_t* counter,
                            void* stream);
@@ -309,6 +318,11 @@ int idrk_rt_minsdf_resolve(const idrk_ray_state_t* h_state, const int32_t* ray_o
  * min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6)) when max_norm > 0, then Adam (no weight decay,
  * bias correction with `step` >= 1) updates p, m, v in place. */
 int idrk_sumsq(const float* g, int64_t n, float* out, void* stream);
+/* idrk_sumsq_det: *out = sum(g^2) (overwritten) with a summation order that depends only on (n, n_partials): CTA b leaves
+ * its partial in partials[b] (device scratch, n_partials floats), one block adds them in a fixed order.  Data-parallel
+ * replicas must derive the SAME clip factor from the all-reduced bucket; the atomic form above differs in the last bits
+ * from run to run and lets replicas drift apart. */
+int idrk_sumsq_det(const float* g, int64_t n, float* out, float* partials, int32_t n_partials, void* stream);
 int idrk_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int32_t step, float max_norm, const float* sumsq, float grad_scale, void* stream);
 

@@ -26,6 +26,23 @@ def test_clip_adam_matches_torch():
         assert torch.allclose(p, pr.detach(), atol=2e-6, rtol=1e-5), t
 
 
+def test_sumsq_det_is_repeatable_and_correct():
+    """The trainer's squared-norm reduction: bit-identical from call to call (replicas must agree on the clip factor),
+    equal to a float64 sum within fp32 accumulation error."""
+    from idrk import kernels as K
+    g = torch.randn(12_345_679, generator=torch.Generator().manual_seed(3)).to(DEV) * 1e-3
+    out = torch.zeros(1, device=DEV)
+    part = torch.zeros(1184, device=DEV)
+    vals = []
+    for _ in range(5):
+        part.fill_(7.0)
+        K.sumsq_det(g, out, part)
+        vals.append(out.clone())
+    assert all(torch.equal(vals[0], v) for v in vals[1:])
+    ref = float((g.double() ** 2).sum())
+    assert abs(float(vals[0]) - ref) <= 2e-6 * ref
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_trainer_step_reduces_loss_and_matches_manual_step(use_graph):
     from idrk.dist import DataParallelTrainer
