@@ -478,7 +478,7 @@ def run_ours(args):
     hbm, bf16, bf16_sus, src = peaks()
     tf32_peak = 0.5 * bf16_sus
     zero = {"ms": 0.0, "flops": 0.0, "calls": 0}
-    g = prof.get("idrk_gemm_f16s_big", zero)          # fp16-pair launches with >= 8192 rows (the 100-sample sweeps)
+    g = prof.get("idrk_gemm_f16s_big", zero)          # fp16-pair launches with >= 16384 rows (the 100-sample sweeps)
     contraction = [prof.get(k, zero) for k in ("idrk_gemm", "idrk_gemm_2cta", "idrk_gemm_f16s", "idrk_gemm_f16s_big")]
     achieved = (g["flops"] / (g["ms"] * 1e-3) / 1e12) if g["ms"] > 0 else 0.0
     all_ms, all_fl = sum(c["ms"] for c in contraction), sum(c["flops"] for c in contraction)
@@ -515,7 +515,7 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"kernel": "gemm_f16s_kernel (tcgen05 kind::f16 fp16-pair MLP contraction tiles; launches with >= 8192 rows)",
+        "roofline": {"kernel": "gemm_f16s_kernel (tcgen05 kind::f16 fp16-pair MLP contraction tiles; launches with >= 16384 rows: the 100-sample sweeps)",
                      "bound": "tensor", "achieved": round(achieved, 2), "peak": round(f16_peak, 1), "unit": "TFLOP/s",
                      "frac": round(achieved / f16_peak, 4), "traffic": TRAFFIC.get("gemm_f16s_dram_bytes_per_launch"),
                      "traffic_note": "DRAM bytes of one full M=32700 launch (ncu --set full, profiles/r01_gemm_f16s_ncu_full_summary.txt); "

@@ -704,7 +704,8 @@ def gemm_f16s(A_h, A_l, B_h, B_l, M: int, N: int, Kc: int, *, C=None, C_h=None, 
     e.ldh = half_ld(C_h) if C_h is not None else 0
     e.mode, e.act_param, e.scale = mode, float(act), float(scale)
     if PROFILE.enabled:
-        PROFILE.pending_tag = ("_big" if M >= 8192 else "") + "[f16s M=%d N=%d K=%d mode=%d%s]" % (
+        # "_big": the 100-sample sweeps' chunks (32 K rows); the sphere-tracing queries have capacities of 2 N .. 6 N rows
+        PROFILE.pending_tag = ("_big" if M >= 16384 else "") + "[f16s M=%d N=%d K=%d mode=%d%s]" % (
             M, N, Kc, mode, " cnt" if m_count is not None else "")
         if m_count is not None:
             cnt = m_count.clone()

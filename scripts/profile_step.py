@@ -33,7 +33,7 @@ def main():
     model = quiet_build(IDRNetwork, _conf()).cuda().train()
     use_graph = len(sys.argv) > 2 and sys.argv[2] == "graph"
     tr = DataParallelTrainer(model, IDRLoss(0.1, 100.0, 50.0), lr=1e-4, use_cuda_graph=use_graph)
-    inp, rgb = synthetic_batch(bench.N_RAYS, seed=1)
+    inp, rgb = synthetic_batch(int(os.environ.get("IDRK_PROFILE_RAYS", bench.N_RAYS)), seed=1)
     inp = {k: v.cuda() for k, v in inp.items()}
     gt = {"rgb": rgb.cuda()}
     for _ in range(3):
@@ -73,7 +73,7 @@ def sections():
     torch.manual_seed(0)
     model = quiet_build(IDRNetwork, bench.model_conf()).cuda().train()
     tr = DataParallelTrainer(model, IDRLoss(0.1, 100.0, 50.0), lr=1e-4, use_cuda_graph=True)
-    inp, rgb = synthetic_batch(bench.N_RAYS, seed=1)
+    inp, rgb = synthetic_batch(int(os.environ.get("IDRK_PROFILE_RAYS", bench.N_RAYS)), seed=1)
     inp = {k: v.cuda() for k, v in inp.items()}
     gt = {"rgb": rgb.cuda()}
     for _ in range(4):
