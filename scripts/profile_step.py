@@ -46,6 +46,7 @@ def main():
     torch.cuda.synchronize()
     print("wall ms/step (plain): %.2f" % ((time.perf_counter() - t0) / 5 * 1e3))
     tr.use_cuda_graph = False
+    model.ray_tracer.use_cuda_graph = False          # CUDA events cannot bracket kernels inside a replayed graph
     K.PROFILE.reset(enabled=True, detail=True)
     tr.step(inp, gt)
     prof = K.PROFILE.summary()
