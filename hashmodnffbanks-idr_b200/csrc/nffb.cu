@@ -19,7 +19,8 @@ namespace idrk {
 
 constexpr int NFFB_MAX_W = 64;          // filter-bank width (2 outputs per lane)
 constexpr int NFFB_MAX_LAYERS = 16;
-constexpr int NFFB_WARPS = 8;
+constexpr int NFFB_WARPS = 16;
+constexpr int NFFB_P = 4;               // points a warp walks through the layers together
 
 struct NffbDev {
     GridDev grid;
@@ -38,19 +39,26 @@ __device__ __forceinline__ float warp_sum_all(float v) {
     return v;
 }
 
-// y[o] = b[o] + sum_k Wt[k][o] v[k] for the lane's two outputs (o = lane, lane + 32); v in shared memory
-__device__ __forceinline__ void matvec(const float* __restrict__ Wt, const float* __restrict__ bias, const float* v, int n_in,
-                                       int W, int lane, float& y0, float& y1) {
-    float a0 = 0.f, a1 = 0.f;
+// y[i][.] = b + sum_k Wt[k][o] v_i[k] for the lane's two outputs (o = lane, lane + 32) and the warp's NFFB_P points.
+// The kernel is bound by shared-memory wavefronts, not FMAs: with one point per warp every k cost 3 of them (2 weight
+// reads + 1 vector broadcast) for 2 FMAs.  Here the points' vectors are interleaved in shared memory (v[k][point]), so
+// one 16-byte broadcast serves 4 points and the two weight reads are shared by them: 3 wavefronts for 8 FMAs.  Each
+// point's sum still runs over k in order: bit-identical to the one-point form.
+__device__ __forceinline__ void matvec4(const float* __restrict__ Wt, const float* __restrict__ bias, const float* v, int n_in,
+                                        int W, int lane, float (&y0)[NFFB_P], float (&y1)[NFFB_P]) {
+    float a0[NFFB_P] = {0.f, 0.f, 0.f, 0.f}, a1[NFFB_P] = {0.f, 0.f, 0.f, 0.f};
     const float* w = Wt + lane;
+    const float4* v4 = reinterpret_cast<const float4*>(v);
 #pragma unroll 4
     for (int k = 0; k < n_in; ++k) {
-        const float vk = v[k];
-        a0 = fmaf(w[k * NFFB_MAX_W], vk, a0);
-        a1 = fmaf(w[k * NFFB_MAX_W + 32], vk, a1);
+        const float4 vk = v4[k];
+        const float w0 = w[k * NFFB_MAX_W], w1 = w[k * NFFB_MAX_W + 32];
+        a0[0] = fmaf(w0, vk.x, a0[0]); a0[1] = fmaf(w0, vk.y, a0[1]); a0[2] = fmaf(w0, vk.z, a0[2]); a0[3] = fmaf(w0, vk.w, a0[3]);
+        a1[0] = fmaf(w1, vk.x, a1[0]); a1[1] = fmaf(w1, vk.y, a1[1]); a1[2] = fmaf(w1, vk.z, a1[2]); a1[3] = fmaf(w1, vk.w, a1[3]);
     }
-    y0 = a0 + (lane < W ? bias[lane] : 0.f);
-    y1 = a1 + (lane + 32 < W ? bias[lane + 32] : 0.f);
+    const float b0 = lane < W ? bias[lane] : 0.f, b1 = lane + 32 < W ? bias[lane + 32] : 0.f;
+#pragma unroll
+    for (int i = 0; i < NFFB_P; ++i) { y0[i] = a0[i] + b0; y1[i] = a1[i] + b1; }
 }
 
 __global__ void __launch_bounds__(NFFB_WARPS * 32)
@@ -58,7 +66,8 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
                        const int* __restrict__ m_count) {
     pdl_wait();
     pdl_trigger();
-    extern __shared__ float smem[];
+    extern __shared__ float4 smem4[];
+    float* smem = reinterpret_cast<float*>(smem4);
     if (m_count != nullptr) { const long long c = *m_count; n = c < n ? c : n; }
     if (n <= 0) return;                     // gated tracer query: skip the weight staging
     const int W = d.width, NL = d.n_lin;
@@ -67,7 +76,7 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
     const int n_mats = NL + 1 + (d.style ? 1 : 0);                 // SIREN layers, out layer, style transform
     float* s_w = smem;
     float* s_b = s_w + (size_t)n_mats * NFFB_MAX_W * NFFB_MAX_W;
-    float* s_v = s_b + n_mats * NFFB_MAX_W + warp * (2 * NFFB_MAX_W + 32);     // [z | e | chunk columns]
+    float* s_v = s_b + n_mats * NFFB_MAX_W + warp * (NFFB_P * (2 * NFFB_MAX_W + 32));     // [z | e | chunk columns] x points
     for (int m = 0; m < n_mats; ++m) {
         const float* src_w = m < NL ? d.lin_w[m] : (m == NL ? d.out_w : d.sty_w);
         const float* src_b = m < NL ? d.lin_b[m] : (m == NL ? d.out_b : d.sty_b);
@@ -80,94 +89,118 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
         for (int i = threadIdx.x; i < NFFB_MAX_W; i += blockDim.x) s_b[m * NFFB_MAX_W + i] = i < W ? src_b[i] : 0.f;
     }
     __syncthreads();
-    float* zs = s_v;                       // current SIREN activations
-    float* es = s_v + NFFB_MAX_W;          // encoded chunk / (e + z)
-    float* gs = s_v + 2 * NFFB_MAX_W;      // the grid columns the chunks are cut from
+    float* zs = s_v;                                   // current SIREN activations       [k][point]
+    float* es = s_v + NFFB_P * NFFB_MAX_W;             // encoded chunk / (e + z)         [k][point]
+    float* gs = s_v + 2 * NFFB_P * NFFB_MAX_W;         // grid columns the chunks are cut from [c][point]
     const GridDev& g = d.grid;
     const int C = g.n_fourier, F = g.n_feat;
     const int n_cols = (NL - 1) * d.chunk;                          // grid columns consumed by chunks 0 .. NL-2
     const int dch = d.chunk;
     const int head = d.include_input ? 2 * dch : 0;
+    const float den = 2.f * d.bound;
 
+    const long long n_groups = (n + NFFB_P - 1) / NFFB_P;
     const long long wstride = (long long)gridDim.x * NFFB_WARPS;
-    for (long long p = (long long)blockIdx.x * NFFB_WARPS + warp; p < n; p += wstride) {
-        const float p0 = x[p * ldx + 0], p1 = x[p * ldx + 1], p2 = x[p * ldx + 2];
-        const float z00 = p0 / d.bound, z01 = p1 / d.bound, z02 = p2 / d.bound;
-        const float den = 2.f * d.bound;
-        const float u0 = (p0 + d.bound) / den, u1 = (p1 + d.bound) / den, u2 = (p2 + d.bound) / den;
-        // ---- grid columns (grid_enc(u)[:, 3:]): Fourier sin | cos | level features, arithmetic of hash_encode.cu
-        for (int c = lane; c < n_cols; c += 32) {
-            float v;
-            if (c < 2 * C) {
-                const int j = c < C ? c : c - C;
-                float xp = __fmul_rn(__fmul_rn(u0, 6.283185307179586f), g.B[j]);
-                xp = __fmaf_rn(__fmul_rn(u1, 6.283185307179586f), g.B[C + j], xp);
-                xp = __fmaf_rn(__fmul_rn(u2, 6.283185307179586f), g.B[2 * C + j], xp);
-                float sn, cs;
-                sincos_fast(xp, &sn, &cs);
-                v = c < C ? sn : cs;
-            } else {
-                const int l = (c - 2 * C) / F, f = (c - 2 * C) - l * F;
-                const float r = g.res[l];
-                const uint32_t h = hash3(trunc_u32(__fmul_rn(u0, r)), trunc_u32(__fmul_rn(u1, r)), trunc_u32(__fmul_rn(u2, r)));
-                v = __ldg(g.tables[l] + (size_t)wrap(h, g.rows[l], g.pow2mask[l], g.magic[l]) * F + f);
+    for (long long grp = (long long)blockIdx.x * NFFB_WARPS + warp; grp < n_groups; grp += wstride) {
+        const long long pbase = grp * NFFB_P;
+        float u[NFFB_P][3];
+#pragma unroll
+        for (int i = 0; i < NFFB_P; ++i) {
+            const long long p = pbase + i < n ? pbase + i : n - 1;          // tail: recompute the last point, never stored
+            const float p0 = x[p * ldx + 0], p1 = x[p * ldx + 1], p2 = x[p * ldx + 2];
+            u[i][0] = (p0 + d.bound) / den; u[i][1] = (p1 + d.bound) / den; u[i][2] = (p2 + d.bound) / den;
+            if (lane < 3) zs[lane * NFFB_P + i] = (lane == 0 ? p0 : (lane == 1 ? p1 : p2)) / d.bound;
+            // ---- grid columns (grid_enc(u)[:, 3:]): Fourier sin | cos | level features, arithmetic of hash_encode.cu
+            for (int c = lane; c < n_cols; c += 32) {
+                float v;
+                if (c < 2 * C) {
+                    const int j = c < C ? c : c - C;
+                    float xp = __fmul_rn(__fmul_rn(u[i][0], 6.283185307179586f), g.B[j]);
+                    xp = __fmaf_rn(__fmul_rn(u[i][1], 6.283185307179586f), g.B[C + j], xp);
+                    xp = __fmaf_rn(__fmul_rn(u[i][2], 6.283185307179586f), g.B[2 * C + j], xp);
+                    float sn, cs;
+                    sincos_fast(xp, &sn, &cs);
+                    v = c < C ? sn : cs;
+                } else {
+                    const int l = (c - 2 * C) / F, f = (c - 2 * C) - l * F;
+                    const float r = g.res[l];
+                    const uint32_t h = hash3(trunc_u32(__fmul_rn(u[i][0], r)), trunc_u32(__fmul_rn(u[i][1], r)), trunc_u32(__fmul_rn(u[i][2], r)));
+                    v = __ldg(g.tables[l] + (size_t)wrap(h, g.rows[l], g.pow2mask[l], g.magic[l]) * F + f);
+                }
+                gs[c * NFFB_P + i] = v;
             }
-            gs[c] = v;
         }
-        if (lane < 3) zs[lane] = lane == 0 ? z00 : (lane == 1 ? z01 : z02);
         __syncwarp();
-        float f0 = 0.f, f1 = 0.f;                                   // the lane's two output features
+        float f0[NFFB_P] = {0.f, 0.f, 0.f, 0.f}, f1[NFFB_P] = {0.f, 0.f, 0.f, 0.f};     // the lane's two output features per point
         for (int j = 0; j < NL; ++j) {
-            float y0, y1;
-            matvec(s_w + (size_t)j * NFFB_MAX_W * NFFB_MAX_W, s_b + j * NFFB_MAX_W, zs, j == 0 ? 3 : W, W, lane, y0, y1);
-            const float z0 = sinf(y0 * d.w0), z1 = sinf(y1 * d.w0);
+            float y0[NFFB_P], y1[NFFB_P];
+            matvec4(s_w + (size_t)j * NFFB_MAX_W * NFFB_MAX_W, s_b + j * NFFB_MAX_W, zs, j == 0 ? 3 : W, W, lane, y0, y1);
+            float z0[NFFB_P], z1[NFFB_P];
+#pragma unroll
+            for (int i = 0; i < NFFB_P; ++i) { z0[i] = sinf(y0[i] * d.w0); z1[i] = sinf(y1[i] * d.w0); }
             __syncwarp();
-            zs[lane] = z0; zs[lane + 32] = z1;
+            reinterpret_cast<float4*>(zs)[lane] = make_float4(z0[0], z0[1], z0[2], z0[3]);
+            reinterpret_cast<float4*>(zs)[lane + 32] = make_float4(z1[0], z1[1], z1[2], z1[3]);
             if (j > 0) {
                 // E = PositionalEncoding(chunk_{j-1}): [c | c | sin(b0 c) | cos(b0 c) | sin(b1 c) | ...]
-                const float* ch = gs + (j - 1) * dch;
-                float e0 = 0.f, e1 = 0.f;
+                const float* ch = gs + (j - 1) * dch * NFFB_P;
+                float e0[NFFB_P], e1[NFFB_P];
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     const int o = lane + 32 * t;
-                    float v = 0.f;
+                    float v[NFFB_P] = {0.f, 0.f, 0.f, 0.f};
                     if (o < W) {
                         if (o < head) {
-                            v = ch[o % dch];
+                            const float4 c4 = reinterpret_cast<const float4*>(ch)[o % dch];
+                            v[0] = c4.x; v[1] = c4.y; v[2] = c4.z; v[3] = c4.w;
                         } else {
                             const int q = (o - head) / dch, jx = (o - head) - q * dch;
-                            const float a = __fmul_rn(ch[jx], d.bands[q >> 1]);
-                            v = (q & 1) ? cosf(a) : sinf(a);
+                            const float4 c4 = reinterpret_cast<const float4*>(ch)[jx];
+                            const float band = d.bands[q >> 1];
+                            const float a[NFFB_P] = {__fmul_rn(c4.x, band), __fmul_rn(c4.y, band), __fmul_rn(c4.z, band), __fmul_rn(c4.w, band)};
+#pragma unroll
+                            for (int i = 0; i < NFFB_P; ++i) v[i] = (q & 1) ? cosf(a[i]) : sinf(a[i]);
                         }
                     }
-                    if (t == 0) e0 = v; else e1 = v;
+#pragma unroll
+                    for (int i = 0; i < NFFB_P; ++i) { if (t == 0) e0[i] = v[i]; else e1[i] = v[i]; }
                 }
                 if (d.style) {
-                    es[lane] = e0; es[lane + 32] = e1;
+                    reinterpret_cast<float4*>(es)[lane] = make_float4(e0[0], e0[1], e0[2], e0[3]);
+                    reinterpret_cast<float4*>(es)[lane + 32] = make_float4(e1[0], e1[1], e1[2], e1[3]);
                     __syncwarp();
-                    float s0, s1;
-                    matvec(s_w + (size_t)(NL + 1) * NFFB_MAX_W * NFFB_MAX_W, s_b + (NL + 1) * NFFB_MAX_W, es, W, W, lane, s0, s1);
-                    const float m0 = lane < W ? s0 : 0.f, m1 = lane + 32 < W ? s1 : 0.f;
-                    const float mu = warp_sum_all(m0 + m1) / (float)W;
-                    const float c0 = lane < W ? s0 - mu : 0.f, c1 = lane + 32 < W ? s1 - mu : 0.f;
-                    const float var = warp_sum_all(c0 * c0 + c1 * c1) / (float)W;
-                    const float inv = 1.f / sqrtf(var + d.eps);
-                    e0 = c0 * inv; e1 = c1 * inv;
+                    float s0[NFFB_P], s1[NFFB_P];
+                    matvec4(s_w + (size_t)(NL + 1) * NFFB_MAX_W * NFFB_MAX_W, s_b + (NL + 1) * NFFB_MAX_W, es, W, W, lane, s0, s1);
+#pragma unroll
+                    for (int i = 0; i < NFFB_P; ++i) {
+                        const float m0 = lane < W ? s0[i] : 0.f, m1 = lane + 32 < W ? s1[i] : 0.f;
+                        const float mu = warp_sum_all(m0 + m1) / (float)W;
+                        const float c0 = lane < W ? s0[i] - mu : 0.f, c1 = lane + 32 < W ? s1[i] - mu : 0.f;
+                        const float var = warp_sum_all(c0 * c0 + c1 * c1) / (float)W;
+                        const float inv = 1.f / sqrtf(var + d.eps);
+                        e0[i] = c0 * inv; e1[i] = c1 * inv;
+                    }
                     __syncwarp();
                 }
-                es[lane] = e0 + z0; es[lane + 32] = e1 + z1;
+                reinterpret_cast<float4*>(es)[lane] = make_float4(e0[0] + z0[0], e0[1] + z0[1], e0[2] + z0[2], e0[3] + z0[3]);
+                reinterpret_cast<float4*>(es)[lane + 32] = make_float4(e1[0] + z1[0], e1[1] + z1[1], e1[2] + z1[2], e1[3] + z1[3]);
                 __syncwarp();
-                float o0, o1;
-                matvec(s_w + (size_t)NL * NFFB_MAX_W * NFFB_MAX_W, s_b + NL * NFFB_MAX_W, es, W, W, lane, o0, o1);
-                f0 += o0; f1 += o1;
+                float o0[NFFB_P], o1[NFFB_P];
+                matvec4(s_w + (size_t)NL * NFFB_MAX_W * NFFB_MAX_W, s_b + NL * NFFB_MAX_W, es, W, W, lane, o0, o1);
+#pragma unroll
+                for (int i = 0; i < NFFB_P; ++i) { f0[i] += o0[i]; f1[i] += o1[i]; }
             }
             __syncwarp();
         }
-        float* orow = out + p * (long long)ld_out;
-        if (lane < 3) orow[lane] = lane == 0 ? u0 : (lane == 1 ? u1 : u2);
-        if (lane < W) orow[3 + lane] = f0 / d.levels_div;
-        if (lane + 32 < W) orow[3 + lane + 32] = f1 / d.levels_div;
-        for (int c = 3 + W + lane; c < ld_out; c += 32) orow[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NFFB_P; ++i) {
+            if (pbase + i >= n) break;
+            float* orow = out + (pbase + i) * (long long)ld_out;
+            if (lane < 3) orow[lane] = lane == 0 ? u[i][0] : (lane == 1 ? u[i][1] : u[i][2]);
+            if (lane < W) orow[3 + lane] = f0[i] / d.levels_div;
+            if (lane + 32 < W) orow[3 + lane + 32] = f1[i] / d.levels_div;
+            for (int c = 3 + W + lane; c < ld_out; c += 32) orow[c] = 0.f;
+        }
         __syncwarp();
     }
 }
@@ -202,13 +235,13 @@ extern "C" int idrk_nffb_encode_fwd(const idrk_nffb_t* h, const float* x, int64_
     d.out_w = h->out_w; d.out_b = h->out_b; d.sty_w = h->style_w; d.sty_b = h->style_b;
     const int n_mats = h->n_lin + 1 + (h->style ? 1 : 0);
     const size_t smem = ((size_t)n_mats * NFFB_MAX_W * NFFB_MAX_W + (size_t)n_mats * NFFB_MAX_W +
-                         (size_t)NFFB_WARPS * (2 * NFFB_MAX_W + 32)) * sizeof(float);
+                         (size_t)NFFB_WARPS * NFFB_P * (2 * NFFB_MAX_W + 32)) * sizeof(float);
     if (smem > 220 * 1024) return IDRK_E_UNSUP;
     IDRK_CUDA_TRY(cudaFuncSetAttribute(nffb_encode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nffb_encode_fwd_kernel, NFFB_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     long long grid = (long long)per_sm * sm_count();
-    const long long need = (n + NFFB_WARPS - 1) / NFFB_WARPS;
+    const long long need = (n + NFFB_WARPS * NFFB_P - 1) / (NFFB_WARPS * NFFB_P);
     if (grid > need) grid = need;
     IDRK_CUDA_TRY(launch_k(nffb_encode_fwd_kernel, dim3((unsigned)grid), dim3(NFFB_WARPS * 32), smem, (cudaStream_t)stream,
                            d, x, (long long)n, (int)ldx, out, (int)ld_out, m_count));
