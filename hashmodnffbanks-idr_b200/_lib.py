@@ -112,7 +112,8 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_hash_encode_f16pair", "idrk_camera_rays", "idrk_idr_loss", "idrk_scale3",
            "idrk_fourier_dx_fwd", "idrk_fourier_dx_bwd", "idrk_morton_sort_workspace", "idrk_morton_sort",
            "idrk_hash_encode_bwd_det_workspace", "idrk_hash_encode_bwd_det", "idrk_sdf_squash_rows", "idrk_sumsq_det",
-           "idrk_rt_linesearch_points", "idrk_rt_linesearch_resolve"]
+           "idrk_rt_linesearch_points", "idrk_rt_linesearch_resolve",
+           "idrk_gemm_p16", "idrk_split_p16", "idrk_weight_norm_fwd_p16", "idrk_act_bwd_p16"]
 
 
 class NffbDesc(ctypes.Structure):
@@ -131,6 +132,18 @@ class EpilogueH(ctypes.Structure):
                 ("ldc", ctypes.c_int32), ("ldh", ctypes.c_int32), ("mode", ctypes.c_int32),
                 ("act_param", ctypes.c_float), ("scale", ctypes.c_float),
                 ("dot_w", ctypes.c_void_p), ("dot_out", ctypes.c_void_p), ("ld_dot", ctypes.c_int32)]
+
+
+class EpilogueP(ctypes.Structure):
+    """Mirror of idrk_epilogue_p16_t."""
+    _fields_ = [("C", ctypes.c_void_p), ("S", ctypes.c_void_p), ("C_h", ctypes.c_void_p), ("C_l", ctypes.c_void_p),
+                ("bias", ctypes.c_void_p), ("aux", ctypes.c_void_p),
+                ("ldc", ctypes.c_int32), ("lds", ctypes.c_int32), ("ldh", ctypes.c_int32), ("ldaux", ctypes.c_int32),
+                ("c_fmt", ctypes.c_int32), ("mode", ctypes.c_int32), ("act_param", ctypes.c_float), ("scale", ctypes.c_float),
+                ("accumulate", ctypes.c_int32)]
+
+
+P16_FP16, P16_BF16 = 0, 1
 
 
 class RayStateDesc(ctypes.Structure):
@@ -207,6 +220,10 @@ def _declare(L):
     L.idrk_rt_minsdf_points.argtypes = [rs, vp, i32, i32, i32, vp, vp, vp, vp]
     L.idrk_rt_minsdf_resolve.argtypes = [rs, vp, i32, i32, vp, vp, vp, vp]
     L.idrk_act_bwd.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i64, i32, i32, f32, f32, vp, vp, vp, i32, vp]
+    L.idrk_gemm_p16.argtypes = [i32, i64, i32, i32, vp, vp, i32, i32, vp, vp, i32, i32, c.POINTER(EpilogueP), vp, i32, vp]
+    L.idrk_split_p16.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, i32, vp, vp]
+    L.idrk_weight_norm_fwd_p16.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp]
+    L.idrk_act_bwd_p16.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, i64, i32, i32, f32, f32, vp, i32, vp, vp, i32, i32, vp]
     L.idrk_gemm_f16s.argtypes = [i64, i32, i32, vp, vp, i32, vp, vp, i32, c.POINTER(EpilogueH), vp, vp]
     L.idrk_split_f16.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp, vp]
     L.idrk_nffb_encode_fwd.argtypes = [c.POINTER(NffbDesc), vp, i64, i32, vp, i32, vp, vp]

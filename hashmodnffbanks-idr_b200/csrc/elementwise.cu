@@ -2,6 +2,8 @@
 // backward (legacy nn.utils.weight_norm, dim=0: W = g * v / ||v||_row), bias gradients (column sums)
 // and the SDF head (last Linear row 0 + the Laplace-density squash of
 // implicit_differentiable_renderer.py:112 / density_net.py:20-30).
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace idrk {
@@ -10,6 +12,20 @@ __device__ __forceinline__ float tf32_round(float v) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
     return __uint_as_float(u);
+}
+
+// 16-bit pair x ~= h + l * 2^-11 (fmt 0: fp16, clamped to the format's range; 1: bf16), see csrc/gemm_p16.cu
+__device__ __forceinline__ void pair16(float x, int fmt, uint16_t& h, uint16_t& l) {
+    if (fmt == 0) {
+        x = fminf(fmaxf(x, -65504.f), 65504.f);
+        const __half hh = __float2half_rn(x);
+        const __half ll = __float2half_rn((x - __half2float(hh)) * 2048.f);
+        h = __half_as_ushort(hh); l = __half_as_ushort(ll);
+    } else {
+        const __nv_bfloat16 hh = __float2bfloat16_rn(x);
+        const __nv_bfloat16 ll = __float2bfloat16_rn((x - __bfloat162float(hh)) * 2048.f);
+        h = __bfloat16_as_ushort(hh); l = __bfloat16_as_ushort(ll);
+    }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -43,7 +59,8 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, long long rows, i
 // one warp per output row n
 __global__ void weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v, int N, int K, int ldv,
                                        float* __restrict__ W, float* __restrict__ W_hi, float* __restrict__ W_lo, int ldw,
-                                       float* __restrict__ Wt, float* __restrict__ Wt_hi, float* __restrict__ Wt_lo, int ldwt) {
+                                       float* __restrict__ Wt, float* __restrict__ Wt_hi, float* __restrict__ Wt_lo, int ldwt,
+                                       uint16_t* __restrict__ Wp_h, uint16_t* __restrict__ Wp_l, int ldp, int p_fmt) {
     pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
     pdl_trigger();
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -59,6 +76,7 @@ __global__ void weight_norm_fwd_kernel(const float* __restrict__ g, const float*
         const float h = tf32_round(w), l = tf32_round(w - h);
         if (W) W[(long long)n * ldw + k] = w;
         if (W_hi) { W_hi[(long long)n * ldw + k] = h; W_lo[(long long)n * ldw + k] = l; }
+        if (Wp_h) { uint16_t ph, pl; pair16(w, p_fmt, ph, pl); Wp_h[(long long)n * ldp + k] = ph; Wp_l[(long long)n * ldp + k] = pl; }
         if (k < K) {
             if (Wt) Wt[(long long)k * ldwt + n] = w;
             if (Wt_hi) { Wt_hi[(long long)k * ldwt + n] = h; Wt_lo[(long long)k * ldwt + n] = l; }
@@ -180,7 +198,8 @@ __global__ void sdf_squash_rows_kernel(const float* __restrict__ x, long long ro
 __global__ void act_bwd_kernel(const float* __restrict__ dH, int ld_dh, const float* __restrict__ dS, int ld_ds,
                                const float* __restrict__ S, int ld_s, const float* __restrict__ H, int ld_h,
                                long long rows, int cols, int mode, float act, float scale,
-                               float* __restrict__ dZ, float* __restrict__ hi, float* __restrict__ lo, int ld_out) {
+                               float* __restrict__ dZ, float* __restrict__ hi, float* __restrict__ lo, int ld_out,
+                               uint16_t* __restrict__ ph, uint16_t* __restrict__ pl, int ldp, int p_fmt) {
     pdl_wait();                 // programmatic dependent launch: everything below may touch the producer's data
     pdl_trigger();
     const long long total = rows * (long long)ld_out;
@@ -201,6 +220,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ dH, int ld_dh, const fl
         }
         dZ[i] = v;
         if (hi) { const float h = tf32_round(v); hi[i] = h; lo[i] = tf32_round(v - h); }
+        if (ph) { uint16_t a, b; pair16(v, p_fmt, a, b); ph[r * ldp + c] = a; pl[r * ldp + c] = b; }
     }
 }
 
@@ -209,7 +229,8 @@ __global__ void act_bwd_kernel(const float* __restrict__ dH, int ld_dh, const fl
 __global__ void act_bwd_vec4_kernel(const float* __restrict__ dH, int ld_dh, const float* __restrict__ dS, int ld_ds,
                                     const float* __restrict__ S, int ld_s, const float* __restrict__ H, int ld_h,
                                     long long rows, int cols, int mode, float act, float scale,
-                                    float* __restrict__ dZ, float* __restrict__ hi, float* __restrict__ lo, int ld_out) {
+                                    float* __restrict__ dZ, float* __restrict__ hi, float* __restrict__ lo, int ld_out,
+                                    uint16_t* __restrict__ ph, uint16_t* __restrict__ pl, int ldp, int p_fmt) {
     pdl_wait();
     pdl_trigger();
     const int q = ld_out >> 2;
@@ -253,6 +274,13 @@ __global__ void act_bwd_vec4_kernel(const float* __restrict__ dH, int ld_dh, con
             *reinterpret_cast<float4*>(hi + i * 4) = make_float4(a[0], a[1], a[2], a[3]);
             *reinterpret_cast<float4*>(lo + i * 4) = make_float4(b[0], b[1], b[2], b[3]);
         }
+        if (ph) {
+            uint16_t a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pair16(v[k], p_fmt, a[k], b[k]);
+            *reinterpret_cast<uint2*>(ph + r * ldp + c) = make_uint2(a[0] | ((uint32_t)a[1] << 16), a[2] | ((uint32_t)a[3] << 16));
+            *reinterpret_cast<uint2*>(pl + r * ldp + c) = make_uint2(b[0] | ((uint32_t)b[1] << 16), b[2] | ((uint32_t)b[3] << 16));
+        }
     }
 }
 
@@ -278,15 +306,30 @@ extern "C" int idrk_split_tf32(const float* x, int64_t rows, int32_t cols, int32
     return 0;
 }
 
-extern "C" int idrk_weight_norm_fwd(const float* g, const float* v, int32_t N, int32_t K, int32_t ldv,
-                                    float* W, float* W_hi, float* W_lo, int32_t ldw,
-                                    float* Wt, float* Wt_hi, float* Wt_lo, int32_t ldwt, void* stream) {
+static int weight_norm_fwd_impl(const float* g, const float* v, int32_t N, int32_t K, int32_t ldv,
+                               float* W, float* W_hi, float* W_lo, int32_t ldw,
+                               float* Wt, float* Wt_hi, float* Wt_lo, int32_t ldwt,
+                               void* Wp_h, void* Wp_l, int32_t ldp, int32_t p_fmt, void* stream) {
     if (!v || N < 1 || K < 1 || ldv < K || ldw < K) return IDRK_E_ARG;
     if ((W_hi == nullptr) != (W_lo == nullptr) || (Wt_hi == nullptr) != (Wt_lo == nullptr)) return IDRK_E_ARG;
     if ((Wt || Wt_hi) && ldwt < N) return IDRK_E_ARG;
-    IDRK_CUDA_TRY(launch_k(weight_norm_fwd_kernel, dim3((N + 7) / 8), dim3(256), 0, (cudaStream_t)stream, g, v, N, K, ldv, W, W_hi, W_lo, ldw, Wt, Wt_hi, Wt_lo, ldwt));
+    if ((Wp_h == nullptr) != (Wp_l == nullptr) || (Wp_h && (ldp < ldw || (p_fmt & ~1)))) return IDRK_E_ARG;
+    IDRK_CUDA_TRY(launch_k(weight_norm_fwd_kernel, dim3((N + 7) / 8), dim3(256), 0, (cudaStream_t)stream, g, v, N, K, ldv, W, W_hi, W_lo, ldw,
+                           Wt, Wt_hi, Wt_lo, ldwt, (uint16_t*)Wp_h, (uint16_t*)Wp_l, ldp, p_fmt));
     IDRK_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int idrk_weight_norm_fwd(const float* g, const float* v, int32_t N, int32_t K, int32_t ldv,
+                                    float* W, float* W_hi, float* W_lo, int32_t ldw,
+                                    float* Wt, float* Wt_hi, float* Wt_lo, int32_t ldwt, void* stream) {
+    return weight_norm_fwd_impl(g, v, N, K, ldv, W, W_hi, W_lo, ldw, Wt, Wt_hi, Wt_lo, ldwt, nullptr, nullptr, 0, 0, stream);
+}
+
+extern "C" int idrk_weight_norm_fwd_p16(const float* g, const float* v, int32_t N, int32_t K, int32_t ldv, float* W, int32_t ldw,
+                                        void* W_h, void* W_l, int32_t ldp, int32_t fmt, void* stream) {
+    if (!W_h || !W_l) return IDRK_E_ARG;
+    return weight_norm_fwd_impl(g, v, N, K, ldv, W, nullptr, nullptr, ldw, nullptr, nullptr, nullptr, 0, W_h, W_l, ldp, fmt, stream);
 }
 
 extern "C" int idrk_weight_norm_bwd(const float* g, const float* v, const float* dW, int32_t N, int32_t K, int32_t ldv,
@@ -339,11 +382,13 @@ extern "C" int idrk_sdf_squash_rows(const float* x, int64_t rows, int32_t cols, 
     return 0;
 }
 
-extern "C" int idrk_act_bwd(const float* dH, int32_t ld_dh, const float* dS, int32_t ld_ds, const float* S, int32_t ld_s,
-                            const float* H, int32_t ld_h, int64_t rows, int32_t cols, int32_t mode, float act, float scale,
-                            float* dZ, float* dZ_hi, float* dZ_lo, int32_t ld_out, void* stream) {
+static int act_bwd_impl(const float* dH, int32_t ld_dh, const float* dS, int32_t ld_ds, const float* S, int32_t ld_s,
+                        const float* H, int32_t ld_h, int64_t rows, int32_t cols, int32_t mode, float act, float scale,
+                        float* dZ, float* dZ_hi, float* dZ_lo, int32_t ld_out, void* P_h, void* P_l, int32_t ldp, int32_t p_fmt,
+                        void* stream) {
     if (!S || !dZ || (!dH && !dS) || rows < 0 || cols < 1 || ld_out < cols || ld_s < cols) return IDRK_E_ARG;
     if ((dZ_hi == nullptr) != (dZ_lo == nullptr)) return IDRK_E_ARG;
+    if ((P_h == nullptr) != (P_l == nullptr) || (P_h && (ldp < ld_out || (p_fmt & ~1)))) return IDRK_E_ARG;
     if (dS && (mode == IDRK_EPI_SINE || mode == IDRK_EPI_TANH) && !H) return IDRK_E_ARG;
     if (rows == 0) return 0;
     const bool need_h = dS && (mode == IDRK_EPI_SINE || mode == IDRK_EPI_TANH);
@@ -351,15 +396,33 @@ extern "C" int idrk_act_bwd(const float* dH, int32_t ld_dh, const float* dS, int
                       (!dH || ((ld_dh & 3) == 0 && aligned16(dH))) && (!dS || ((ld_ds & 3) == 0 && aligned16(dS))) &&
                       (!need_h || ((ld_h & 3) == 0 && aligned16(H))) && (!dZ_hi || (aligned16(dZ_hi) && aligned16(dZ_lo))) &&
                       ld_s >= ((cols + 3) & ~3) && (!dH || ld_dh >= ((cols + 3) & ~3)) && (!dS || ld_ds >= ((cols + 3) & ~3)) &&
-                      (!need_h || ld_h >= ((cols + 3) & ~3));
+                      (!need_h || ld_h >= ((cols + 3) & ~3)) &&
+                      (!P_h || ((ldp & 3) == 0 && (reinterpret_cast<uintptr_t>(P_h) & 7) == 0 && (reinterpret_cast<uintptr_t>(P_l) & 7) == 0));
     if (vec4) {
         IDRK_CUDA_TRY(launch_k(act_bwd_vec4_kernel, dim3(ew_blocks(rows * (long long)(ld_out >> 2), 256)), dim3(256), 0, (cudaStream_t)stream,
-            dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, dZ_hi, dZ_lo, ld_out));
+            dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, dZ_hi, dZ_lo, ld_out,
+            (uint16_t*)P_h, (uint16_t*)P_l, ldp, p_fmt));
         IDRK_LAUNCH_CHECK();
         return 0;
     }
-    IDRK_CUDA_TRY(launch_k(act_bwd_kernel, dim3(ew_blocks(rows * (long long)ld_out, 256)), dim3(256), 0, (cudaStream_t)stream, 
-        dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, dZ_hi, dZ_lo, ld_out));
+    IDRK_CUDA_TRY(launch_k(act_bwd_kernel, dim3(ew_blocks(rows * (long long)ld_out, 256)), dim3(256), 0, (cudaStream_t)stream,
+        dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, dZ_hi, dZ_lo, ld_out,
+        (uint16_t*)P_h, (uint16_t*)P_l, ldp, p_fmt));
     IDRK_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int idrk_act_bwd(const float* dH, int32_t ld_dh, const float* dS, int32_t ld_ds, const float* S, int32_t ld_s,
+                            const float* H, int32_t ld_h, int64_t rows, int32_t cols, int32_t mode, float act, float scale,
+                            float* dZ, float* dZ_hi, float* dZ_lo, int32_t ld_out, void* stream) {
+    return act_bwd_impl(dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, dZ_hi, dZ_lo, ld_out,
+                        nullptr, nullptr, 0, 0, stream);
+}
+
+extern "C" int idrk_act_bwd_p16(const float* dH, int32_t ld_dh, const float* dS, int32_t ld_ds, const float* S, int32_t ld_s,
+                                const float* H, int32_t ld_h, int64_t rows, int32_t cols, int32_t mode, float act, float scale,
+                                float* dZ, int32_t ld_out, void* dZ_h, void* dZ_l, int32_t ld_pair, int32_t fmt, void* stream) {
+    if (!dZ_h || !dZ_l) return IDRK_E_ARG;
+    return act_bwd_impl(dH, ld_dh, dS, ld_ds, S, ld_s, H, ld_h, rows, cols, mode, act, scale, dZ, nullptr, nullptr, ld_out,
+                        dZ_h, dZ_l, ld_pair, fmt, stream);
 }

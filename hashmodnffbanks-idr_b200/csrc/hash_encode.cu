@@ -1007,7 +1007,7 @@ static int launch_bwd(const GridDev& g, const GradDev& gd, const float* x, long 
 
 using namespace idrk;
 
-extern "C" int idrk_version(void) { return 3; }   // 3: idrk_camera_rays / idrk_idr_loss / idrk_scale3 (render_glue.cu); 2: idrk_epilogue_f16_t gained dot_w / dot_out / ld_dot, IDRK_HASH_NGP, idrk_hash_encode_f16pair
+extern "C" int idrk_version(void) { return 4; }   // 4: idrk_gemm_p16 / idrk_split_p16 / idrk_weight_norm_fwd_p16 / idrk_act_bwd_p16; 3: idrk_camera_rays / idrk_idr_loss / idrk_scale3 (render_glue.cu); 2: idrk_epilogue_f16_t gained dot_w / dot_out / ld_dot, IDRK_HASH_NGP, idrk_hash_encode_f16pair
 
 extern "C" int idrk_device_sm_count(int* out_sms) {
     if (!out_sms) return IDRK_E_ARG;

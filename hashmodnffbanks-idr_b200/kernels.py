@@ -714,3 +714,97 @@ def gemm_f16s(A_h, A_l, B_h, B_l, M: int, N: int, Kc: int, *, C=None, C_h=None, 
             PROFILE.pending_flops = 2.0 * M * N * Kc
     check(lib().idrk_gemm_f16s(M, N, Kc, ptr(A_h), ptr(A_l), half_ld(A_h), ptr(B_h), ptr(B_l), half_ld(B_h),
                                ctypes.byref(e), ptr(m_count), stream_ptr()), "idrk_gemm_f16s")
+
+
+# ---------------------------------------------------------------------------------------------
+# 16-bit-pair contraction of the DIFFERENTIABLE path (csrc/gemm_p16.cu)
+# ---------------------------------------------------------------------------------------------
+from ._lib import EpilogueP, P16_FP16, P16_BF16  # noqa: E402
+
+_training_p16 = True
+
+def set_training_operands(name: str):
+    """Operand format of the autograd path's contractions under set_precision("3xtf32"): "p16" = pairs of 16-bit floats
+    x ~= h + l * 2^-11 (default: bf16 pairs - full fp32 range, ~17 significant bits; 4 bytes per element, kind::f16
+    tensor rate) or "tf32x3" = tf32 hi / lo pairs (8 bytes per element, kind::tf32)."""
+    global _training_p16
+    if name not in ("p16", "tf32x3"):
+        raise ValueError(name)
+    _training_p16 = name == "p16"
+
+
+def training_p16() -> bool:
+    return _training_p16 and _default_precision == PREC_3XTF32
+
+
+def empty_pair16(rows: int, cols: int, device, fmt: int):
+    dt = torch.float16 if fmt == P16_FP16 else torch.bfloat16
+    buf = torch.empty((2, max(rows, 1), pad8(cols)), device=device, dtype=dt)
+    return buf[0, :rows, :cols], buf[1, :rows, :cols]
+
+
+def split_p16(x: torch.Tensor, fmt: int, m_count: Optional[torch.Tensor] = None):
+    """(h, l, fmt) pair of a 2-D fp32 tensor."""
+    x = rows2d(x, "x")
+    r, c = x.shape
+    h, l = empty_pair16(r, c, x.device, fmt)
+    if r:
+        check(lib().idrk_split_p16(ptr(x), r, c, ld_of(x), 1.0, ptr(h), ptr(l), pad8(c), pad8(c) - c, fmt, ptr(m_count),
+                                   stream_ptr()), "idrk_split_p16")
+    return h, l, fmt
+
+
+def gemm_p16(layout: int, A, B, M: int, N: int, Kc: int, *, C=None, C_pair=None, S=None, bias=None, aux=None,
+             mode=EPI_NONE, act=0.0, scale=1.0, accumulate=False, m_count=None, split_k=1):
+    """Raw launcher.  A, B: (h, l, fmt) pairs (rows padded to 8 halves); C_pair: (C_h, C_l, fmt) output pair."""
+    e = EpilogueP()
+    if C is None and C_pair is None:
+        raise _lib.IdrkError("gemm_p16 needs an output")
+    e.C = C.data_ptr() if C is not None else None
+    e.S = S.data_ptr() if S is not None else None
+    if C_pair is not None:
+        e.C_h, e.C_l, e.c_fmt = C_pair[0].data_ptr(), C_pair[1].data_ptr(), int(C_pair[2])
+        e.ldh = half_ld(C_pair[0])
+    e.bias = bias.data_ptr() if bias is not None else None
+    e.aux = aux.data_ptr() if aux is not None else None
+    e.ldc = op_ld(C) if C is not None else 0
+    e.lds = op_ld(S) if S is not None else 0
+    e.ldaux = op_ld(aux) if aux is not None else 0
+    e.mode, e.act_param, e.scale, e.accumulate = mode, float(act), float(scale), int(bool(accumulate))
+    if PROFILE.enabled:
+        PROFILE.pending_tag = "[p16 %s M=%d N=%d K=%d mode=%d fmt=%d%d%s]" % ("NT NN TN".split()[layout], M, N, Kc, mode, A[2], B[2],
+                                                                           " split%d" % split_k if split_k > 1 else "")
+        PROFILE.pending_flops = 2.0 * M * N * Kc
+    check(lib().idrk_gemm_p16(layout, M, N, Kc, ptr(A[0]), ptr(A[1]), int(A[2]), half_ld(A[0]), ptr(B[0]), ptr(B[1]), int(B[2]),
+                              half_ld(B[0]), ctypes.byref(e), ptr(m_count), split_k, stream_ptr()), "idrk_gemm_p16")
+
+
+def weight_norm_fwd_p16(g: Optional[torch.Tensor], v: torch.Tensor, fmt: int):
+    """W = g v / ||v|| as fp32 and as a 16-bit pair (one launch)."""
+    v = rows2d(v, "weight_v")
+    N, Kd = v.shape
+    W = empty_padded(N, Kd, v.device)
+    h, l = empty_pair16(N, Kd, v.device, fmt)
+    gg = g.reshape(-1).contiguous() if g is not None else None
+    check(lib().idrk_weight_norm_fwd_p16(ptr(gg), ptr(v), N, Kd, ld_of(v), ptr(W), pad4(Kd), ptr(h), ptr(l), pad8(Kd), fmt,
+                                         stream_ptr()), "idrk_weight_norm_fwd_p16")
+    return W, (h, l, fmt)
+
+
+def act_bwd_p16(dH, dS, S, H, mode: int, act: float, scale: float, fmt: int):
+    """dZ = dH * S * scale + dS * act''(Z) as fp32 and as a 16-bit pair."""
+    S = rows2d(S, "S")
+    rows, cols = S.shape
+    dev = S.device
+    dZ = empty_padded(rows, cols, dev)
+    h, l = empty_pair16(rows, cols, dev, fmt)
+    if rows == 0:
+        return dZ, (h, l, fmt)
+    dH = rows2d(dH, "dH") if dH is not None else None
+    dS = rows2d(dS, "dS") if dS is not None else None
+    H = rows2d(H, "H") if H is not None else None
+    check(lib().idrk_act_bwd_p16(ptr(dH), ld_of(dH) if dH is not None else 0, ptr(dS), ld_of(dS) if dS is not None else 0,
+                                 ptr(S), ld_of(S), ptr(H), ld_of(H) if H is not None else 0, rows, cols, mode, float(act),
+                                 float(scale), ptr(dZ), pad4(cols), ptr(h), ptr(l), pad8(cols), fmt, stream_ptr()),
+          "idrk_act_bwd_p16")
+    return dZ, (h, l, fmt)

@@ -36,30 +36,60 @@ def _three_pass() -> bool:
     return K.get_precision() == K.PREC_3XTF32
 
 
-def tag_split(t: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
-    """Remembers the (hi, lo) 3xTF32 operand pair of `t` on the tensor object (valid for its current version)."""
-    t._idrk_split = (hi, lo, t._version)
+def _split_mode() -> Optional[str]:
+    """Operand format of the autograd path's contractions: "p16" (16-bit pairs, csrc/gemm_p16.cu), "tf32" (hi / lo
+    pairs, csrc/gemm.cu) or None (single pass / FFMA: no split operands)."""
+    if not _three_pass():
+        return None
+    return "p16" if K.training_p16() else "tf32"
+
+
+def _pack_key(pack):
+    return "tf32" if len(pack) == 2 else int(pack[2])
+
+
+def tag_split(t: torch.Tensor, *pack) -> torch.Tensor:
+    """Remembers a split operand of `t` on the tensor object (valid for its current version): (hi, lo) tf32 pair or
+    (h, l, fmt) 16-bit pair; one per format."""
+    cur = getattr(t, "_idrk_split", None)
+    ver = (t._version, WEIGHTS_EPOCH[0])       # the fused optimiser rewrites parameters without moving tensor._version
+    if cur is None or cur[1] != ver:
+        cur = ({}, ver)
+        t._idrk_split = cur
+    cur[0][_pack_key(pack)] = tuple(pack)
     return t
 
 
-def split_of(t: torch.Tensor):
-    """(hi, lo) pair produced by an upstream kernel epilogue for exactly this tensor, or None."""
+def split_of(t: torch.Tensor, fmt: Optional[int] = None):
+    """Split operand recorded for exactly this tensor in the current operand format, or None.  16-bit pairs: `fmt`
+    selects the pair format (default bf16)."""
     sp = getattr(t, "_idrk_split", None)
-    if sp is None or sp[2] != t._version or not _three_pass():
+    mode = _split_mode()
+    if sp is None or sp[1] != (t._version, WEIGHTS_EPOCH[0]) or mode is None:
         return None
-    return sp[0], sp[1]
+    return sp[0].get("tf32" if mode == "tf32" else (K.P16_BF16 if fmt is None else fmt))
 
 
-def make_split(t: torch.Tensor):
-    """(hi, lo) operand pair of `t` for the current precision (None when a single pass is used)."""
-    if not _three_pass():
+def make_split(t: torch.Tensor, fmt: Optional[int] = None):
+    """Split operand of `t` for the current operand format (None when a single pass is used), cached on the tensor.
+    16-bit pairs are bf16 (the full fp32 range, ~17 bits) unless the caller asks for fp16 pairs (`fmt`; ~22 bits,
+    |x| < 65504 - the SIREN layers of the filter banks, whose sin(w0 .) chains amplify operand rounding)."""
+    mode = _split_mode()
+    if mode is None:
         return None
-    sp = split_of(t)
-    return sp if sp is not None else K.split_tf32(K.operand(t.detach()))
+    sp = split_of(t, fmt)
+    if sp is not None:
+        return sp
+    if mode == "p16":
+        sp = K.split_p16(t.detach(), K.P16_BF16 if fmt is None else fmt)
+    else:
+        sp = K.split_tf32(K.operand(t.detach()))
+    tag_split(t, *sp)
+    return sp
 
 
 def _prep(t: torch.Tensor, split=None):
-    """(main, lo) operand pair for the current precision."""
+    """(main, lo) operand pair for the current precision (tf32 / fp32 kernels)."""
     if _three_pass():
         if split is None:
             split = split_of(t)
@@ -69,8 +99,27 @@ def _prep(t: torch.Tensor, split=None):
     return K.operand(t.detach()), None
 
 
+def _pack_for(t: torch.Tensor, pack, fmt: int):
+    """16-bit pair of `t` in `fmt`: the caller's pack when it has that format, else the tensor's cached / a fresh split."""
+    if pack is not None and len(pack) == 3 and pack[2] == fmt:
+        return pack
+    return make_split(t, fmt)
+
+
+def _act_bwd_tagged(dH, dS, S, H, mode: int, act: float, scale: float, want_split: bool = True) -> torch.Tensor:
+    """dZ of the fused activation backward, tagged with its split operand (cotangent: bf16 pair in the 16-bit format)."""
+    sm = _split_mode() if want_split else None
+    if sm == "p16":
+        dZ, pack = K.act_bwd_p16(dH, dS, S, H, mode, act, scale, K.P16_BF16)
+        return tag_split(dZ, *pack)
+    dZ, hi, lo = K.act_bwd(dH, dS, S, H, mode, act, scale, sm == "tf32")
+    if hi is not None:
+        tag_split(dZ, hi, lo)
+    return dZ
+
+
 def _raw_mm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int, bias=None,
-            mode=K.EPI_NONE, act=0.0, scale=1.0, want_s=False, a_split=None, b_split=None, split_out=False):
+            mode=K.EPI_NONE, act=0.0, scale=1.0, want_s=False, a_split=None, b_split=None, split_out=False, op_fmt=None):
     dev = A.device
     split_k = 1
     if layout == K.GEMM_TN and Kc >= 1024 and M > 0:
@@ -83,6 +132,22 @@ def _raw_mm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: i
     S = K.empty_padded(M, N, dev) if want_s else None
     if M == 0:
         return C, S
+    if _split_mode() == "p16":
+        # one launch cannot mix fp16 and bf16 pairs: everything is a bf16 pair unless the caller asks for fp16 (`op_fmt`)
+        fmt = K.P16_BF16 if op_fmt is None else op_fmt
+        a, b = _pack_for(A, a_split, fmt), _pack_for(B, b_split, fmt)
+        C_pair = None
+        if split_out and split_k == 1:
+            C_pair = (*K.empty_pair16(M, N, dev, fmt), fmt)
+        K.gemm_p16(layout, a, b, M, N, Kc, C=C, C_pair=C_pair, S=S, bias=bias, mode=mode, act=act, scale=scale,
+                   split_k=split_k)
+        if C_pair is not None:
+            tag_split(C, *C_pair)
+        return C, S
+    if a_split is not None and len(a_split) == 3:
+        a_split = None
+    if b_split is not None and len(b_split) == 3:
+        b_split = None
     a, a_lo = _prep(A, a_split)
     b, b_lo = _prep(B, b_split)
     C_hi = C_lo = None
@@ -203,10 +268,7 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, X, W, b):
-        ctx.x_split, ctx.w_split = split_of(X), split_of(W)
-        if _three_pass():
-            ctx.x_split = ctx.x_split or make_split(X)
-            ctx.w_split = ctx.w_split or make_split(W)
+        ctx.x_split, ctx.w_split = make_split(X), make_split(W)
         ctx.save_for_backward(X, W)
         ctx.has_bias = b is not None
         ctx.bias_ref = b
@@ -239,10 +301,7 @@ class _MulAct(torch.autograd.Function):
     def forward(ctx, dH, S, scale):
         ctx.scale = scale
         ctx.save_for_backward(dH, S)
-        dZ, hi, lo = K.act_bwd(dH.detach(), None, S.detach(), None, K.EPI_RELU, 0.0, scale, _three_pass())
-        if hi is not None:
-            tag_split(dZ, hi, lo)
-        return dZ
+        return _act_bwd_tagged(dH.detach(), None, S.detach(), None, K.EPI_RELU, 0.0, scale)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -250,11 +309,9 @@ class _MulAct(torch.autograd.Function):
         dH, S = ctx.saved_tensors
         g_dH = g_S = None
         if ctx.needs_input_grad[0]:
-            g_dH, hi, lo = K.act_bwd(g, None, S, None, K.EPI_RELU, 0.0, ctx.scale, _three_pass())
-            if hi is not None:
-                tag_split(g_dH, hi, lo)
+            g_dH = _act_bwd_tagged(g, None, S, None, K.EPI_RELU, 0.0, ctx.scale)
         if ctx.needs_input_grad[1]:
-            g_S = K.act_bwd(g, None, dH, None, K.EPI_RELU, 0.0, ctx.scale, False)[0]
+            g_S = _act_bwd_tagged(g, None, dH, None, K.EPI_RELU, 0.0, ctx.scale, want_split=False)
         return g_dH, g_S, None
 
 
@@ -268,13 +325,13 @@ class _LinearAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, X, W, b, mode, act, scale):
-        ctx.x_split, ctx.w_split = split_of(X), split_of(W)
-        if _three_pass():
-            ctx.x_split = ctx.x_split or make_split(X)
-            ctx.w_split = ctx.w_split or make_split(W)
+        # SIREN layers (filter banks): sin(w0 z) multiplies operand rounding by w0, so their forward products use
+        # fp16 pairs (inputs and sine outputs are bounded); their backward products re-split to bf16 on demand
+        fmt = K.P16_FP16 if (mode == "sine" and _split_mode() == "p16") else None
+        ctx.x_split, ctx.w_split = make_split(X, fmt), make_split(W, fmt)
         H, S = _raw_mm(K.GEMM_NT, X, W, X.shape[0], W.shape[0], X.shape[1],
                        bias=b.detach() if b is not None else None, mode=_ACT_MODES[mode], act=act, scale=scale,
-                       want_s=True, a_split=ctx.x_split, b_split=ctx.w_split, split_out=True)
+                       want_s=True, a_split=ctx.x_split, b_split=ctx.w_split, split_out=True, op_fmt=fmt)
         ctx.mode, ctx.act, ctx.scale, ctx.has_bias = mode, act, scale, b is not None
         ctx.bias_ref = b
         if ACT_PATTERN_TAP[0] is not None and mode == "relu":
@@ -290,12 +347,10 @@ class _LinearAct(torch.autograd.Function):
             return None, None, None, None, None, None
         if not torch.is_grad_enabled():
             # plain (first-order) backward: one fused kernel forms dZ and its 3xTF32 operand pair
-            dZ, hi, lo = K.act_bwd(dH, dS if ctx.mode != "relu" else None, S, H, _ACT_MODES[ctx.mode], ctx.act, ctx.scale,
-                                   _three_pass()) if (dH is not None or ctx.mode != "relu") else (None, None, None)
+            dZ = _act_bwd_tagged(dH, dS if ctx.mode != "relu" else None, S, H, _ACT_MODES[ctx.mode], ctx.act,
+                                 ctx.scale) if (dH is not None or ctx.mode != "relu") else None
             if dZ is None:
                 return None, None, None, None, None, None
-            if hi is not None:
-                tag_split(dZ, hi, lo)
             return (*_layer_backward(ctx, dZ, X, W), None, None, None)
         dZ = None
         if dH is not None:
@@ -361,10 +416,13 @@ class _WeightNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, g, v):
         ctx.save_for_backward(g, v)
-        split = _three_pass()
-        out = K.weight_norm_fwd(g.detach(), v.detach(), split, False)
+        sm = _split_mode()
+        if sm == "p16":
+            W, pack = K.weight_norm_fwd_p16(g.detach(), v.detach(), K.P16_BF16)
+            return tag_split(W, *pack)
+        out = K.weight_norm_fwd(g.detach(), v.detach(), sm == "tf32", False)
         W = out["W"]
-        if split:
+        if sm == "tf32":
             tag_split(W, out["W_hi"], out["W_lo"])
         return W
 

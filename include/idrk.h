@@ -57,7 +57,7 @@ typedef struct idrk_hashgrid {
 } idrk_hashgrid_t;
 
 /* -- version / capability ------------------------------------------------------------- */
-int idrk_version(void);                        /* ABI version, currently 3 (2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_sumsq_det; idrk_rt_linesearch_points / _resolve; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
+int idrk_version(void);                        /* ABI version, currently 4 (3 -> 4: idrk_gemm_p16, idrk_split_p16, idrk_weight_norm_fwd_p16, idrk_act_bwd_p16; 2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_sumsq_det; idrk_rt_linesearch_points / _resolve; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
 int idrk_device_sm_count(int* out_sms);        /* SM count of the current device */
 
 /* -- K1: hash-grid encode forward -------------------------------------------------------
@@ -215,6 +215,44 @@ int idrk_gemm_f16s(int64_t M, int32_t N, int32_t K, const void* A_h, const void*
 int idrk_split_f16(const float* x, int64_t rows, int32_t cols, int32_t ldx, float scale, void* h, void* l,
                    int32_t ld_out, int32_t pad_cols, void* h2, void* l2, int32_t ld_out2, int32_t pad_cols2,
                    float scale2, const int32_t* m_count, void* stream);
+
+/* -- K4p: 16-bit-pair contraction for the DIFFERENTIABLE MLP path (csrc/gemm_p16.cu) ------------------------------
+ * Same operation set as idrk_gemm (layouts NT / NN / TN, bias, activation + derivative outputs, split-K) - i.e. the
+ * Linear / Softplus / ReLU / tanh / sine layers of ImplicitNetwork.forward / .gradient and RenderingNetwork.forward and
+ * their first- and second-order autograd (implicit_differentiable_renderer.py:96-128,215-223) - on operands stored as
+ * pairs of 16-bit floats  x ~= h + l * 2^-11  instead of the 8-byte 3xTF32 pair:
+ *   fmt 0 (IDRK_P16_FP16): h = fp16(x), l = fp16((x - h) 2^11): ~22 bits, |x| < 65504 (weights, activations);
+ *   fmt 1 (IDRK_P16_BF16): h = bf16(x), l = bf16((x - h) 2^11): ~17 bits, full fp32 range (cotangents).
+ * A and B of one call must share the format (mixed fp16 x bf16 instructions fault on sm_100a: IDRK_E_UNSUP); the output pair
+ * may use either.  lda, ldb, ldh % 8 == 0 and 16-byte aligned bases (TMA).  Outputs: fp32 C and / or the
+ * pair (C_h, C_l) in c_fmt, optionally S = act'(z); accumulate / split_k > 1: atomic adds into a zero-initialised fp32 C. */
+#define IDRK_P16_FP16 0
+#define IDRK_P16_BF16 1
+typedef struct idrk_epilogue_p16 {
+    float* C;            /* [M, ldc] fp32 (nullable when the pair is written)   */
+    float* S;            /* [M, lds] activation derivative (nullable)           */
+    void* C_h;           /* [M, ldh] high halves (nullable, with C_l)           */
+    void* C_l;           /* [M, ldh] scaled low halves                          */
+    const float* bias;   /* [N] (nullable)                                      */
+    const float* aux;    /* [M, ldaux] for IDRK_EPI_MUL_AUX                     */
+    int32_t ldc, lds, ldh, ldaux;
+    int32_t c_fmt;       /* IDRK_P16_* of (C_h, C_l)                            */
+    int32_t mode;        /* IDRK_EPI_*                                          */
+    float act_param, scale;
+    int32_t accumulate;
+} idrk_epilogue_p16_t;
+int idrk_gemm_p16(int32_t layout, int64_t M, int32_t N, int32_t K, const void* A_h, const void* A_l, int32_t a_fmt,
+                  int32_t lda, const void* B_h, const void* B_l, int32_t b_fmt, int32_t ldb,
+                  const idrk_epilogue_p16_t* epi, const int32_t* m_count, int32_t split_k, void* stream);
+/* fp32 -> 16-bit pair of scale * x; columns [cols, cols + pad_cols) zero-filled; ld_out even. */
+int idrk_split_p16(const float* x, int64_t rows, int32_t cols, int32_t ldx, float scale, void* h, void* l,
+                   int32_t ld_out, int32_t pad_cols, int32_t fmt, const int32_t* m_count, void* stream);
+/* idrk_weight_norm_fwd / idrk_act_bwd (below) with the operand written as a 16-bit pair instead of the tf32 hi / lo pair */
+int idrk_weight_norm_fwd_p16(const float* g, const float* v, int32_t N, int32_t K, int32_t ldv, float* W, int32_t ldw,
+                             void* W_h, void* W_l, int32_t ldp, int32_t fmt, void* stream);
+int idrk_act_bwd_p16(const float* dH, int32_t ld_dh, const float* dS, int32_t ld_ds, const float* S, int32_t ld_s,
+                     const float* H, int32_t ld_h, int64_t rows, int32_t cols, int32_t mode, float act, float scale,
+                     float* dZ, int32_t ld_out, void* dZ_h, void* dZ_l, int32_t ld_pair, int32_t fmt, void* stream);
 
 /* -- helpers around the MLP tiles ----------------------------------------------------------
  * idrk_split_tf32: v = scale * x; hi = tf32(v), lo = tf32(v - hi) for 3xTF32 operands (lo nullable -> plain

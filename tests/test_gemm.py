@@ -232,3 +232,115 @@ def test_split_f16_two_destinations():
     assert ((rec2 - 0.5 * x[:700].double()).abs() / x[:700].double().abs().clamp_min(1e-6)).max().item() < 1e-6
     assert (big_h[:, :485] == 7.0).all() and (big_h[700:] == 7.0).all()      # nothing outside the slot / the count
     assert (h[:700, 27:] == 0).all()                                             # pad columns zero-filled
+
+
+# ---------------------------------------------------------------------------------------------
+# 16-bit-pair contraction of the differentiable path (csrc/gemm_p16.cu): fp16 pairs ~22 bits, bf16 pairs ~17 bits
+# ---------------------------------------------------------------------------------------------
+P16_TOL = {(0, 0): 2e-6, (1, 1): 2e-5}      # relative to sum |a||b| per output
+
+
+def _run_p16(layout, M, N, Kc, fa, fb, scale_a=1.0, scale_b=1.0, **kw):
+    from idrk import kernels as K
+    A = (_mk((M, Kc), 1) if layout != K.GEMM_TN else _mk((Kc, M), 1)) * scale_a
+    B = (_mk((N, Kc), 2) if layout == K.GEMM_NT else _mk((Kc, N), 2)) * scale_b
+    C = K.empty_padded(M, N, DEV)
+    C.fill_(float("nan"))
+    K.gemm_p16(layout, K.split_p16(A, fa), K.split_p16(B, fb), M, N, Kc, C=C, **kw)
+    A64 = A.double() if layout != K.GEMM_TN else A.double().t()
+    B64 = B.double() if layout == K.GEMM_NT else B.double().t()
+    return C, A64 @ B64.t(), A64.abs() @ B64.abs().t()
+
+
+@pytest.mark.parametrize("fmts", [(0, 0), (1, 1)])
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (300, 445, 67), (2048, 512, 512), (4096, 512, 512), (77, 3, 512),
+                                   (1000, 257, 40), (4096, 256, 39)])
+def test_gemm_p16_plain(layout, fmts, shape):
+    M, N, Kc = shape
+    C, ref, mag = _run_p16(layout, M, N, Kc, *fmts)
+    err = ((C.double() - ref).abs() / (mag + 1e-30)).max().item()
+    assert err < P16_TOL[fmts], err
+
+
+def test_gemm_p16_bf16_pair_keeps_the_fp32_range():
+    """Cotangent-sized operands (1e-9 ... 1e-12) that fp16 pairs would flush: bf16 pairs keep 17 bits at any magnitude."""
+    C, ref, mag = _run_p16(1, 1024, 512, 512, 1, 1, scale_a=1e-9)
+    assert ((C.double() - ref).abs() / mag).max().item() < 2e-5
+    C, ref, mag = _run_p16(2, 512, 512, 2048, 1, 1, scale_a=1e-12, scale_b=1e6)
+    assert ((C.double() - ref).abs() / mag).max().item() < 2e-5
+
+
+@pytest.mark.parametrize("fmts", [(0, 0), (1, 1)])
+def test_gemm_p16_split_k(fmts):
+    from idrk import kernels as K
+    M, N, Kc = 512, 512, 5000
+    A, B = _mk((Kc, M), 3), _mk((Kc, N), 4)
+    C = torch.zeros(M, N, device=DEV)
+    K.gemm_p16(K.GEMM_TN, K.split_p16(A, fmts[0]), K.split_p16(B, fmts[1]), M, N, Kc, C=C, split_k=8)
+    ref = A.double().t() @ B.double()
+    mag = A.double().abs().t() @ B.double().abs()
+    assert ((C.double() - ref).abs() / mag).max().item() < P16_TOL[fmts]
+
+
+def test_gemm_p16_rejects_mixed_formats():
+    from idrk import kernels as K
+    from idrk._lib import IdrkError
+    A, B = _mk((128, 64), 1), _mk((128, 64), 2)
+    with pytest.raises(IdrkError):
+        K.gemm_p16(K.GEMM_NT, K.split_p16(A, 0), K.split_p16(B, 1), 128, 128, 64, C=K.empty_padded(128, 128, DEV))
+
+
+@pytest.mark.parametrize("c_fmt", [0, 1])
+@pytest.mark.parametrize("shape", [(700, 445, 67), (4096, 512, 512), (2048, 512, 39)])
+def test_gemm_p16_softplus_epilogue_and_pair_output(c_fmt, shape):
+    from idrk import kernels as K
+    M, N, Kc = shape
+    A, W, b = _mk((M, Kc), 5) * 0.1, _mk((N, Kc), 6) * 0.1, _mk((N,), 7) * 0.01
+    H, S = K.empty_padded(M, N, DEV), K.empty_padded(M, N, DEV)
+    Ch, Cl = K.empty_pair16(M, N, DEV, c_fmt)
+    K.gemm_p16(K.GEMM_NT, K.split_p16(A, 1), K.split_p16(W, 1), M, N, Kc, C=H, C_pair=(Ch, Cl, c_fmt), S=S, bias=b,
+               mode=K.EPI_SOFTPLUS, act=100.0, scale=0.5)
+    z = (A.double() @ W.double().t() + b.double())
+    ref = torch.nn.functional.softplus(z, beta=100) * 0.5
+    assert torch.allclose(H.double(), ref, atol=5e-6, rtol=2e-5)
+    assert torch.allclose(S.double(), torch.sigmoid(100 * z), atol=5e-4)
+    pair = Ch.double() + Cl.double() / 2048.0
+    assert torch.allclose(pair, H.double(), atol=1e-9, rtol=3e-7 if c_fmt == 0 else 1e-5)
+
+
+@pytest.mark.parametrize("mode", ["relu", "sine", "tanh", "none"])
+def test_gemm_p16_other_epilogues(mode):
+    from idrk import kernels as K
+    M, N, Kc = 1000, 256, 120
+    A, W, b = _mk((M, Kc), 15) * 0.2, _mk((N, Kc), 16) * 0.2, _mk((N,), 17) * 0.1
+    H, S = K.empty_padded(M, N, DEV), K.empty_padded(M, N, DEV)
+    em = {"relu": K.EPI_RELU, "sine": K.EPI_SINE, "tanh": K.EPI_TANH, "none": K.EPI_NONE}[mode]
+    K.gemm_p16(K.GEMM_NT, K.split_p16(A, 0), K.split_p16(W, 0), M, N, Kc, C=H, S=S, bias=b, mode=em, act=30.0, scale=1.0)
+    z = (A.double() @ W.double().t() + b.double())
+    ref, dref = {"relu": (z.clamp_min(0), (z > 0).double()), "sine": (torch.sin(30 * z), 30 * torch.cos(30 * z)),
+                 "tanh": (torch.tanh(z), 1 - torch.tanh(z) ** 2), "none": (z, torch.ones_like(z))}[mode]
+    tol = 2e-4 if mode == "sine" else 5e-6
+    assert (H.double() - ref).abs().max().item() < tol
+    if mode != "relu":
+        assert (S.double() - dref).abs().max().item() < (1e-2 if mode == "sine" else 1e-5)
+    else:
+        far = z.abs() > 1e-5
+        assert torch.equal(S.double()[far], dref[far])
+
+
+def test_p16_helpers_match_the_fp32_kernels():
+    """weight_norm / act_bwd with a 16-bit pair output: fp32 results identical to the tf32-pair entry points, pair == value."""
+    from idrk import kernels as K
+    v, g = _mk((445, 512), 10), _mk((445, 1), 11).abs() + 0.1
+    W, (h, l, fmt) = K.weight_norm_fwd_p16(g, v, 0)
+    ref = K.weight_norm_fwd(g, v, False, False)["W"]
+    assert torch.equal(W, ref)
+    assert torch.allclose(h.double() + l.double() / 2048, ref.double(), atol=1e-9, rtol=3e-7)
+    dH, S = _mk((3000, 445), 20) * 1e-6, torch.rand(3000, 445, device=DEV)
+    dS, H = _mk((3000, 445), 21) * 1e-7, _mk((3000, 445), 22)
+    for mode in (K.EPI_SOFTPLUS, K.EPI_TANH, K.EPI_RELU):
+        a = K.act_bwd(dH, dS if mode != K.EPI_RELU else None, S, H, mode, 100.0, 0.5, False)[0]
+        b, (bh, bl, _) = K.act_bwd_p16(dH, dS if mode != K.EPI_RELU else None, S, H, mode, 100.0, 0.5, 1)
+        assert torch.equal(a, b)
+        assert torch.allclose(bh.double() + bl.double() / 2048, a.double(), atol=0, rtol=1e-5)

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for s in header_symbols():
         assert hasattr(lib, s), "libidrk.so does not export %s" % s
-    assert lib.idrk_version() == 3
+    assert lib.idrk_version() == 4
     assert sorted(_lib.EXPORTS) == header_symbols()
 
 
