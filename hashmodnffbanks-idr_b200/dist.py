@@ -153,6 +153,15 @@ class DataParallelTrainer:
         self._static_out = None
         self._graph_key = None
         self._retired_graphs = []
+        # ONE graph for trace + shade + loss + backward (fixed cameras, device-driven tracer); IDRK_WHOLE_GRAPH=0 keeps the
+        # two-graph form (tracer graph, eager glue, shade graph) for A/B runs
+        import os
+        self.whole_step_graph = os.environ.get("IDRK_WHOLE_GRAPH", "1") != "0"
+        self._wgraph = None
+        self._wkey = None
+        self._wstatic = None
+        self._wout = None
+        self._wlaunches = 0
 
     @property
     def lr(self) -> float:
@@ -217,9 +226,13 @@ class DataParallelTrainer:
             losses = self.loss_fn(out, {"rgb": rgb})
             self.bucket.zero_grad()
             K.DIRECT_GRADS[0] = True                     # kernels accumulate leaf gradients straight into the bucket
+            from . import mlp
+            mlp.LEAF_SIDE.begin(self.bucket.flat.device)  # weight / bias gradient work runs on a side stream (mlp._LeafSide)
             try:
                 losses["loss"].backward()
+                mlp.LEAF_SIDE.finish()
             finally:
+                mlp.LEAF_SIDE.active = False
                 K.DIRECT_GRADS[0] = False
             self.bucket.gather_stray_grads()
         finally:
@@ -261,19 +274,96 @@ class DataParallelTrainer:
         K._lib.LAUNCHES[0] += self._graph_launches          # idrk kernels inside the replayed graph
         return self._static_out
 
+    # -- whole step in one CUDA graph ---------------------------------------------------------------
+    def _whole_step_supported(self, model_input) -> bool:
+        model = self.model
+        if not (self.whole_step_graph and self.use_cuda_graph and model.training and hasattr(model, "ray_tracer")):
+            return False
+        uv, pose, intr = model_input["uv"], model_input["pose"], model_input["intrinsics"]
+        if not (uv.is_cuda and uv.dtype == torch.float32 and pose.dtype == torch.float32 and intr.dtype == torch.float32):
+            return False
+        if pose.requires_grad or uv.requires_grad or intr.requires_grad:       # trainable cameras keep the eager ray set-up
+            return False
+        from .model.ray_tracing import _Evaluator
+        return _Evaluator(model.implicit_network.sdf).fast
+
+    def _trace_and_backward(self, inp, eik, rgb):
+        model = self.model
+        model.implicit_network.refresh_inference_weights(force=True)    # weight folding of the tracer's SDF pipeline
+        traced = model.trace(inp)
+        return self._shade_and_backward(traced, eik, rgb)
+
+    def _graphed_step(self, model_input, rgb):
+        """trace + shade + loss + backward replayed from ONE graph.  Host randomness (min-SDF steps, ray_tracing.py:277;
+        eikonal points, implicit_differentiable_renderer.py:279) is drawn per step in the reference's order and copied
+        into static device buffers; everything else of the step lives in the graph: camera rays, the tracer's launch
+        sequence, the hand-over of its results to the differentiable part (no clones / copies between two graphs)."""
+        model, rt, lf = self.model, self.model.ray_tracer, self.loss_fn
+        dev = self.bucket.flat.device
+        names = ("uv", "pose", "intrinsics", "object_mask")
+        key = tuple((k, tuple(model_input[k].shape)) for k in names) + (tuple(rgb.shape), ) + (
+            float(getattr(lf, "alpha", 0.0)), float(getattr(lf, "eikonal_weight", 0.0)), float(getattr(lf, "mask_weight", 0.0)),
+            K.get_precision(), K.training_p16(), int(rt.n_steps), K.SCRATCH_GENERATION[0])
+        n = model_input["uv"].shape[0] * model_input["uv"].shape[1]
+        # host draws, in the order the two-graph path makes them
+        u = rt.injected_min_sdf_steps
+        if u is None:
+            u = torch.empty(int(rt.n_steps)).uniform_(0.0, 1.0, generator=rt.sample_generator)
+        eik = model._draw_eikonal(n, dev)
+        if self._wgraph is None or key != self._wkey:
+            if self._wgraph is not None:
+                self._retired_graphs.append((self._wgraph, self._wstatic))
+            st_inp = {k: model_input[k].detach().clone() for k in names}
+            self._wstatic = (st_inp, eik.clone(), rgb.clone(), torch.empty(int(rt.n_steps), device=dev, dtype=torch.float32))
+            st_inp, st_eik, st_rgb, st_u = self._wstatic
+            st_u.copy_(u.to(dev).float())
+            prev = (rt.use_cuda_graph, rt.injected_min_sdf_steps)
+            rt.use_cuda_graph, rt.injected_min_sdf_steps = False, st_u
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):                   # warm-up outside capture (allocator, lazy inits, arena growth)
+                        self._trace_and_backward(st_inp, st_eik, st_rgb)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                self._wgraph = torch.cuda.CUDAGraph()
+                l0 = K._lib.LAUNCHES[0]
+                with torch.cuda.graph(self._wgraph):
+                    losses = self._trace_and_backward(st_inp, st_eik, st_rgb)
+                    self._wout = {k: v.detach() for k, v in losses.items()}
+                self._wlaunches = K._lib.LAUNCHES[0] - l0
+            finally:
+                rt.use_cuda_graph, rt.injected_min_sdf_steps = prev
+            rt._stats["cuda_graph"] = True
+            self._wkey = key[:-1] + (K.SCRATCH_GENERATION[0],)
+            K.note_graph_captured()
+        st_inp, st_eik, st_rgb, st_u = self._wstatic
+        for k in names:
+            st_inp[k].copy_(model_input[k])
+        st_eik.copy_(eik)
+        st_rgb.copy_(rgb)
+        st_u.copy_(u.to(dev, non_blocking=True).float())
+        self._wgraph.replay()
+        K._lib.LAUNCHES[0] += self._wlaunches
+        return self._wout
+
     def step(self, model_input, ground_truth) -> torch.Tensor:
         from . import mlp
         b = self.bucket
         model = self.model
-        traced = model.trace(model_input)
-        dev = traced["dists"].device
-        n = traced["dists"].shape[0]
-        eik = model._draw_eikonal(n, dev)
-        rgb = ground_truth["rgb"].to(dev)
-        if self.use_cuda_graph and model.training:
-            losses = self._graphed(traced, eik, rgb)
+        if self._whole_step_supported(model_input):
+            losses = self._graphed_step(model_input, ground_truth["rgb"].to(b.flat.device))
         else:
-            losses = self._shade_and_backward(traced, eik, rgb)
+            traced = model.trace(model_input)
+            dev = traced["dists"].device
+            n = traced["dists"].shape[0]
+            eik = model._draw_eikonal(n, dev)
+            rgb = ground_truth["rgb"].to(dev)
+            if self.use_cuda_graph and model.training:
+                losses = self._graphed(traced, eik, rgb)
+            else:
+                losses = self._shade_and_backward(traced, eik, rgb)
         scale = allreduce_mean_(b.grad, self.world)
         self.t += 1
         K.sumsq_det(b.grad, self.sumsq, self.sumsq_partials)

@@ -11,6 +11,7 @@ Two execution paths share the same kernel:
   count (`m_count`) so the ray tracer never syncs with the host.
 """
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -247,17 +248,104 @@ def colsum(x):
 _direct_target = K.direct_grad_target
 
 
+class _LeafSide:
+    """Leaf-gradient work of a trainer step on a SIDE stream.
+
+    The backward pass of a step is one long chain of small dependent launches (dZ -> dX -> dZ -> ...); the weight-gradient
+    contractions (dW = dZ^T X), the bias column sums and the weight-norm backward only feed the optimiser, so they do not
+    belong on that chain.  Between `begin()` and `finish()` (DataParallelTrainer brackets loss.backward() with them)
+    every weight-normalised layer's dW is ACCUMULATED by the TN contraction (atomic split-K epilogue) into one zeroed
+    buffer per weight - all uses of a shared weight land in the same buffer, so autograd's add kernels disappear - on the
+    side stream, autograd gets None for it, and `finish()` runs the weight-norm backward from those buffers straight into
+    the flat gradient bucket and joins the streams.  Inside a CUDA-graph capture the fork / join become graph edges, i.e.
+    a parallel branch.  Operands the side stream reads are kept referenced until the join (no allocator reuse races).
+    Only used when gradients are not being recorded (first-order backward)."""
+
+    def __init__(self):
+        self.active = False
+        self.stream = None
+        self.keep: List = []
+        self.acc: Dict = {}
+        self.enabled = os.environ.get("IDRK_LEAF_SIDE", "1") != "0"       # A/B switch
+
+    def begin(self, device):
+        if not self.enabled:
+            return
+        if self.stream is None or self.stream.device != torch.device(device):
+            self.stream = torch.cuda.Stream(device)
+        self.active, self.keep, self.acc = True, [], {}
+        self.forked = False
+
+    def fork(self):
+        self.stream.wait_stream(torch.cuda.current_stream())
+        self.forked = True
+        return torch.cuda.stream(self.stream)
+
+    def finish(self):
+        if not self.active:
+            return
+        try:
+            if self.acc:
+                with torch.no_grad(), self.fork():
+                    for g, v, buf, tg, tv in self.acc.values():
+                        K.weight_norm_bwd(g, v, buf, into=(tg, tv))
+            if self.forked:
+                torch.cuda.current_stream().wait_stream(self.stream)
+        finally:
+            self.active, self.keep, self.acc = False, [], {}
+
+
+LEAF_SIDE = _LeafSide()
+
+
+def _tn_accumulate(dZ, dsp, X, xsp, buf):
+    """buf[out, in] += dZ^T X on the current stream (split-K with atomic accumulation; `buf` zero-initialised)."""
+    M, N, Kc = dZ.shape[1], X.shape[1], dZ.shape[0]
+    tiles = ((M + 127) // 128) * ((N + 63) // 64)
+    split_k = max(1, min(Kc // 256, 148 // max(tiles, 1))) if Kc >= 1024 else 1
+    if _split_mode() == "p16":
+        K.gemm_p16(K.GEMM_TN, dsp, xsp, M, N, Kc, C=buf, accumulate=True, split_k=split_k)
+    else:
+        K.gemm(K.GEMM_TN, dsp[0], xsp[0], M, N, Kc, A_lo=dsp[1], B_lo=xsp[1], C=buf, accumulate=True, split_k=split_k)
+
+
 def _layer_backward(ctx, dZ, X, W):
     """Shared backward of Z = X W^T + b: one hi/lo split of dZ feeds both contractions."""
     need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-    dsp = make_split(dZ) if (need_x and need_w) else None
+    need_b = ctx.has_bias and ctx.needs_input_grad[2]
+    b_tgt = _direct_target(getattr(ctx, "bias_ref", None)) if need_b else None
+    if b_tgt is not None and not (b_tgt.dim() == 1 and b_tgt.numel() == dZ.shape[1]):
+        b_tgt = None
+    side = None
+    if LEAF_SIDE.active and need_w and not torch.is_grad_enabled() and _split_mode() is not None and dZ.shape[0] > 0:
+        wn = getattr(ctx, "w_ref", None)
+        if wn is not None:
+            tg, tv = _direct_target(wn[0]), _direct_target(wn[1])
+            if tg is not None and tv is not None and (not need_b or b_tgt is not None):
+                side = (wn[0], wn[1], tg, tv)
+    dsp = make_split(dZ) if ((need_x and need_w) or side is not None) else None
+    if side is not None:
+        g, v, tg, tv = side
+        ent = LEAF_SIDE.acc.get(id(v))
+        if ent is None:
+            n_out, n_in = W.shape
+            buf = K.ZERO_POOL.take(n_out * K.pad4(n_in), dZ.device).view(n_out, K.pad4(n_in))[:, :n_in]
+            ent = LEAF_SIDE.acc[id(v)] = (g, v, buf, tg, tv)
+        xsp = _pack_for(X, ctx.x_split, K.P16_BF16) if _split_mode() == "p16" else (ctx.x_split or make_split(X))
+        dZd = dZ.detach()
+        with LEAF_SIDE.fork():
+            _tn_accumulate(dZd, dsp, X, xsp, ent[2])
+            if need_b:
+                K.colsum(dZd, into=b_tgt)
+        LEAF_SIDE.keep.append((dZ, dsp, X, xsp))
+        dX = mm_nn(dZ, W, dsp, ctx.w_split) if need_x else None
+        return dX, None, None
     dX = mm_nn(dZ, W, dsp, ctx.w_split) if need_x else None
     dW = mm_tn(dZ, X, dsp, ctx.x_split) if need_w else None
     db = None
-    if ctx.has_bias and ctx.needs_input_grad[2]:
-        tgt = _direct_target(getattr(ctx, "bias_ref", None))
-        if tgt is not None and tgt.dim() == 1 and tgt.numel() == dZ.shape[1]:
-            K.colsum(dZ.detach(), into=tgt)
+    if need_b:
+        if b_tgt is not None:
+            K.colsum(dZ.detach(), into=b_tgt)
         else:
             db = colsum(dZ)
     return dX, dW, db
@@ -272,6 +360,7 @@ class _Linear(torch.autograd.Function):
         ctx.save_for_backward(X, W)
         ctx.has_bias = b is not None
         ctx.bias_ref = b
+        ctx.w_ref = getattr(W, "_idrk_wn", None)
         return _raw_mm(K.GEMM_NT, X, W, X.shape[0], W.shape[0], X.shape[1], bias=b.detach() if b is not None else None,
                        a_split=ctx.x_split, b_split=ctx.w_split)[0]
 
@@ -334,6 +423,7 @@ class _LinearAct(torch.autograd.Function):
                        want_s=True, a_split=ctx.x_split, b_split=ctx.w_split, split_out=True, op_fmt=fmt)
         ctx.mode, ctx.act, ctx.scale, ctx.has_bias = mode, act, scale, b is not None
         ctx.bias_ref = b
+        ctx.w_ref = getattr(W, "_idrk_wn", None)
         if ACT_PATTERN_TAP[0] is not None and mode == "relu":
             ACT_PATTERN_TAP[0].append(S.detach().clone())
         ctx.save_for_backward(X, W, H, S)
@@ -419,11 +509,13 @@ class _WeightNorm(torch.autograd.Function):
         sm = _split_mode()
         if sm == "p16":
             W, pack = K.weight_norm_fwd_p16(g.detach(), v.detach(), K.P16_BF16)
-            return tag_split(W, *pack)
-        out = K.weight_norm_fwd(g.detach(), v.detach(), sm == "tf32", False)
-        W = out["W"]
-        if sm == "tf32":
-            tag_split(W, out["W_hi"], out["W_lo"])
+            tag_split(W, *pack)
+        else:
+            out = K.weight_norm_fwd(g.detach(), v.detach(), sm == "tf32", False)
+            W = out["W"]
+            if sm == "tf32":
+                tag_split(W, out["W_hi"], out["W_lo"])
+        W._idrk_wn = (g, v)                 # lets a trainer step route this weight's gradient work off the main chain (_LeafSide)
         return W
 
     @staticmethod
