@@ -188,13 +188,27 @@ class _MMNN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, B, a_split, b_split):
         ctx.a_split, ctx.b_split = (a_split or split_of(A)), (b_split or split_of(B))
+        ctx.b_ref = getattr(B, "_idrk_wn", None)
         ctx.save_for_backward(A, B)
         return _raw_mm(K.GEMM_NN, A, B, A.shape[0], B.shape[1], A.shape[1], a_split=ctx.a_split, b_split=ctx.b_split)[0]
 
     @staticmethod
     def backward(ctx, dC):
         A, B = ctx.saved_tensors
-        dsp = make_split(dC) if (ctx.needs_input_grad[0] and ctx.needs_input_grad[1]) else None
+        ent = None
+        if ctx.needs_input_grad[1] and dC.shape[0] > 0:
+            # B is a layer weight inside the recorded backward (dX = dZ W): its gradient A^T dC joins the weight's
+            # accumulation buffer on the side stream (mlp._LeafSide) instead of going through autograd's adds
+            ent = _leaf_entry(ctx.b_ref, B.shape, dC.device)
+        dsp = make_split(dC) if ((ctx.needs_input_grad[0] and ctx.needs_input_grad[1]) or ent is not None) else None
+        if ent is not None:
+            asp = _pack_for(A, ctx.a_split, K.P16_BF16) if _split_mode() == "p16" else (ctx.a_split or make_split(A))
+            Ad, dCd = A.detach(), dC.detach()
+            with LEAF_SIDE.fork():
+                _tn_accumulate(Ad, asp, dCd, dsp, ent[2])
+            LEAF_SIDE.keep.append((A, asp, dC, dsp))
+            dA = mm_nt(dC, B, dsp, ctx.b_split) if ctx.needs_input_grad[0] else None
+            return dA, None, None, None
         dA = mm_nt(dC, B, dsp, ctx.b_split) if ctx.needs_input_grad[0] else None
         dB = mm_tn(A, dC, ctx.a_split, dsp) if ctx.needs_input_grad[1] else None
         return dA, dB, None, None
@@ -298,6 +312,22 @@ class _LeafSide:
 LEAF_SIDE = _LeafSide()
 
 
+def _leaf_entry(wn, shape, device):
+    """Accumulation buffer of a weight-normalised weight W = g v / ||v|| (wn = (g, v)) for this step, or None when the
+    side path does not apply (not a trainer step, gradients being recorded, no direct gradient targets)."""
+    if not LEAF_SIDE.active or wn is None or torch.is_grad_enabled() or _split_mode() is None:
+        return None
+    ent = LEAF_SIDE.acc.get(id(wn[1]))
+    if ent is None:
+        tg, tv = _direct_target(wn[0]), _direct_target(wn[1])
+        if tg is None or tv is None:
+            return None
+        n_out, n_in = shape
+        buf = K.ZERO_POOL.take(n_out * K.pad4(n_in), device).view(n_out, K.pad4(n_in))[:, :n_in]
+        ent = LEAF_SIDE.acc[id(wn[1])] = (wn[0], wn[1], buf, tg, tv)
+    return ent
+
+
 def _tn_accumulate(dZ, dsp, X, xsp, buf):
     """buf[out, in] += dZ^T X on the current stream (split-K with atomic accumulation; `buf` zero-initialised)."""
     M, N, Kc = dZ.shape[1], X.shape[1], dZ.shape[0]
@@ -313,24 +343,16 @@ def _layer_backward(ctx, dZ, X, W):
     """Shared backward of Z = X W^T + b: one hi/lo split of dZ feeds both contractions."""
     need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     need_b = ctx.has_bias and ctx.needs_input_grad[2]
+    if getattr(ctx, "w_ref", None) is not None:
+        W._idrk_wn = ctx.w_ref            # the unpacked saved tensor is a new object: keep the weight's identity for mm_nn
     b_tgt = _direct_target(getattr(ctx, "bias_ref", None)) if need_b else None
     if b_tgt is not None and not (b_tgt.dim() == 1 and b_tgt.numel() == dZ.shape[1]):
         b_tgt = None
-    side = None
-    if LEAF_SIDE.active and need_w and not torch.is_grad_enabled() and _split_mode() is not None and dZ.shape[0] > 0:
-        wn = getattr(ctx, "w_ref", None)
-        if wn is not None:
-            tg, tv = _direct_target(wn[0]), _direct_target(wn[1])
-            if tg is not None and tv is not None and (not need_b or b_tgt is not None):
-                side = (wn[0], wn[1], tg, tv)
-    dsp = make_split(dZ) if ((need_x and need_w) or side is not None) else None
-    if side is not None:
-        g, v, tg, tv = side
-        ent = LEAF_SIDE.acc.get(id(v))
-        if ent is None:
-            n_out, n_in = W.shape
-            buf = K.ZERO_POOL.take(n_out * K.pad4(n_in), dZ.device).view(n_out, K.pad4(n_in))[:, :n_in]
-            ent = LEAF_SIDE.acc[id(v)] = (g, v, buf, tg, tv)
+    ent = None
+    if need_w and dZ.shape[0] > 0 and (not need_b or b_tgt is not None):
+        ent = _leaf_entry(getattr(ctx, "w_ref", None), W.shape, dZ.device)
+    dsp = make_split(dZ) if ((need_x and need_w) or ent is not None) else None
+    if ent is not None:
         xsp = _pack_for(X, ctx.x_split, K.P16_BF16) if _split_mode() == "p16" else (ctx.x_split or make_split(X))
         dZd = dZ.detach()
         with LEAF_SIDE.fork():
@@ -506,6 +528,7 @@ class _WeightNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, g, v):
         ctx.save_for_backward(g, v)
+        ctx.set_materialize_grads(False)        # every use may have routed its dW through mlp._LeafSide: then dW is None
         sm = _split_mode()
         if sm == "p16":
             W, pack = K.weight_norm_fwd_p16(g.detach(), v.detach(), K.P16_BF16)
@@ -521,6 +544,8 @@ class _WeightNorm(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dW):
+        if dW is None:
+            return None, None
         g, v = ctx.saved_tensors
         tg, tv = _direct_target(g), _direct_target(v)
         if tg is not None and tv is not None and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
