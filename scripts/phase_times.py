@@ -88,7 +88,18 @@ def main():
     print("  secant (8 steps)        : %.3f ms" % (t[1] - t2[1]))
     print("  min-SDF sweep           : %.3f ms" % (t[1] - t3[1]))
     print("  sampler sweep + resolve : %.3f ms" % (t[1] - (t[1] - t2[1]) - (t[1] - t3[1])))
-    # shade + loss + backward graph of the trainer, optimiser
+    # shade + loss + backward graph of the trainer and the optimiser, in the two-graph form of the step (the whole-step graph
+    # cannot be bracketed inside): tracer graph | eager hand-over | shade graph | optimiser
+    tr.whole_step_graph = False
+    for _ in range(4):
+        tr.step(inp, gt)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(10):
+        tr.step(inp, gt)
+    e.record()
+    torch.cuda.synchronize()
+    print("whole step, two-graph form: %.3f ms" % (s.elapsed_time(e) / 10))
     acc = {"trace_call": 0.0, "shade_bwd_graph": 0.0, "optimiser": 0.0}
     for _ in range(10):
         a, b, c, d = (torch.cuda.Event(enable_timing=True) for _ in range(4))
@@ -106,7 +117,7 @@ def main():
         acc["shade_bwd_graph"] += b.elapsed_time(c) / 10
         acc["optimiser"] += c.elapsed_time(d) / 10
     for k, v in acc.items():
-        print("%-26s: %.3f ms" % (k, v))
+        print("%-26s: %.3f ms  (host-synchronised per section: includes launch latency)" % (k, v))
 
 
 if __name__ == "__main__":
