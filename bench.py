@@ -205,6 +205,15 @@ def hash_encode_section(torch, hbm, src):
                 if k.startswith(("fwd_presorted", "bwd_presorted", "fwd_perm", "bwd_perm", "fwd_sort_included",
                                  "bwd_sort_included", "pair_", "sort_ms")):
                     d[k] = round(r[k], 4)
+            if "sort_ms" in r and mode == "trilinear":
+                # what the module path (autograd_ops._HashEncode) does with an unordered batch of this size: ONE Morton sort in
+                # the forward, the permutation reused by the backward of the same step
+                d["module_path"] = {"fwd_frac_of_hbm_peak": round(r["fwd_sort_included_frac"], 4),
+                                    "bwd_frac_of_hbm_peak": round(r["bwd_perm_frac"], 4),
+                                    "fwd_plus_bwd_frac_of_hbm_peak": round(r["pair_one_sort_frac"], 4),
+                                    "note": "forward = sort + Z-order walk, backward = Z-order walk through the forward's "
+                                            "permutation (run aggregation), pair = both with the one sort; the plain keys "
+                                            "above walk the batch in the given (uniform random) order"}
             if "sort_ms" in r:
                 d["ordered_walk_note"] = ("presorted: the batch is already in Z-order; perm: the uniform-random batch is walked "
                                           "through the permutation of the library's Morton radix sort (sort_ms, 2^24 points); "
