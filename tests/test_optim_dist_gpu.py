@@ -216,3 +216,41 @@ def test_graphs_survive_growth_of_shared_scratch():
     for step in range(3, 6):
         _same_step(a, b, inp, gt, step)
     del junk, big
+
+
+def test_trainer_gradients_across_operand_formats_and_leaf_side_path():
+    """The flat gradient bucket of one trainer step (eager, same state, same trace inputs) under: the default (bf16 operand
+    pairs, weight / bias gradient work on the side stream with per-weight accumulation), the same without the side stream
+    (autograd accumulates weight gradients, csrc unchanged), and tf32 hi/lo pairs (round-1 format).  Side stream on / off:
+    same arithmetic, other summation order -> 2e-5 of max; bf16 pairs vs tf32 pairs: 1e-3 of max (measured ~2e-5)."""
+    from idrk import kernels as K, mlp
+    tr, inp, gt = _small_trainer(False, rays=512)
+    model = tr.model
+    eik = model.injected_eikonal_points.to(DEV)
+    traced = model.trace(inp)
+
+    def grads():
+        tr._shade_and_backward(traced, eik, gt["rgb"])
+        torch.cuda.synchronize()
+        return tr.bucket.grad.clone()
+    g_side = grads()
+    assert g_side.abs().max() > 0
+    prev = mlp.LEAF_SIDE.enabled
+    try:
+        mlp.LEAF_SIDE.enabled = False
+        g_main = grads()
+    finally:
+        mlp.LEAF_SIDE.enabled = prev
+    K.set_training_operands("tf32x3")
+    try:
+        g_tf32 = grads()
+    finally:
+        K.set_training_operands("p16")
+    scale = g_tf32.abs().max()
+    assert (g_side - g_main).abs().max() <= 2e-5 * scale
+    assert (g_side - g_tf32).abs().max() <= 1e-3 * scale
+    # per parameter, relative to that parameter's own largest gradient entry
+    for p, o in zip(tr.bucket.params, tr.bucket.offsets):
+        a, b = g_side[o:o + p.numel()], g_tf32[o:o + p.numel()]
+        if b.abs().max() > 0:
+            assert (a - b).abs().max() <= 2e-3 * b.abs().max()
