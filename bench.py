@@ -235,13 +235,13 @@ def hash_encode_section(torch, hbm, src):
     return out
 
 
-def sweep_layer_probe(torch, reps=40):
-    """One layer of a 100-sample sweep chunk (M = 32700 rows, N = K = 512, softplus + pair output, csrc/gemm.cu
-    gemm_f16s_kernel) launched back to back `reps` times between two CUDA events: the dominant kernel's steady-state time
-    per launch without the per-launch event brackets of the instrumented pass.  Ping-pong operand buffers like the SDF
-    pipeline's (a layer reads the pair the previous one wrote; 67 MB each: L2-resident between launches as in the step)."""
+def sweep_layer_probe(torch, reps=20):
+    """One layer of the 100-sample sweep (M = 2048 rays x 100 samples = 204800 rows, N = K = 512, softplus + pair output,
+    csrc/gemm.cu gemm_f16s_kernel) launched back to back `reps` times between two CUDA events: the dominant kernel's
+    steady-state time per launch without the per-launch event brackets of the instrumented pass.  Ping-pong operand buffers
+    like the SDF pipeline's (a layer reads the pair the previous one wrote, 419 MB each: beyond L2, as in the step)."""
     from idrk import kernels as K
-    M, N, Kc = 32700, 512, 512
+    M, N, Kc = N_RAYS * 100, 512, 512
     g = torch.Generator(device="cuda").manual_seed(3)
     W = torch.randn(N, Kc, device="cuda", generator=g) * 0.05
     b = torch.randn(N, device="cuda", generator=g) * 0.01
@@ -584,7 +584,7 @@ def run_ours(args):
                          "note": "what bounds this kernel (DESIGN.md section 9): bytes TMA delivers into the SMs' shared memory "
                                  "(64 KB per 128 x 128 tile and k block of pair operands = 7.9 x the layer's unique bytes) over "
                                  "the chip-wide L2 output cap of ~6300 B/clk (microarchitecture guide, LTS throughput cap) at the "
-                                 "sampled SM clock; measured by steady_state_probe (one sweep layer, M = 32700, launched back to "
+                                 "sampled SM clock; measured by steady_state_probe (one sweep layer, M = 204800, launched back to "
                                  "back between two CUDA events)"},
                      "measured_in": "an instrumented eager pass (2 steps) after the timed region: CUDA graphs off so that "
                                     "events can bracket each launch"},

@@ -28,9 +28,11 @@ from ..utils import rend_util
 
 import os as _os
 
-# points per SDF call in the sampler / min-SDF sweeps: small enough that a layer's input + output operand pairs
-# (2 x rows x 512 x 8 B) stay resident in the 126 MB L2 instead of round-tripping through HBM
-_SDF_CHUNK_POINTS = int(_os.environ.get("IDRK_SDF_CHUNK", "32768"))
+# Points per SDF call in the sampler / min-SDF sweeps.  Round 1 used 32768 (activations of a chunk stay in L2); with the
+# fp16-pair pipeline the sweep's layers run at the same speed from HBM, and fewer, larger chunks mean fewer launches, no
+# gated-off chunk launches and no short tail chunk: measured whole step 6.48 ms (32768) / 6.35 (65536) / 6.27-6.33 (262144,
+# one chunk for 2048 rays) / 6.28-6.30 (2^19, 2^20); cfg3 at 65536 rays 149 -> 141 ms, cfg4 165 -> 155 ms.
+_SDF_CHUNK_POINTS = int(_os.environ.get("IDRK_SDF_CHUNK", "262144"))
 
 
 class _Evaluator:
@@ -107,7 +109,7 @@ class _TraceState:
         """Static buffers of the device-driven sampler / secant / min-SDF phases (allocated on first use)."""
         if self._tail is None or self._tail["ns"] != ns:
             N, dev = self.N, self.dev
-            rpc = max(1, _SDF_CHUNK_POINTS // ns)
+            rpc = max(1, min(_SDF_CHUNK_POINTS // ns, N))        # never more rows than the batch can need
             n_chunks = (N + rpc - 1) // rpc
             zbuf = torch.empty(4 * N, device=dev, dtype=torch.float32)
             self._tail = {
