@@ -33,6 +33,18 @@ def weights_changed():
 # ---------------------------------------------------------------------------------------------
 # operand preparation
 # ---------------------------------------------------------------------------------------------
+# Width of the output tiles the split-K factor of the weight-gradient (TN) contractions is sized for: the factor is chosen so
+# that tiles x splits fills the SMs once (IDRK_TN_TILE: A/B knob)
+TN_TILE_N = int(os.environ.get("IDRK_TN_TILE", "64"))
+
+
+def _tn_split_k(M: int, N: int, Kc: int) -> int:
+    if Kc < 1024 or M <= 0:
+        return 1
+    tiles = ((M + 127) // 128) * ((N + TN_TILE_N - 1) // TN_TILE_N)
+    return max(1, min(Kc // 256, 148 // max(tiles, 1)))
+
+
 def _three_pass() -> bool:
     return K.get_precision() == K.PREC_3XTF32
 
@@ -122,10 +134,7 @@ def _act_bwd_tagged(dH, dS, S, H, mode: int, act: float, scale: float, want_spli
 def _raw_mm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int, bias=None,
             mode=K.EPI_NONE, act=0.0, scale=1.0, want_s=False, a_split=None, b_split=None, split_out=False, op_fmt=None):
     dev = A.device
-    split_k = 1
-    if layout == K.GEMM_TN and Kc >= 1024 and M > 0:
-        tiles = ((M + 127) // 128) * ((N + 63) // 64)
-        split_k = max(1, min(Kc // 256, 148 // max(tiles, 1)))
+    split_k = _tn_split_k(M, N, Kc) if layout == K.GEMM_TN else 1
     if split_k > 1:                                   # split-K accumulates with atomics: zero-initialised output
         C = K.ZERO_POOL.take(M * K.pad4(N), dev).view(M, K.pad4(N))[:, :N]
     else:
@@ -331,8 +340,7 @@ def _leaf_entry(wn, shape, device):
 def _tn_accumulate(dZ, dsp, X, xsp, buf):
     """buf[out, in] += dZ^T X on the current stream (split-K with atomic accumulation; `buf` zero-initialised)."""
     M, N, Kc = dZ.shape[1], X.shape[1], dZ.shape[0]
-    tiles = ((M + 127) // 128) * ((N + 63) // 64)
-    split_k = max(1, min(Kc // 256, 148 // max(tiles, 1))) if Kc >= 1024 else 1
+    split_k = _tn_split_k(M, N, Kc)
     if _split_mode() == "p16":
         K.gemm_p16(K.GEMM_TN, dsp, xsp, M, N, Kc, C=buf, accumulate=True, split_k=split_k)
     else:
