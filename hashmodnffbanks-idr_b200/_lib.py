@@ -113,7 +113,7 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_fourier_dx_fwd", "idrk_fourier_dx_bwd", "idrk_morton_sort_workspace", "idrk_morton_sort",
            "idrk_hash_encode_bwd_det_workspace", "idrk_hash_encode_bwd_det", "idrk_sdf_squash_rows", "idrk_sumsq_det",
            "idrk_rt_linesearch_points", "idrk_rt_linesearch_resolve",
-           "idrk_gemm_p16", "idrk_split_p16", "idrk_weight_norm_fwd_p16", "idrk_act_bwd_p16"]
+           "idrk_gemm_p16", "idrk_split_p16", "idrk_weight_norm_fwd_p16", "idrk_act_bwd_p16", "idrk_nffb_encode_f16pair"]
 
 
 class NffbDesc(ctypes.Structure):
@@ -227,6 +227,7 @@ def _declare(L):
     L.idrk_gemm_f16s.argtypes = [i64, i32, i32, vp, vp, i32, vp, vp, i32, c.POINTER(EpilogueH), vp, vp]
     L.idrk_split_f16.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp, vp]
     L.idrk_nffb_encode_fwd.argtypes = [c.POINTER(NffbDesc), vp, i64, i32, vp, i32, vp, vp]
+    L.idrk_nffb_encode_f16pair.argtypes = [c.POINTER(NffbDesc), vp, i64, i32, vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp]
     L.idrk_hash_encode_f16pair.argtypes = [c.POINTER(HashGridDesc), vp, i64, i32, vp, vp, vp, i32, i32, vp, vp, i32, i32, f32, vp]
     L.idrk_camera_rays.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp]
     L.idrk_idr_loss.argtypes = [vp, i32, vp, vp, vp, vp, i32, i64, vp, i32, i64, f32, f32, f32, vp, vp, vp, vp, vp]

@@ -13,6 +13,7 @@
 // layer weights live transposed in shared memory (lane o reads Wt[k][o]: conflict free), the running vectors in a
 // warp-private shared buffer (broadcast reads).  Accurate sinf / cosf for the SIREN and positional terms (arguments
 // reach |w0 z| ~ 1e2), the hash-grid columns with the exact arithmetic of hash_encode.cu.
+#include <cuda_fp16.h>
 #include "hash_common.cuh"
 
 namespace idrk {
@@ -32,6 +33,20 @@ struct NffbDev {
     const float* out_w; const float* out_b;   // [width, width]
     const float* sty_w; const float* sty_b;   // [width, width] (style only)
 };
+
+// Optional second form of the output: the fp16 pair (h, l = (v - h) 2^11) the SDF pipeline's contraction consumes, plus a
+// scaled second copy (the skip connection's columns) - written instead of the fp32 row when h != nullptr.
+struct NffbPairOut {
+    __half* h; __half* l; int ld, pad;
+    __half* h2; __half* l2; int ld2, pad2; float scale2;
+};
+
+__device__ __forceinline__ void store_pair(__half* h, __half* l, long long o, float v) {
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    const __half hv = __float2half_rn(v);
+    h[o] = hv;
+    l[o] = __float2half_rn((v - __half2float(hv)) * 2048.f);
+}
 
 __device__ __forceinline__ float warp_sum_all(float v) {
 #pragma unroll
@@ -61,9 +76,9 @@ __device__ __forceinline__ void matvec4(const float* __restrict__ Wt, const floa
     for (int i = 0; i < NFFB_P; ++i) { y0[i] = a0[i] + b0; y1[i] = a1[i] + b1; }
 }
 
-__global__ void __launch_bounds__(NFFB_WARPS * 32)
+__global__ void __launch_bounds__(NFFB_WARPS * 32, 1)
 nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n, int ldx, float* __restrict__ out, int ld_out,
-                       const int* __restrict__ m_count) {
+                       const int* __restrict__ m_count, const NffbPairOut po) {
     pdl_wait();
     pdl_trigger();
     extern __shared__ float4 smem4[];
@@ -142,33 +157,35 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
             reinterpret_cast<float4*>(zs)[lane] = make_float4(z0[0], z0[1], z0[2], z0[3]);
             reinterpret_cast<float4*>(zs)[lane + 32] = make_float4(z1[0], z1[1], z1[2], z1[3]);
             if (j > 0) {
-                // E = PositionalEncoding(chunk_{j-1}): [c | c | sin(b0 c) | cos(b0 c) | sin(b1 c) | ...]
+                // E = PositionalEncoding(chunk_{j-1}): [c | c | sin(b0 c) | cos(b0 c) | sin(b1 c) | ...].  Column o and column
+                // o + dch share their argument (sin / cos of the same band x chunk value), and lanes of one warp would run
+                // both the sinf and the cosf path (the band index changes every dch lanes): instead one lane evaluates
+                // sincosf ONCE per (band, chunk column) for the 4 points and the row is assembled in shared memory
+                // (dch x n_bands calls per point instead of 2 W divergent ones).
                 const float* ch = gs + (j - 1) * dch * NFFB_P;
-                float e0[NFFB_P], e1[NFFB_P];
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int o = lane + 32 * t;
-                    float v[NFFB_P] = {0.f, 0.f, 0.f, 0.f};
-                    if (o < W) {
-                        if (o < head) {
-                            const float4 c4 = reinterpret_cast<const float4*>(ch)[o % dch];
-                            v[0] = c4.x; v[1] = c4.y; v[2] = c4.z; v[3] = c4.w;
-                        } else {
-                            const int q = (o - head) / dch, jx = (o - head) - q * dch;
-                            const float4 c4 = reinterpret_cast<const float4*>(ch)[jx];
-                            const float band = d.bands[q >> 1];
-                            const float a[NFFB_P] = {__fmul_rn(c4.x, band), __fmul_rn(c4.y, band), __fmul_rn(c4.z, band), __fmul_rn(c4.w, band)};
-#pragma unroll
-                            for (int i = 0; i < NFFB_P; ++i) v[i] = (q & 1) ? cosf(a[i]) : sinf(a[i]);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < NFFB_P; ++i) { if (t == 0) e0[i] = v[i]; else e1[i] = v[i]; }
+                float4* es4 = reinterpret_cast<float4*>(es);
+                for (int o = lane; o < head; o += 32) es4[o] = reinterpret_cast<const float4*>(ch)[o % dch];
+                for (int idx = lane; idx < dch * d.n_bands; idx += 32) {
+                    const int m = idx / dch, jx = idx - m * dch;
+                    const float4 c4 = reinterpret_cast<const float4*>(ch)[jx];
+                    const float band = d.bands[m];
+                    float sx, sy, sz, sw, cx, cy, cz, cw;
+                    sincosf(__fmul_rn(c4.x, band), &sx, &cx);
+                    sincosf(__fmul_rn(c4.y, band), &sy, &cy);
+                    sincosf(__fmul_rn(c4.z, band), &sz, &cz);
+                    sincosf(__fmul_rn(c4.w, band), &sw, &cw);
+                    es4[head + (2 * m) * dch + jx] = make_float4(sx, sy, sz, sw);
+                    es4[head + (2 * m + 1) * dch + jx] = make_float4(cx, cy, cz, cw);
                 }
-                if (d.style) {
-                    reinterpret_cast<float4*>(es)[lane] = make_float4(e0[0], e0[1], e0[2], e0[3]);
-                    reinterpret_cast<float4*>(es)[lane + 32] = make_float4(e1[0], e1[1], e1[2], e1[3]);
+                for (int o = W + lane; o < NFFB_MAX_W; o += 32) es4[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+                float e0[NFFB_P], e1[NFFB_P];
+                if (!d.style) {
+                    const float4 a4 = es4[lane], b4 = es4[lane + 32];
+                    e0[0] = a4.x; e0[1] = a4.y; e0[2] = a4.z; e0[3] = a4.w;
+                    e1[0] = b4.x; e1[1] = b4.y; e1[2] = b4.z; e1[3] = b4.w;
                     __syncwarp();
+                } else {
                     float s0[NFFB_P], s1[NFFB_P];
                     matvec4(s_w + (size_t)(NL + 1) * NFFB_MAX_W * NFFB_MAX_W, s_b + (NL + 1) * NFFB_MAX_W, es, W, W, lane, s0, s1);
 #pragma unroll
@@ -195,6 +212,26 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
 #pragma unroll
         for (int i = 0; i < NFFB_P; ++i) {
             if (pbase + i >= n) break;
+            if (po.h != nullptr) {
+                // the fp16 pair of the SDF pipeline's operand (+ the skip connection's scaled copy), pads zero-filled
+                const long long o1 = (pbase + i) * (long long)po.ld, o2 = (pbase + i) * (long long)po.ld2;
+                const __half zero = __float2half_rn(0.f);
+                if (lane < 3) {
+                    store_pair(po.h, po.l, o1 + lane, u[i][lane == 0 ? 0 : (lane == 1 ? 1 : 2)]);
+                    if (po.h2) store_pair(po.h2, po.l2, o2 + lane, u[i][lane == 0 ? 0 : (lane == 1 ? 1 : 2)] * po.scale2);
+                }
+                if (lane < W) {
+                    store_pair(po.h, po.l, o1 + 3 + lane, f0[i] / d.levels_div);
+                    if (po.h2) store_pair(po.h2, po.l2, o2 + 3 + lane, f0[i] / d.levels_div * po.scale2);
+                }
+                if (lane + 32 < W) {
+                    store_pair(po.h, po.l, o1 + 3 + lane + 32, f1[i] / d.levels_div);
+                    if (po.h2) store_pair(po.h2, po.l2, o2 + 3 + lane + 32, f1[i] / d.levels_div * po.scale2);
+                }
+                for (int c = 3 + W + lane; c < 3 + W + po.pad; c += 32) { po.h[o1 + c] = zero; po.l[o1 + c] = zero; }
+                if (po.h2) for (int c = 3 + W + lane; c < 3 + W + po.pad2; c += 32) { po.h2[o2 + c] = zero; po.l2[o2 + c] = zero; }
+                continue;
+            }
             float* orow = out + (pbase + i) * (long long)ld_out;
             if (lane < 3) orow[lane] = lane == 0 ? u[i][0] : (lane == 1 ? u[i][1] : u[i][2]);
             if (lane < W) orow[3 + lane] = f0[i] / d.levels_div;
@@ -209,9 +246,9 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
 
 using namespace idrk;
 
-extern "C" int idrk_nffb_encode_fwd(const idrk_nffb_t* h, const float* x, int64_t n, int32_t ldx, float* out, int32_t ld_out,
-                                    const int32_t* m_count, void* stream) {
-    if (!h || !x || !out || n < 0 || ldx < 3) return IDRK_E_ARG;
+static int nffb_encode_impl(const idrk_nffb_t* h, const float* x, int64_t n, int32_t ldx, float* out, int32_t ld_out,
+                            const int32_t* m_count, const NffbPairOut& po, void* stream) {
+    if (!h || !x || (!out && !po.h) || n < 0 || ldx < 3) return IDRK_E_ARG;
     NffbDev d;
     int rc = fill_grid(&h->grid, d.grid);
     if (rc) return rc;
@@ -221,7 +258,9 @@ extern "C" int idrk_nffb_encode_fwd(const idrk_nffb_t* h, const float* x, int64_
     if (h->width != h->chunk * ((h->include_input ? 2 : 0) + 2 * h->n_bands)) return IDRK_E_ARG;
     const int n_cols = (h->n_lin - 1) * h->chunk;
     if (n_cols > 32 || n_cols > 2 * h->grid.n_fourier + h->grid.n_levels * h->grid.n_feat) return IDRK_E_UNSUP;
-    if (ld_out < 3 + h->width || !h->out_w || !h->out_b) return IDRK_E_ARG;
+    if ((out && ld_out < 3 + h->width) || !h->out_w || !h->out_b) return IDRK_E_ARG;
+    if (po.h && (!po.l || po.pad < 0 || po.ld < 3 + h->width + po.pad)) return IDRK_E_ARG;
+    if (po.h2 && (!po.h || !po.l2 || po.pad2 < 0 || po.ld2 < 3 + h->width + po.pad2)) return IDRK_E_ARG;
     if (h->style && (!h->style_w || !h->style_b)) return IDRK_E_ARG;
     if (n == 0) return 0;
     for (int i = 0; i < 32; ++i) d.bands[i] = i < h->n_bands ? h->bands[i] : 0.f;
@@ -244,7 +283,23 @@ extern "C" int idrk_nffb_encode_fwd(const idrk_nffb_t* h, const float* x, int64_
     const long long need = (n + NFFB_WARPS * NFFB_P - 1) / (NFFB_WARPS * NFFB_P);
     if (grid > need) grid = need;
     IDRK_CUDA_TRY(launch_k(nffb_encode_fwd_kernel, dim3((unsigned)grid), dim3(NFFB_WARPS * 32), smem, (cudaStream_t)stream,
-                           d, x, (long long)n, (int)ldx, out, (int)ld_out, m_count));
+                           d, x, (long long)n, (int)ldx, out, (int)ld_out, m_count, po));
     IDRK_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int idrk_nffb_encode_fwd(const idrk_nffb_t* h, const float* x, int64_t n, int32_t ldx, float* out, int32_t ld_out,
+                                    const int32_t* m_count, void* stream) {
+    if (!out) return IDRK_E_ARG;
+    NffbPairOut po = {};
+    return nffb_encode_impl(h, x, n, ldx, out, ld_out, m_count, po, stream);
+}
+
+extern "C" int idrk_nffb_encode_f16pair(const idrk_nffb_t* h, const float* x, int64_t n, int32_t ldx, const int32_t* m_count,
+                                        void* out_h, void* out_l, int32_t ld_out, int32_t pad_cols,
+                                        void* out_h2, void* out_l2, int32_t ld_out2, int32_t pad_cols2, float scale2, void* stream) {
+    if (!out_h || !out_l) return IDRK_E_ARG;
+    if ((out_h2 == nullptr) != (out_l2 == nullptr)) return IDRK_E_ARG;
+    NffbPairOut po = {(__half*)out_h, (__half*)out_l, ld_out, pad_cols, (__half*)out_h2, (__half*)out_l2, ld_out2, pad_cols2, scale2};
+    return nffb_encode_impl(h, x, n, ldx, nullptr, 0, m_count, po, stream);
 }

@@ -619,18 +619,9 @@ def empty_half(rows: int, cols: int, device) -> torch.Tensor:
     return torch.empty((rows, pad8(cols)), device=device, dtype=torch.float16)[:, :cols]
 
 
-def nffb_encode_fwd(ffb, x: torch.Tensor, out: Optional[torch.Tensor] = None, m_count: Optional[torch.Tensor] = None,
-                    rows: Optional[int] = None) -> torch.Tensor:
-    """K7: the whole FourierFilterBanks forward (no autograd) in one launch.  `ffb` is the module
-    (model/embeddings/nffb3d.py); returns the padded [n, pad4(3 + width)] buffer."""
-    x = rows2d(x, "x")
-    n = x.shape[0] if rows is None else rows
+def _nffb_desc(ffb):
+    """idrk_nffb_t of a FourierFilterBanks module (model/embeddings/nffb3d.py) + the tensors it points into."""
     W = ffb.feature_Vector_size
-    ld = pad4(3 + W)
-    if out is None:
-        out = torch.empty((n, ld), device=x.device, dtype=torch.float32)
-    if n == 0:
-        return out
     grid = ffb.grid_enc
     d = _lib.NffbDesc()
     d.grid = grid.spec().desc(tuple(t.detach() for t in grid.tables()), grid.freq_encoding.B)
@@ -655,9 +646,41 @@ def nffb_encode_fwd(ffb, x: torch.Tensor, out: Optional[torch.Tensor] = None, m_
         sw, sb = st.linear_transform.weight.detach().contiguous(), st.linear_transform.bias.detach().contiguous()
         keep += [sw, sb]
         d.style_w, d.style_b, d.eps = sw.data_ptr(), sb.data_ptr(), float(st.eps)
+    return d, keep
+
+
+def nffb_encode_fwd(ffb, x: torch.Tensor, out: Optional[torch.Tensor] = None, m_count: Optional[torch.Tensor] = None,
+                    rows: Optional[int] = None) -> torch.Tensor:
+    """K7: the whole FourierFilterBanks forward (no autograd) in one launch.  `ffb` is the module
+    (model/embeddings/nffb3d.py); returns the padded [n, pad4(3 + width)] buffer."""
+    x = rows2d(x, "x")
+    n = x.shape[0] if rows is None else rows
+    ld = pad4(3 + ffb.feature_Vector_size)
+    if out is None:
+        out = torch.empty((n, ld), device=x.device, dtype=torch.float32)
+    if n == 0:
+        return out
+    d, keep = _nffb_desc(ffb)
     check(lib().idrk_nffb_encode_fwd(ctypes.byref(d), ptr(x), n, ld_of(x), ptr(out), ld_of(out), ptr(m_count), stream_ptr()),
           "idrk_nffb_encode_fwd")
     return out
+
+
+def nffb_encode_f16pair(ffb, x: torch.Tensor, rows: int, h: torch.Tensor, l: torch.Tensor, ld_out: int, pad_cols: int = 0,
+                        m_count: Optional[torch.Tensor] = None, second=None):
+    """K7: the filter-bank embedding of the first min(rows, *m_count) points written directly as the fp16 pair the SDF
+    pipeline's contraction consumes (and, with `second = (h2, l2, ld_out2, pad_cols2, scale2)`, a scaled second copy)."""
+    x = rows2d(x, "x")
+    if rows == 0:
+        return
+    h2, l2, ld2, pad2, scale2 = second if second is not None else (None, None, 0, 0, 0.0)
+    d, keep = _nffb_desc(ffb)
+    check(lib().idrk_nffb_encode_f16pair(ctypes.byref(d), ptr(x), rows, ld_of(x), ptr(m_count), ptr(h), ptr(l), ld_out, pad_cols,
+                                         ptr(h2), ptr(l2), ld2, pad2, float(scale2), stream_ptr()), "idrk_nffb_encode_f16pair")
+
+
+def nffb_pair_supported(ffb) -> bool:
+    return nffb_fused_supported(ffb)
 
 
 def nffb_fused_supported(ffb) -> bool:

@@ -127,6 +127,12 @@ class ImplicitNetwork(nn.Module):
             K.hash_encode_fwd(grid.spec(), pts, grid.tables(), grid.freq_encoding.B, out=emb, m_count=m_count, rows=rows)
         elif self._fused_filter_bank() is not None:
             ffb = self.embed_model.embedder_obj
+            if K.inference_fp16x2() and K.nffb_pair_supported(ffb):
+                # one launch: filter-bank encode straight into the fp16-pair operand (+ the skip connection's scaled copy)
+                def encode(h, l, ld, pad, second):
+                    K.nffb_encode_f16pair(ffb, pts, rows, h, l, ld, pad, m_count, second)
+                pipe.run(None, rows, want="sdf", m_count=m_count, out=out, encode=encode)
+                return
             emb = pipe._buf("emb", rows, ffb.embeddings_dim, pts.device)
             K.nffb_encode_fwd(ffb, pts, out=emb, m_count=m_count, rows=rows)
         else:

@@ -57,7 +57,7 @@ typedef struct idrk_hashgrid {
 } idrk_hashgrid_t;
 
 /* -- version / capability ------------------------------------------------------------- */
-int idrk_version(void);                        /* ABI version, currently 4 (3 -> 4: idrk_gemm_p16, idrk_split_p16, idrk_weight_norm_fwd_p16, idrk_act_bwd_p16; 2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_sumsq_det; idrk_rt_linesearch_points / _resolve; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
+int idrk_version(void);                        /* ABI version, currently 4 (3 -> 4: idrk_nffb_encode_f16pair, idrk_gemm_p16, idrk_split_p16, idrk_weight_norm_fwd_p16, idrk_act_bwd_p16; 2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_sumsq_det; idrk_rt_linesearch_points / _resolve; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
 int idrk_device_sm_count(int* out_sms);        /* SM count of the current device */
 
 /* -- K1: hash-grid encode forward -------------------------------------------------------
@@ -184,6 +184,12 @@ typedef struct idrk_nffb {
 } idrk_nffb_t;
 int idrk_nffb_encode_fwd(const idrk_nffb_t* desc, const float* x, int64_t n, int32_t ldx, float* out, int32_t ld_out,
                          const int32_t* m_count, void* stream);
+/* The same encoder inside the ray tracer's SDF queries, written directly as the fp16-pair operand of idrk_gemm_f16s
+ * (h = fp16(v), l = fp16((v - h) 2^11); columns [3 + width, 3 + width + pad_cols) zero-filled) and, with out_h2 != NULL,
+ * a second pair of scale2 * v (the skip connection's copy of the embedding). */
+int idrk_nffb_encode_f16pair(const idrk_nffb_t* desc, const float* x, int64_t n, int32_t ldx, const int32_t* m_count,
+                             void* out_h, void* out_l, int32_t ld_out, int32_t pad_cols,
+                             void* out_h2, void* out_l2, int32_t ld_out2, int32_t pad_cols2, float scale2, void* stream);
 
 /* -- K4c: fp16-pair contraction for the no-grad SDF path ------------------------------------
  * Operands are pairs of IEEE halves  x ~= h + l * 2^-11  (h = fp16(x), l = fp16((x - h) * 2^11)): 4 bytes per element,

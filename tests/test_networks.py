@@ -120,7 +120,7 @@ def test_full_width_vs_oracle(prec, rel):
 
 @pytest.mark.parametrize("tag", ["ffb", "style"])
 def test_fused_filter_bank_encoder_matches_module_and_golden(golden, tag):
-    """csrc/nffb.cu (one launch, FP32 FMAs) vs the module path (contraction / posenc kernels) vs the reference's
+    """csrc/nffb.cu (one launch; fp16-pair mma.sync tiles, or FP32 FMAs with IDRK_NFFB_TC=0) vs the module path (contraction / posenc kernels) vs the reference's
     golden embedding-dependent outputs; plus the device-side row count (rows beyond it are not written)."""
     from idrk import kernels as K
     g = golden("networks")
@@ -144,3 +144,18 @@ def test_fused_filter_bank_encoder_matches_module_and_golden(golden, tag):
         full = ffb(xs)
     assert close(out[:1234, :ffb.embeddings_dim], full[:1234], rel=2e-4, abs_=2e-6)
     assert (out[1234:] == 7.0).all()
+    # pair-output form (the SDF pipeline's operand, tensor-core kernel): h + l / 2^11 == the fp32 row to fp16-pair rounding,
+    # the scaled second copy lands in its column slot, pads are zero, rows beyond the count untouched
+    if K.nffb_pair_supported(ffb):
+        E = ffb.embeddings_dim
+        ld, ld2, off = K.pad8(E), K.pad8(100 + E), 100
+        h, l = (torch.full((3001, ld), 3.0, device=DEV, dtype=torch.float16) for _ in range(2))
+        h2, l2 = (torch.full((3001, ld2), 3.0, device=DEV, dtype=torch.float16) for _ in range(2))
+        K.nffb_encode_f16pair(ffb, xs, 3001, h, l, ld, ld - E, cnt, second=(h2[:, off:], l2[:, off:], ld2, ld2 - off - E, 0.5))
+        ref32 = out[:1234, :E].double()
+        got1 = h[:1234, :E].double() + l[:1234, :E].double() / 2048.0
+        got2 = h2[:1234, off:off + E].double() + l2[:1234, off:off + E].double() / 2048.0
+        assert (got1 - ref32).abs().max().item() <= 4e-7 * max(1.0, ref32.abs().max().item())
+        assert (got2 - 0.5 * ref32).abs().max().item() <= 4e-7 * max(1.0, ref32.abs().max().item())
+        assert (h[:1234, E:] == 0).all() and (l[:1234, E:] == 0).all() and (h2[:1234, off + E:] == 0).all()
+        assert (h[1234:] == 3.0).all() and (h2[1234:] == 3.0).all() and (h2[:, :off] == 3.0).all()
