@@ -162,6 +162,11 @@ scan_sums_kernel(uint32_t* __restrict__ sums, int m) {
 }
 
 // Stable scatter of one tile.  In-tile order = (warp, round, lane) = input order, so equal digits keep their order.
+// The tile is first sorted by digit INSIDE shared memory (local position = exclusive digit prefix of the tile + the
+// item's stable rank within its digit) and then written out in that order: neighbouring threads write neighbouring
+// elements of a digit run, so a run (16 items on average) leaves as whole sectors.  Writing each item straight from the
+// lane that ranked it cost one 32-byte sector per 4-byte store (ncu: 7.9 M write sectors per 4 M pairs, 7.6 x the payload)
+// and made this kernel 90 % of the sort.
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n, int shift, int n_tiles,
                   const uint32_t* __restrict__ counts_scanned, const uint32_t* __restrict__ tile_offsets,
@@ -169,10 +174,15 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict_
     pdl_wait();
     pdl_trigger();
     __shared__ uint32_t cnt[RS_WARPS][257];                  // digit 256 = out-of-range lanes of the last tile
+    __shared__ uint32_t s_key[RS_TILE], s_val[RS_TILE];
+    __shared__ uint32_t lbase[256];                          // exclusive digit prefix inside the tile
+    __shared__ uint32_t gbase[256];                          // global position of the tile's first item of each digit
+    __shared__ uint32_t s_wsum[RS_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
-    const long long w0 = (long long)blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
+    const long long t0 = (long long)blockIdx.x * RS_TILE;
+    const long long w0 = t0 + warp * (RS_ITEMS * 32);
     uint32_t key[RS_ITEMS], val[RS_ITEMS], rk[RS_ITEMS];      // rk = (in-warp rank << 9) | digit
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
@@ -190,22 +200,42 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict_
         __syncwarp();
     }
     __syncthreads();
-    {   // per digit: global base of this tile + exclusive prefix over the warps
+    {   // per digit (one thread each): exclusive prefix over the warps, tile total, global base; then the digit prefix of the tile
         const int d = threadIdx.x;
-        const size_t ci = (size_t)d * n_tiles + blockIdx.x;
-        uint32_t run = counts_scanned[ci] + tile_offsets[ci / SCAN_TILE];
+        uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = cnt[w][d]; cnt[w][d] = run; run += c; }
+        const size_t ci = (size_t)d * n_tiles + blockIdx.x;
+        gbase[d] = counts_scanned[ci] + tile_offsets[ci / SCAN_TILE];
+        uint32_t inc = run;                                   // inclusive scan of the tile's digit counts over 256 threads
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) woff += (w < warp) ? s_wsum[w] : 0u;
+        lbase[d] = woff + inc - run;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const uint32_t d = rk[r] & 511u;
         if (d < 256u) {
-            const uint32_t pos = cnt[warp][d] + (rk[r] >> 9);
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+            const uint32_t lp = lbase[d] + cnt[warp][d] + (rk[r] >> 9);
+            s_key[lp] = key[r];
+            s_val[lp] = val[r];
         }
+    }
+    __syncthreads();
+    const long long rem = n - t0;
+    const int tile_n = rem < RS_TILE ? (int)rem : RS_TILE;
+    for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
+        const uint32_t k = s_key[i];
+        const uint32_t d = (k >> shift) & 255u;
+        const uint32_t pos = gbase[d] + ((uint32_t)i - lbase[d]);
+        keys_out[pos] = k;
+        vals_out[pos] = s_val[i];
     }
 }
 
