@@ -43,11 +43,11 @@ class _FourierDx(torch.autograd.Function):
 
 
 # 8-corner modes on big unordered batches: walk the points in Z-order (one Morton radix sort per forward, shared with the
-# backward).  Measured on 2^24 uniform points, L = 16, F = 2, SORT INCLUDED (profiles/r02_hash_encode_sweep.txt, fractions
-# of the HBM roofline): forward + table-gradient pair 0.49 -> 0.69 at T = 2^19 and 0.36 -> 0.55 at T = 2^22; the forward
-# alone loses a little while the tables sit in L2 (0.67 -> 0.62) and wins once they do not (T = 2^22: 0.35 -> 0.61).  At
-# T = 2^24 (1.2 GB) nothing is gained.  The reference-mode passes (one gather per level) are bound by their row traffic and
-# lose from a permuted walk: never sorted.  Hence: sort when a backward will share the permutation, or when the tables
+# backward).  Measured on 2^24 uniform points, L = 16, F = 2, SORT INCLUDED (profiles/r02_hash_encode_sweep_sort_v2.txt,
+# fractions of the HBM roofline): forward + table-gradient pair 0.49 -> 0.70 at T = 2^19 and 0.40 -> 0.53 at T = 2^22; the
+# forward alone is level while the tables sit in L2 (0.67 -> 0.67) and wins once they do not (T = 2^22: 0.35-0.47 -> 0.60).
+# At T = 2^24 (1.2 GB) nothing is gained.  The reference-mode passes (one gather per level) are bound by their row traffic
+# and lose from a permuted walk: never sorted.  Hence: sort when a backward will share the permutation, or when the tables
 # exceed L2; never beyond 512 MB of tables or below 2^18 points.
 AUTO_SORT = {"enabled": os.environ.get("IDRK_HASH_AUTO_SORT", "1") != "0", "min_points": 1 << 18,
              "l2_table_bytes": 96 << 20, "max_table_bytes": 512 << 20}
