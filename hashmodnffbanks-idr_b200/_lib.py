@@ -113,7 +113,7 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_fourier_dx_fwd", "idrk_fourier_dx_bwd", "idrk_morton_sort_workspace", "idrk_morton_sort",
            "idrk_hash_encode_bwd_det_workspace", "idrk_hash_encode_bwd_det", "idrk_sdf_squash_rows", "idrk_sumsq_det",
            "idrk_rt_linesearch_points", "idrk_rt_linesearch_resolve",
-           "idrk_gemm_p16", "idrk_split_p16", "idrk_weight_norm_fwd_p16", "idrk_act_bwd_p16", "idrk_nffb_encode_f16pair"]
+           "idrk_gemm_p16", "idrk_split_p16", "idrk_weight_norm_fwd_p16", "idrk_act_bwd_p16", "idrk_nffb_encode_f16pair", "idrk_rt_iter_tail"]
 
 
 class NffbDesc(ctypes.Structure):
@@ -211,6 +211,7 @@ def _declare(L):
     L.idrk_rt_end.argtypes = [rs, vp, vp, i32, vp]
     L.idrk_rt_linesearch_points.argtypes = [rs, vp, vp, fp, i32, vp, vp, vp]
     L.idrk_rt_linesearch_resolve.argtypes = [rs, vp, vp, fp, i32, vp]
+    L.idrk_rt_iter_tail.argtypes = [rs, vp, vp, fp, i32, f32, vp, vp]
     L.idrk_rt_select_sampler.argtypes = [rs, vp, vp, vp, vp]
     L.idrk_rt_sampler_points.argtypes = [rs, vp, i32, i32, i32, vp, vp, vp, vp]
     L.idrk_rt_chunk_counts.argtypes = [vp, i32, i32, i32, vp, vp]

@@ -229,6 +229,57 @@ __global__ void rt_end_kernel(RayState S, const int* __restrict__ gate, const fl
     S.unf_e[i] = S.unf_e[i] && ok;
 }
 
+// Tail of a sphere-tracing iteration as ONE launch: resolve the line search (above), close the iteration (rt_end_kernel)
+// and open the next one (rt_top_kernel without a gather) - three per-ray passes over the same state with no dependence
+// between rays; only the count of unfinished rays (the next iteration's gate) crosses threads, through one atomic per warp.
+__global__ void rt_iter_tail_kernel(RayState S, const int* __restrict__ gate, const float* __restrict__ vals, LsFactors F, int n_ls,
+                                    float thr, int* __restrict__ n_unf) {
+    pdl_wait();
+    pdl_trigger();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = *gate != 0;
+    bool any = false;
+    if (i < S.n) {
+        float t0 = S.t0[i], t1 = S.t1[i];
+        float ns = S.nxt_s[i], ne = S.nxt_e[i];
+        bool us = S.unf_s[i], ue = S.unf_e[i];
+        if (live) {
+            const int sa = S.slot_s[i], sb = S.slot_e[i];
+            if (sa >= 0) {
+                float t = t0, v = 0.f;
+                const float cur = S.cur_s[i];
+                for (int k = 0; k < n_ls; ++k) {
+                    t = __fsub_rn(t, __fmul_rn(F.f[k], cur));
+                    v = vals[sa + k];
+                    if (!(v < 0.f)) break;
+                }
+                t0 = t; ns = v; S.t0[i] = t; S.nxt_s[i] = v; store3(S.ps, i, ray_point(S, i, t));
+            }
+            if (sb >= 0) {
+                float t = t1, v = 0.f;
+                const float cur = S.cur_e[i];
+                for (int k = 0; k < n_ls; ++k) {
+                    t = __fadd_rn(t, __fmul_rn(F.f[k], cur));
+                    v = vals[sb + k];
+                    if (!(v < 0.f)) break;
+                }
+                t1 = t; ne = v; S.t1[i] = t; S.nxt_e[i] = v; store3(S.pe, i, ray_point(S, i, t));
+            }
+            S.slot_s[i] = -1; S.slot_e[i] = -1;
+            const bool ok = t0 < t1;                       // rt_end_kernel
+            us = us && ok; ue = ue && ok;
+        }
+        float cs = us ? ns : 0.f, ce = ue ? ne : 0.f;      // rt_top_kernel, gather_mode 0
+        if (cs <= thr) cs = 0.f;
+        if (ce <= thr) ce = 0.f;
+        us = us && (cs > thr); ue = ue && (ce > thr);
+        S.cur_s[i] = cs; S.cur_e[i] = ce; S.unf_s[i] = us; S.unf_e[i] = ue;
+        any = us || ue;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_unf, __popc(m));
+}
+
 // after sphere tracing (:39-42): network mask and the list of rays handed to the sampler
 __global__ void rt_select_sampler_kernel(RayState S, unsigned char* __restrict__ net_mask, int* __restrict__ ray_of_slot,
                                          int* __restrict__ counter) {
@@ -510,6 +561,17 @@ extern "C" int idrk_rt_linesearch_resolve(const idrk_ray_state_t* h_state, const
     LsFactors F;
     for (int k = 0; k < 8; ++k) F.f[k] = k < n_ls ? h_factors[k] : 0.f;
     IDRK_CUDA_TRY(launch_k(rt_linesearch_resolve_kernel, dim3(blocks), dim3(threads), 0, st, S, gate, vals, F, (int)n_ls));
+    IDRK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int idrk_rt_iter_tail(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, const float* h_factors,
+                                 int32_t n_ls, float sdf_threshold, int32_t* n_unfinished, void* stream) {
+    RT_PRELUDE();
+    if (!gate || !vals || !h_factors || !n_unfinished || n_ls < 1 || n_ls > 8) return IDRK_E_ARG;
+    LsFactors F;
+    for (int k = 0; k < 8; ++k) F.f[k] = k < n_ls ? h_factors[k] : 0.f;
+    IDRK_CUDA_TRY(launch_k(rt_iter_tail_kernel, dim3(blocks), dim3(threads), 0, st, S, gate, vals, F, (int)n_ls, sdf_threshold, n_unfinished));
     IDRK_LAUNCH_CHECK();
     return 0;
 }

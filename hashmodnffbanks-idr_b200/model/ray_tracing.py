@@ -181,8 +181,13 @@ class RayTracing(nn.Module):
                 check(L.idrk_rt_linesearch_points(S, ptr(gate), ptr(T.vals), factors, n_ls, ptr(T.pts), ptr(c), sp),
                       "idrk_rt_linesearch_points")
                 ev.on_device_count(T.pts, T.cap, c, T.vals)
-                check(L.idrk_rt_linesearch_resolve(S, ptr(gate), ptr(T.vals), factors, n_ls, sp), "idrk_rt_linesearch_resolve")
-            check(L.idrk_rt_end(S, ptr(gate), ptr(T.vals), 1 if n_ls == 0 else 0, sp), "idrk_rt_end")
+                # resolve the search, close the iteration and open the next one (its gate) in one launch
+                nxt = T.new_counter()
+                check(L.idrk_rt_iter_tail(S, ptr(gate), ptr(T.vals), factors, n_ls, float(self.sdf_threshold), ptr(nxt), sp),
+                      "idrk_rt_iter_tail")
+                gate = nxt
+                continue
+            check(L.idrk_rt_end(S, ptr(gate), ptr(T.vals), 1, sp), "idrk_rt_end")
             gate = T.new_counter()
             check(L.idrk_rt_top(S, None, 0, float(self.sdf_threshold), ptr(gate), sp), "idrk_rt_top")
 

@@ -57,7 +57,7 @@ typedef struct idrk_hashgrid {
 } idrk_hashgrid_t;
 
 /* -- version / capability ------------------------------------------------------------- */
-int idrk_version(void);                        /* ABI version, currently 4 (3 -> 4: idrk_nffb_encode_f16pair, idrk_gemm_p16, idrk_split_p16, idrk_weight_norm_fwd_p16, idrk_act_bwd_p16; 2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_sumsq_det; idrk_rt_linesearch_points / _resolve; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
+int idrk_version(void);                        /* ABI version, currently 4 (3 -> 4: idrk_rt_iter_tail, idrk_nffb_encode_f16pair, idrk_gemm_p16, idrk_split_p16, idrk_weight_norm_fwd_p16, idrk_act_bwd_p16; 2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_sumsq_det; idrk_rt_linesearch_points / _resolve; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
 int idrk_device_sm_count(int* out_sms);        /* SM count of the current device */
 
 /* -- K1: hash-grid encode forward -------------------------------------------------------
@@ -331,6 +331,11 @@ int idrk_rt_linesearch_points(const idrk_ray_state_t* h_state, const int32_t* ga
 int idrk_rt_linesearch_resolve(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, const float* h_factors,
                                int32_t n_ls, void* stream);
 int idrk_rt_end(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, int32_t gather_mode, void* stream);
+/* idrk_rt_linesearch_resolve + idrk_rt_end + the next iteration's idrk_rt_top (gather_mode 0) in ONE launch: the three are
+ * per-ray passes over the same state (ray_tracing.py:167-186 and the loop top :131-142 of the following iteration);
+ * *n_unfinished (zero-initialised) receives the next gate. */
+int idrk_rt_iter_tail(const idrk_ray_state_t* h_state, const int32_t* gate, const float* vals, const float* h_factors,
+                      int32_t n_ls, float sdf_threshold, int32_t* n_unfinished, void* stream);
 int idrk_rt_select_sampler(const idrk_ray_state_t* h_state, uint8_t* net_mask, int32_t* ray_of_slot, int32_t* counter,
                            void* stream);
 /* n_dev (nullable, device int32): when given, the number of valid slots is min(host bound, *n_dev) so the caller
