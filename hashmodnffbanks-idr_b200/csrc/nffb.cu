@@ -6,7 +6,7 @@
 //     g  = grid_enc(u)[:, 3:]                      (Fourier sin | cos | level features; chunks of 2F columns)
 //     z_{j+1} = sin(w0 (A_j z_j + a_j))                                        j = 0 .. NL-1
 //     for j >= 1:  E = PositionalEncoding(chunk_{j-1});  e = style ? rownorm(M E + m) : E
-//                  f += O (e + z_{j+1}) + o
+//                  f += O (e + z_{j+1}) + o            (evaluated as O (sum_j (e + z_{j+1})) + (NL - 1) o: out_layer is linear)
 //     out = [u | f / L]
 // The module path runs this as ~45 launches (tiny 56-wide contractions, positional encodings, adds) per SDF query;
 // the widths are far below a tensor-core tile, so here ONE warp walks one point through all layers with FP32 FMAs:
@@ -199,14 +199,23 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
                     }
                     __syncwarp();
                 }
-                reinterpret_cast<float4*>(es)[lane] = make_float4(e0[0] + z0[0], e0[1] + z0[1], e0[2] + z0[2], e0[3] + z0[3]);
-                reinterpret_cast<float4*>(es)[lane + 32] = make_float4(e1[0] + z1[0], e1[1] + z1[1], e1[2] + z1[2], e1[3] + z1[3]);
-                __syncwarp();
-                float o0[NFFB_P], o1[NFFB_P];
-                matvec4(s_w + (size_t)NL * NFFB_MAX_W * NFFB_MAX_W, s_b + NL * NFFB_MAX_W, es, W, W, lane, o0, o1);
+                // out_layer is linear: sum (e + z) over the levels, apply it once after the loop (as the module path does)
 #pragma unroll
-                for (int i = 0; i < NFFB_P; ++i) { f0[i] += o0[i]; f1[i] += o1[i]; }
+                for (int i = 0; i < NFFB_P; ++i) { f0[i] += e0[i] + z0[i]; f1[i] += e1[i] + z1[i]; }
             }
+            __syncwarp();
+        }
+        {
+            reinterpret_cast<float4*>(es)[lane] = make_float4(f0[0], f0[1], f0[2], f0[3]);
+            reinterpret_cast<float4*>(es)[lane + 32] = make_float4(f1[0], f1[1], f1[2], f1[3]);
+            __syncwarp();
+            float o0[NFFB_P], o1[NFFB_P];
+            matvec4(s_w + (size_t)NL * NFFB_MAX_W * NFFB_MAX_W, s_b + NL * NFFB_MAX_W, es, W, W, lane, o0, o1);
+            // matvec4 added the bias once: sum_j (O u_j + o) = O sum_j u_j + (NL - 1) o
+            const float b0 = lane < W ? s_b[NL * NFFB_MAX_W + lane] : 0.f, b1 = lane + 32 < W ? s_b[NL * NFFB_MAX_W + lane + 32] : 0.f;
+            const float nb = (float)(NL - 2);
+#pragma unroll
+            for (int i = 0; i < NFFB_P; ++i) { f0[i] = fmaf(nb, b0, o0[i]); f1[i] = fmaf(nb, b1, o1[i]); }
             __syncwarp();
         }
 #pragma unroll

@@ -88,7 +88,11 @@ class FourierFilterBanks(nn.Module):
         u = (input + self.bound) / (2 * self.bound)
         grid = self.grid_enc(u)[..., input.shape[-1]:]
         bands = self.ff_enc[0].freq_bands
-        total = None
+        # The reference applies out_layer to (e_j + z_{j+1}) of every level and sums the results (nffb3d.py:163-190); the
+        # layer is linear, so the sum is taken first and out_layer runs ONCE:  sum_j (O u_j + o) = O (sum_j u_j) + n o.
+        # Same value up to the fp32 summation order; 4 of 5 contractions (and their backward / recorded-backward
+        # launches) disappear.  csrc/nffb.cu does the same.
+        usum, n_out = None, 0
         for layer in range(self.n_nffb_layers - 1):
             lin = getattr(self, "ff_lin" + str(layer))
             z = mlp.linear_act(z, lin.weight, lin.bias, "sine", float(self.sin_w0))
@@ -97,6 +101,7 @@ class FourierFilterBanks(nn.Module):
                 e = ops.positional_encoding(chunk, bands, self.include_input)
                 if self.modulationApplied:
                     e = self.StyleAttentionBlock(u, e)
-                o = mlp.linear(e + z, self.out_layer.weight, self.out_layer.bias)
-                total = o if total is None else total + o
+                usum = e + z if usum is None else usum + (e + z)
+                n_out += 1
+        total = mlp.linear(usum, self.out_layer.weight, self.out_layer.bias * float(n_out))
         return torch.cat([u, total / L], dim=-1)
