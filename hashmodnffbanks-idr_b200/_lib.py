@@ -113,7 +113,7 @@ EXPORTS = ["idrk_version", "idrk_device_sm_count", "idrk_hash_encode_fwd", "idrk
            "idrk_fourier_dx_fwd", "idrk_fourier_dx_bwd", "idrk_morton_sort_workspace", "idrk_morton_sort",
            "idrk_hash_encode_bwd_det_workspace", "idrk_hash_encode_bwd_det", "idrk_sdf_squash_rows", "idrk_sumsq_det",
            "idrk_rt_linesearch_points", "idrk_rt_linesearch_resolve",
-           "idrk_gemm_p16", "idrk_split_p16", "idrk_weight_norm_fwd_p16", "idrk_act_bwd_p16", "idrk_nffb_encode_f16pair", "idrk_rt_iter_tail"]
+           "idrk_gemm_p16", "idrk_split_p16", "idrk_weight_norm_fwd_p16", "idrk_act_bwd_p16", "idrk_nffb_encode_f16pair", "idrk_rt_iter_tail", "idrk_posenc_dx_bwd"]
 
 
 class NffbDesc(ctypes.Structure):
@@ -195,6 +195,7 @@ def _declare(L):
     fp = c.POINTER(c.c_float)
     L.idrk_posenc_fwd.argtypes = [vp, i64, i32, i32, fp, i32, i32, vp, i32, vp]
     L.idrk_posenc_bwd.argtypes = [vp, i64, i32, i32, fp, i32, i32, vp, i32, vp, i32, vp]
+    L.idrk_posenc_dx_bwd.argtypes = [vp, i32, vp, i64, i32, i32, fp, i32, i32, vp, i32, vp, i32, vp, i32, vp]
     L.idrk_gemm.argtypes = [i32, i32, i64, i32, i32, vp, vp, i32, vp, vp, i32, c.POINTER(Epilogue), vp, i32, vp]
     L.idrk_split_tf32.argtypes = [vp, i64, i32, i32, f32, vp, vp, i32, i32, vp, vp]
     L.idrk_weight_norm_fwd.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp]

@@ -156,6 +156,26 @@ def fourier_feature(x: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 # positional encoding
 # ---------------------------------------------------------------------------------------------
+class _PosEncDx(torch.autograd.Function):
+    """d/dx of the positional encoding on the RECORDED backward pass (ImplicitNetwork.gradient, create_graph=True, through
+    the filter banks' encodings): one kernel that stays differentiable in x and dy (one more kernel) - ~9 tensor ops per
+    band did it before, each with its own backward ops in the loss's backward (~1000 launches of a filter-bank step)."""
+
+    @staticmethod
+    def forward(ctx, x, dy, bands, include_input):
+        ctx.bands, ctx.include_input = bands, include_input
+        ctx.save_for_backward(x, dy)
+        return K.posenc_bwd(x.detach(), bands, include_input, dy.detach())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, dy = ctx.saved_tensors
+        g_dy, g_x = K.posenc_dx_bwd(g, x, ctx.bands, ctx.include_input, dy, want_gdy=ctx.needs_input_grad[1],
+                                    want_gx=ctx.needs_input_grad[0])
+        return g_x, g_dy, None, None
+
+
 class _PosEnc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bands, include_input):
@@ -171,6 +191,8 @@ class _PosEnc(torch.autograd.Function):
             return None, None, None
         bands, inc = ctx.bands, ctx.include_input
         if torch.is_grad_enabled() and (dy.requires_grad or x.requires_grad):
+            if dy.dtype == torch.float32 and x.dtype == torch.float32 and dy.dim() == 2:
+                return _PosEncDx.apply(x, dy, bands, inc), None, None
             d = x.shape[1]
             base = 2 * d if inc else 0
             dx = dy[:, :d] + dy[:, d:2 * d] if inc else torch.zeros_like(x)

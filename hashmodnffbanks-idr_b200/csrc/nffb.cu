@@ -19,6 +19,10 @@
 namespace idrk {
 
 constexpr int NFFB_MAX_W = 64;          // filter-bank width (2 outputs per lane)
+constexpr int NFFB_LDW = NFFB_MAX_W + 1;   // pitch of a staged (transposed) weight row: the staging writes of consecutive k for
+                                           // one output column land in different banks, the mat-vec reads (consecutive columns
+                                           // for one k) stay conflict-free
+constexpr int NFFB_MAT = NFFB_MAX_W * NFFB_LDW;    // floats per staged matrix (4160: the buffers behind stay 16-byte aligned)
 constexpr int NFFB_MAX_LAYERS = 16;
 constexpr int NFFB_WARPS = 16;
 constexpr int NFFB_P = 4;               // points a warp walks through the layers together
@@ -67,7 +71,7 @@ __device__ __forceinline__ void matvec4(const float* __restrict__ Wt, const floa
 #pragma unroll 4
     for (int k = 0; k < n_in; ++k) {
         const float4 vk = v4[k];
-        const float w0 = w[k * NFFB_MAX_W], w1 = w[k * NFFB_MAX_W + 32];
+        const float w0 = w[k * NFFB_LDW], w1 = w[k * NFFB_LDW + 32];
         a0[0] = fmaf(w0, vk.x, a0[0]); a0[1] = fmaf(w0, vk.y, a0[1]); a0[2] = fmaf(w0, vk.z, a0[2]); a0[3] = fmaf(w0, vk.w, a0[3]);
         a1[0] = fmaf(w1, vk.x, a1[0]); a1[1] = fmaf(w1, vk.y, a1[1]); a1[2] = fmaf(w1, vk.z, a1[2]); a1[3] = fmaf(w1, vk.w, a1[3]);
     }
@@ -90,16 +94,18 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
     // shared layout: transposed weights [mat][k][NFFB_MAX_W] (zero padded), biases [mat][NFFB_MAX_W], per-warp vectors
     const int n_mats = NL + 1 + (d.style ? 1 : 0);                 // SIREN layers, out layer, style transform
     float* s_w = smem;
-    float* s_b = s_w + (size_t)n_mats * NFFB_MAX_W * NFFB_MAX_W;
+    float* s_b = s_w + (size_t)n_mats * NFFB_MAT;
     float* s_v = s_b + n_mats * NFFB_MAX_W + warp * (NFFB_P * (2 * NFFB_MAX_W + 32));     // [z | e | chunk columns] x points
     for (int m = 0; m < n_mats; ++m) {
         const float* src_w = m < NL ? d.lin_w[m] : (m == NL ? d.out_w : d.sty_w);
         const float* src_b = m < NL ? d.lin_b[m] : (m == NL ? d.out_b : d.sty_b);
         const int n_in = m == 0 ? 3 : W;
-        float* dw = s_w + (size_t)m * NFFB_MAX_W * NFFB_MAX_W;
+        float* dw = s_w + (size_t)m * NFFB_MAT;
+        // consecutive threads read consecutive k of one output row (coalesced; the strided form cost ~40 us per launch, most
+        // of a 4096-point tracer query) and write the transposed element
         for (int i = threadIdx.x; i < NFFB_MAX_W * NFFB_MAX_W; i += blockDim.x) {
-            const int k = i / NFFB_MAX_W, o = i - k * NFFB_MAX_W;
-            dw[i] = (k < n_in && o < W) ? src_w[o * n_in + k] : 0.f;
+            const int o = i / NFFB_MAX_W, k = i - o * NFFB_MAX_W;
+            dw[k * NFFB_LDW + o] = (k < n_in && o < W) ? src_w[o * n_in + k] : 0.f;
         }
         for (int i = threadIdx.x; i < NFFB_MAX_W; i += blockDim.x) s_b[m * NFFB_MAX_W + i] = i < W ? src_b[i] : 0.f;
     }
@@ -149,7 +155,7 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
         float f0[NFFB_P] = {0.f, 0.f, 0.f, 0.f}, f1[NFFB_P] = {0.f, 0.f, 0.f, 0.f};     // the lane's two output features per point
         for (int j = 0; j < NL; ++j) {
             float y0[NFFB_P], y1[NFFB_P];
-            matvec4(s_w + (size_t)j * NFFB_MAX_W * NFFB_MAX_W, s_b + j * NFFB_MAX_W, zs, j == 0 ? 3 : W, W, lane, y0, y1);
+            matvec4(s_w + (size_t)j * NFFB_MAT, s_b + j * NFFB_MAX_W, zs, j == 0 ? 3 : W, W, lane, y0, y1);
             float z0[NFFB_P], z1[NFFB_P];
 #pragma unroll
             for (int i = 0; i < NFFB_P; ++i) { z0[i] = sinf(y0[i] * d.w0); z1[i] = sinf(y1[i] * d.w0); }
@@ -187,7 +193,7 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
                     __syncwarp();
                 } else {
                     float s0[NFFB_P], s1[NFFB_P];
-                    matvec4(s_w + (size_t)(NL + 1) * NFFB_MAX_W * NFFB_MAX_W, s_b + (NL + 1) * NFFB_MAX_W, es, W, W, lane, s0, s1);
+                    matvec4(s_w + (size_t)(NL + 1) * NFFB_MAT, s_b + (NL + 1) * NFFB_MAX_W, es, W, W, lane, s0, s1);
 #pragma unroll
                     for (int i = 0; i < NFFB_P; ++i) {
                         const float m0 = lane < W ? s0[i] : 0.f, m1 = lane + 32 < W ? s1[i] : 0.f;
@@ -210,7 +216,7 @@ nffb_encode_fwd_kernel(const NffbDev d, const float* __restrict__ x, long long n
             reinterpret_cast<float4*>(es)[lane + 32] = make_float4(f1[0], f1[1], f1[2], f1[3]);
             __syncwarp();
             float o0[NFFB_P], o1[NFFB_P];
-            matvec4(s_w + (size_t)NL * NFFB_MAX_W * NFFB_MAX_W, s_b + NL * NFFB_MAX_W, es, W, W, lane, o0, o1);
+            matvec4(s_w + (size_t)NL * NFFB_MAT, s_b + NL * NFFB_MAX_W, es, W, W, lane, o0, o1);
             // matvec4 added the bias once: sum_j (O u_j + o) = O sum_j u_j + (NL - 1) o
             const float b0 = lane < W ? s_b[NL * NFFB_MAX_W + lane] : 0.f, b1 = lane + 32 < W ? s_b[NL * NFFB_MAX_W + lane + 32] : 0.f;
             const float nb = (float)(NL - 2);
@@ -282,7 +288,7 @@ static int nffb_encode_impl(const idrk_nffb_t* h, const float* x, int64_t n, int
     }
     d.out_w = h->out_w; d.out_b = h->out_b; d.sty_w = h->style_w; d.sty_b = h->style_b;
     const int n_mats = h->n_lin + 1 + (h->style ? 1 : 0);
-    const size_t smem = ((size_t)n_mats * NFFB_MAX_W * NFFB_MAX_W + (size_t)n_mats * NFFB_MAX_W +
+    const size_t smem = ((size_t)n_mats * NFFB_MAT + (size_t)n_mats * NFFB_MAX_W +
                          (size_t)NFFB_WARPS * NFFB_P * (2 * NFFB_MAX_W + 32)) * sizeof(float);
     if (smem > 220 * 1024) return IDRK_E_UNSUP;
     IDRK_CUDA_TRY(cudaFuncSetAttribute(nffb_encode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -224,6 +224,22 @@ def posenc_bwd(x: torch.Tensor, bands: Sequence[float], include_input: bool, dy:
     return dx
 
 
+def posenc_dx_bwd(g: torch.Tensor, x: torch.Tensor, bands: Sequence[float], include_input: bool, dy: torch.Tensor,
+                  want_gdy: bool = True, want_gx: bool = True):
+    """Backward of posenc_bwd's map (x, dy) -> dx: (g_dy [n, width] or None, g_x [n, d] or None) for g = dL/d dx."""
+    g, x, dy = rows2d(g, "g"), rows2d(x, "x"), rows2d(dy, "dy")
+    n, d = x.shape
+    width = posenc_width(d, len(bands), include_input)
+    g_dy = torch.empty((n, pad4(width)), device=x.device, dtype=torch.float32) if want_gdy else None
+    g_x = torch.empty((n, d), device=x.device, dtype=torch.float32) if want_gx else None
+    if n == 0 or (g_dy is None and g_x is None):
+        return (g_dy[:, :width] if g_dy is not None else None), g_x
+    hb = (ctypes.c_float * max(len(bands), 1))(*bands)
+    check(lib().idrk_posenc_dx_bwd(ptr(g), ld_of(g), ptr(x), n, d, ld_of(x), hb, len(bands), int(include_input), ptr(dy), ld_of(dy),
+                                   ptr(g_dy), pad4(width) if g_dy is not None else 0, ptr(g_x), d, stream_ptr()), "idrk_posenc_dx_bwd")
+    return (g_dy[:, :width] if g_dy is not None else None), g_x
+
+
 # ---------------------------------------------------------------------------------------------
 # MLP contraction tiles
 # ---------------------------------------------------------------------------------------------

@@ -57,7 +57,7 @@ typedef struct idrk_hashgrid {
 } idrk_hashgrid_t;
 
 /* -- version / capability ------------------------------------------------------------- */
-int idrk_version(void);                        /* ABI version, currently 4 (3 -> 4: idrk_rt_iter_tail, idrk_nffb_encode_f16pair, idrk_gemm_p16, idrk_split_p16, idrk_weight_norm_fwd_p16, idrk_act_bwd_p16; 2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_sumsq_det; idrk_rt_linesearch_points / _resolve; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
+int idrk_version(void);                        /* ABI version, currently 4 (3 -> 4: idrk_posenc_dx_bwd, idrk_rt_iter_tail, idrk_nffb_encode_f16pair, idrk_gemm_p16, idrk_split_p16, idrk_weight_norm_fwd_p16, idrk_act_bwd_p16; 2 -> 3: idrk_hash_encode_fwd gained `perm`, idrk_hash_encode_bwd `flags` and `perm`; idrk_morton_sort; idrk_hash_encode_bwd_det; idrk_sdf_squash_rows; idrk_sumsq_det; idrk_rt_linesearch_points / _resolve; idrk_camera_rays, idrk_idr_loss, idrk_scale3, idrk_fourier_dx_fwd / _bwd; 1 -> 2: idrk_epilogue_f16_t grew dot_w / dot_out / ld_dot; IDRK_HASH_NGP; idrk_hash_encode_f16pair) */
 int idrk_device_sm_count(int* out_sms);        /* SM count of the current device */
 
 /* -- K1: hash-grid encode forward -------------------------------------------------------
@@ -120,6 +120,12 @@ int idrk_posenc_fwd(const float* x, int64_t n, int32_t d, int32_t ldx, const flo
                     int32_t include_input, float* out, int32_t ld_out, void* stream);
 int idrk_posenc_bwd(const float* x, int64_t n, int32_t d, int32_t ldx, const float* h_bands, int32_t n_bands,
                     int32_t include_input, const float* dy, int32_t ld_dy, float* dx, int32_t ld_dx, void* stream);
+/* Backward of idrk_posenc_bwd's map (x, dy) -> dx, for the RECORDED backward of the encoding (ImplicitNetwork.gradient with
+ * create_graph=True through the filter banks' positional encodings, nffb3d.py:170-173): given g = d L / d dx it writes
+ * g_dy [n, ld_gdy] (all `width` columns, pads zero) and / or g_x [n, d] (either may be NULL). */
+int idrk_posenc_dx_bwd(const float* g, int32_t ld_g, const float* x, int64_t n, int32_t d, int32_t ldx, const float* h_bands,
+                       int32_t n_bands, int32_t include_input, const float* dy, int32_t ld_dy, float* g_dy, int32_t ld_gdy,
+                       float* g_x, int32_t ld_gx, void* stream);
 
 /* -- K4: MLP contraction tiles (tcgen05 / TMEM / TMA) --------------------------------------
  * Replaces the nn.Linear + activation pairs of ImplicitNetwork.forward

@@ -24,7 +24,13 @@ def main():
     from tests_support import quiet_build
     K.set_precision("3xtf32")
     torch.manual_seed(0)
-    model = quiet_build(IDRNetwork, bench.model_conf()).cuda().train()
+    conf = bench.model_conf()
+    which = os.environ.get("IDRK_PROFILE_CONF", "")          # FFB | StyleModNFFB: the filter-bank configurations (cfg3 / cfg4 models)
+    if which:
+        from tests_support import make_conf
+        conf = (make_conf("FFB", 6, 5, 16, 512, 0.45, view_type="FFB") if which == "FFB" else
+                make_conf("StyleModNFFB", 6, 22, 16, 512, 0.45, view_type="StyleModNFFB"))
+    model = quiet_build(IDRNetwork, conf).cuda().train()
     tr = DataParallelTrainer(model, IDRLoss(0.1, 100.0, 50.0), lr=1e-4, use_cuda_graph=True)
     inp, rgb = synthetic_batch(bench.N_RAYS, seed=1)
     inp = {k: v.cuda() for k, v in inp.items()}

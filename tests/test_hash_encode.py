@@ -512,3 +512,37 @@ def test_fourier_prefix_max_error_is_recorded():
         float(xp64.abs().max()), err_exact, err_sfu))
     assert err_sfu <= 6e-7, err_sfu
     assert err_exact <= 2e-6, err_exact
+
+
+@pytest.mark.parametrize("include_input", [True, False])
+def test_posenc_recorded_backward_is_one_differentiable_kernel(include_input):
+    """Double backward through the positional encoding (the filter banks inside ImplicitNetwork.gradient with
+    create_graph=True): the recorded d/dx is one kernel with its own backward kernel (autograd_ops._PosEncDx); first- and
+    second-order results vs the same computation in float64 tensor ops."""
+    from idrk import autograd_ops as ops
+    gen = torch.Generator().manual_seed(11)
+    n, d = 3001, 4
+    bands = [2.0 ** k for k in range(6)]
+    x0 = (torch.rand(n, d, generator=gen) * 2 - 1)
+    width = d * ((2 if include_input else 0) + 2 * len(bands))
+    w0 = torch.randn(n, width, generator=gen)
+
+    def run(x, w, enc):
+        y = enc(x)
+        (gx,) = torch.autograd.grad((y * w).sum(), x, create_graph=True)
+        loss = (gx ** 2).sum() + y.sum()
+        loss.backward()
+        return y.detach(), gx.detach(), x.grad.detach(), w.grad.detach()
+
+    def enc_ref(x):
+        cols = [x, x] if include_input else []
+        for f in bands:
+            cols += [torch.sin(x * f), torch.cos(x * f)]
+        return torch.cat(cols, 1)
+    xr, wr = x0.double().requires_grad_(True), w0.double().requires_grad_(True)
+    ref = run(xr, wr, enc_ref)
+    xg, wg = x0.to(DEV).requires_grad_(True), w0.to(DEV).requires_grad_(True)
+    got = run(xg, wg, lambda x: ops.positional_encoding(x, bands, include_input))
+    for a, b, name in zip(got, ref, ("y", "dy/dx", "d loss / dx", "d loss / dw")):
+        scale = b.abs().max().item()
+        assert (a.cpu().double() - b).abs().max().item() <= 2e-5 * scale, name
