@@ -254,3 +254,22 @@ def test_trainer_gradients_across_operand_formats_and_leaf_side_path():
         a, b = g_side[o:o + p.numel()], g_tf32[o:o + p.numel()]
         if b.abs().max() > 0:
             assert (a - b).abs().max() <= 2e-3 * b.abs().max()
+
+
+@pytest.mark.parametrize("prec", ["tf32", "fp32"])
+def test_trainer_step_in_the_single_pass_precision_modes(prec):
+    """set_precision("tf32" | "fp32") (no split operands, hence no side-stream weight-gradient path): a graphed trainer
+    step runs, stays finite, and its loss agrees with the default mode's to the mode's accuracy."""
+    from idrk import kernels as K
+    ref, inp, gt = _small_trainer(True)
+    l_ref = float(ref.step(inp, gt))
+    K.set_precision(prec)
+    try:
+        tr, inp2, gt2 = _small_trainer(True)
+        l = float(tr.step(inp2, gt2))
+        l2 = float(tr.step(inp2, gt2))
+        assert torch.isfinite(tr.bucket.flat).all()
+    finally:
+        K.set_precision("3xtf32")
+    assert abs(l - l_ref) <= (5e-2 if prec == "tf32" else 1e-4) * max(1.0, abs(l_ref)), (l, l_ref)
+    assert l2 == l2
