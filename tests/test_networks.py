@@ -120,7 +120,7 @@ def test_full_width_vs_oracle(prec, rel):
 
 @pytest.mark.parametrize("tag", ["ffb", "style"])
 def test_fused_filter_bank_encoder_matches_module_and_golden(golden, tag):
-    """csrc/nffb.cu (one launch; fp16-pair mma.sync tiles, or FP32 FMAs with IDRK_NFFB_TC=0) vs the module path (contraction / posenc kernels) vs the reference's
+    """csrc/nffb.cu (one launch, FP32 FMAs) vs the module path (contraction / posenc kernels) vs the reference's
     golden embedding-dependent outputs; plus the device-side row count (rows beyond it are not written)."""
     from idrk import kernels as K
     g = golden("networks")
