@@ -997,8 +997,10 @@ extern "C" int idrk_gemm(int32_t layout, int32_t precision, int64_t M, int32_t N
 
     const int terms = precision == IDRK_PREC_3XTF32 ? 3 : 1;
     if (terms == 3 && (!A_lo || !B_lo)) return IDRK_E_ARG;
-    if (layout == IDRK_GEMM_NT && M >= 8192 && N >= 256 && split_k == 1 && use_2cta()) {
-        // large forward / inference batches: CTA-pair kernel (256 x 256 tiles, half the B ingress per SM)
+    if (layout == IDRK_GEMM_NT && M >= 16384 && N >= 256 && split_k == 1 && use_2cta()) {
+        // large forward / inference batches: CTA-pair kernel (256 x 256 tiles, half the B ingress per SM).  Measured
+        // (3xTF32, N = K = 512, back-to-back launches): M = 8192 31.7 vs 27.6 us for the single-CTA kernel, 16384 48.0 vs
+        // 48.7, 32768 77.6 vs 83.8 - it pays from ~16 K rows
         CUtensorMap tA, tAl, tB, tBl;
         int rc;
         if ((rc = make_tmap(&tA, A, (uint64_t)K, (uint64_t)M, lda, BM))) return rc;

@@ -322,7 +322,7 @@ def gemm(layout: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, Kc: int,
         PROFILE.pending_tag = "[%s M=%d N=%d K=%d mode=%d%s%s]" % ("NT NN TN".split()[layout], M, N, Kc, mode,
                                                                   " cnt" if m_count is not None else "",
                                                                   " split%d" % split_k if split_k > 1 else "")
-        if layout == GEMM_NT and M >= 8192 and N >= 256 and split_k == 1:
+        if layout == GEMM_NT and M >= 16384 and N >= 256 and split_k == 1:
             PROFILE.pending_tag = "_2cta" + PROFILE.pending_tag
         if m_count is not None:
             cnt = m_count.clone()
